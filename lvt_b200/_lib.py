@@ -1,0 +1,109 @@
+"""ctypes binding of liblvt_b200.so — the C-ABI declared in include/lvt_b200.h.
+
+There is deliberately no fallback: if the shared library is missing or the device is not a
+B200 the product path raises.  (The CPU oracle under oracle/ is test infrastructure only.)
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "liblvt_b200.so")
+
+_lib = None
+
+
+class LvtError(RuntimeError):
+    pass
+
+
+class LvtGemm(ctypes.Structure):
+    """Mirror of `struct LvtGemm` (include/lvt_b200.h)."""
+    _fields_ = [
+        ("M", ctypes.c_int), ("N", ctypes.c_int), ("K", ctypes.c_int), ("batch", ctypes.c_int),
+        ("splits", ctypes.c_int),
+        ("a", ctypes.c_void_p), ("a_mn_major", ctypes.c_int), ("a_cin", ctypes.c_int),
+        ("a_zdiv", ctypes.c_int),
+        ("a_ld", ctypes.c_longlong), ("a_s_blk", ctypes.c_longlong), ("a_s_zlo", ctypes.c_longlong),
+        ("a_s_zhi", ctypes.c_longlong),
+        ("b", ctypes.c_void_p), ("b_mn_major", ctypes.c_int), ("b_cin", ctypes.c_int),
+        ("b_zdiv", ctypes.c_int),
+        ("b_ld", ctypes.c_longlong), ("b_s_blk", ctypes.c_longlong), ("b_s_zlo", ctypes.c_longlong),
+        ("b_s_zhi", ctypes.c_longlong),
+        ("mode", ctypes.c_int), ("flags", ctypes.c_int), ("alpha", ctypes.c_float),
+        ("out_f32", ctypes.c_void_p), ("out_bf16", ctypes.c_void_p), ("res", ctypes.c_void_p),
+        ("aux_bf16", ctypes.c_void_p), ("bias", ctypes.c_void_p), ("bias_mod", ctypes.c_int),
+        ("o_cin", ctypes.c_int), ("o_zdiv", ctypes.c_int),
+        ("o_ld", ctypes.c_longlong), ("o_s_blk", ctypes.c_longlong), ("o_s_zlo", ctypes.c_longlong),
+        ("o_s_zhi", ctypes.c_longlong),
+        ("lse", ctypes.c_void_p), ("delta", ctypes.c_void_p),
+        ("bank_t", ctypes.c_void_p), ("bank_h", ctypes.c_void_p), ("bank_w", ctypes.c_void_p),
+        ("bt", ctypes.c_int), ("bh", ctypes.c_int), ("bw", ctypes.c_int), ("heads", ctypes.c_int),
+    ]
+
+
+_vp, _i, _ll, _d, _f = (ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_double,
+                        ctypes.c_float)
+# symbol -> (restype, argtypes); one entry per function include/lvt_b200.h declares
+SYMBOLS = {
+    "lvt_abi_version": (_i, []),
+    "lvt_last_error": (ctypes.c_char_p, []),
+    "lvt_device_check": (_i, []),
+    "lvt_launch_count": (_ll, []),
+    "lvt_launch_count_reset": (None, []),
+    "lvt_vq_argmin": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "lvt_vq_ema_update": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _d, _d, _vp]),
+    "lvt_vq_gather": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "lvt_gemm_bf16": (_i, [ctypes.POINTER(LvtGemm), _vp]),
+}
+
+
+def load():
+    """Load the shared library (once). Raises LvtError when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise LvtError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; "
+            "g.build()'` (or `make -C lvt_b200/csrc`). lvt_b200 has no CPU / PyTorch fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = load().lvt_last_error()
+        raise LvtError(f"{what} failed ({rc}): {msg.decode() if msg else ''}")
+
+
+def stream_ptr():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    if t is None:
+        return None
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def require_device():
+    lib = load()
+    if not torch.cuda.is_available():
+        raise LvtError("lvt_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    check(lib.lvt_device_check(), "lvt_device_check")
+    return lib
+
+
+def launch_count():
+    return int(load().lvt_launch_count())
+
+
+def launch_count_reset():
+    load().lvt_launch_count_reset()

@@ -1,0 +1,46 @@
+// lvt_b200 :: library-level C-ABI entry points (error string, device check, launch counter).
+#include <atomic>
+#include <stdarg.h>
+#include <stdio.h>
+
+#include "../../include/lvt_b200.h"
+#include "common.cuh"
+
+static thread_local char g_last_error[1024] = "";
+static std::atomic<long long> g_launches{0};
+
+void lvt_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_last_error, sizeof(g_last_error), fmt, ap);
+  va_end(ap);
+}
+
+void lvt_count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+extern "C" int lvt_abi_version(void) { return LVT_B200_ABI_VERSION; }
+
+extern "C" const char* lvt_last_error(void) { return g_last_error; }
+
+extern "C" long long lvt_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+extern "C" void lvt_launch_count_reset(void) { g_launches.store(0, std::memory_order_relaxed); }
+
+extern "C" int lvt_device_check(void) {
+  int dev = -1;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) {
+    lvt_set_error("no CUDA device: %s", cudaGetErrorString(e));
+    cudaGetLastError();
+    return LVT_ERR_NO_DEVICE;
+  }
+  int major = 0, minor = 0;
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
+  if (major != 10) {
+    lvt_set_error("device %d is sm_%d%d; lvt_b200 is built for sm_100a only and has no fallback",
+                  dev, major, minor);
+    return LVT_ERR_NO_DEVICE;
+  }
+  return LVT_OK;
+}

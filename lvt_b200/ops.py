@@ -1,0 +1,144 @@
+"""Thin Python wrappers over the C-ABI (include/lvt_b200.h): raw device pointers of torch
+tensors + the current CUDA stream go straight into liblvt_b200.so.  torch is only the owner of
+device memory and streams here; no torch op sits on these paths.
+"""
+import ctypes
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import LvtGemm, check, ptr, stream_ptr
+
+EPI_LINEAR, EPI_SOFTMAX, EPI_DS = 0, 1, 2
+GEMM_RELU, GEMM_MASK, GEMM_ATOMIC, GEMM_CAUSAL = 1, 2, 4, 8
+
+
+def _cuda_contig(t, dtype, name):
+    if not t.is_cuda:
+        raise _lib.LvtError(f"{name} must be a CUDA tensor (lvt_b200 has no CPU path)")
+    if t.dtype != dtype:
+        raise _lib.LvtError(f"{name} must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise _lib.LvtError(f"{name} must be contiguous")
+    return t
+
+
+# --------------------------------------------------------------------------------------------
+# VQ codebook
+# --------------------------------------------------------------------------------------------
+def vq_argmin(z_e, codebook, want_zq=False, counts=None, sums=None):
+    """z_e [n, num*D, h, w] fp32 NCHW; codebook [num, K, D] fp32 -> idx [n, num, h, w] int64
+    (+ z_q [n, num*D, h, w] gathered from `codebook` when want_zq).  Accumulates EMA statistics
+    into counts [num,K] / sums [num,K,D] when given.  (vq_utils.py:7-24, vq_embedding.py:36-55)"""
+    lib = _lib.require_device()
+    _cuda_contig(z_e, torch.float32, "z_e")
+    _cuda_contig(codebook, torch.float32, "codebook")
+    n, c, h, w = z_e.shape
+    num, K, D = codebook.shape
+    if c != num * D:
+        raise _lib.LvtError(f"z_e has {c} channels, codebook expects {num}*{D}")
+    idx = torch.empty((n, num, h, w), dtype=torch.int64, device=z_e.device)
+    zq = torch.empty_like(z_e) if want_zq else None
+    check(lib.lvt_vq_argmin(ptr(z_e), ptr(codebook), ptr(idx), ptr(zq), ptr(counts), ptr(sums),
+                            n, num, K, D, h * w, stream_ptr()), "lvt_vq_argmin")
+    return (idx, zq) if want_zq else idx
+
+
+def vq_gather(idx, codebook):
+    """idx [n, num, h, w] int64 -> [n, num*D, h, w] fp32 NCHW (vq_embedding.py:92-97 + permute)."""
+    lib = _lib.require_device()
+    _cuda_contig(idx, torch.int64, "idx")
+    _cuda_contig(codebook, torch.float32, "codebook")
+    n, num, h, w = idx.shape
+    num2, K, D = codebook.shape
+    assert num == num2
+    out = torch.empty((n, num * D, h, w), dtype=torch.float32, device=idx.device)
+    check(lib.lvt_vq_gather(ptr(idx), ptr(codebook), ptr(out), n, num, K, D, h * w, stream_ptr()),
+          "lvt_vq_gather")
+    return out
+
+
+def vq_ema_update(codebook, running_size, running_sum, counts, sums, decay=0.99, eps=1e-5):
+    lib = _lib.require_device()
+    num, K, D = codebook.shape
+    check(lib.lvt_vq_ema_update(ptr(codebook), ptr(running_size), ptr(running_sum), ptr(counts),
+                                ptr(sums), num, K, D, float(decay), float(eps), stream_ptr()),
+          "lvt_vq_ema_update")
+
+
+# --------------------------------------------------------------------------------------------
+# GEMM
+# --------------------------------------------------------------------------------------------
+@dataclass
+class Operand:
+    """Addressing of one GEMM operand / of the output (see `struct LvtGemm`)."""
+    data: int                 # device pointer
+    ld: int                   # stride of the strided coordinate (elements)
+    mn_major: bool = False
+    cin: int = 0              # 0 -> full extent (plain 2-D)
+    s_blk: int = 0
+    zdiv: int = 1
+    s_zlo: int = 0
+    s_zhi: int = 0
+
+
+def op_kmajor(t, rows=None):
+    """2-D tensor [rows, K] (row stride arbitrary, last dim contiguous) as a K-major operand."""
+    assert t.stride(-1) == 1
+    return Operand(t.data_ptr(), t.stride(0))
+
+
+def op_mnmajor(t):
+    """2-D tensor [K, rows] (last dim contiguous) as an MN-major operand (i.e. used transposed)."""
+    assert t.stride(-1) == 1
+    return Operand(t.data_ptr(), t.stride(0), mn_major=True)
+
+
+def gemm(M, N, K, a: Operand, b: Operand, out: Operand, out_f32=None, out_bf16=None, batch=1,
+         splits=1, alpha=1.0, mode=EPI_LINEAR, flags=0, bias=None, bias_mod=0, res=None, aux=None,
+         lse=None, delta=None, banks=None, block=None, heads=1):
+    """D[z] = epilogue(alpha * A[z] @ B[z]^T); pointers may be torch tensors or ints."""
+    lib = _lib.require_device()
+
+    def p(x):
+        if x is None:
+            return None
+        if isinstance(x, int):
+            return ctypes.c_void_p(x)
+        return ctypes.c_void_p(x.data_ptr())
+
+    g = LvtGemm()
+    g.M, g.N, g.K, g.batch, g.splits = M, N, K, batch, splits
+    g.a = a.data
+    g.a_mn_major = int(a.mn_major)
+    g.a_cin = a.cin or (M if a.mn_major else K)
+    g.a_zdiv, g.a_ld, g.a_s_blk, g.a_s_zlo, g.a_s_zhi = a.zdiv, a.ld, a.s_blk, a.s_zlo, a.s_zhi
+    g.b = b.data
+    g.b_mn_major = int(b.mn_major)
+    g.b_cin = b.cin or (N if b.mn_major else K)
+    g.b_zdiv, g.b_ld, g.b_s_blk, g.b_s_zlo, g.b_s_zhi = b.zdiv, b.ld, b.s_blk, b.s_zlo, b.s_zhi
+    g.mode, g.flags, g.alpha = mode, flags, alpha
+    g.out_f32, g.out_bf16 = p(out_f32), p(out_bf16)
+    g.res, g.aux_bf16, g.bias, g.bias_mod = p(res), p(aux), p(bias), bias_mod
+    g.o_cin = out.cin or N
+    g.o_zdiv, g.o_ld, g.o_s_blk, g.o_s_zlo, g.o_s_zhi = out.zdiv, out.ld, out.s_blk, out.s_zlo, out.s_zhi
+    g.lse, g.delta = p(lse), p(delta)
+    if banks is not None:
+        g.bank_t, g.bank_h, g.bank_w = p(banks[0]), p(banks[1]), p(banks[2])
+        g.bt, g.bh, g.bw = block
+    g.heads = heads
+    check(lib.lvt_gemm_bf16(ctypes.byref(g), stream_ptr()), "lvt_gemm_bf16")
+
+
+def linear_bf16(x, w, bias=None, relu=False, out_dtype=torch.bfloat16, res=None):
+    """y = x @ w^T (+bias) (+res) [relu]; x [M,K] bf16, w [N,K] bf16 (nn.Linear layout)."""
+    M, K = x.shape
+    N = w.shape[0]
+    y = torch.empty((M, N), dtype=out_dtype, device=x.device)
+    gemm(M, N, K, op_kmajor(x), op_kmajor(w), Operand(y.data_ptr(), N),
+         out_f32=y if out_dtype == torch.float32 else None,
+         out_bf16=y if out_dtype == torch.bfloat16 else None,
+         bias=bias, res=res, flags=GEMM_RELU if relu else 0)
+    return y
