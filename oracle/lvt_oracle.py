@@ -355,10 +355,13 @@ def masked_conv3d(x: Tensor, weight: Tensor, bias: Tensor) -> Tensor:
     """MaskedConv3d.forward (vt_utils.py:183-200): causal pad (w: k//2 both sides, h and t: k-1 in
     front), taps [:, :, -1, -1, kw//2:] zeroed, VALID conv."""
     kt, kh, kw = weight.shape[2:]
-    w = weight.clone()
     if kw // 2 > 0:
-        w[:, :, -1, -1, kw // 2:] = 0
-    return F.conv3d(F.pad(x, [kw // 2, kw // 2, kh - 1, 0, kt - 1, 0]), w, bias)
+        # like the reference, the masked taps are zeroed IN PLACE in the parameter's data (so
+        # autograd still reports a non-zero gradient for them; they are re-zeroed before every
+        # use, hence never influence an output).  The CUDA path keeps them at zero instead.
+        with torch.no_grad():
+            weight[:, :, -1, -1, kw // 2:] = 0
+    return F.conv3d(F.pad(x, [kw // 2, kw // 2, kh - 1, 0, kt - 1, 0]), weight, bias)
 
 
 def vt_decoder(slc: Tensor, zl: Tensor, sd, cfg: VTConfig) -> Tensor:

@@ -1,0 +1,128 @@
+"""CPU: pins the oracle (oracle/lvt_oracle.py, oracle/vq_oracle.c) against golden vectors
+produced by the UNMODIFIED reference (tests/golden/make_golden.py, run in the authoring
+container).  Integer results bit-exact; floating point within the stated tolerances
+(the oracle uses the same ATen CPU ops as the reference, so agreement is ~1e-6)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import lvt_oracle as O
+from oracle import vq as ovq
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+torch.set_num_threads(min(8, os.cpu_count() or 1))
+
+
+def _load(name):
+    return np.load(os.path.join(GOLD, name))
+
+
+def test_vq_oracle_matches_reference_bitwise():
+    fix = _load("vq.npz")
+    g = torch.Generator().manual_seed(3)
+    for D in (64, 256):
+        x = torch.randn((1024, D), generator=g) * 0.3
+        cb = torch.randn((512, D), generator=g) * 0.3
+        # C oracle works on NCHW input with DVQ groups: present x as [n=1, D, hw=1024, 1]
+        z = x.t().reshape(1, D, 1024, 1).contiguous()
+        idx, dist = ovq.vq_argmin_c(z, cb[None], want_dist=True)
+        assert np.array_equal(idx.view(-1).numpy(), fix[f"D{D}:idx"])
+        # distances bit-identical to the reference's addmm (fp32 bit patterns)
+        got = dist.view(1024, 512)[:4].numpy()
+        assert np.array_equal(got.view(np.uint32), fix[f"D{D}:dist_rows"].view(np.uint32))
+        # and the literal torch restatement agrees as well
+        assert np.array_equal(ovq.vq_torch(x, cb)[0].numpy(), fix[f"D{D}:idx"])
+
+
+def test_mapper_restatement_matches_reference():
+    fix = _load("mapper.npz")
+    specs = {"DSFVT": ((7, 1, 1), (16, 1, 1), 1, 16), "DSSVT": ((1, 3, 3), (1, 2, 2), 1, 4),
+             "DSTSVT": ((5, 3, 3), (4, 2, 2), 1, 16)}
+    for name, (kernel, stride, n_prime, T) in specs.items():
+        cfg = O.VTConfig(kernel=kernel, stride=stride, n_prime=n_prime, video_shape=(T, 16, 16))
+        idx2abc, _ = O.subscale_order(*stride)
+        for i in range(3):
+            video = O.synth_latent_video(500 + i, cfg)
+            abc = idx2abc[int(fix[f"{name}:{i}:slice_idx"])]
+            got = O.prepare_slice(video, abc, cfg)
+            for k in ("context", "slice", "ignore_mask"):
+                assert np.array_equal(got[k].numpy(), fix[f"{name}:{i}:{k}"]), (name, i, k)
+
+
+def test_reference_embedded_mask_tests():
+    """The reference's own embedded unit tests (vt_utils.py:17-21,36-45,60-72), restated."""
+    idx2abc, abc2idx = O.subscale_order(4, 2, 2)
+    assert len(idx2abc) == len(abc2idx) and min(abc2idx.values()) >= 0 and max(abc2idx.values()) < len(idx2abc)
+    assert O.slice_mask(0, 1, 1, 1, 2, 2, 4, 4, 4, dtype=torch.float).sum().item() == 4 * 2 * 2
+    vm = O.visible_abc_mask(1, 0, 0, 2, 2, 1, 4, 4, 4, dtype=torch.float)
+    _, a2i = O.subscale_order(2, 2, 1)
+    assert vm.sum().item() == 2 * 2 * 4 * a2i[(1, 0, 0)]
+    # test_masked_conv3d (:203-206): shape preserved
+    x = torch.rand(2, 3, 10, 30, 40)
+    assert O.masked_conv3d(x, torch.ones(3, 3, 3, 3, 3), torch.zeros(3)).shape == x.shape
+
+
+def _vqvae_setup(init, fix):
+    cfg = O.VQVAEConfig()
+    eshape, gshape = O.vqvae_param_shapes(cfg)
+    we, wg = O.synth_weights(eshape, seed=11), O.synth_weights(gshape, seed=12)
+    x = torch.rand((8, 3, 64, 64), generator=torch.Generator().manual_seed(1234))
+    gcb = torch.Generator().manual_seed(5)
+    if init == "default":
+        cb = (torch.rand((4, 512, 64), generator=gcb) * 2 - 1) / 512
+    else:
+        cb = torch.randn((4, 512, 64), generator=gcb) * torch.tensor(fix["spread_std"])
+    return cfg, we, wg, x, cb
+
+
+@pytest.mark.parametrize("init", ["default", "spread"])
+def test_vqvae_oracle_matches_reference(init):
+    fix = _load("vqvae.npz")
+    cfg, we, wg, x, cb = _vqvae_setup(init, fix)
+    with torch.no_grad():
+        recon, latent = O.vqvae_inference(x, we, wg, cb, cfg)
+    assert np.array_equal(latent.numpy(), fix[f"{init}:latent"])  # bit-exact code indices
+    assert np.allclose(recon[:, :, ::5, ::7].numpy(), fix[f"{init}:recon_sub"], rtol=1e-5, atol=1e-6)
+    # the C restatement gives the same indices from the same z_e
+    with torch.no_grad():
+        z_e = O.res_encoder((x - 0.5) / 0.5, we, cfg.n_layers)
+    assert np.array_equal(ovq.vq_argmin_c(z_e, cb).numpy(), fix[f"{init}:latent"])
+    # one supervised step (EMA, GPU semantics)
+    we_g = {k: v.clone().requires_grad_(True) for k, v in we.items()}
+    wg_g = {k: v.clone().requires_grad_(True) for k, v in wg.items()}
+    losses, aux = O.vqvae_supervised_loss(x, we_g, wg_g, cb, torch.zeros(4, 512), cb.clone(), cfg)
+    sum(losses.values()).backward()
+    for k in ("loss_reconstruction", "loss_commitment"):
+        assert np.allclose(losses[k].item(), fix[f"{init}:{k}"], rtol=1e-5), k
+    assert np.allclose(aux["codebooks"][:, ::16, ::8].numpy(), fix[f"{init}:codebook_after_sub"], rtol=1e-4, atol=1e-7)
+    assert np.allclose(aux["running_size"].numpy(), fix[f"{init}:running_size"], rtol=1e-5, atol=1e-7)
+    for k in ("layers.0.weight", "layers.4.weight", "layers.6.block.3.weight"):
+        assert np.allclose(we_g[k].grad.double().norm().item(), fix[f"{init}:gE:{k}"], rtol=1e-4), k
+    for k in ("layers.0.weight", "layers.4.weight", "layers.6.weight"):
+        assert np.allclose(wg_g[k].grad.double().norm().item(), fix[f"{init}:gG:{k}"], rtol=1e-4), k
+
+
+@pytest.mark.parametrize("tag,layers,batch", [("dsfvt_l2", 2, 3), ("dsfvt_full", 8, 2)])
+def test_dsfvt_oracle_matches_reference(tag, layers, batch):
+    fix = _load(tag + ".npz")
+    cfg = O.VTConfig(blocks_e=tuple([(1, 16, 16)] * layers), heads_e=tuple([8] * layers),
+                     blocks_d=tuple([(1, 16, 16)] * layers), heads_d=tuple([8] * layers))
+    sd = {k: v.requires_grad_(True) for k, v in O.synth_weights(O.dsfvt_param_shapes(cfg), seed=1234).items()}
+    context, slc, slice_idx, ignore = O.synth_vt_batch(batch, seed=77, cfg=cfg)
+    assert np.array_equal(slice_idx.numpy(), fix["slice_idx"]) and context.sum().item() == fix["context_sum"]
+    loss = O.vt_supervised_loss(context, slc, slice_idx, ignore, sd, cfg)
+    loss.backward()
+    assert np.allclose(loss.item(), fix["loss"], rtol=1e-6)
+    with torch.no_grad():
+        logits = torch.stack(O.vt_logits(context, slc, slice_idx, sd, cfg))
+    assert np.allclose(logits[:, :, ::7, 0, ::3, ::5].numpy(), fix["logits_sub"], rtol=1e-4, atol=1e-5)
+    assert np.allclose(logits.double().sum().item(), fix["logits_sum"], rtol=1e-5)
+    for key in fix.files:
+        if key.startswith("gnorm:"):
+            k = key[6:]
+            g = sd[k].grad
+            assert np.allclose(g.double().norm().item(), fix[key], rtol=1e-4), k
+            sub = g.reshape(-1)[::max(1, g.numel() // 64)][:64].numpy()
+            assert np.allclose(sub, fix["gsub:" + k], rtol=1e-3, atol=1e-7), k
