@@ -130,6 +130,80 @@ typedef struct LvtGemm {
 
 int lvt_gemm_bf16(const LvtGemm* g, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * DSFVT bandwidth-bound operators
+ * ---------------------------------------------------------------------------------------- */
+/* nn.LayerNorm(d) forward (vt_attention.py:121,138; videotransformer.py:143): x fp32 [M,d] ->
+ * y bf16 [M,d]; mean/rstd [M] are saved for the backward.  d in {128,256,512,1024}.          */
+int lvt_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y_bf16,
+                      float* mean, float* rstd, int M, int d, float eps, void* stream);
+/* LayerNorm backward: dx = [dres +] dLN(dy); written as fp32 (dx_f32) and/or bf16 (dx_bf16);
+ * dgamma/dbeta [d] are ACCUMULATED (+=).  d in {128,256,512}.                                */
+int lvt_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd,
+                      const float* gamma, const float* dres, float* dx_f32, void* dx_bf16,
+                      float* dgamma, float* dbeta, int M, int d, void* stream);
+/* out[n] += sum_m x[m*ld + n], x bf16 (bias gradients of nn.Linear / Conv3d).                */
+int lvt_colsum_bf16(const void* x, float* out, int M, int N, long long ld, void* stream);
+/* delta[b,h,i] = sum_d dO[b*L+i, h*da+d] * O[b*L+i, h*da+d] (softmax backward row term of
+ * ScaledDotProductAttention, vt_attention.py:75-80); dO, O bf16 [nb*L, H*da].                */
+int lvt_attn_delta(const void* dO, const void* O, float* delta, int nb, int H, int L, int da,
+                   void* stream);
+/* Gradient of dt_bank/dh_bank/dw_bank (BlockLocalAttention.get_B, vt_attention.py:169-174):
+ * dS bf16 [nb, H, 256, 256]; dbank_x [H, 2*bx-1] ACCUMULATED.                                */
+int lvt_relpos_bank_grad(const void* dS, float* dbank_t, float* dbank_h, float* dbank_w, int nb,
+                         int H, int bt, int bh, int bw, void* stream);
+/* VTEncoder front end (videotransformer.py:41-53): pad-aware one-hot -> Conv3d(nc*nv -> de,
+ * kernel, stride) -> + slice_embedding[slice_idx], evaluated as a gather-sum.
+ *   context [B, nc, Tc, Hc, Wc] int64 (pad_value entries contribute nothing)
+ *   wt      [nc, kt, kh, kw, nv, de] fp32 = encoder.conv.weight permuted (lvt_permute4)
+ *   out     bf16 [B*to*ho*wo, de]   (to = (Tc-kt)/st+1, ...);  ctx_shape/kernel/stride: int[3]
+ * backward: dout fp32 [rows, de] is scattered (+=) into dwt and dslice_emb.                  */
+int lvt_vt_enc_front_fwd(const int64_t* context, const int64_t* slice_idx, const float* wt,
+                         const float* bias, const float* slice_emb, void* out_bf16, int B, int nc,
+                         int nv, int de, const int* ctx_shape, const int* kernel,
+                         const int* stride, int pad_value, void* stream);
+int lvt_vt_enc_front_bwd(const int64_t* context, const int64_t* slice_idx, const float* dout,
+                         float* dwt, float* dslice_emb, int B, int nc, int nv, int de,
+                         const int* ctx_shape, const int* kernel, const int* stride,
+                         int pad_value, void* stream);
+/* VTDecoder front end (videotransformer.py:80-89 embed_sum + the im2col of MaskedConv3d,
+ * vt_utils.py:183-200): out bf16 [B*t*h*w, ntaps*de]; row m, tap q = sum_k emb[k, slice[b,k,
+ * pos(m)+taps[q]]] or 0 outside the slice.  emb [nc, nv, de] fp32; taps int[ntaps*3] (device).
+ * backward: dA fp32 [rows, ntaps*de] -> demb [nc, nv, de] ACCUMULATED.                       */
+int lvt_vt_dec_front_fwd(const int64_t* slice, const float* emb, const int* taps, void* out_bf16,
+                         int B, int nc, int nv, int de, int t, int h, int w, int ntaps,
+                         void* stream);
+int lvt_vt_dec_front_bwd(const int64_t* slice, const float* dA, const int* taps, float* demb, int B,
+                         int nc, int nv, int de, int t, int h, int w, int ntaps, void* stream);
+/* ChannelPredictor U[k] one-hot half + ReLU (videotransformer.py:148-150):
+ * a[m,:] = relu(u[m,:] + sum_{j<k} ut[j*nv + slice[b,j,pos], :]); u fp32 [M,d] (dense half incl.
+ * bias), ut fp32 [k*nv, d] = U[k].weight[:, d:]^T, a bf16 [M,d].  backward scatters du (bf16)
+ * into dut (+=).                                                                            */
+int lvt_chpred_combine_fwd(const float* u, const float* ut, const int64_t* slice, void* a_bf16,
+                           int M, int nc, int nv, int d, int thw, int k, void* stream);
+int lvt_chpred_combine_bwd(const void* du_bf16, const int64_t* slice, float* dut, int M, int nc,
+                           int nv, int d, int thw, int k, void* stream);
+/* loss = 1/nc * sum_k mean_valid CE(logits[k], slice[:,k]) with the shared ignore mask
+ * (meta_arch/vt.py:305-312).  logits fp32 [nc, B*thw, nv]; slice int64 [B, nc, thw]; ignore
+ * uint8 [B, thw]; dlogits bf16 [nc, B*thw, nv] (optional) receives dloss/dlogits; loss: 1 float
+ * (overwritten); count_scratch: 1 int.                                                      */
+int lvt_cross_entropy(const float* logits, const int64_t* slice, const uint8_t* ignore,
+                      void* dlogits_bf16, float* loss, int* count_scratch, int B, int nc, int nv,
+                      int thw, void* stream);
+/* torch.optim.RMSprop / Adam steps (solver/build.py:62-72) over flat fp32 buffers of n elements
+ * (n % 4 == 0), gradients pre-multiplied by grad_scale; p_bf16 (optional) receives the bf16
+ * shadow copy the GEMMs read.                                                               */
+int lvt_rmsprop_step(float* p, const float* g, float* sq, float* buf, void* p_bf16, long long n,
+                     float lr, float alpha, float momentum, float eps, float grad_scale,
+                     void* stream);
+int lvt_adam_step(float* p, const float* g, float* m, float* v, void* p_bf16, long long n, float lr,
+                  float beta1, float beta2, float eps, int step, float grad_scale, void* stream);
+int lvt_cast_bf16(const float* in, void* out_bf16, long long n, void* stream);
+/* out[sum i_k*out_strides[k]] (=|+=) in[sum i_k*in_strides[k]] over dims[4] (layout packing of
+ * the small weights: one-hot conv, masked conv taps, U[k] one-hot halves).                  */
+int lvt_permute4(const float* in, void* out, int out_is_bf16, int accumulate, const int* dims,
+                 const long long* in_strides, const long long* out_strides, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -56,6 +56,22 @@ SYMBOLS = {
     "lvt_vq_ema_update": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _d, _d, _vp]),
     "lvt_vq_gather": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "lvt_gemm_bf16": (_i, [ctypes.POINTER(LvtGemm), _vp]),
+    "lvt_layernorm_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp]),
+    "lvt_layernorm_bwd": (_i, [_vp] * 10 + [_i, _i, _vp]),
+    "lvt_colsum_bf16": (_i, [_vp, _vp, _i, _i, _ll, _vp]),
+    "lvt_attn_delta": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "lvt_relpos_bank_grad": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "lvt_vt_enc_front_fwd": (_i, [_vp] * 6 + [_i] * 4 + [_vp] * 3 + [_i, _vp]),
+    "lvt_vt_enc_front_bwd": (_i, [_vp] * 5 + [_i] * 4 + [_vp] * 3 + [_i, _vp]),
+    "lvt_vt_dec_front_fwd": (_i, [_vp] * 4 + [_i] * 8 + [_vp]),
+    "lvt_vt_dec_front_bwd": (_i, [_vp] * 4 + [_i] * 8 + [_vp]),
+    "lvt_chpred_combine_fwd": (_i, [_vp] * 4 + [_i] * 6 + [_vp]),
+    "lvt_chpred_combine_bwd": (_i, [_vp] * 3 + [_i] * 6 + [_vp]),
+    "lvt_cross_entropy": (_i, [_vp] * 6 + [_i] * 4 + [_vp]),
+    "lvt_rmsprop_step": (_i, [_vp] * 5 + [_ll] + [_f] * 5 + [_vp]),
+    "lvt_adam_step": (_i, [_vp] * 5 + [_ll] + [_f] * 4 + [_i, _f, _vp]),
+    "lvt_cast_bf16": (_i, [_vp, _vp, _ll, _vp]),
+    "lvt_permute4": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),
 }
 
 

@@ -1,0 +1,711 @@
+"""DSFVT execution engine: the whole VideoTransformer forward / backward as a fixed sequence of
+C-ABI launches (include/lvt_b200.h) over pre-allocated HBM buffers.
+
+Reference semantics: vidgen/modeling/autoregressive/videotransformer.py:11-248,
+vt_attention.py:10-202, vt_utils.py:183-200 and the loss of meta_arch/vt.py:301-314.
+
+Data layout in HBM (M = B * t*h*w tokens of the slice, token-major everywhere; the reference's
+(B,C,T,H,W) <-> (B,thw,C) transposes around every layer, vt_attention.py:183-188, disappear):
+  residual stream x        fp32 [M, d]
+  GEMM operands            bf16 (LayerNorm outputs, qkv [M, 3*H*da], attention probabilities
+                           P [B, H, L, L], head-concat o [M, H*da], FFN hidden a1 [M, d])
+  parameters               one flat fp32 master buffer (+ flat fp32 gradient, + flat bf16 shadow
+                           read by the GEMMs through TMA), laid out so that w_q|w_k|w_v of a layer
+                           are contiguous ([3H, d, da] blocked MN-major B operand)
+No torch op runs on this path; torch owns the device memory and the stream only.
+"""
+import ctypes
+import math
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from ... import _lib, ops
+from ..._lib import check, ptr, stream_ptr
+from ...ops import Operand, gemm
+
+LN_EPS = 1e-5
+_ALIGN = 64  # elements; keeps every parameter 256 B (fp32) / 128 B (bf16) aligned for TMA
+
+
+class VTSpec:
+    """MODEL.AUTOREGRESSIVE.VT.* (reference config/defaults.py:36-53)."""
+
+    def __init__(self, nc=4, nv=512, kernel=(7, 1, 1), stride=(16, 1, 1), de=128, d=512, da=128,
+                 blocks_e=((1, 16, 16),) * 8, heads_e=(8,) * 8, blocks_d=((1, 16, 16),) * 8,
+                 heads_d=(8,) * 8, pad_value=-1, ignore_index=-100, share_p=False,
+                 share_embeddings=False, class_num=0):
+        self.nc, self.nv = int(nc), int(nv)
+        self.kernel, self.stride = tuple(kernel), tuple(stride)
+        self.de, self.d, self.da = int(de), int(d), int(da)
+        self.blocks_e = tuple(tuple(b) for b in blocks_e)
+        self.blocks_d = tuple(tuple(b) for b in blocks_d)
+        self.heads_e, self.heads_d = tuple(heads_e), tuple(heads_d)
+        self.pad_value, self.ignore_index = int(pad_value), int(ignore_index)
+        if share_p or share_embeddings or class_num:
+            raise _lib.LvtError("lvt_b200 implements the shipped VT configs: SHARE_P=False, "
+                                "SHARE_EMBEDDINGS=False, CLASS_NUM=0")
+        heads = set(self.heads_e) | set(self.heads_d)
+        if len(heads) != 1:
+            raise _lib.LvtError("all attention layers must use the same number of heads")
+        self.H = heads.pop()
+        blocks = set(self.blocks_e) | set(self.blocks_d)
+        if len(blocks) != 1:
+            raise _lib.LvtError("all attention layers must use the same block shape")
+        self.block = blocks.pop()
+        if self.block[0] * self.block[1] * self.block[2] != 256:
+            raise _lib.LvtError("attention blocks must hold 256 positions (all shipped configs do)")
+
+    def param_shapes(self):
+        """Names / shapes / order of the reference state_dict parameters
+        (videotransformer.py:11-33,62-78,104-137; vt_attention.py:98-104,132-144)."""
+        s = {}
+        kt, kh, kw = self.kernel
+        s["encoder.conv.weight"] = (self.de, self.nc * self.nv, kt, kh, kw)
+        s["encoder.conv.bias"] = (self.de,)
+        s["encoder.slice_embedding.weight"] = (self.stride[0] * self.stride[1] * self.stride[2], self.de)
+        s["encoder.linear_projector.weight"] = (self.d, self.de, 1, 1, 1)
+
+        def bla(prefix):
+            t, h, w = self.block
+            s[prefix + "dt_bank"] = (self.H, 2 * t - 1)
+            s[prefix + "dh_bank"] = (self.H, 2 * h - 1)
+            s[prefix + "dw_bank"] = (self.H, 2 * w - 1)
+            for n in ("w_q", "w_k", "w_v"):  # contiguous on purpose (blocked [3H, d, da] operand)
+                s[prefix + "mha." + n] = (self.H, self.d, self.da)
+            s[prefix + "mha.layer_norm.weight"] = (self.d,)
+            s[prefix + "mha.layer_norm.bias"] = (self.d,)
+            s[prefix + "mha.proj.weight"] = (self.d, self.H * self.da)
+            s[prefix + "ffn.0.weight"] = (self.d,)
+            s[prefix + "ffn.0.bias"] = (self.d,)
+            s[prefix + "ffn.1.weight"] = (self.d, self.d)
+            s[prefix + "ffn.1.bias"] = (self.d,)
+            s[prefix + "ffn.3.weight"] = (self.d, self.d)
+            s[prefix + "ffn.3.bias"] = (self.d,)
+
+        for i in range(len(self.blocks_e)):
+            bla(f"encoder.block_local_attention.{i}.")
+        for k in range(self.nc):
+            s[f"decoder.ch_embedder.{k}.weight"] = (self.nv, self.de)
+        s["decoder.conv.conv.weight"] = (self.d, self.de, 3, 3, 3)
+        s["decoder.conv.conv.bias"] = (self.d,)
+        s["decoder.linear_projector.weight"] = (self.d, self.d, 1, 1, 1)
+        for i in range(len(self.blocks_d)):
+            bla(f"decoder.block_local_attention.{i}.")
+        s["ch_predictor.layer_norm.weight"] = (self.d,)
+        s["ch_predictor.layer_norm.bias"] = (self.d,)
+        for k in range(self.nc):
+            s[f"ch_predictor.U.{k}.weight"] = (self.d, self.d + k * self.nv)
+            s[f"ch_predictor.U.{k}.bias"] = (self.d,)
+        for k in range(self.nc):
+            s[f"ch_predictor.P.{k}.weight"] = (self.nv, self.d)
+            s[f"ch_predictor.P.{k}.bias"] = (self.nv,)
+        return s
+
+
+class ParamStore:
+    """Flat fp32 master / gradient / bf16 shadow buffers with named views."""
+
+    def __init__(self, shapes: Dict[str, Tuple[int, ...]], device):
+        self.shapes = dict(shapes)
+        self.offsets = {}
+        off = 0
+        for name, shp in shapes.items():
+            self.offsets[name] = off
+            n = int(np.prod(shp))
+            off += (n + _ALIGN - 1) // _ALIGN * _ALIGN
+        self.numel = off
+        self.device = device
+        self.master = torch.zeros(off, dtype=torch.float32, device=device)
+        self.grad = torch.zeros(off, dtype=torch.float32, device=device)
+        self.shadow = torch.zeros(off, dtype=torch.bfloat16, device=device)
+        self.p = {n: self._view(self.master, n) for n in shapes}
+        self.g = {n: self._view(self.grad, n) for n in shapes}
+
+    def _view(self, flat, name):
+        o = self.offsets[name]
+        n = int(np.prod(self.shapes[name]))
+        return flat[o:o + n].view(self.shapes[name])
+
+    # raw device addresses
+    def pf(self, name):  # fp32 master
+        return self.master.data_ptr() + 4 * self.offsets[name]
+
+    def gf(self, name):  # fp32 grad
+        return self.grad.data_ptr() + 4 * self.offsets[name]
+
+    def pb(self, name):  # bf16 shadow
+        return self.shadow.data_ptr() + 2 * self.offsets[name]
+
+    def load(self, tensors: Dict[str, torch.Tensor]):
+        for n, t in tensors.items():
+            if n in self.p:
+                self.p[n].copy_(t.to(self.device, torch.float32).view(self.shapes[n]))
+
+
+def _vp(x):
+    return ctypes.c_void_p(x) if isinstance(x, int) else ptr(x)
+
+
+def _i3(v):
+    return (ctypes.c_int * 3)(*[int(a) for a in v])
+
+
+class _Layer:
+    """Saved activations of one BlockLocalAttention layer (all needed by its backward)."""
+    __slots__ = ("x", "mean1", "rstd1", "ln1", "qkv", "P", "o", "h", "mean2", "rstd2", "ln2", "a1", "y",
+                 "y_bf16")
+
+
+class VTWorkspace:
+    """All activations / scratch for a batch of B slices (allocated once per B)."""
+
+    def __init__(self, spec: VTSpec, B: int, slice_shape, ctx_shape, ntaps, device, train=True):
+        f32, bf16 = torch.float32, torch.bfloat16
+        self.B = B
+        self.slice_shape = tuple(slice_shape)
+        self.ctx_shape = tuple(ctx_shape)
+        thw = slice_shape[0] * slice_shape[1] * slice_shape[2]
+        self.thw, self.M = thw, B * thw
+        M, d, H, da, de, nv, nc = self.M, spec.d, spec.H, spec.da, spec.de, spec.nv, spec.nc
+        L = 256
+        self.nseq = M // L
+        e = lambda shape, dt: torch.empty(shape, dtype=dt, device=device)  # noqa: E731
+        # static inputs (graph-capturable)
+        self.context = torch.zeros((B, nc) + self.ctx_shape, dtype=torch.int64, device=device)
+        self.slice = torch.zeros((B, nc) + self.slice_shape, dtype=torch.int64, device=device)
+        self.slice_idx = torch.zeros((B,), dtype=torch.int64, device=device)
+        self.ignore = torch.zeros((B, thw), dtype=torch.uint8, device=device)
+        self.loss = torch.zeros((1,), dtype=f32, device=device)
+        self.count = torch.zeros((1,), dtype=torch.int32, device=device)
+        n_layers = len(spec.blocks_e) + len(spec.blocks_d)
+        self.layers: List[_Layer] = []
+        self.e0 = e((M, de), bf16)
+        self.x0 = e((M, d), f32)
+        self.A0 = e((M, ntaps * de), bf16)
+        self.y0 = e((M, d), f32)
+        n_saved = n_layers if train else 1
+        for i in range(n_saved):
+            ly = _Layer()
+            ly.mean1, ly.rstd1, ly.mean2, ly.rstd2 = (e((M,), f32) for _ in range(4))
+            ly.ln1, ly.ln2, ly.a1 = e((M, d), bf16), e((M, d), bf16), e((M, d), bf16)
+            ly.qkv = e((M, 3 * H * da), bf16)
+            ly.P = e((self.nseq, H, L, L), bf16)
+            ly.o = e((M, H * da), bf16)
+            ly.h = e((M, d), f32)
+            ly.y = e((M, d), f32)
+            ly.y_bf16 = None
+            self.layers.append(ly)
+        if not train:  # ping-pong residual buffers for inference
+            self.y_alt = e((M, d), f32)
+        self.zl_bf16 = e((M, d), bf16)
+        # predictor
+        self.mean_p, self.rstd_p = e((M,), f32), e((M,), f32)
+        self.ln_y = e((M, d), bf16)
+        self.u = e((M, d), f32)
+        self.a = e((nc, M, d), bf16)
+        self.logits = e((nc, M, nv), f32)
+        if train:
+            self.dlogits = e((nc, M, nv), bf16)
+            self.du = e((M, d), bf16)
+            self.dln = e((M, d), f32)
+            self.dy, self.dy_bf16 = e((M, d), f32), e((M, d), bf16)
+            self.dh, self.dh_bf16 = e((M, d), f32), e((M, d), bf16)
+            self.dz1 = e((M, d), bf16)
+            self.do = e((M, H * da), bf16)
+            self.delta = e((self.nseq, H, L), f32)
+            self.dS = e((self.nseq, H, L, L), bf16)
+            self.dqkv = e((M, 3 * H * da), bf16)
+            self.dA0 = e((M, ntaps * de), f32)
+            self.de0, self.de0_bf16 = e((M, de), f32), e((M, de), bf16)
+
+
+class VTEngine:
+    def __init__(self, spec: VTSpec, device="cuda"):
+        _lib.require_device()
+        self.spec = spec
+        self.device = torch.device(device)
+        self.store = ParamStore(spec.param_shapes(), self.device)
+        self.lib = _lib.load()
+        self._ws: Dict[Tuple, VTWorkspace] = {}
+        self._posenc: Dict[Tuple, torch.Tensor] = {}
+        s = spec
+        ktaps = s.kernel[0] * s.kernel[1] * s.kernel[2]
+        f32 = torch.float32
+        # re-laid-out small weights (refreshed from the master by refresh_shadows())
+        self.enc_wt = torch.zeros((s.nc, ktaps, s.nv, s.de), dtype=f32, device=self.device)
+        self.enc_dwt = torch.zeros_like(self.enc_wt)
+        self.ut = [None] + [torch.zeros((k * s.nv, s.d), dtype=f32, device=self.device) for k in range(1, s.nc)]
+        self.dut = [None] + [torch.zeros_like(self.ut[k]) for k in range(1, s.nc)]
+        self._taps_cache = {}
+        self.conv_wp = None  # packed masked-conv weight, depends on the slice shape (live taps)
+        self.shadows_fresh = False
+
+    # ------------------------------------------------------------------ parameters
+    def load_state_dict(self, tensors):
+        self.store.load(tensors)
+        # MaskedConv3d keeps its masked taps at zero (vt_utils.py:198-199)
+        self.store.p["decoder.conv.conv.weight"][:, :, -1, -1, 1:] = 0
+        self.shadows_fresh = False
+
+    def _live_taps(self, slice_shape):
+        """MaskedConv3d(de, d, (3,3,3)) taps that can touch data (vt_utils.py:183-200):
+        offsets (it-2, ih-2, iw-1); taps with it == ih == 2 and iw >= 1 are masked."""
+        key = tuple(slice_shape)
+        if key not in self._taps_cache:
+            t, h, w = slice_shape
+            taps = []
+            for it in range(3):
+                for ih in range(3):
+                    for iw in range(3):
+                        if it == 2 and ih == 2 and iw >= 1:
+                            continue
+                        dt, dh, dw = it - 2, ih - 2, iw - 1
+                        if -dt > t - 1 or -dh > h - 1 or abs(dw) > w - 1:
+                            continue
+                        taps.append((it, ih, iw))
+            offs = torch.tensor([[it - 2, ih - 2, iw - 1] for it, ih, iw in taps], dtype=torch.int32,
+                                device=self.device).contiguous()
+            ntaps = len(taps)
+            wp = torch.zeros((self.spec.d, ntaps * self.spec.de), dtype=torch.bfloat16, device=self.device)
+            dwp = torch.zeros((self.spec.d, ntaps * self.spec.de), dtype=torch.float32, device=self.device)
+            self._taps_cache[key] = (taps, offs, wp, dwp)
+            self.shadows_fresh = False
+        return self._taps_cache[key]
+
+    def _permute4(self, src, dst, bf16, acc, dims, istr, ostr):
+        check(self.lib.lvt_permute4(_vp(src), _vp(dst), int(bf16), int(acc), (ctypes.c_int * 4)(*dims),
+                                    (ctypes.c_longlong * 4)(*istr), (ctypes.c_longlong * 4)(*ostr),
+                                    stream_ptr()), "lvt_permute4")
+
+    def refresh_shadows(self):
+        """master fp32 -> bf16 shadow + the re-laid-out small weights (after load / optimizer)."""
+        s, st = self.spec, self.store
+        check(self.lib.lvt_cast_bf16(ptr(st.master), ptr(st.shadow), st.numel, stream_ptr()), "lvt_cast_bf16")
+        self._refresh_special()
+        self.shadows_fresh = True
+
+    def _refresh_special(self):
+        s, st = self.spec, self.store
+        ktaps = s.kernel[0] * s.kernel[1] * s.kernel[2]
+        # encoder.conv.weight [de, nc*nv, ktaps] -> enc_wt [nc, ktaps, nv, de]
+        self._permute4(st.pf("encoder.conv.weight"), self.enc_wt, False, False,
+                       (s.nc, ktaps, s.nv, s.de), (s.nv * ktaps, 1, ktaps, s.nc * s.nv * ktaps),
+                       (ktaps * s.nv * s.de, s.nv * s.de, s.de, 1))
+        # U[k].weight[:, d + r] -> ut[k][r, :]
+        for k in range(1, s.nc):
+            ld = s.d + k * s.nv
+            self._permute4(st.pf(f"ch_predictor.U.{k}.weight") + 4 * s.d, self.ut[k], False, False,
+                           (1, 1, k * s.nv, s.d), (0, 0, 1, ld), (0, 0, s.d, 1))
+        # decoder.conv.conv.weight [d, de, 27] -> wp [d, ntaps*de] (bf16), live taps only
+        for key, (taps, offs, wp, dwp) in self._taps_cache.items():
+            ntaps = len(taps)
+            for q, (it, ih, iw) in enumerate(taps):
+                tap = (it * 3 + ih) * 3 + iw
+                self._permute4(st.pf("decoder.conv.conv.weight") + 4 * tap, wp.data_ptr() + 2 * q * s.de,
+                               True, False, (1, 1, s.d, s.de), (0, 0, s.de * 27, 27), (0, 0, ntaps * s.de, 1))
+
+    def zero_grad(self):
+        self.store.grad.zero_()
+
+    def _zero_special_grads(self):
+        self.enc_dwt.zero_()
+        for k in range(1, self.spec.nc):
+            self.dut[k].zero_()
+        for key, (taps, offs, wp, dwp) in self._taps_cache.items():
+            dwp.zero_()
+
+    def _fold_special_grads(self, slice_shape):
+        """re-laid-out gradients -> master gradient layout (+=)."""
+        s, st = self.spec, self.store
+        ktaps = s.kernel[0] * s.kernel[1] * s.kernel[2]
+        self._permute4(self.enc_dwt, st.gf("encoder.conv.weight"), False, True,
+                       (s.nc, ktaps, s.nv, s.de), (ktaps * s.nv * s.de, s.nv * s.de, s.de, 1),
+                       (s.nv * ktaps, 1, ktaps, s.nc * s.nv * ktaps))
+        for k in range(1, s.nc):
+            ld = s.d + k * s.nv
+            self._permute4(self.dut[k], st.gf(f"ch_predictor.U.{k}.weight") + 4 * s.d, False, True,
+                           (1, 1, k * s.nv, s.d), (0, 0, s.d, 1), (0, 0, 1, ld))
+        taps, offs, wp, dwp = self._live_taps(slice_shape)
+        ntaps = len(taps)
+        for q, (it, ih, iw) in enumerate(taps):
+            tap = (it * 3 + ih) * 3 + iw
+            self._permute4(dwp.data_ptr() + 4 * q * s.de, st.gf("decoder.conv.conv.weight") + 4 * tap,
+                           False, True, (1, 1, s.d, s.de), (0, 0, ntaps * s.de, 1), (0, 0, s.de * 27, 27))
+
+    # ------------------------------------------------------------------ workspaces
+    def workspace(self, B, slice_shape, ctx_shape, train=True) -> VTWorkspace:
+        key = (B, tuple(slice_shape), tuple(ctx_shape), train)
+        if key not in self._ws:
+            if tuple(slice_shape) != self.spec.block:
+                raise _lib.LvtError(f"slice {tuple(slice_shape)} must equal the attention block "
+                                    f"{self.spec.block} (true for every shipped config)")
+            taps = self._live_taps(slice_shape)[0]
+            self._ws[key] = VTWorkspace(self.spec, B, slice_shape, ctx_shape, len(taps), self.device, train)
+        return self._ws[key]
+
+    def posenc_table(self, slice_shape):
+        """PositionalEncoding (vt_attention.py:10-50) as a constant [thw, d] table."""
+        key = tuple(slice_shape)
+        if key not in self._posenc:
+            d = self.spec.d
+            n = d // 6
+            inc = np.log(1.0e4 / 1.0) / n
+            inv = (1.0 * torch.exp(torch.arange(n).float() * -inc))
+            tab = torch.zeros((d,) + key)
+            for dim in range(3):
+                pos = torch.arange(key[dim], dtype=torch.float)
+                stime = pos.view(-1, 1) * inv.view(1, -1)
+                sig = torch.cat([torch.sin(stime), torch.cos(stime)], 1).T
+                view = [2 * n, 1, 1, 1]
+                view[1 + dim] = key[dim]
+                tab[dim * 2 * n:(dim + 1) * 2 * n] += sig.reshape(view)
+            self._posenc[key] = tab.reshape(d, -1).t().contiguous().to(self.device)
+        return self._posenc[key]
+
+    # ------------------------------------------------------------------ small launch helpers
+    def _ln_fwd(self, x, g, b, y, mean, rstd, M):
+        check(self.lib.lvt_layernorm_fwd(_vp(x), _vp(g), _vp(b), _vp(y), _vp(mean), _vp(rstd), M, self.spec.d,
+                                         LN_EPS, stream_ptr()), "lvt_layernorm_fwd")
+
+    def _ln_bwd(self, dy, x, mean, rstd, g, dres, dx, dxb, dg, db, M):
+        check(self.lib.lvt_layernorm_bwd(_vp(dy), _vp(x), _vp(mean), _vp(rstd), _vp(g), _vp(dres), _vp(dx),
+                                         _vp(dxb), _vp(dg), _vp(db), M, self.spec.d, stream_ptr()),
+              "lvt_layernorm_bwd")
+
+    def _colsum(self, x, out, M, N, ld=None):
+        check(self.lib.lvt_colsum_bf16(_vp(x), _vp(out), M, N, ld or N, stream_ptr()), "lvt_colsum_bf16")
+
+    @staticmethod
+    def _splits(m, n, k):
+        tiles = ((m + 127) // 128) * ((n + 127) // 128)
+        return int(max(1, min(k // 512, (2 * 148 + tiles - 1) // tiles)))
+
+    def _wgrad(self, dy_ptr, ld_dy, x_ptr, ld_x, out: Operand, n_out, n_in, tokens):
+        """dW[n_out, n_in] += dY[tokens, n_out]^T X[tokens, n_in] (split-K, fp32 red.add)."""
+        gemm(n_out, n_in, tokens, Operand(dy_ptr, ld_dy, mn_major=True), Operand(x_ptr, ld_x, mn_major=True),
+             out, out_f32=out.data, splits=self._splits(n_out, n_in, tokens), flags=ops.GEMM_ATOMIC)
+
+    # ------------------------------------------------------------------ one attention layer
+    def _qkv_op(self, buf_ptr, which, mn, L):
+        s = self.spec
+        ld = 3 * s.H * s.da
+        return Operand(buf_ptr + 2 * which * s.H * s.da, ld, mn_major=mn, cin=s.da, zdiv=s.H, s_zlo=s.da,
+                       s_zhi=L * ld)
+
+    def _layer_fwd(self, prefix, ws: VTWorkspace, ly: _Layer, x, y, causal, y_bf16=None):
+        s, st = self.spec, self.store
+        M, d, H, da, L = ws.M, s.d, s.H, s.da, 256
+        nz = ws.nseq * H
+        # pre-LN + fused QKV projection (vt_attention.py:120-124)
+        self._ln_fwd(x, st.pf(prefix + "mha.layer_norm.weight"), st.pf(prefix + "mha.layer_norm.bias"),
+                     ly.ln1, ly.mean1, ly.rstd1, M)
+        gemm(M, 3 * H * da, d, Operand(ly.ln1.data_ptr(), d),
+             Operand(st.pb(prefix + "mha.w_q"), da, mn_major=True, cin=da, s_blk=d * da),
+             Operand(ly.qkv.data_ptr(), 3 * H * da), out_bf16=ly.qkv)
+        # P = softmax(QK^T/sqrt(da) + B [causal -1e4]) (vt_attention.py:63-79), O = P V (:80)
+        banks = (st.pf(prefix + "dt_bank"), st.pf(prefix + "dh_bank"), st.pf(prefix + "dw_bank"))
+        gemm(L, L, da, self._qkv_op(ly.qkv.data_ptr(), 0, False, L), self._qkv_op(ly.qkv.data_ptr(), 1, False, L),
+             Operand(ly.P.data_ptr(), L, zdiv=1, s_zhi=L * L), out_bf16=ly.P, batch=nz,
+             alpha=1.0 / math.sqrt(da), mode=ops.EPI_SOFTMAX, flags=ops.GEMM_CAUSAL if causal else 0,
+             banks=banks, block=s.block, heads=H)
+        gemm(L, da, L, Operand(ly.P.data_ptr(), L, zdiv=1, s_zhi=L * L), self._qkv_op(ly.qkv.data_ptr(), 2, True, L),
+             Operand(ly.o.data_ptr(), H * da, cin=da, zdiv=H, s_zlo=da, s_zhi=L * H * da), out_bf16=ly.o,
+             batch=nz)
+        # output projection + residual (:127-128)
+        gemm(M, d, H * da, Operand(ly.o.data_ptr(), H * da), Operand(st.pb(prefix + "mha.proj.weight"), H * da),
+             Operand(ly.h.data_ptr(), d), out_f32=ly.h, res=x)
+        # FFN: LN -> Linear -> ReLU -> Linear, + residual (vt_attention.py:138,186)
+        self._ln_fwd(ly.h, st.pf(prefix + "ffn.0.weight"), st.pf(prefix + "ffn.0.bias"), ly.ln2, ly.mean2,
+                     ly.rstd2, M)
+        gemm(M, d, d, Operand(ly.ln2.data_ptr(), d), Operand(st.pb(prefix + "ffn.1.weight"), d),
+             Operand(ly.a1.data_ptr(), d), out_bf16=ly.a1, bias=st.pf(prefix + "ffn.1.bias"), flags=ops.GEMM_RELU)
+        gemm(M, d, d, Operand(ly.a1.data_ptr(), d), Operand(st.pb(prefix + "ffn.3.weight"), d),
+             Operand(_vp(y).value, d), out_f32=y, out_bf16=y_bf16, bias=st.pf(prefix + "ffn.3.bias"), res=ly.h)
+
+    def _layer_bwd(self, prefix, ws: VTWorkspace, ly: _Layer, x, dy, dy_bf16, dx, dx_bf16):
+        """dy (fp32 + bf16 copy) = gradient wrt the layer output; writes dx (fp32 + bf16)."""
+        s, st = self.spec, self.store
+        M, d, H, da, L = ws.M, s.d, s.H, s.da, 256
+        nz = ws.nseq * H
+        scale = 1.0 / math.sqrt(da)
+        dyb = _vp(dy_bf16).value
+        # ---- FFN
+        self._colsum(dyb, st.gf(prefix + "ffn.3.bias"), M, d)
+        self._wgrad(dyb, d, ly.a1.data_ptr(), d, Operand(st.gf(prefix + "ffn.3.weight"), d), d, d, M)
+        gemm(M, d, d, Operand(dyb, d), Operand(st.pb(prefix + "ffn.3.weight"), d, mn_major=True),
+             Operand(ws.dz1.data_ptr(), d), out_bf16=ws.dz1, aux=ly.a1, flags=ops.GEMM_MASK)
+        self._colsum(ws.dz1, st.gf(prefix + "ffn.1.bias"), M, d)
+        self._wgrad(ws.dz1.data_ptr(), d, ly.ln2.data_ptr(), d, Operand(st.gf(prefix + "ffn.1.weight"), d), d, d, M)
+        gemm(M, d, d, Operand(ws.dz1.data_ptr(), d), Operand(st.pb(prefix + "ffn.1.weight"), d, mn_major=True),
+             Operand(ws.dln.data_ptr(), d), out_f32=ws.dln)
+        self._ln_bwd(ws.dln, ly.h, ly.mean2, ly.rstd2, st.pf(prefix + "ffn.0.weight"), dy, ws.dh, ws.dh_bf16,
+                     st.gf(prefix + "ffn.0.weight"), st.gf(prefix + "ffn.0.bias"), M)
+        # ---- attention output projection
+        dhb = ws.dh_bf16.data_ptr()
+        self._wgrad(dhb, d, ly.o.data_ptr(), H * da, Operand(st.gf(prefix + "mha.proj.weight"), H * da), d, H * da, M)
+        gemm(M, H * da, d, Operand(dhb, d), Operand(st.pb(prefix + "mha.proj.weight"), H * da, mn_major=True),
+             Operand(ws.do.data_ptr(), H * da), out_bf16=ws.do)
+        # ---- softmax attention backward
+        check(self.lib.lvt_attn_delta(ptr(ws.do), ptr(ly.o), ptr(ws.delta), ws.nseq, H, L, da, stream_ptr()),
+              "lvt_attn_delta")
+        P_k = Operand(ly.P.data_ptr(), L, zdiv=1, s_zhi=L * L)
+        P_mn = Operand(ly.P.data_ptr(), L, mn_major=True, zdiv=1, s_zhi=L * L)
+        do_k = Operand(ws.do.data_ptr(), H * da, cin=da, zdiv=H, s_zlo=da, s_zhi=L * H * da)
+        do_mn = Operand(ws.do.data_ptr(), H * da, mn_major=True, cin=da, zdiv=H, s_zlo=da, s_zhi=L * H * da)
+        dS_k = Operand(ws.dS.data_ptr(), L, zdiv=1, s_zhi=L * L)
+        dS_mn = Operand(ws.dS.data_ptr(), L, mn_major=True, zdiv=1, s_zhi=L * L)
+        qkv, dqkv = ly.qkv.data_ptr(), ws.dqkv.data_ptr()
+        out_blk = lambda which: self._qkv_op(dqkv, which, False, L)  # noqa: E731
+        # dV = P^T dO
+        gemm(L, da, L, P_mn, do_mn, out_blk(2), out_bf16=out_blk(2).data, batch=nz)
+        # dS = P * (dO V^T - delta)
+        gemm(L, L, da, do_k, self._qkv_op(qkv, 2, False, L), dS_k, out_bf16=ws.dS, batch=nz, mode=ops.EPI_DS,
+             aux=ly.P, delta=ws.delta)
+        # dQ = scale * dS K ; dK = scale * dS^T Q
+        gemm(L, da, L, dS_k, self._qkv_op(qkv, 1, True, L), out_blk(0), out_bf16=out_blk(0).data, batch=nz,
+             alpha=scale)
+        gemm(L, da, L, dS_mn, self._qkv_op(qkv, 0, True, L), out_blk(1), out_bf16=out_blk(1).data, batch=nz,
+             alpha=scale)
+        check(self.lib.lvt_relpos_bank_grad(ptr(ws.dS), _vp(st.gf(prefix + "dt_bank")),
+                                            _vp(st.gf(prefix + "dh_bank")), _vp(st.gf(prefix + "dw_bank")),
+                                            ws.nseq, H, s.block[0], s.block[1], s.block[2], stream_ptr()),
+              "lvt_relpos_bank_grad")
+        # ---- QKV projection
+        gemm(d, 3 * H * da, M, Operand(ly.ln1.data_ptr(), d, mn_major=True),
+             Operand(dqkv, 3 * H * da, mn_major=True),
+             Operand(st.gf(prefix + "mha.w_q"), da, cin=da, s_blk=d * da), out_f32=st.gf(prefix + "mha.w_q"),
+             splits=self._splits(d, 3 * H * da, M), flags=ops.GEMM_ATOMIC)
+        gemm(M, d, 3 * H * da, Operand(dqkv, 3 * H * da),
+             Operand(st.pb(prefix + "mha.w_q"), da, mn_major=False, cin=da, s_blk=d * da),
+             Operand(ws.dln.data_ptr(), d), out_f32=ws.dln)
+        self._ln_bwd(ws.dln, x, ly.mean1, ly.rstd1, st.pf(prefix + "mha.layer_norm.weight"), ws.dh, dx, dx_bf16,
+                     st.gf(prefix + "mha.layer_norm.weight"), st.gf(prefix + "mha.layer_norm.bias"), M)
+
+    # ------------------------------------------------------------------ whole network
+    def set_inputs(self, ws: VTWorkspace, context, slc, slice_idx, ignore_mask=None):
+        """Stage one batch into the static input buffers (H2D copies when given host tensors)."""
+        ws.context.copy_(context.reshape(ws.context.shape), non_blocking=True)
+        ws.slice.copy_(slc.reshape(ws.slice.shape), non_blocking=True)
+        ws.slice_idx.copy_(slice_idx.reshape(-1), non_blocking=True)
+        if ignore_mask is not None:
+            ws.ignore.copy_(ignore_mask.reshape(ws.ignore.shape).to(torch.uint8), non_blocking=True)
+        else:
+            ws.ignore.zero_()
+
+    def forward(self, ws: VTWorkspace, train=True, want_loss=True):
+        """VideoTransformer.forward(mode="logits") (videotransformer.py:232-239) [+ the CE loss of
+        meta_arch/vt.py:305-312].  Results: ws.logits [nc, M, nv] fp32, ws.loss."""
+        s, st = self.spec, self.store
+        if not self.shadows_fresh:
+            self.refresh_shadows()
+        M, d, de, nv, nc = ws.M, s.d, s.de, s.nv, s.nc
+        t, h, w = ws.slice_shape
+        taps, offs, wp, dwp = self._live_taps(ws.slice_shape)
+        ntaps = len(taps)
+        nE, nD = len(s.blocks_e), len(s.blocks_d)
+
+        def layer(i):
+            return ws.layers[i] if train else ws.layers[0]
+
+        # ---- encoder (videotransformer.py:35-59)
+        check(self.lib.lvt_vt_enc_front_fwd(ptr(ws.context), ptr(ws.slice_idx), ptr(self.enc_wt),
+                                            _vp(st.pf("encoder.conv.bias")),
+                                            _vp(st.pf("encoder.slice_embedding.weight")), ptr(ws.e0), ws.B, nc, nv,
+                                            de, _i3(ws.ctx_shape), _i3(s.kernel), _i3(s.stride), s.pad_value,
+                                            stream_ptr()), "lvt_vt_enc_front_fwd")
+        gemm(M, d, de, Operand(ws.e0.data_ptr(), de), Operand(st.pb("encoder.linear_projector.weight"), de),
+             Operand(ws.x0.data_ptr(), d), out_f32=ws.x0)
+        x = ws.x0
+        for i in range(nE):
+            ly = layer(i)
+            y = ly.y if train else (ws.y_alt if x is ly.y else ly.y)
+            self._layer_fwd(f"encoder.block_local_attention.{i}.", ws, ly, x, y, causal=False,
+                            y_bf16=ws.zl_bf16 if i == nE - 1 else None)
+            x = y
+        # ---- decoder (videotransformer.py:91-101)
+        check(self.lib.lvt_vt_dec_front_fwd(ptr(ws.slice), _vp(st.pf("decoder.ch_embedder.0.weight")), ptr(offs),
+                                            ptr(ws.A0), ws.B, nc, nv, de, t, h, w, ntaps, stream_ptr()),
+              "lvt_vt_dec_front_fwd")
+        gemm(M, d, ntaps * de, Operand(ws.A0.data_ptr(), ntaps * de), Operand(wp.data_ptr(), ntaps * de),
+             Operand(ws.y0.data_ptr(), d), out_f32=ws.y0, bias=self.posenc_table(ws.slice_shape), bias_mod=ws.thw)
+        gemm(M, d, d, Operand(ws.zl_bf16.data_ptr(), d), Operand(st.pb("decoder.linear_projector.weight"), d),
+             Operand(ws.y0.data_ptr(), d), out_f32=ws.y0, res=ws.y0, bias=st.pf("decoder.conv.conv.bias"))
+        x = ws.y0
+        for i in range(nD):
+            ly = layer(nE + i)
+            y = ly.y if train else (ws.y_alt if x is ly.y else ly.y)
+            self._layer_fwd(f"decoder.block_local_attention.{i}.", ws, ly, x, y, causal=True)
+            x = y
+        ws.y_final = x
+        # ---- channel predictor (videotransformer.py:138-160)
+        self._ln_fwd(x, st.pf("ch_predictor.layer_norm.weight"), st.pf("ch_predictor.layer_norm.bias"), ws.ln_y,
+                     ws.mean_p, ws.rstd_p, M)
+        for k in range(nc):
+            ld = d + k * nv
+            gemm(M, d, d, Operand(ws.ln_y.data_ptr(), d), Operand(st.pb(f"ch_predictor.U.{k}.weight"), ld),
+                 Operand(ws.u.data_ptr(), d), out_f32=ws.u, bias=st.pf(f"ch_predictor.U.{k}.bias"))
+            check(self.lib.lvt_chpred_combine_fwd(ptr(ws.u), ptr(self.ut[k]) if k else None, ptr(ws.slice),
+                                                  ptr(ws.a[k]), M, nc, nv, d, ws.thw, k, stream_ptr()),
+                  "lvt_chpred_combine_fwd")
+            gemm(M, nv, d, Operand(ws.a[k].data_ptr(), d), Operand(st.pb(f"ch_predictor.P.{k}.weight"), d),
+                 Operand(ws.logits[k].data_ptr(), nv), out_f32=ws.logits[k], bias=st.pf(f"ch_predictor.P.{k}.bias"))
+        if want_loss:
+            check(self.lib.lvt_cross_entropy(ptr(ws.logits), ptr(ws.slice), ptr(ws.ignore),
+                                             ptr(ws.dlogits) if train else None, ptr(ws.loss), ptr(ws.count),
+                                             ws.B, nc, nv, ws.thw, stream_ptr()), "lvt_cross_entropy")
+        return ws.loss
+
+    def backward(self, ws: VTWorkspace):
+        """Gradient of ws.loss wrt every parameter, ACCUMULATED into the flat gradient buffer."""
+        s, st = self.spec, self.store
+        M, d, de, nv, nc = ws.M, s.d, s.de, s.nv, s.nc
+        t, h, w = ws.slice_shape
+        taps, offs, wp, dwp = self._live_taps(ws.slice_shape)
+        ntaps = len(taps)
+        nE, nD = len(s.blocks_e), len(s.blocks_d)
+        self._zero_special_grads()
+        # ---- channel predictor
+        for k in range(nc):
+            ld = d + k * nv
+            dl = ws.dlogits[k].data_ptr()
+            self._colsum(dl, st.gf(f"ch_predictor.P.{k}.bias"), M, nv)
+            self._wgrad(dl, nv, ws.a[k].data_ptr(), d, Operand(st.gf(f"ch_predictor.P.{k}.weight"), d), nv, d, M)
+            gemm(M, d, nv, Operand(dl, nv), Operand(st.pb(f"ch_predictor.P.{k}.weight"), d, mn_major=True),
+                 Operand(ws.du.data_ptr(), d), out_bf16=ws.du, aux=ws.a[k], flags=ops.GEMM_MASK)
+            self._colsum(ws.du, st.gf(f"ch_predictor.U.{k}.bias"), M, d)
+            self._wgrad(ws.du.data_ptr(), d, ws.ln_y.data_ptr(), d,
+                        Operand(st.gf(f"ch_predictor.U.{k}.weight"), ld), d, d, M)
+            check(self.lib.lvt_chpred_combine_bwd(ptr(ws.du), ptr(ws.slice), ptr(self.dut[k]) if k else None, M, nc,
+                                                  nv, d, ws.thw, k, stream_ptr()), "lvt_chpred_combine_bwd")
+            gemm(M, d, d, Operand(ws.du.data_ptr(), d),
+                 Operand(st.pb(f"ch_predictor.U.{k}.weight"), ld, mn_major=True),
+                 Operand(ws.dln.data_ptr(), d), out_f32=ws.dln, res=ws.dln if k else None)
+        self._ln_bwd(ws.dln, ws.y_final, ws.mean_p, ws.rstd_p, st.pf("ch_predictor.layer_norm.weight"), None,
+                     ws.dy, ws.dy_bf16, st.gf("ch_predictor.layer_norm.weight"),
+                     st.gf("ch_predictor.layer_norm.bias"), M)
+        # ---- decoder stack
+        for i in reversed(range(nD)):
+            ly = ws.layers[nE + i]
+            x = ws.layers[nE + i - 1].y if i > 0 else ws.y0
+            self._layer_bwd(f"decoder.block_local_attention.{i}.", ws, ly, x, ws.dy, ws.dy_bf16, ws.dy, ws.dy_bf16)
+        # ---- decoder front: y0 = conv(emb) + posenc + bias + zl Wlp^T
+        dyb = ws.dy_bf16.data_ptr()
+        self._colsum(dyb, st.gf("decoder.conv.conv.bias"), M, d)
+        self._wgrad(dyb, d, ws.zl_bf16.data_ptr(), d, Operand(st.gf("decoder.linear_projector.weight"), d), d, d, M)
+        self._wgrad(dyb, d, ws.A0.data_ptr(), ntaps * de, Operand(dwp.data_ptr(), ntaps * de), d, ntaps * de, M)
+        gemm(M, ntaps * de, d, Operand(dyb, d), Operand(wp.data_ptr(), ntaps * de, mn_major=True),
+             Operand(ws.dA0.data_ptr(), ntaps * de), out_f32=ws.dA0)
+        check(self.lib.lvt_vt_dec_front_bwd(ptr(ws.slice), ptr(ws.dA0), ptr(offs),
+                                            _vp(st.gf("decoder.ch_embedder.0.weight")), ws.B, nc, nv, de, t, h, w,
+                                            ntaps, stream_ptr()), "lvt_vt_dec_front_bwd")
+        # gradient entering the encoder stack: dzl = dy0 Wlp_d
+        # (written to the dh buffers: the GEMM may not overwrite its own A operand)
+        gemm(M, d, d, Operand(dyb, d), Operand(st.pb("decoder.linear_projector.weight"), d, mn_major=True),
+             Operand(ws.dh.data_ptr(), d), out_f32=ws.dh, out_bf16=ws.dh_bf16)
+        # ---- encoder stack
+        for i in reversed(range(nE)):
+            ly = ws.layers[i]
+            x = ws.layers[i - 1].y if i > 0 else ws.x0
+            first = i == nE - 1
+            self._layer_bwd(f"encoder.block_local_attention.{i}.", ws, ly, x, ws.dh if first else ws.dy,
+                            ws.dh_bf16 if first else ws.dy_bf16, ws.dy, ws.dy_bf16)
+        # ---- encoder front: x0 = e0 Wlp_e^T ; e0 = gather-sum + bias + slice_emb
+        dxb = ws.dy_bf16.data_ptr()
+        self._wgrad(dxb, d, ws.e0.data_ptr(), de, Operand(st.gf("encoder.linear_projector.weight"), de), d, de, M)
+        gemm(M, de, d, Operand(dxb, d), Operand(st.pb("encoder.linear_projector.weight"), de, mn_major=True),
+             Operand(ws.de0.data_ptr(), de), out_f32=ws.de0, out_bf16=ws.de0_bf16)
+        self._colsum(ws.de0_bf16, st.gf("encoder.conv.bias"), M, de)
+        check(self.lib.lvt_vt_enc_front_bwd(ptr(ws.context), ptr(ws.slice_idx), ptr(ws.de0), ptr(self.enc_dwt),
+                                            _vp(st.gf("encoder.slice_embedding.weight")), ws.B, nc, nv, de,
+                                            _i3(ws.ctx_shape), _i3(s.kernel), _i3(s.stride), s.pad_value,
+                                            stream_ptr()), "lvt_vt_enc_front_bwd")
+        self._fold_special_grads(ws.slice_shape)
+
+    # ------------------------------------------------------------------ optimizer
+    def init_optimizer(self, name="rmsprop", lr=2e-5, alpha=0.95, momentum=0.9, eps=1e-8, betas=(0.9, 0.9)):
+        """torch.optim.RMSprop / Adam state over the flat buffers (reference solver/build.py:62-72)."""
+        self.opt = dict(name=name, lr=lr, alpha=alpha, momentum=momentum, eps=eps, betas=betas, step=0)
+        self.opt_s1 = torch.zeros_like(self.store.master)
+        self.opt_s2 = torch.zeros_like(self.store.master)
+
+    def optimizer_step(self, grad_scale=1.0):
+        o, st = self.opt, self.store
+        o["step"] += 1
+        if o["name"] == "rmsprop":
+            check(self.lib.lvt_rmsprop_step(ptr(st.master), ptr(st.grad), ptr(self.opt_s1), ptr(self.opt_s2),
+                                            ptr(st.shadow), st.numel, o["lr"], o["alpha"], o["momentum"], o["eps"],
+                                            grad_scale, stream_ptr()), "lvt_rmsprop_step")
+        else:
+            check(self.lib.lvt_adam_step(ptr(st.master), ptr(st.grad), ptr(self.opt_s1), ptr(self.opt_s2),
+                                         ptr(st.shadow), st.numel, o["lr"], o["betas"][0], o["betas"][1], o["eps"],
+                                         o["step"], grad_scale, stream_ptr()), "lvt_adam_step")
+        self._refresh_special()
+        self.shadows_fresh = True
+
+    def train_step(self, ws: VTWorkspace, grad_hook=None, grad_scale=1.0):
+        """forward + backward + optimizer on the batch staged in `ws` (trainer.py:79-87)."""
+        self.zero_grad()
+        self.forward(ws, train=True)
+        self.backward(ws)
+        if grad_hook is not None:
+            grad_hook(self.store.grad)  # data-parallel all-reduce of the flat gradient
+        self.optimizer_step(grad_scale)
+        return ws.loss
+
+
+class GraphedTrainStep:
+    """The DSFVT train step (zero_grad + forward + backward [+ gradient all-reduce] + optimizer)
+    captured once into CUDA graphs and replayed: one host launch per step instead of ~700.
+    With world_size > 1 the flat fp32 gradient is summed across ranks with one NCCL all-reduce
+    between the two graphs (reference: DDP over self.model, meta_arch/vt.py:61-63) and averaged
+    by the optimizer kernel's grad_scale."""
+
+    def __init__(self, engine: VTEngine, ws: VTWorkspace, world_size=1, allreduce=None):
+        self.engine, self.ws = engine, ws
+        self.world_size = world_size
+        self.allreduce = allreduce
+        self.g_fb = None
+        self.g_opt = None
+        self.launches_per_step = 0
+
+    def _fwd_bwd(self):
+        self.engine.zero_grad()
+        self.engine.forward(self.ws, train=True)
+        self.engine.backward(self.ws)
+
+    def _opt(self):
+        self.engine.optimizer_step(grad_scale=1.0 / self.world_size)
+
+    def capture(self, warmup=2):
+        eng = self.engine
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):  # eager warm-up: sets kernel attributes, builds TMA maps
+                self._fwd_bwd()
+                if self.allreduce is not None:
+                    self.allreduce(eng.store.grad)
+                self._opt()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        n0 = _lib.launch_count()
+        self.g_fb = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.g_fb):
+            self._fwd_bwd()
+        if self.allreduce is None:
+            # single rank: optimizer joins the same graph region
+            pass
+        self.g_opt = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.g_opt):
+            self._opt()
+        self.launches_per_step = _lib.launch_count() - n0
+        torch.cuda.synchronize()
+
+    def step(self):
+        self.g_fb.replay()
+        if self.allreduce is not None:
+            self.allreduce(self.engine.store.grad)
+        self.g_opt.replay()
+        return self.ws.loss

@@ -1,0 +1,57 @@
+"""CPU: host-side logic of the product (slice construction, config, C-ABI surface)."""
+import os
+import re
+
+import numpy as np
+import torch
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_prepare_slices_matches_reference_mapper():
+    from lvt_b200.data import prepare_slices, subscale_order, synthetic_latent_video
+    fix = np.load(os.path.join(GOLD, "mapper.npz"))
+    specs = {"DSFVT": ((7, 1, 1), (16, 1, 1), 1, 16), "DSSVT": ((1, 3, 3), (1, 2, 2), 1, 4),
+             "DSTSVT": ((5, 3, 3), (4, 2, 2), 1, 16)}
+    for name, (kernel, stride, n_prime, T) in specs.items():
+        idx2abc, _ = subscale_order(*stride)
+        for i in range(3):
+            video = synthetic_latent_video(500 + i, (T, 4, 16, 16))
+            abc = idx2abc[int(fix[f"{name}:{i}:slice_idx"])]
+            got = prepare_slices(video, abc, kernel, stride, n_prime)
+            for k in ("context", "slice", "ignore_mask"):
+                assert np.array_equal(got[k].numpy(), fix[f"{name}:{i}:{k}"]), (name, i, k)
+
+
+def test_synthetic_batch_agrees_with_oracle_generator():
+    from lvt_b200.data import synthetic_vt_batch
+    from oracle import lvt_oracle as O
+    got = synthetic_vt_batch(3, seed=77)
+    want = O.synth_vt_batch(3, seed=77, cfg=O.VTConfig())
+    for a, b in zip(got, want):
+        assert torch.equal(a, b)
+
+
+def test_cabi_library_exports_every_declared_symbol():
+    """include/lvt_b200.h <-> liblvt_b200.so <-> ctypes table (no compute without a GPU)."""
+    from lvt_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "lvt_b200.h")).read()
+    declared = set(re.findall(r"\b(lvt_[a-z0-9_]+)\s*\(", header))
+    lib = _lib.load()
+    assert lib.lvt_abi_version() == 1
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+        assert name in _lib.SYMBOLS, f"{name} missing from the ctypes table"
+    assert declared == set(_lib.SYMBOLS)
+
+
+def test_product_fails_loudly_without_gpu():
+    from lvt_b200 import _lib, ops
+    if torch.cuda.is_available():
+        return
+    try:
+        ops.vq_argmin(torch.zeros(1, 256, 16, 16), torch.zeros(4, 512, 64))
+    except _lib.LvtError:
+        return
+    raise AssertionError("expected LvtError on a machine without a B200")
