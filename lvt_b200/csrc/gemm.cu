@@ -1,11 +1,14 @@
 // lvt_b200 :: bf16 GEMM on the 5th-gen tensor cores (tcgen05.mma, accumulators in TMEM,
-// operands staged by TMA into 128B-swizzled shared memory, mbarrier pipeline).
+// operands staged by TMA into 128B-swizzled shared memory, mbarrier pipelines).
 //
-// One CTA computes one 128 x BN output tile (BN = 128 or 256):
-//   warp 0   : TMA producer        (one elected lane)
-//   warp 1   : TMEM owner + MMA issuer (one elected lane issues tcgen05.mma)
-//   warps 2-5: epilogue, TMEM -> registers -> global (each warp owns the TMEM lane quarter
-//              warp_id % 4, i.e. 32 rows of the tile)
+// Persistent, warp-specialised kernel, one CTA per SM, 128 x BN output tiles (BN = 128 / 256):
+//   warp 0    : TMA producer           (one elected lane, STAGES-deep smem ring across tiles)
+//   warp 1    : TMEM owner + MMA issuer (one elected lane issues tcgen05.mma)
+//   warps 2-5 : epilogue group 0  -> TMEM accumulator buffer 0 (even tiles of this CTA)
+//   warps 6-9 : epilogue group 1  -> TMEM accumulator buffer 1 (odd tiles)
+// The accumulator is double-buffered in TMEM (2 x BN columns), so the MMAs of tile i+1 overlap the
+// epilogue of tile i.  Epilogue: TMEM -> registers (lane == row) -> per-warp smem transpose ->
+// coalesced 16 B global accesses (bias / residual / mask reads and the stores).
 // Replaces the cuBLAS calls under torch.bmm / nn.Linear / 1x1x1 Conv3d on the DSFVT path
 // (reference: vidgen/modeling/autoregressive/vt_attention.py:63-80,120-128,138 and
 // videotransformer.py:57,99,148-156) and their autograd backward.
@@ -24,12 +27,22 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
 constexpr int A_TILE_BYTES = BM * BK * 2;  // 16 KiB
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 320;           // 10 warps
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int STG_STRIDE = 20;             // floats per staged row (16 data + 4 pad): conflict-free float4
+constexpr int STG_BYTES_PER_WARP = 32 * STG_STRIDE * 4;
+
+// epilogue kinds (compile-time)
+constexpr int EK_LINEAR = 0;
+constexpr int EK_SOFTMAX_1x16x16 = 1;
+constexpr int EK_SOFTMAX_4x8x8 = 2;
+constexpr int EK_DS = 3;
 
 struct GemmParams {
   int M, N, K, batch, splits;
+  int tiles_m, tiles_n, total_tiles, kb_per;
   int a_cin, a_zdiv, b_cin, b_zdiv;
-  int mode, flags;
+  int flags;
   float alpha;
   float* out_f32;
   __nv_bfloat16* out_bf16;
@@ -44,16 +57,17 @@ struct GemmParams {
   const float* bank_t;
   const float* bank_h;
   const float* bank_w;
-  int bt, bh, bw, heads;
+  int heads;
 };
 
-template <int BN, int STAGES>
+template <int BN>
 struct SmemLayout {
   static constexpr int B_TILE_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
-  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
-  static constexpr int BANK_OFFSET = BAR_OFFSET + 256;       // barriers + tmem ptr
-  static constexpr int TOTAL = BANK_OFFSET + 1024 /*banks*/ + 1024 /*alignment slack*/;
+  static constexpr int STAGES = BN == 256 ? 4 : 6;
+  static constexpr int STG_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int BAR_OFFSET = STG_OFFSET + NUM_EPI_WARPS * STG_BYTES_PER_WARP;
+  static constexpr int TOTAL = BAR_OFFSET + 256 + 1024 /*alignment slack*/;
 };
 
 LVT_DEVICE_INLINE void red_add_v4(float* addr, float a, float b, float c, float d) {
@@ -62,32 +76,44 @@ LVT_DEVICE_INLINE void red_add_v4(float* addr, float a, float b, float c, float 
                : "memory");
 }
 
-template <int BN, int STAGES, bool A_MN, bool B_MN>
+struct TileCoord {
+  int m0, n0, z, kb_begin, num_kb;
+};
+
+LVT_DEVICE_INLINE TileCoord decode_tile(const GemmParams& p, int tile, int bn) {
+  TileCoord t;
+  const int tn = tile % p.tiles_n;
+  int r = tile / p.tiles_n;
+  const int tm = r % p.tiles_m;
+  r /= p.tiles_m;
+  const int split = r % p.splits;
+  t.z = r / p.splits;
+  t.m0 = tm * BM;
+  t.n0 = tn * bn;
+  const int kb_total = (p.K + BK - 1) / BK;
+  t.kb_begin = split * p.kb_per;
+  t.num_kb = max(0, min(kb_total, t.kb_begin + p.kb_per) - t.kb_begin);
+  return t;
+}
+
+template <int BN, bool A_MN, bool B_MN, int EK>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                  const GemmParams p) {
-  using L = SmemLayout<BN, STAGES>;
+  using L = SmemLayout<BN>;
+  constexpr int STAGES = L::STAGES;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte alignment
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
   uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full_bar = empty_bar + STAGES;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
-  float* s_bank = reinterpret_cast<float*>(smem + L::BANK_OFFSET);
+  uint64_t* tmem_full_bar = empty_bar + STAGES;   // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * BN;
-  const int m0 = blockIdx.y * BM;
-  const int z = blockIdx.z / p.splits;
-  const int split = blockIdx.z - z * p.splits;
-  const int kb_total = (p.K + BK - 1) / BK;
-  const int kb_per = (kb_total + p.splits - 1) / p.splits;
-  const int kb_begin = split * kb_per;
-  const int kb_end = min(kb_total, kb_begin + kb_per);
-  const int num_kb = max(0, kb_end - kb_begin);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_a);
@@ -97,24 +123,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    mbar_init(&tmem_full_bar[0], 1);
+    mbar_init(&tmem_full_bar[1], 1);
+    mbar_init(&tmem_empty_bar[0], 4);  // one arrive per epilogue warp of the group
+    mbar_init(&tmem_empty_bar[1], 4);
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_ptr_smem, BN);
+    tmem_alloc(tmem_ptr_smem, 2 * BN);
     tmem_relinquish();
-  }
-  if (p.mode == LVT_EPI_SOFTMAX && warp >= 2) {
-    // stage this head's relative-position banks: [dt | dh | dw]
-    const int head = z % p.heads;
-    const int nt = 2 * p.bt - 1, nh = 2 * p.bh - 1, nw = 2 * p.bw - 1;
-    for (int i = threadIdx.x - 64; i < nt + nh + nw; i += 128) {
-      float v;
-      if (i < nt) v = p.bank_t[head * nt + i];
-      else if (i < nt + nh) v = p.bank_h[head * nh + (i - nt)];
-      else v = p.bank_w[head * nw + (i - nt - nh)];
-      s_bank[i] = v;
-    }
   }
   tc_fence_before();
   __syncthreads();
@@ -124,34 +141,38 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (elect_one()) {
-      const int a_zlo = z % p.a_zdiv, a_zhi = z / p.a_zdiv;
-      const int b_zlo = z % p.b_zdiv, b_zhi = z / p.b_zdiv;
-      for (int it = 0; it < num_kb; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
-        const int k0 = (kb_begin + it) * BK;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        mbar_arrive_expect_tx(&full_bar[s], L::STAGE_BYTES);
-        uint8_t* a_dst = smem + s * L::STAGE_BYTES;
-        uint8_t* b_dst = a_dst + A_TILE_BYTES;
-        if (!A_MN) {
-          tma_load_5d(a_dst, &tm_a, &full_bar[s], k0 % p.a_cin, m0, k0 / p.a_cin, a_zlo, a_zhi);
-        } else {
+      uint32_t kiter = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(p, tile, BN);
+        const int a_zlo = t.z % p.a_zdiv, a_zhi = t.z / p.a_zdiv;
+        const int b_zlo = t.z % p.b_zdiv, b_zhi = t.z / p.b_zdiv;
+        for (int it = 0; it < t.num_kb; ++it, ++kiter) {
+          const int s = kiter % STAGES;
+          const uint32_t ph = (kiter / STAGES) & 1;
+          const int k0 = (t.kb_begin + it) * BK;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          mbar_arrive_expect_tx(&full_bar[s], L::STAGE_BYTES);
+          uint8_t* a_dst = smem + s * L::STAGE_BYTES;
+          uint8_t* b_dst = a_dst + A_TILE_BYTES;
+          if (!A_MN) {
+            tma_load_5d(a_dst, &tm_a, &full_bar[s], k0 % p.a_cin, t.m0, k0 / p.a_cin, a_zlo, a_zhi);
+          } else {
 #pragma unroll
-          for (int j = 0; j < BM / 64; ++j) {
-            const int c = m0 + 64 * j;
-            tma_load_5d(a_dst + j * (64 * BK * 2), &tm_a, &full_bar[s], c % p.a_cin, k0,
-                        c / p.a_cin, a_zlo, a_zhi);
+            for (int j = 0; j < BM / 64; ++j) {
+              const int c = t.m0 + 64 * j;
+              tma_load_5d(a_dst + j * (64 * BK * 2), &tm_a, &full_bar[s], c % p.a_cin, k0, c / p.a_cin,
+                          a_zlo, a_zhi);
+            }
           }
-        }
-        if (!B_MN) {
-          tma_load_5d(b_dst, &tm_b, &full_bar[s], k0 % p.b_cin, n0, k0 / p.b_cin, b_zlo, b_zhi);
-        } else {
+          if (!B_MN) {
+            tma_load_5d(b_dst, &tm_b, &full_bar[s], k0 % p.b_cin, t.n0, k0 / p.b_cin, b_zlo, b_zhi);
+          } else {
 #pragma unroll
-          for (int j = 0; j < BN / 64; ++j) {
-            const int c = n0 + 64 * j;
-            tma_load_5d(b_dst + j * (64 * BK * 2), &tm_b, &full_bar[s], c % p.b_cin, k0,
-                        c / p.b_cin, b_zlo, b_zhi);
+            for (int j = 0; j < BN / 64; ++j) {
+              const int c = t.n0 + 64 * j;
+              tma_load_5d(b_dst + j * (64 * BK * 2), &tm_b, &full_bar[s], c % p.b_cin, k0, c / p.b_cin,
+                          b_zlo, b_zhi);
+            }
           }
         }
       }
@@ -160,237 +181,271 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     // ------------------------------------------------------------------ MMA issuer
     if (elect_one()) {
       constexpr uint32_t idesc = umma_idesc(BM, BN, /*bf16*/ 1, A_MN, B_MN);
-      for (int it = 0; it < num_kb; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
-        mbar_wait(&full_bar[s], ph);
+      uint32_t kiter = 0, titer = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++titer) {
+        const TileCoord t = decode_tile(p, tile, BN);
+        const uint32_t buf = titer & 1;
+        mbar_wait(&tmem_empty_bar[buf], ((titer >> 1) & 1) ^ 1);  // epilogue drained this buffer
         tc_fence_after();
-        const uint32_t a_base = smem_u32(smem + s * L::STAGE_BYTES);
-        const uint32_t b_base = a_base + A_TILE_BYTES;
+        const uint32_t tmem_d = tmem_base + buf * BN;
+        for (int it = 0; it < t.num_kb; ++it, ++kiter) {
+          const int s = kiter % STAGES;
+          const uint32_t ph = (kiter / STAGES) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(smem + s * L::STAGE_BYTES);
+          const uint32_t b_base = a_base + A_TILE_BYTES;
 #pragma unroll
-        for (int k4 = 0; k4 < BK / 16; ++k4) {
-          // K-major: advance 16 bf16 = 32 B inside the 128 B swizzle row.
-          // MN-major: advance 16 k-rows = 2 swizzle atoms of 1024 B.
-          const uint64_t adesc = A_MN ? umma_smem_desc(a_base + k4 * 2048, 64 * BK * 2, 1024)
-                                      : umma_smem_desc(a_base + k4 * 32, 16, 1024);
-          const uint64_t bdesc = B_MN ? umma_smem_desc(b_base + k4 * 2048, 64 * BK * 2, 1024)
-                                      : umma_smem_desc(b_base + k4 * 32, 16, 1024);
-          umma_bf16_ss(tmem_base, adesc, bdesc, idesc, (it > 0 || k4 > 0) ? 1u : 0u);
+          for (int k4 = 0; k4 < BK / 16; ++k4) {
+            // K-major: advance 16 bf16 = 32 B inside the 128 B swizzle row.
+            // MN-major: advance 16 k-rows = 2 swizzle atoms of 1024 B.
+            const uint64_t adesc = A_MN ? umma_smem_desc(a_base + k4 * 2048, 64 * BK * 2, 1024)
+                                        : umma_smem_desc(a_base + k4 * 32, 16, 1024);
+            const uint64_t bdesc = B_MN ? umma_smem_desc(b_base + k4 * 2048, 64 * BK * 2, 1024)
+                                        : umma_smem_desc(b_base + k4 * 32, 16, 1024);
+            umma_bf16_ss(tmem_d, adesc, bdesc, idesc, (it > 0 || k4 > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);  // frees the smem slot when these MMAs retire
         }
-        umma_commit(&empty_bar[s]);  // frees the smem slot when these MMAs retire
+        umma_commit(&tmem_full_bar[buf]);  // accumulator of this tile complete
       }
-      umma_commit(tmem_full_bar);  // accumulator complete
     }
   } else {
     // ------------------------------------------------------------------ epilogue warps
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
-    const int row = m0 + q * 32 + lane;
-    const bool row_ok = row < p.M;
-    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    const long long o_base = (long long)(z / p.o_zdiv) * p.o_s_zhi +
-                             (long long)(z % p.o_zdiv) * p.o_s_zlo + (long long)row * p.o_ld;
-    if (num_kb > 0) {
-      mbar_wait(tmem_full_bar, 0);
-      tc_fence_after();
-    }
-    uint32_t r[32];
+    const int ew = warp - 2;        // 0..7
+    const int grp = ew >> 2;        // epilogue group == TMEM buffer
+    const int q = warp & 3;         // TMEM lane quarter this warp may access
+    float* stg = reinterpret_cast<float*>(smem + L::STG_OFFSET + ew * STG_BYTES_PER_WARP);
+    // coalesced mapping inside a 32-row x 16-col chunk: 4 lanes cover one row (4 x 16 B)
+    const int c_row = lane >> 2;    // + 8 * it
+    const int c_pc = lane & 3;      // 16-byte piece -> columns 4*c_pc .. 4*c_pc+3
+    uint32_t titer = grp;
+    for (int tile = blockIdx.x + grp * gridDim.x; tile < p.total_tiles; tile += 2 * gridDim.x, titer += 2) {
+      const TileCoord t = decode_tile(p, tile, BN);
+      const uint32_t buf = grp;
+      const uint32_t taddr = tmem_base + buf * BN + (static_cast<uint32_t>(q * 32) << 16);
+      const long long o_zbase = (long long)(t.z / p.o_zdiv) * p.o_s_zhi + (long long)(t.z % p.o_zdiv) * p.o_s_zlo;
+      const int row_base = t.m0 + q * 32;
+      if (t.num_kb > 0) {
+        mbar_wait(&tmem_full_bar[buf], (titer >> 1) & 1);
+        tc_fence_after();
+      }
 
-    if (p.mode == LVT_EPI_LINEAR) {
+      if constexpr (EK == EK_LINEAR || EK == EK_DS) {
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        const int col0 = n0 + c0;
-        if (col0 >= p.N) break;  // warp-uniform
-        if (num_kb > 0) {
-          tmem_ld_32x32(taddr + c0, r);
-          tmem_ld_wait();
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) r[i] = 0;
-        }
-        if (!row_ok) continue;
-        const long long off = o_base + (long long)(col0 / p.o_cin) * p.o_s_blk + (col0 % p.o_cin);
-        const bool full = (col0 + 32 <= p.N);
-        float v[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * p.alpha;
-        if (p.bias) {
-          const float* bp = p.bias + (p.bias_mod > 0 ? (long long)(row % p.bias_mod) * p.N : 0) + col0;
-          if (full) {
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              const float4 b4 = *reinterpret_cast<const float4*>(bp + i);
-              v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
-            }
+        for (int c0 = 0; c0 < BN; c0 += 16) {
+          const int col0 = t.n0 + c0;
+          if (col0 >= p.N) break;  // warp-uniform
+          uint32_t r[16];
+          if (t.num_kb > 0) {
+            tmem_ld_32x16(taddr + c0, r);
+            tmem_ld_wait();
           } else {
-            for (int i = 0; i < 32 && col0 + i < p.N; ++i) v[i] += bp[i];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) r[i] = 0;
           }
-        }
-        if (p.res) {
-          const float* rp = p.res + off;
-          if (full) {
+          // lane == row: stage alpha*acc
+          float* srow = stg + lane * STG_STRIDE;
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              const float4 b4 = *reinterpret_cast<const float4*>(rp + i);
-              v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
-            }
-          } else {
-            for (int i = 0; i < 32 && col0 + i < p.N; ++i) v[i] += rp[i];
-          }
-        }
-        if (p.flags & LVT_GEMM_RELU) {
+          for (int i = 0; i < 16; i += 4)
+            *reinterpret_cast<float4*>(srow + i) =
+                make_float4(__uint_as_float(r[i]) * p.alpha, __uint_as_float(r[i + 1]) * p.alpha,
+                            __uint_as_float(r[i + 2]) * p.alpha, __uint_as_float(r[i + 3]) * p.alpha);
+          __syncwarp();
+          const int col = col0 + 4 * c_pc;
+          const bool vec_ok = col + 4 <= p.N;
+          const long long o_col = (long long)(col / p.o_cin) * p.o_s_blk + (col % p.o_cin);
+          float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (EK == EK_LINEAR && p.bias && p.bias_mod == 0 && vec_ok)
+            bias4 = *reinterpret_cast<const float4*>(p.bias + col);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
-        }
-        if (p.flags & LVT_GEMM_MASK) {
-          const __nv_bfloat16* ap = p.aux + off;
-          if (full) {
-#pragma unroll
-            for (int i = 0; i < 32; i += 8) {
-              const uint4 u = *reinterpret_cast<const uint4*>(ap + i);
-              const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                // bf16 > 0  <=>  sign bit clear and magnitude non-zero
-                const uint32_t lo = w[j] & 0xFFFFu, hi = w[j] >> 16;
-                if (!(lo != 0 && lo < 0x8000u)) v[i + 2 * j] = 0.f;
-                if (!(hi != 0 && hi < 0x8000u)) v[i + 2 * j + 1] = 0.f;
+          for (int it = 0; it < 4; ++it) {
+            const int rl = c_row + 8 * it;
+            const int row = row_base + rl;
+            float4 v = *reinterpret_cast<const float4*>(stg + rl * STG_STRIDE + 4 * c_pc);
+            if (row >= p.M || col >= p.N) continue;
+            const long long off = o_zbase + (long long)row * p.o_ld + o_col;
+            if (vec_ok) {
+              if constexpr (EK == EK_DS) {
+                const float dl = p.delta[(long long)t.z * p.M + row];
+                const uint2 pu = *reinterpret_cast<const uint2*>(p.aux + off);
+                const float2 p0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pu.x));
+                const float2 p1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pu.y));
+                v.x = p0.x * (v.x - dl); v.y = p0.y * (v.y - dl);
+                v.z = p1.x * (v.z - dl); v.w = p1.y * (v.w - dl);
+                uint2 u;
+                u.x = pack_bf16x2(v.x, v.y);
+                u.y = pack_bf16x2(v.z, v.w);
+                *reinterpret_cast<uint2*>(p.out_bf16 + off) = u;
+              } else {
+                if (p.bias) {
+                  if (p.bias_mod > 0)
+                    bias4 = *reinterpret_cast<const float4*>(p.bias + (long long)(row % p.bias_mod) * p.N + col);
+                  v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w;
+                }
+                if (p.res) {
+                  const float4 r4 = *reinterpret_cast<const float4*>(p.res + off);
+                  v.x += r4.x; v.y += r4.y; v.z += r4.z; v.w += r4.w;
+                }
+                if (p.flags & LVT_GEMM_RELU) {
+                  v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+                }
+                if (p.flags & LVT_GEMM_MASK) {
+                  const uint2 mu = *reinterpret_cast<const uint2*>(p.aux + off);
+                  // bf16 > 0  <=>  sign bit clear and magnitude non-zero
+                  const uint32_t a0 = mu.x & 0xFFFFu, a1 = mu.x >> 16, a2 = mu.y & 0xFFFFu, a3 = mu.y >> 16;
+                  if (!(a0 != 0 && a0 < 0x8000u)) v.x = 0.f;
+                  if (!(a1 != 0 && a1 < 0x8000u)) v.y = 0.f;
+                  if (!(a2 != 0 && a2 < 0x8000u)) v.z = 0.f;
+                  if (!(a3 != 0 && a3 < 0x8000u)) v.w = 0.f;
+                }
+                if (p.out_f32) {
+                  if (p.flags & LVT_GEMM_ATOMIC) red_add_v4(p.out_f32 + off, v.x, v.y, v.z, v.w);
+                  else *reinterpret_cast<float4*>(p.out_f32 + off) = v;
+                }
+                if (p.out_bf16) {
+                  uint2 u;
+                  u.x = pack_bf16x2(v.x, v.y);
+                  u.y = pack_bf16x2(v.z, v.w);
+                  *reinterpret_cast<uint2*>(p.out_bf16 + off) = u;
+                }
+              }
+            } else {
+              // ragged N tail: element-wise
+              float ve[4] = {v.x, v.y, v.z, v.w};
+              for (int e = 0; e < 4 && col + e < p.N; ++e) {
+                float x = ve[e];
+                if constexpr (EK == EK_DS) {
+                  x = __bfloat162float(p.aux[off + e]) * (x - p.delta[(long long)t.z * p.M + row]);
+                  p.out_bf16[off + e] = __float2bfloat16(x);
+                } else {
+                  if (p.bias) x += p.bias[(p.bias_mod > 0 ? (long long)(row % p.bias_mod) * p.N : 0) + col + e];
+                  if (p.res) x += p.res[off + e];
+                  if (p.flags & LVT_GEMM_RELU) x = fmaxf(x, 0.f);
+                  if ((p.flags & LVT_GEMM_MASK) && !(__bfloat162float(p.aux[off + e]) > 0.f)) x = 0.f;
+                  if (p.out_f32) {
+                    if (p.flags & LVT_GEMM_ATOMIC) atomicAdd(p.out_f32 + off + e, x);
+                    else p.out_f32[off + e] = x;
+                  }
+                  if (p.out_bf16) p.out_bf16[off + e] = __float2bfloat16(x);
+                }
               }
             }
-          } else {
-            for (int i = 0; i < 32 && col0 + i < p.N; ++i)
-              if (!(__bfloat162float(ap[i]) > 0.f)) v[i] = 0.f;
           }
+          __syncwarp();
         }
-        if (p.out_f32) {
-          float* op = p.out_f32 + off;
-          if (p.flags & LVT_GEMM_ATOMIC) {
-            if (full) {
+      } else {
+        // -------- attention probabilities: one thread owns one query row and all 256 keys
+        // v = alpha*acc + B[head, i, j]; causal: j > i -> -1e4 (vt_attention.py:63-74); the
+        // relative-position bias is separable, so each thread keeps its row's bank slices in
+        // registers: B[i, j] = bt[tj] + bh[hj] + bw[wj]  (get_B, vt_attention.py:169-174).
+        constexpr int BT = EK == EK_SOFTMAX_1x16x16 ? 1 : 4;
+        constexpr int BH = EK == EK_SOFTMAX_1x16x16 ? 16 : 8;
+        constexpr int BW = EK == EK_SOFTMAX_1x16x16 ? 16 : 8;
+        static_assert(BN == 256 || EK == EK_LINEAR || EK == EK_DS, "softmax epilogue needs BN == 256");
+        constexpr int NH = 32 / BW;  // distinct key-h values inside one 32-column chunk
+        const int row = row_base + lane;  // 0..255 inside the block (M == 256)
+        const int head = t.z % p.heads;
+        const int ti = row / (BH * BW), hi = (row / BW) % BH, wi = row % BW;
+        const float kLog2e = 1.4426950408889634f;
+        // bank slices of this row, pre-scaled into the log2 domain
+        float bt[BT], bh[BH], bw[BW];
 #pragma unroll
-              for (int i = 0; i < 32; i += 4) red_add_v4(op + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
-            } else {
-              for (int i = 0; i < 32 && col0 + i < p.N; ++i) atomicAdd(op + i, v[i]);
-            }
-          } else if (full) {
+        for (int x = 0; x < BT; ++x) bt[x] = kLog2e * __ldg(p.bank_t + head * (2 * BT - 1) + (ti - x + BT - 1));
 #pragma unroll
-            for (int i = 0; i < 32; i += 4)
-              *reinterpret_cast<float4*>(op + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-          } else {
-            for (int i = 0; i < 32 && col0 + i < p.N; ++i) op[i] = v[i];
-          }
-        }
-        if (p.out_bf16) {
-          __nv_bfloat16* op = p.out_bf16 + off;
-          if (full) {
+        for (int x = 0; x < BH; ++x) bh[x] = kLog2e * __ldg(p.bank_h + head * (2 * BH - 1) + (hi - x + BH - 1));
 #pragma unroll
-            for (int i = 0; i < 32; i += 8) {
-              uint4 u;
-              u.x = pack_bf16x2(v[i], v[i + 1]);
-              u.y = pack_bf16x2(v[i + 2], v[i + 3]);
-              u.z = pack_bf16x2(v[i + 4], v[i + 5]);
-              u.w = pack_bf16x2(v[i + 6], v[i + 7]);
-              *reinterpret_cast<uint4*>(op + i) = u;
-            }
-          } else {
-            for (int i = 0; i < 32 && col0 + i < p.N; ++i) op[i] = __float2bfloat16(v[i]);
-          }
-        }
-      }
-    } else if (p.mode == LVT_EPI_SOFTMAX) {
-      // One thread owns one query row and all 256 keys of its block (BN == N == 256).
-      // v = alpha*acc + B[head, i, j]; causal: j > i -> -1e4 (vt_attention.py:63-74).
-      if constexpr (BN == 256) {
-        const int nt = 2 * p.bt - 1, nh = 2 * p.bh - 1;
-        const float* sb_t = s_bank;
-        const float* sb_h = s_bank + nt;
-        const float* sb_w = s_bank + nt + nh;
-        const int hw = p.bh * p.bw;
-        const int ti = row / hw, hi = (row / p.bw) % p.bh, wi = row % p.bw;
+        for (int x = 0; x < BW; ++x) bw[x] = kLog2e * __ldg(p.bank_w + head * (2 * BW - 1) + (wi - x + BW - 1));
         const bool causal = (p.flags & LVT_GEMM_CAUSAL) != 0;
-        auto logit = [&](float acc, int j) -> float {
-          const int tj = j / hw, hj = (j / p.bw) % p.bh, wj = j % p.bw;
-          float v = acc * p.alpha + (sb_t[ti - tj + p.bt - 1] + sb_h[hi - hj + p.bh - 1] +
-                                     sb_w[wi - wj + p.bw - 1]);
-          if (causal && j > row) v = -1e4f;
+        const float a2 = p.alpha * kLog2e;
+        const float kMasked = -1e4f * kLog2e;
+        uint32_t r[32];
+        float cb[NH];  // bt[tj] + bh[hj] for the key-h values of the current chunk
+        auto chunk_bias = [&](int c0) {
+          const int tjv = c0 / (BH * BW);
+          const int hbase = (c0 / BW) % BH;
+          float bts = bt[0];
+#pragma unroll
+          for (int x = 1; x < BT; ++x)
+            if (tjv == x) bts = bt[x];
+#pragma unroll
+          for (int y = 0; y < NH; ++y) {
+            float v = bh[y];
+#pragma unroll
+            for (int hb = NH; hb < BH; hb += NH)
+              if (hbase == hb) v = bh[hb + y];
+            cb[y] = v + bts;
+          }
+        };
+        // logit in the log2 domain: (alpha*acc + B) * log2(e); i = column inside the chunk
+        auto logit2 = [&](uint32_t acc, int c0, int i) -> float {
+          float v = __uint_as_float(acc) * a2 + (cb[i / BW] + bw[i % BW]);
+          if (causal && c0 + i > row) v = kMasked;
           return v;
         };
         float mx = -INFINITY;
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
+        for (int c0 = 0; c0 < 256; c0 += 32) {
           tmem_ld_32x32(taddr + c0, r);
+          chunk_bias(c0);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, logit(__uint_as_float(r[i]), c0 + i));
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, logit2(r[i], c0, i));
         }
         float sum = 0.f;
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
+        for (int c0 = 0; c0 < 256; c0 += 32) {
           tmem_ld_32x32(taddr + c0, r);
+          chunk_bias(c0);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) sum += __expf(logit(__uint_as_float(r[i]), c0 + i) - mx);
+          for (int i = 0; i < 32; ++i) sum += exp2f(logit2(r[i], c0, i) - mx);
         }
         const float inv = 1.f / sum;
-        if (row_ok && p.lse) p.lse[(long long)z * p.M + row] = mx + __logf(sum);
+        if (p.lse) p.lse[(long long)t.z * p.M + row] = (mx + log2f(sum)) * 0.6931471805599453f;
+        __nv_bfloat16* stg16 = reinterpret_cast<__nv_bfloat16*>(stg);  // 32 rows x (32 bf16 + pad) = 80 B rows
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
+        for (int c0 = 0; c0 < 256; c0 += 32) {
           tmem_ld_32x32(taddr + c0, r);
+          chunk_bias(c0);
           tmem_ld_wait();
-          if (!row_ok) continue;
-          __nv_bfloat16* op = p.out_bf16 + o_base + c0;
+          uint4* srow = reinterpret_cast<uint4*>(stg16 + lane * (STG_STRIDE * 2));
 #pragma unroll
           for (int i = 0; i < 32; i += 8) {
             float e[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-              e[j] = __expf(logit(__uint_as_float(r[i + j]), c0 + i + j) - mx) * inv;
+            for (int j = 0; j < 8; ++j) e[j] = exp2f(logit2(r[i + j], c0, i + j) - mx) * inv;
             uint4 u;
             u.x = pack_bf16x2(e[0], e[1]);
             u.y = pack_bf16x2(e[2], e[3]);
             u.z = pack_bf16x2(e[4], e[5]);
             u.w = pack_bf16x2(e[6], e[7]);
-            *reinterpret_cast<uint4*>(op + i) = u;
+            srow[i / 8] = u;
           }
+          __syncwarp();
+          // coalesced store: 4 lanes x 16 B cover one 64 B row chunk
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const int rl = c_row + 8 * it;
+            const uint4 u = *reinterpret_cast<const uint4*>(stg16 + rl * (STG_STRIDE * 2) + 8 * c_pc);
+            const long long off = o_zbase + (long long)(row_base + rl) * p.o_ld + c0 + 8 * c_pc;
+            *reinterpret_cast<uint4*>(p.out_bf16 + off) = u;
+          }
+          __syncwarp();
         }
       }
-    } else {  // LVT_EPI_DS: dS = P * (alpha*acc - delta[row])
-      const float dl = row_ok ? p.delta[(long long)z * p.M + row] : 0.f;
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        const int col0 = n0 + c0;
-        if (col0 >= p.N) break;
-        tmem_ld_32x32(taddr + c0, r);
-        tmem_ld_wait();
-        if (!row_ok) continue;
-        const long long off = o_base + (long long)(col0 / p.o_cin) * p.o_s_blk + (col0 % p.o_cin);
-        const __nv_bfloat16* ap = p.aux + off;
-        __nv_bfloat16* op = p.out_bf16 + off;
-#pragma unroll
-        for (int i = 0; i < 32; i += 8) {
-          const uint4 pu = *reinterpret_cast<const uint4*>(ap + i);
-          const __nv_bfloat162* pp = reinterpret_cast<const __nv_bfloat162*>(&pu);
-          float e[8];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float2 pf = __bfloat1622float2(pp[j]);
-            e[2 * j] = pf.x * (__uint_as_float(r[i + 2 * j]) * p.alpha - dl);
-            e[2 * j + 1] = pf.y * (__uint_as_float(r[i + 2 * j + 1]) * p.alpha - dl);
-          }
-          uint4 u;
-          u.x = pack_bf16x2(e[0], e[1]);
-          u.y = pack_bf16x2(e[2], e[3]);
-          u.z = pack_bf16x2(e[4], e[5]);
-          u.w = pack_bf16x2(e[6], e[7]);
-          *reinterpret_cast<uint4*>(op + i) = u;
-        }
-      }
+      // this warp no longer reads the accumulator buffer
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
     }
-    tc_fence_before();
   }
 
+  tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, BN);
+    tmem_dealloc(tmem_base, 2 * BN);
   }
 }
 
@@ -499,11 +554,11 @@ int make_operand_map(CUtensorMap* out, const void* base, long long c_extent, lon
   return LVT_OK;
 }
 
-template <int BN, int STAGES, bool A_MN, bool B_MN>
-int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, dim3 grid,
+template <int BN, bool A_MN, bool B_MN, int EK>
+int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int grid,
                 cudaStream_t stream) {
-  using L = SmemLayout<BN, STAGES>;
-  auto kern = gemm_bf16_kernel<BN, STAGES, A_MN, B_MN>;
+  using L = SmemLayout<BN>;
+  auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, EK>;
   static bool configured = false;
   if (!configured) {
     LVT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
@@ -515,13 +570,24 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& 
   return LVT_OK;
 }
 
-template <int BN, int STAGES>
-int dispatch_major(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, dim3 grid,
+template <int BN, int EK>
+int dispatch_major(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int grid,
                    bool a_mn, bool b_mn, cudaStream_t stream) {
-  if (!a_mn && !b_mn) return launch_gemm<BN, STAGES, false, false>(ta, tb, p, grid, stream);
-  if (!a_mn && b_mn) return launch_gemm<BN, STAGES, false, true>(ta, tb, p, grid, stream);
-  if (a_mn && !b_mn) return launch_gemm<BN, STAGES, true, false>(ta, tb, p, grid, stream);
-  return launch_gemm<BN, STAGES, true, true>(ta, tb, p, grid, stream);
+  if (!a_mn && !b_mn) return launch_gemm<BN, false, false, EK>(ta, tb, p, grid, stream);
+  if (!a_mn && b_mn) return launch_gemm<BN, false, true, EK>(ta, tb, p, grid, stream);
+  if (a_mn && !b_mn) return launch_gemm<BN, true, false, EK>(ta, tb, p, grid, stream);
+  return launch_gemm<BN, true, true, EK>(ta, tb, p, grid, stream);
+}
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
 }
 
 }  // namespace
@@ -533,40 +599,57 @@ extern "C" int lvt_gemm_bf16(const LvtGemm* g, void* stream_) {
                 g->M, g->N, g->K, g->batch);
   LVT_CHECK_ARG(g->a && g->b, "lvt_gemm_bf16: null operand");
   LVT_CHECK_ARG(g->out_f32 || g->out_bf16, "lvt_gemm_bf16: no output");
-  const int splits = g->splits > 0 ? g->splits : 1;
+  int splits = g->splits > 0 ? g->splits : 1;
   LVT_CHECK_ARG(splits == 1 || ((g->flags & LVT_GEMM_ATOMIC) && !g->out_bf16 && g->mode == LVT_EPI_LINEAR),
                 "lvt_gemm_bf16: split-K needs LVT_GEMM_ATOMIC fp32 output only");
   LVT_CHECK_ARG(!(g->flags & LVT_GEMM_ATOMIC) || (g->out_f32 && !g->res),
                 "lvt_gemm_bf16: atomic output needs out_f32 and no residual");
   LVT_CHECK_ARG(g->a_cin > 0 && g->b_cin > 0 && g->o_cin > 0 && g->a_zdiv > 0 && g->b_zdiv > 0 && g->o_zdiv > 0,
                 "lvt_gemm_bf16: cin/zdiv must be positive");
-  LVT_CHECK_ARG(g->o_cin % 32 == 0 || g->o_cin >= g->N, "lvt_gemm_bf16: o_cin must be a multiple of 32");
-  LVT_CHECK_ARG(g->o_ld % 8 == 0 && g->o_s_blk % 8 == 0 && g->o_s_zlo % 8 == 0 && g->o_s_zhi % 8 == 0,
-                "lvt_gemm_bf16: output strides must be multiples of 8 elements");
+  LVT_CHECK_ARG(g->o_cin % 16 == 0 || g->o_cin >= g->N, "lvt_gemm_bf16: o_cin must be a multiple of 16");
+  LVT_CHECK_ARG(g->o_ld % 4 == 0 && g->o_s_blk % 4 == 0 && g->o_s_zlo % 4 == 0 && g->o_s_zhi % 4 == 0,
+                "lvt_gemm_bf16: output strides must be multiples of 4 elements");
   if (g->flags & LVT_GEMM_MASK) LVT_CHECK_ARG(g->aux_bf16, "lvt_gemm_bf16: MASK needs aux_bf16");
 
   int bn = 128;
+  int ek = EK_LINEAR;
   if (g->mode == LVT_EPI_SOFTMAX) {
-    LVT_CHECK_ARG(g->N == 256 && g->out_bf16 && g->bank_t && g->bank_h && g->bank_w &&
-                      g->bt * g->bh * g->bw == g->M && g->M == 256 && g->heads > 0,
-                  "lvt_gemm_bf16: SOFTMAX mode needs M == N == 256 == bt*bh*bw, banks and out_bf16");
-    LVT_CHECK_ARG(2 * (g->bt + g->bh + g->bw) - 3 <= 256, "lvt_gemm_bf16: relative-position banks too large");
+    LVT_CHECK_ARG(g->N == 256 && g->out_bf16 && g->bank_t && g->bank_h && g->bank_w && g->M == 256 && g->heads > 0,
+                  "lvt_gemm_bf16: SOFTMAX mode needs M == N == 256, banks and out_bf16");
+    if (g->bt == 1 && g->bh == 16 && g->bw == 16) ek = EK_SOFTMAX_1x16x16;
+    else if (g->bt == 4 && g->bh == 8 && g->bw == 8) ek = EK_SOFTMAX_4x8x8;
+    else {
+      lvt_set_error("lvt_gemm_bf16: SOFTMAX mode supports attention blocks (1,16,16) and (4,8,8), got (%d,%d,%d)",
+                    g->bt, g->bh, g->bw);
+      return LVT_ERR_INVALID;
+    }
+    LVT_CHECK_ARG(!g->a_mn_major && !g->b_mn_major, "lvt_gemm_bf16: SOFTMAX mode needs K-major Q and K");
+    LVT_CHECK_ARG(g->o_cin >= g->N && g->o_ld % 8 == 0, "lvt_gemm_bf16: SOFTMAX output must be plain rows");
     bn = 256;
   } else if (g->mode == LVT_EPI_DS) {
     LVT_CHECK_ARG(g->out_bf16 && g->aux_bf16 && g->delta, "lvt_gemm_bf16: DS mode needs out_bf16, aux_bf16 (P) and delta");
+    ek = EK_DS;
     bn = (g->N % 256 == 0) ? 256 : 128;
   } else {
     LVT_CHECK_ARG(g->mode == LVT_EPI_LINEAR, "lvt_gemm_bf16: unknown epilogue mode %d", g->mode);
-    // wide tiles when they still fill the machine
-    const long long tiles256 = (long long)((g->M + BM - 1) / BM) * ((g->N + 255) / 256) * g->batch * splits;
-    bn = (g->N % 256 == 0 && tiles256 >= 2 * 148) ? 256 : 128;
+    bn = (g->N % 256 == 0) ? 256 : 128;
   }
 
   GemmParams p;
   memset(&p, 0, sizeof(p));
-  p.M = g->M; p.N = g->N; p.K = g->K; p.batch = g->batch; p.splits = splits;
+  p.M = g->M; p.N = g->N; p.K = g->K; p.batch = g->batch;
+  const int kb_total = (g->K + BK - 1) / BK;
+  if (splits > kb_total) splits = kb_total;
+  p.kb_per = (kb_total + splits - 1) / splits;
+  splits = (kb_total + p.kb_per - 1) / p.kb_per;  // no empty split
+  p.splits = splits;
+  p.tiles_m = (g->M + BM - 1) / BM;
+  p.tiles_n = (g->N + bn - 1) / bn;
+  const long long total = (long long)p.tiles_m * p.tiles_n * splits * g->batch;
+  LVT_CHECK_ARG(total < (1ll << 30), "lvt_gemm_bf16: too many tiles");
+  p.total_tiles = (int)total;
   p.a_cin = g->a_cin; p.a_zdiv = g->a_zdiv; p.b_cin = g->b_cin; p.b_zdiv = g->b_zdiv;
-  p.mode = g->mode; p.flags = g->flags; p.alpha = g->alpha;
+  p.flags = g->flags; p.alpha = g->alpha;
   p.out_f32 = g->out_f32; p.out_bf16 = reinterpret_cast<__nv_bfloat16*>(g->out_bf16);
   p.res = g->res; p.aux = reinterpret_cast<const __nv_bfloat16*>(g->aux_bf16);
   p.bias = g->bias; p.bias_mod = g->bias_mod;
@@ -574,7 +657,7 @@ extern "C" int lvt_gemm_bf16(const LvtGemm* g, void* stream_) {
   p.o_ld = g->o_ld; p.o_s_blk = g->o_s_blk; p.o_s_zlo = g->o_s_zlo; p.o_s_zhi = g->o_s_zhi;
   p.lse = g->lse; p.delta = g->delta;
   p.bank_t = g->bank_t; p.bank_h = g->bank_h; p.bank_w = g->bank_w;
-  p.bt = g->bt; p.bh = g->bh; p.bw = g->bw; p.heads = g->heads > 0 ? g->heads : 1;
+  p.heads = g->heads > 0 ? g->heads : 1;
 
   CUtensorMap ta, tb;
   int rc;
@@ -588,8 +671,15 @@ extern "C" int lvt_gemm_bf16(const LvtGemm* g, void* stream_) {
            : make_operand_map(&tb, g->b, g->K, g->N, g->b_cin, g->b_ld, g->b_s_blk, g->batch, g->b_zdiv, g->b_s_zlo, g->b_s_zhi, bn);
   if (rc) return rc;
 
-  dim3 grid((g->N + bn - 1) / bn, (g->M + BM - 1) / BM, g->batch * splits);
-  LVT_CHECK_ARG(grid.y <= 65535 && grid.z <= 65535, "lvt_gemm_bf16: grid too large");
-  if (bn == 256) return dispatch_major<256, 4>(ta, tb, p, grid, g->a_mn_major != 0, g->b_mn_major != 0, stream);
-  return dispatch_major<128, 3>(ta, tb, p, grid, g->a_mn_major != 0, g->b_mn_major != 0, stream);
+  const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+  const bool amn = g->a_mn_major != 0, bmn = g->b_mn_major != 0;
+  if (ek == EK_SOFTMAX_1x16x16) return launch_gemm<256, false, false, EK_SOFTMAX_1x16x16>(ta, tb, p, grid, stream);
+  if (ek == EK_SOFTMAX_4x8x8) return launch_gemm<256, false, false, EK_SOFTMAX_4x8x8>(ta, tb, p, grid, stream);
+  if (ek == EK_DS) {
+    LVT_CHECK_ARG(!amn && !bmn, "lvt_gemm_bf16: DS mode needs K-major dO and V");
+    if (bn == 256) return launch_gemm<256, false, false, EK_DS>(ta, tb, p, grid, stream);
+    return launch_gemm<128, false, false, EK_DS>(ta, tb, p, grid, stream);
+  }
+  if (bn == 256) return dispatch_major<256, EK_LINEAR>(ta, tb, p, grid, amn, bmn, stream);
+  return dispatch_major<128, EK_LINEAR>(ta, tb, p, grid, amn, bmn, stream);
 }
