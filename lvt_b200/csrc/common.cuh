@@ -151,6 +151,27 @@ LVT_DEVICE_INLINE void tma_load_5d(void* smem_dst, const CUtensorMap* m, uint64_
       : "memory");
 }
 
+// TMA store, shared -> global (bulk async group completion)
+LVT_DEVICE_INLINE void tma_store_5d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2,
+                                    int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+      :
+      : "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3),
+        "r"(c4)
+      : "memory");
+}
+LVT_DEVICE_INLINE void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all but the newest N bulk groups of this thread have finished READING their smem source
+template <int N>
+LVT_DEVICE_INLINE void bulk_wait_group_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N>
+LVT_DEVICE_INLINE void bulk_wait_group() {
+  asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+
 // ----------------------------------------------------------------------------------------
 // tcgen05 / TMEM
 // ----------------------------------------------------------------------------------------

@@ -29,8 +29,10 @@ constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
 constexpr int A_TILE_BYTES = BM * BK * 2;  // 16 KiB
 constexpr int NUM_THREADS = 320;           // 10 warps
 constexpr int NUM_EPI_WARPS = 8;
-constexpr int STG_STRIDE = 20;             // floats per staged row (16 data + 4 pad): conflict-free float4
-constexpr int STG_BYTES_PER_WARP = 32 * STG_STRIDE * 4;
+// per-warp transpose buffer: 32 rows x 4 units of 16 B, unit k of row r stored at r*4 + (k ^ ((r>>1)&3))
+// -> both the row-per-lane writes and the 4-lanes-per-row reads are bank-conflict free
+constexpr int STG_BYTES_PER_WARP = 4096;  // generic path uses 2 KiB; TMA-store slab = 32 rows x 128 B
+LVT_DEVICE_INLINE int stg_unit(int row, int k) { return row * 4 + (k ^ ((row >> 1) & 3)); }
 
 // epilogue kinds (compile-time)
 constexpr int EK_LINEAR = 0;
@@ -50,7 +52,7 @@ struct GemmParams {
   const __nv_bfloat16* aux;
   const float* bias;
   int bias_mod;
-  int o_cin, o_zdiv;
+  int o_cin, o_zdiv, o_shift;  // o_shift: log2(o_cin) for blocked outputs, -1 for plain rows
   long long o_ld, o_s_blk, o_s_zlo, o_s_zhi;
   float* lse;
   const float* delta;
@@ -96,10 +98,12 @@ LVT_DEVICE_INLINE TileCoord decode_tile(const GemmParams& p, int tile, int bn) {
   return t;
 }
 
-template <int BN, bool A_MN, bool B_MN, int EK>
+// ST: 0 = staged generic epilogue (residual / mask / atomic / dual output / ragged N),
+//     1 = TMA-store epilogue, bf16 output,  2 = TMA-store epilogue, fp32 output
+template <int BN, bool A_MN, bool B_MN, int EK, int ST>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
-                 const GemmParams p) {
+                 const __grid_constant__ CUtensorMap tm_o, const GemmParams p) {
   using L = SmemLayout<BN>;
   constexpr int STAGES = L::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -231,12 +235,84 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         tc_fence_after();
       }
 
-      if constexpr (EK == EK_LINEAR || EK == EK_DS) {
+      if constexpr (EK == EK_LINEAR && ST != 0) {
+        // -------- TMA-store epilogue: TMEM -> registers -> 128B-swizzled smem slab (32 rows x 128 B per
+        // warp) -> one cp.async.bulk.tensor store per slab.  No per-element address math, no LSU stores.
+        constexpr int SLAB_COLS = ST == 1 ? 64 : 32;  // 128 B per row
+        uint4* const slab = reinterpret_cast<uint4*>(stg);
+        const int o_zlo = t.z % p.o_zdiv, o_zhi = t.z / p.o_zdiv;
+        const float alpha = p.alpha;
+        const bool relu = (p.flags & LVT_GEMM_RELU) != 0;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += SLAB_COLS) {
+          const int col0 = t.n0 + c0;
+          if (col0 >= p.N) break;  // warp-uniform
+          if (lane == 0) bulk_wait_group_read<0>();  // previous store of this warp has drained the slab
+          __syncwarp();
+#pragma unroll
+          for (int h = 0; h < SLAB_COLS / 32; ++h) {
+            uint32_t r[32];
+            tmem_ld_32x32(taddr + c0 + 32 * h, r);
+            tmem_ld_wait();
+            float v[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * alpha;
+            if (p.bias) {
+              const float* bp = p.bias + col0 + 32 * h;
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(bp + i));
+                v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
+              }
+            }
+            if (relu) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+            }
+            if constexpr (ST == 1) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {  // 4 units of 8 bf16
+                uint4 u;
+                u.x = pack_bf16x2(v[8 * k], v[8 * k + 1]);
+                u.y = pack_bf16x2(v[8 * k + 2], v[8 * k + 3]);
+                u.z = pack_bf16x2(v[8 * k + 4], v[8 * k + 5]);
+                u.w = pack_bf16x2(v[8 * k + 6], v[8 * k + 7]);
+                slab[lane * 8 + ((4 * h + k) ^ (lane & 7))] = u;
+              }
+            } else {
+#pragma unroll
+              for (int k = 0; k < 8; ++k)  // 8 units of 4 fp32
+                slab[lane * 8 + (k ^ (lane & 7))] =
+                    make_uint4(__float_as_uint(v[4 * k]), __float_as_uint(v[4 * k + 1]),
+                               __float_as_uint(v[4 * k + 2]), __float_as_uint(v[4 * k + 3]));
+            }
+          }
+          fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA (async proxy)
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_5d(&tm_o, slab, col0 % p.o_cin, row_base, col0 / p.o_cin, o_zlo, o_zhi);
+            bulk_commit_group();
+          }
+        }
+      } else if constexpr (EK == EK_LINEAR || EK == EK_DS) {
+        // per-tile invariants (kept out of the chunk loop: no divisions, 32-bit offsets inside the tile)
+        const long long tile_off = o_zbase + (long long)row_base * p.o_ld;
+        float* const of32 = p.out_f32 ? p.out_f32 + tile_off : nullptr;
+        __nv_bfloat16* const obf = p.out_bf16 ? p.out_bf16 + tile_off : nullptr;
+        const float* const resp = p.res ? p.res + tile_off : nullptr;
+        const __nv_bfloat16* const auxp = p.aux ? p.aux + tile_off : nullptr;
+        const int ld = (int)p.o_ld;
+        const int rows_valid = p.M - row_base;  // rows of this warp's quarter that exist
+        const float* const deltap = (EK == EK_DS) ? p.delta + (long long)t.z * p.M + row_base : nullptr;
+        const int flags = p.flags;
+        const float alpha = p.alpha;
+        float4* const stg4 = reinterpret_cast<float4*>(stg);
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 16) {
           const int col0 = t.n0 + c0;
           if (col0 >= p.N) break;  // warp-uniform
           uint32_t r[16];
+          if (flags & (1 << 29)) break;  // DEBUG: no epilogue work at all
           if (t.num_kb > 0) {
             tmem_ld_32x16(taddr + c0, r);
             tmem_ld_wait();
@@ -244,54 +320,52 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 #pragma unroll
             for (int i = 0; i < 16; ++i) r[i] = 0;
           }
-          // lane == row: stage alpha*acc
-          float* srow = stg + lane * STG_STRIDE;
+          if (flags & (1 << 30)) continue;  // DEBUG: TMEM reads only
+          // lane == row: stage alpha*acc (4 swizzled 16 B units per row)
 #pragma unroll
-          for (int i = 0; i < 16; i += 4)
-            *reinterpret_cast<float4*>(srow + i) =
-                make_float4(__uint_as_float(r[i]) * p.alpha, __uint_as_float(r[i + 1]) * p.alpha,
-                            __uint_as_float(r[i + 2]) * p.alpha, __uint_as_float(r[i + 3]) * p.alpha);
+          for (int k = 0; k < 4; ++k)
+            stg4[stg_unit(lane, k)] =
+                make_float4(__uint_as_float(r[4 * k]) * alpha, __uint_as_float(r[4 * k + 1]) * alpha,
+                            __uint_as_float(r[4 * k + 2]) * alpha, __uint_as_float(r[4 * k + 3]) * alpha);
           __syncwarp();
           const int col = col0 + 4 * c_pc;
           const bool vec_ok = col + 4 <= p.N;
-          const long long o_col = (long long)(col / p.o_cin) * p.o_s_blk + (col % p.o_cin);
+          const int o_col = p.o_shift < 0 ? col
+                                          : (int)((long long)(col >> p.o_shift) * p.o_s_blk) + (col & (p.o_cin - 1));
           float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
           if (EK == EK_LINEAR && p.bias && p.bias_mod == 0 && vec_ok)
             bias4 = *reinterpret_cast<const float4*>(p.bias + col);
 #pragma unroll
           for (int it = 0; it < 4; ++it) {
             const int rl = c_row + 8 * it;
-            const int row = row_base + rl;
-            float4 v = *reinterpret_cast<const float4*>(stg + rl * STG_STRIDE + 4 * c_pc);
-            if (row >= p.M || col >= p.N) continue;
-            const long long off = o_zbase + (long long)row * p.o_ld + o_col;
+            float4 v = stg4[stg_unit(rl, c_pc)];
+            if (rl >= rows_valid || col >= p.N) continue;
+            const int off = rl * ld + o_col;
             if (vec_ok) {
               if constexpr (EK == EK_DS) {
-                const float dl = p.delta[(long long)t.z * p.M + row];
-                const uint2 pu = *reinterpret_cast<const uint2*>(p.aux + off);
+                const float dl = deltap[rl];
+                const uint2 pu = *reinterpret_cast<const uint2*>(auxp + off);
                 const float2 p0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pu.x));
                 const float2 p1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pu.y));
-                v.x = p0.x * (v.x - dl); v.y = p0.y * (v.y - dl);
-                v.z = p1.x * (v.z - dl); v.w = p1.y * (v.w - dl);
                 uint2 u;
-                u.x = pack_bf16x2(v.x, v.y);
-                u.y = pack_bf16x2(v.z, v.w);
-                *reinterpret_cast<uint2*>(p.out_bf16 + off) = u;
+                u.x = pack_bf16x2(p0.x * (v.x - dl), p0.y * (v.y - dl));
+                u.y = pack_bf16x2(p1.x * (v.z - dl), p1.y * (v.w - dl));
+                *reinterpret_cast<uint2*>(obf + off) = u;
               } else {
                 if (p.bias) {
                   if (p.bias_mod > 0)
-                    bias4 = *reinterpret_cast<const float4*>(p.bias + (long long)(row % p.bias_mod) * p.N + col);
+                    bias4 = *reinterpret_cast<const float4*>(p.bias + (long long)((row_base + rl) % p.bias_mod) * p.N + col);
                   v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w;
                 }
-                if (p.res) {
-                  const float4 r4 = *reinterpret_cast<const float4*>(p.res + off);
+                if (resp) {
+                  const float4 r4 = *reinterpret_cast<const float4*>(resp + off);
                   v.x += r4.x; v.y += r4.y; v.z += r4.z; v.w += r4.w;
                 }
-                if (p.flags & LVT_GEMM_RELU) {
+                if (flags & LVT_GEMM_RELU) {
                   v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
                 }
-                if (p.flags & LVT_GEMM_MASK) {
-                  const uint2 mu = *reinterpret_cast<const uint2*>(p.aux + off);
+                if (flags & LVT_GEMM_MASK) {
+                  const uint2 mu = *reinterpret_cast<const uint2*>(auxp + off);
                   // bf16 > 0  <=>  sign bit clear and magnitude non-zero
                   const uint32_t a0 = mu.x & 0xFFFFu, a1 = mu.x >> 16, a2 = mu.y & 0xFFFFu, a3 = mu.y >> 16;
                   if (!(a0 != 0 && a0 < 0x8000u)) v.x = 0.f;
@@ -299,15 +373,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                   if (!(a2 != 0 && a2 < 0x8000u)) v.z = 0.f;
                   if (!(a3 != 0 && a3 < 0x8000u)) v.w = 0.f;
                 }
-                if (p.out_f32) {
-                  if (p.flags & LVT_GEMM_ATOMIC) red_add_v4(p.out_f32 + off, v.x, v.y, v.z, v.w);
-                  else *reinterpret_cast<float4*>(p.out_f32 + off) = v;
+                if (of32) {
+                  if (flags & LVT_GEMM_ATOMIC) red_add_v4(of32 + off, v.x, v.y, v.z, v.w);
+                  else *reinterpret_cast<float4*>(of32 + off) = v;
                 }
-                if (p.out_bf16) {
+                if (obf) {
                   uint2 u;
                   u.x = pack_bf16x2(v.x, v.y);
                   u.y = pack_bf16x2(v.z, v.w);
-                  *reinterpret_cast<uint2*>(p.out_bf16 + off) = u;
+                  *reinterpret_cast<uint2*>(obf + off) = u;
                 }
               }
             } else {
@@ -316,18 +390,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
               for (int e = 0; e < 4 && col + e < p.N; ++e) {
                 float x = ve[e];
                 if constexpr (EK == EK_DS) {
-                  x = __bfloat162float(p.aux[off + e]) * (x - p.delta[(long long)t.z * p.M + row]);
-                  p.out_bf16[off + e] = __float2bfloat16(x);
+                  x = __bfloat162float(auxp[off + e]) * (x - deltap[rl]);
+                  obf[off + e] = __float2bfloat16(x);
                 } else {
-                  if (p.bias) x += p.bias[(p.bias_mod > 0 ? (long long)(row % p.bias_mod) * p.N : 0) + col + e];
-                  if (p.res) x += p.res[off + e];
-                  if (p.flags & LVT_GEMM_RELU) x = fmaxf(x, 0.f);
-                  if ((p.flags & LVT_GEMM_MASK) && !(__bfloat162float(p.aux[off + e]) > 0.f)) x = 0.f;
-                  if (p.out_f32) {
-                    if (p.flags & LVT_GEMM_ATOMIC) atomicAdd(p.out_f32 + off + e, x);
-                    else p.out_f32[off + e] = x;
+                  if (p.bias)
+                    x += p.bias[(p.bias_mod > 0 ? (long long)((row_base + rl) % p.bias_mod) * p.N : 0) + col + e];
+                  if (resp) x += resp[off + e];
+                  if (flags & LVT_GEMM_RELU) x = fmaxf(x, 0.f);
+                  if ((flags & LVT_GEMM_MASK) && !(__bfloat162float(auxp[off + e]) > 0.f)) x = 0.f;
+                  if (of32) {
+                    if (flags & LVT_GEMM_ATOMIC) atomicAdd(of32 + off + e, x);
+                    else of32[off + e] = x;
                   }
-                  if (p.out_bf16) p.out_bf16[off + e] = __float2bfloat16(x);
+                  if (obf) obf[off + e] = __float2bfloat16(x);
                 }
               }
             }
@@ -403,13 +478,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         }
         const float inv = 1.f / sum;
         if (p.lse) p.lse[(long long)t.z * p.M + row] = (mx + log2f(sum)) * 0.6931471805599453f;
-        __nv_bfloat16* stg16 = reinterpret_cast<__nv_bfloat16*>(stg);  // 32 rows x (32 bf16 + pad) = 80 B rows
+        uint4* const stgu = reinterpret_cast<uint4*>(stg);  // 32 rows x 4 units (8 bf16 each), swizzled
+        __nv_bfloat16* const prow = p.out_bf16 + o_zbase + (long long)row_base * p.o_ld;
 #pragma unroll 1
         for (int c0 = 0; c0 < 256; c0 += 32) {
           tmem_ld_32x32(taddr + c0, r);
           chunk_bias(c0);
           tmem_ld_wait();
-          uint4* srow = reinterpret_cast<uint4*>(stg16 + lane * (STG_STRIDE * 2));
 #pragma unroll
           for (int i = 0; i < 32; i += 8) {
             float e[8];
@@ -420,16 +495,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             u.y = pack_bf16x2(e[2], e[3]);
             u.z = pack_bf16x2(e[4], e[5]);
             u.w = pack_bf16x2(e[6], e[7]);
-            srow[i / 8] = u;
+            stgu[stg_unit(lane, i / 8)] = u;
           }
           __syncwarp();
           // coalesced store: 4 lanes x 16 B cover one 64 B row chunk
 #pragma unroll
           for (int it = 0; it < 4; ++it) {
             const int rl = c_row + 8 * it;
-            const uint4 u = *reinterpret_cast<const uint4*>(stg16 + rl * (STG_STRIDE * 2) + 8 * c_pc);
-            const long long off = o_zbase + (long long)(row_base + rl) * p.o_ld + c0 + 8 * c_pc;
-            *reinterpret_cast<uint4*>(p.out_bf16 + off) = u;
+            const uint4 u = stgu[stg_unit(rl, c_pc)];
+            *reinterpret_cast<uint4*>(prow + (long long)rl * p.o_ld + c0 + 8 * c_pc) = u;
           }
           __syncwarp();
         }
@@ -439,6 +513,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
     }
+    if (ST != 0 && lane == 0) bulk_wait_group<0>();  // all TMA stores of this warp are complete
   }
 
   tc_fence_before();
@@ -494,7 +569,7 @@ std::mutex g_map_mutex;
 //   box     (64, box_rows, 1, 1, 1), SWIZZLE_128B
 int make_operand_map(CUtensorMap* out, const void* base, long long c_extent, long long r_extent,
                      int cin, long long ld, long long s_blk, int batch, int zdiv, long long s_zlo,
-                     long long s_zhi, int box_rows) {
+                     long long s_zhi, int box_rows, int esize = 2) {
   PFN_encodeTiled enc = get_encode_fn();
   if (!enc) {
     lvt_set_error("cuTensorMapEncodeTiled driver entry point not available");
@@ -505,7 +580,7 @@ int make_operand_map(CUtensorMap* out, const void* base, long long c_extent, lon
   const long long zhi = (batch + zdiv - 1) / zdiv;
   MapKey key;
   key.base = base;
-  const long long kv[12] = {c_extent, r_extent, cin, ld, s_blk, batch, zdiv, s_zlo, s_zhi, box_rows, 0, 0};
+  const long long kv[12] = {c_extent, r_extent, cin, ld, s_blk, batch, zdiv, s_zlo, s_zhi, box_rows, esize, 0};
   memcpy(key.v, kv, sizeof(kv));
   {
     std::lock_guard<std::mutex> lk(g_map_mutex);
@@ -517,7 +592,7 @@ int make_operand_map(CUtensorMap* out, const void* base, long long c_extent, lon
   }
   cuuint64_t dims[5] = {(cuuint64_t)(cin < c_extent ? cin : c_extent), (cuuint64_t)r_extent,
                         (cuuint64_t)nblk, (cuuint64_t)zlo, (cuuint64_t)zhi};
-  auto fix = [](long long s) -> cuuint64_t { return (cuuint64_t)((s > 0 ? s : 8) * 2); };
+  auto fix = [esize](long long s) -> cuuint64_t { return (cuuint64_t)((s > 0 ? s : 8) * esize); };
   cuuint64_t strides[4] = {fix(ld), fix(nblk > 1 ? s_blk : 8), fix(zlo > 1 ? s_zlo : 8),
                            fix(zhi > 1 ? s_zhi : 8)};
   for (int i = 0; i < 4; ++i) {
@@ -531,9 +606,10 @@ int make_operand_map(CUtensorMap* out, const void* base, long long c_extent, lon
     lvt_set_error("GEMM operand base pointer is not 16-byte aligned");
     return LVT_ERR_INVALID;
   }
-  cuuint32_t box[5] = {64, (cuuint32_t)box_rows, 1, 1, 1};
+  cuuint32_t box[5] = {(cuuint32_t)(128 / esize), (cuuint32_t)box_rows, 1, 1, 1};
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides,
+  CUresult r = enc(out, esize == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5,
+                   const_cast<void*>(base), dims, strides,
                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -554,29 +630,37 @@ int make_operand_map(CUtensorMap* out, const void* base, long long c_extent, lon
   return LVT_OK;
 }
 
-template <int BN, bool A_MN, bool B_MN, int EK>
-int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int grid,
-                cudaStream_t stream) {
+template <int BN, bool A_MN, bool B_MN, int EK, int ST = 0>
+int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const GemmParams& p,
+                int grid, cudaStream_t stream) {
   using L = SmemLayout<BN>;
-  auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, EK>;
+  auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, EK, ST>;
   static bool configured = false;
   if (!configured) {
     LVT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     configured = true;
   }
-  kern<<<grid, NUM_THREADS, L::TOTAL, stream>>>(ta, tb, p);
+  kern<<<grid, NUM_THREADS, L::TOTAL, stream>>>(ta, tb, to, p);
   LVT_CHECK_LAUNCH();
   lvt_count_launch(1);
   return LVT_OK;
 }
 
-template <int BN, int EK>
-int dispatch_major(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int grid,
-                   bool a_mn, bool b_mn, cudaStream_t stream) {
-  if (!a_mn && !b_mn) return launch_gemm<BN, false, false, EK>(ta, tb, p, grid, stream);
-  if (!a_mn && b_mn) return launch_gemm<BN, false, true, EK>(ta, tb, p, grid, stream);
-  if (a_mn && !b_mn) return launch_gemm<BN, true, false, EK>(ta, tb, p, grid, stream);
-  return launch_gemm<BN, true, true, EK>(ta, tb, p, grid, stream);
+template <int BN, int EK, int ST>
+int dispatch_major(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const GemmParams& p,
+                   int grid, bool a_mn, bool b_mn, cudaStream_t stream) {
+  if (!a_mn && !b_mn) return launch_gemm<BN, false, false, EK, ST>(ta, tb, to, p, grid, stream);
+  if (!a_mn && b_mn) return launch_gemm<BN, false, true, EK, ST>(ta, tb, to, p, grid, stream);
+  if (a_mn && !b_mn) return launch_gemm<BN, true, false, EK, ST>(ta, tb, to, p, grid, stream);
+  return launch_gemm<BN, true, true, EK, ST>(ta, tb, to, p, grid, stream);
+}
+
+template <int BN>
+int dispatch_store(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const GemmParams& p,
+                   int grid, bool a_mn, bool b_mn, int st, cudaStream_t stream) {
+  if (st == 1) return dispatch_major<BN, EK_LINEAR, 1>(ta, tb, to, p, grid, a_mn, b_mn, stream);
+  if (st == 2) return dispatch_major<BN, EK_LINEAR, 2>(ta, tb, to, p, grid, a_mn, b_mn, stream);
+  return dispatch_major<BN, EK_LINEAR, 0>(ta, tb, to, p, grid, a_mn, b_mn, stream);
 }
 
 int num_sms() {
@@ -654,6 +738,14 @@ extern "C" int lvt_gemm_bf16(const LvtGemm* g, void* stream_) {
   p.res = g->res; p.aux = reinterpret_cast<const __nv_bfloat16*>(g->aux_bf16);
   p.bias = g->bias; p.bias_mod = g->bias_mod;
   p.o_cin = g->o_cin; p.o_zdiv = g->o_zdiv;
+  p.o_shift = -1;
+  if (g->o_cin < g->N) {
+    int sh = 0;
+    while ((1 << sh) < g->o_cin) ++sh;
+    LVT_CHECK_ARG((1 << sh) == g->o_cin, "lvt_gemm_bf16: a blocked output needs a power-of-two o_cin (got %d)", g->o_cin);
+    p.o_shift = sh;
+  }
+  LVT_CHECK_ARG(g->o_ld < (1ll << 23), "lvt_gemm_bf16: o_ld too large");
   p.o_ld = g->o_ld; p.o_s_blk = g->o_s_blk; p.o_s_zlo = g->o_s_zlo; p.o_s_zhi = g->o_s_zhi;
   p.lse = g->lse; p.delta = g->delta;
   p.bank_t = g->bank_t; p.bank_h = g->bank_h; p.bank_w = g->bank_w;
@@ -671,15 +763,34 @@ extern "C" int lvt_gemm_bf16(const LvtGemm* g, void* stream_) {
            : make_operand_map(&tb, g->b, g->K, g->N, g->b_cin, g->b_ld, g->b_s_blk, g->batch, g->b_zdiv, g->b_s_zlo, g->b_s_zhi, bn);
   if (rc) return rc;
 
+  // TMA-store epilogue when the output is a single plain tensor (no residual / mask / atomic / table bias)
+  int st = 0;
+  CUtensorMap to;
+  memset(&to, 0, sizeof(to));
+  if (ek == EK_LINEAR && !g->res && !(g->flags & (LVT_GEMM_MASK | LVT_GEMM_ATOMIC)) && g->bias_mod == 0 &&
+      (g->out_f32 == nullptr) != (g->out_bf16 == nullptr) && !(g->flags & (3 << 29))) {
+    const int esize = g->out_bf16 ? 2 : 4;
+    const int slab_cols = 128 / esize;
+    const void* obase = g->out_bf16 ? g->out_bf16 : (void*)g->out_f32;
+    if (g->N % slab_cols == 0 && g->o_cin % slab_cols == 0 && (g->o_ld * esize) % 16 == 0 &&
+        (g->o_s_blk * esize) % 16 == 0 && (g->o_s_zlo * esize) % 16 == 0 && (g->o_s_zhi * esize) % 16 == 0 &&
+        (reinterpret_cast<uintptr_t>(obase) & 15) == 0 && (!g->bias || (reinterpret_cast<uintptr_t>(g->bias) & 15) == 0)) {
+      rc = make_operand_map(&to, obase, g->N, g->M, g->o_cin, g->o_ld, g->o_s_blk, g->batch, g->o_zdiv,
+                            g->o_s_zlo, g->o_s_zhi, 32, esize);
+      if (rc) return rc;
+      st = g->out_bf16 ? 1 : 2;
+    }
+  }
+
   const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
   const bool amn = g->a_mn_major != 0, bmn = g->b_mn_major != 0;
-  if (ek == EK_SOFTMAX_1x16x16) return launch_gemm<256, false, false, EK_SOFTMAX_1x16x16>(ta, tb, p, grid, stream);
-  if (ek == EK_SOFTMAX_4x8x8) return launch_gemm<256, false, false, EK_SOFTMAX_4x8x8>(ta, tb, p, grid, stream);
+  if (ek == EK_SOFTMAX_1x16x16) return launch_gemm<256, false, false, EK_SOFTMAX_1x16x16>(ta, tb, to, p, grid, stream);
+  if (ek == EK_SOFTMAX_4x8x8) return launch_gemm<256, false, false, EK_SOFTMAX_4x8x8>(ta, tb, to, p, grid, stream);
   if (ek == EK_DS) {
     LVT_CHECK_ARG(!amn && !bmn, "lvt_gemm_bf16: DS mode needs K-major dO and V");
-    if (bn == 256) return launch_gemm<256, false, false, EK_DS>(ta, tb, p, grid, stream);
-    return launch_gemm<128, false, false, EK_DS>(ta, tb, p, grid, stream);
+    if (bn == 256) return launch_gemm<256, false, false, EK_DS>(ta, tb, to, p, grid, stream);
+    return launch_gemm<128, false, false, EK_DS>(ta, tb, to, p, grid, stream);
   }
-  if (bn == 256) return dispatch_major<256, EK_LINEAR>(ta, tb, p, grid, amn, bmn, stream);
-  return dispatch_major<128, EK_LINEAR>(ta, tb, p, grid, amn, bmn, stream);
+  if (bn == 256) return dispatch_store<256>(ta, tb, to, p, grid, amn, bmn, st, stream);
+  return dispatch_store<128>(ta, tb, to, p, grid, amn, bmn, st, stream);
 }
