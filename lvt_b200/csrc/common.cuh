@@ -161,6 +161,15 @@ LVT_DEVICE_INLINE void tma_store_5d(const CUtensorMap* m, const void* smem_src, 
         "r"(c4)
       : "memory");
 }
+LVT_DEVICE_INLINE void tma_reduce_add_5d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2,
+                                         int c3, int c4) {
+  asm volatile(
+      "cp.reduce.async.bulk.tensor.5d.global.shared::cta.add.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+      :
+      : "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3),
+        "r"(c4)
+      : "memory");
+}
 LVT_DEVICE_INLINE void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // all but the newest N bulk groups of this thread have finished READING their smem source
 template <int N>

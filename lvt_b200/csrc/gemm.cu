@@ -62,13 +62,21 @@ struct GemmParams {
   int heads;
 };
 
-template <int BN>
+// store-path bits (template parameter ST); 0 = staged generic epilogue
+constexpr int ST_TMA = 1;     // epilogue writes 128 B-row slabs to smem and stores them with TMA
+constexpr int ST_F32 = 2;     // slab holds 32 fp32 columns (else 64 bf16 columns)
+constexpr int ST_REDUCE = 4;  // cp.reduce.async.bulk (+=) instead of a plain store (split-K / grad accumulate)
+constexpr int ST_CLOAD = 8;   // a second tensor with the output's addressing is TMA-loaded per slab:
+                              // fp32 residual (added), bf16 ReLU-mask source, or bf16 P of the DS epilogue
+
+template <int BN, int ST>
 struct SmemLayout {
   static constexpr int B_TILE_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
-  static constexpr int STAGES = BN == 256 ? 4 : 6;
+  static constexpr int STAGES = (BN == 256 ? 4 : 6) - ((ST & ST_CLOAD) ? 1 : 0);
+  static constexpr int STG_PER_WARP = (ST & ST_CLOAD) ? 2 * STG_BYTES_PER_WARP : STG_BYTES_PER_WARP;
   static constexpr int STG_OFFSET = STAGES * STAGE_BYTES;
-  static constexpr int BAR_OFFSET = STG_OFFSET + NUM_EPI_WARPS * STG_BYTES_PER_WARP;
+  static constexpr int BAR_OFFSET = STG_OFFSET + NUM_EPI_WARPS * STG_PER_WARP;
   static constexpr int TOTAL = BAR_OFFSET + 256 + 1024 /*alignment slack*/;
 };
 
@@ -103,8 +111,9 @@ LVT_DEVICE_INLINE TileCoord decode_tile(const GemmParams& p, int tile, int bn) {
 template <int BN, bool A_MN, bool B_MN, int EK, int ST>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
-                 const __grid_constant__ CUtensorMap tm_o, const GemmParams p) {
-  using L = SmemLayout<BN>;
+                 const __grid_constant__ CUtensorMap tm_o, const __grid_constant__ CUtensorMap tm_c,
+                 const GemmParams p) {
+  using L = SmemLayout<BN, ST>;
   constexpr int STAGES = L::STAGES;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte alignment
@@ -114,7 +123,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;   // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  uint64_t* c_bar = tmem_empty_bar + 2;           // [NUM_EPI_WARPS] C-slab loads (ST_CLOAD)
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(c_bar + NUM_EPI_WARPS);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -131,6 +141,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     mbar_init(&tmem_full_bar[1], 1);
     mbar_init(&tmem_empty_bar[0], 4);  // one arrive per epilogue warp of the group
     mbar_init(&tmem_empty_bar[1], 4);
+#pragma unroll
+    for (int w = 0; w < NUM_EPI_WARPS; ++w) mbar_init(&c_bar[w], 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -219,34 +231,63 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     const int ew = warp - 2;        // 0..7
     const int grp = ew >> 2;        // epilogue group == TMEM buffer
     const int q = warp & 3;         // TMEM lane quarter this warp may access
-    float* stg = reinterpret_cast<float*>(smem + L::STG_OFFSET + ew * STG_BYTES_PER_WARP);
+    float* stg = reinterpret_cast<float*>(smem + L::STG_OFFSET + ew * L::STG_PER_WARP);
     // coalesced mapping inside a 32-row x 16-col chunk: 4 lanes cover one row (4 x 16 B)
     const int c_row = lane >> 2;    // + 8 * it
     const int c_pc = lane & 3;      // 16-byte piece -> columns 4*c_pc .. 4*c_pc+3
     uint32_t titer = grp;
+    uint32_t c_phase = 0;  // parity of this warp's C-slab barrier
+    (void)c_phase;
     for (int tile = blockIdx.x + grp * gridDim.x; tile < p.total_tiles; tile += 2 * gridDim.x, titer += 2) {
       const TileCoord t = decode_tile(p, tile, BN);
       const uint32_t buf = grp;
       const uint32_t taddr = tmem_base + buf * BN + (static_cast<uint32_t>(q * 32) << 16);
       const long long o_zbase = (long long)(t.z / p.o_zdiv) * p.o_s_zhi + (long long)(t.z % p.o_zdiv) * p.o_s_zlo;
       const int row_base = t.m0 + q * 32;
-      if (t.num_kb > 0) {
+      if ((ST & ST_TMA) == 0 && t.num_kb > 0) {  // (the TMA epilogue waits after prefetching its C slab)
         mbar_wait(&tmem_full_bar[buf], (titer >> 1) & 1);
         tc_fence_after();
       }
 
-      if constexpr (EK == EK_LINEAR && ST != 0) {
-        // -------- TMA-store epilogue: TMEM -> registers -> 128B-swizzled smem slab (32 rows x 128 B per
-        // warp) -> one cp.async.bulk.tensor store per slab.  No per-element address math, no LSU stores.
-        constexpr int SLAB_COLS = ST == 1 ? 64 : 32;  // 128 B per row
+      if constexpr ((EK == EK_LINEAR || EK == EK_DS) && (ST & ST_TMA) != 0) {
+        // -------- TMA epilogue: TMEM -> registers -> 128B-swizzled smem slab (32 rows x 128 B per warp)
+        // -> one cp.async.bulk.tensor store (or reduce-add) per slab.  An optional second tensor
+        // (residual / mask source / P) arrives the same way, prefetched one slab ahead.
+        constexpr bool F32 = (ST & ST_F32) != 0;
+        constexpr bool CLOAD = (ST & ST_CLOAD) != 0;
+        constexpr int SLAB_COLS = F32 ? 32 : 64;  // 128 B per row
         uint4* const slab = reinterpret_cast<uint4*>(stg);
+        const uint4* const cbuf = reinterpret_cast<const uint4*>(reinterpret_cast<uint8_t*>(stg) + STG_BYTES_PER_WARP);
         const int o_zlo = t.z % p.o_zdiv, o_zhi = t.z / p.o_zdiv;
         const float alpha = p.alpha;
         const bool relu = (p.flags & LVT_GEMM_RELU) != 0;
-#pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += SLAB_COLS) {
+        const int ncols = min(BN, p.N - t.n0);
+        float dl = 0.f;
+        if constexpr (EK == EK_DS) dl = (row_base + lane < p.M) ? p.delta[(long long)t.z * p.M + row_base + lane] : 0.f;
+        auto issue_c = [&](int c0) {
           const int col0 = t.n0 + c0;
-          if (col0 >= p.N) break;  // warp-uniform
+          mbar_arrive_expect_tx(&c_bar[ew], STG_BYTES_PER_WARP);
+          tma_load_5d(const_cast<uint4*>(cbuf), &tm_c, &c_bar[ew], col0 % p.o_cin, row_base, col0 / p.o_cin, o_zlo, o_zhi);
+        };
+        if constexpr (CLOAD) {
+          if (lane == 0) issue_c(0);  // overlaps the wait for the accumulator
+        }
+        if (t.num_kb > 0) {
+          mbar_wait(&tmem_full_bar[buf], (titer >> 1) & 1);
+          tc_fence_after();
+        }
+#pragma unroll 1
+        for (int c0 = 0; c0 < ncols; c0 += SLAB_COLS) {
+          const int col0 = t.n0 + c0;
+          uint4 cr[8];  // this lane's row of the C slab (128 B)
+          if constexpr (CLOAD) {
+            mbar_wait(&c_bar[ew], c_phase);
+            c_phase ^= 1;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) cr[k] = cbuf[lane * 8 + (k ^ (lane & 7))];
+            __syncwarp();
+            if (lane == 0 && c0 + SLAB_COLS < ncols) issue_c(c0 + SLAB_COLS);
+          }
           if (lane == 0) bulk_wait_group_read<0>();  // previous store of this warp has drained the slab
           __syncwarp();
 #pragma unroll
@@ -257,19 +298,52 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             float v[32];
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * alpha;
-            if (p.bias) {
-              const float* bp = p.bias + col0 + 32 * h;
+            if constexpr (EK == EK_DS) {
+              // dS = P * (alpha*acc - delta[row]); P = 64 bf16 of this row in cr[]
 #pragma unroll
-              for (int i = 0; i < 32; i += 4) {
-                const float4 b4 = __ldg(reinterpret_cast<const float4*>(bp + i));
-                v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
+              for (int k = 0; k < 4; ++k) {
+                const uint32_t w[4] = {cr[4 * h + k].x, cr[4 * h + k].y, cr[4 * h + k].z, cr[4 * h + k].w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float2 pf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[j]));
+                  v[8 * k + 2 * j] = pf.x * (v[8 * k + 2 * j] - dl);
+                  v[8 * k + 2 * j + 1] = pf.y * (v[8 * k + 2 * j + 1] - dl);
+                }
+              }
+            } else {
+              if (p.bias) {
+                const float* bp = p.bias + col0 + 32 * h;
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                  const float4 b4 = __ldg(reinterpret_cast<const float4*>(bp + i));
+                  v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
+                }
+              }
+              if constexpr (CLOAD && F32) {  // fp32 residual
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                  v[4 * k] += __uint_as_float(cr[k].x); v[4 * k + 1] += __uint_as_float(cr[k].y);
+                  v[4 * k + 2] += __uint_as_float(cr[k].z); v[4 * k + 3] += __uint_as_float(cr[k].w);
+                }
+              }
+              if (relu) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+              }
+              if constexpr (CLOAD && !F32) {  // ReLU backward: keep where the bf16 mask source is > 0
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const uint32_t w[4] = {cr[4 * h + k].x, cr[4 * h + k].y, cr[4 * h + k].z, cr[4 * h + k].w};
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    const uint32_t lo = w[j] & 0xFFFFu, hi = w[j] >> 16;
+                    if (!(lo != 0 && lo < 0x8000u)) v[8 * k + 2 * j] = 0.f;
+                    if (!(hi != 0 && hi < 0x8000u)) v[8 * k + 2 * j + 1] = 0.f;
+                  }
+                }
               }
             }
-            if (relu) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
-            }
-            if constexpr (ST == 1) {
+            if constexpr (!F32) {
 #pragma unroll
               for (int k = 0; k < 4; ++k) {  // 4 units of 8 bf16
                 uint4 u;
@@ -290,7 +364,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA (async proxy)
           __syncwarp();
           if (lane == 0) {
-            tma_store_5d(&tm_o, slab, col0 % p.o_cin, row_base, col0 / p.o_cin, o_zlo, o_zhi);
+            if constexpr ((ST & ST_REDUCE) != 0)
+              tma_reduce_add_5d(&tm_o, slab, col0 % p.o_cin, row_base, col0 / p.o_cin, o_zlo, o_zhi);
+            else
+              tma_store_5d(&tm_o, slab, col0 % p.o_cin, row_base, col0 / p.o_cin, o_zlo, o_zhi);
             bulk_commit_group();
           }
         }
@@ -513,7 +590,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
     }
-    if (ST != 0 && lane == 0) bulk_wait_group<0>();  // all TMA stores of this warp are complete
+    if ((ST & ST_TMA) != 0 && lane == 0) bulk_wait_group<0>();  // all TMA stores of this warp are complete
   }
 
   tc_fence_before();
@@ -630,37 +707,46 @@ int make_operand_map(CUtensorMap* out, const void* base, long long c_extent, lon
   return LVT_OK;
 }
 
+struct Maps {
+  CUtensorMap a, b, o, c;
+};
+
 template <int BN, bool A_MN, bool B_MN, int EK, int ST = 0>
-int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const GemmParams& p,
-                int grid, cudaStream_t stream) {
-  using L = SmemLayout<BN>;
+int launch_gemm(const Maps& m, const GemmParams& p, int grid, cudaStream_t stream) {
+  using L = SmemLayout<BN, ST>;
   auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, EK, ST>;
   static bool configured = false;
   if (!configured) {
     LVT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     configured = true;
   }
-  kern<<<grid, NUM_THREADS, L::TOTAL, stream>>>(ta, tb, to, p);
+  kern<<<grid, NUM_THREADS, L::TOTAL, stream>>>(m.a, m.b, m.o, m.c, p);
   LVT_CHECK_LAUNCH();
   lvt_count_launch(1);
   return LVT_OK;
 }
 
 template <int BN, int EK, int ST>
-int dispatch_major(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const GemmParams& p,
-                   int grid, bool a_mn, bool b_mn, cudaStream_t stream) {
-  if (!a_mn && !b_mn) return launch_gemm<BN, false, false, EK, ST>(ta, tb, to, p, grid, stream);
-  if (!a_mn && b_mn) return launch_gemm<BN, false, true, EK, ST>(ta, tb, to, p, grid, stream);
-  if (a_mn && !b_mn) return launch_gemm<BN, true, false, EK, ST>(ta, tb, to, p, grid, stream);
-  return launch_gemm<BN, true, true, EK, ST>(ta, tb, to, p, grid, stream);
+int dispatch_major(const Maps& m, const GemmParams& p, int grid, bool a_mn, bool b_mn, cudaStream_t stream) {
+  if (!a_mn && !b_mn) return launch_gemm<BN, false, false, EK, ST>(m, p, grid, stream);
+  if (!a_mn && b_mn) return launch_gemm<BN, false, true, EK, ST>(m, p, grid, stream);
+  if (a_mn && !b_mn) return launch_gemm<BN, true, false, EK, ST>(m, p, grid, stream);
+  return launch_gemm<BN, true, true, EK, ST>(m, p, grid, stream);
 }
 
 template <int BN>
-int dispatch_store(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const GemmParams& p,
-                   int grid, bool a_mn, bool b_mn, int st, cudaStream_t stream) {
-  if (st == 1) return dispatch_major<BN, EK_LINEAR, 1>(ta, tb, to, p, grid, a_mn, b_mn, stream);
-  if (st == 2) return dispatch_major<BN, EK_LINEAR, 2>(ta, tb, to, p, grid, a_mn, b_mn, stream);
-  return dispatch_major<BN, EK_LINEAR, 0>(ta, tb, to, p, grid, a_mn, b_mn, stream);
+int dispatch_store(const Maps& m, const GemmParams& p, int grid, bool a_mn, bool b_mn, int st,
+                   cudaStream_t stream) {
+  switch (st) {
+    case ST_TMA: return dispatch_major<BN, EK_LINEAR, ST_TMA>(m, p, grid, a_mn, b_mn, stream);
+    case ST_TMA | ST_F32: return dispatch_major<BN, EK_LINEAR, ST_TMA | ST_F32>(m, p, grid, a_mn, b_mn, stream);
+    case ST_TMA | ST_F32 | ST_REDUCE:
+      return dispatch_major<BN, EK_LINEAR, ST_TMA | ST_F32 | ST_REDUCE>(m, p, grid, a_mn, b_mn, stream);
+    case ST_TMA | ST_F32 | ST_CLOAD:
+      return dispatch_major<BN, EK_LINEAR, ST_TMA | ST_F32 | ST_CLOAD>(m, p, grid, a_mn, b_mn, stream);
+    case ST_TMA | ST_CLOAD: return dispatch_major<BN, EK_LINEAR, ST_TMA | ST_CLOAD>(m, p, grid, a_mn, b_mn, stream);
+    default: return dispatch_major<BN, EK_LINEAR, 0>(m, p, grid, a_mn, b_mn, stream);
+  }
 }
 
 int num_sms() {
@@ -751,46 +837,67 @@ extern "C" int lvt_gemm_bf16(const LvtGemm* g, void* stream_) {
   p.bank_t = g->bank_t; p.bank_h = g->bank_h; p.bank_w = g->bank_w;
   p.heads = g->heads > 0 ? g->heads : 1;
 
-  CUtensorMap ta, tb;
+  Maps m;
+  memset(&m, 0, sizeof(m));
   int rc;
   // contiguous / strided extents per major-ness
   rc = g->a_mn_major
-           ? make_operand_map(&ta, g->a, g->M, g->K, g->a_cin, g->a_ld, g->a_s_blk, g->batch, g->a_zdiv, g->a_s_zlo, g->a_s_zhi, BK)
-           : make_operand_map(&ta, g->a, g->K, g->M, g->a_cin, g->a_ld, g->a_s_blk, g->batch, g->a_zdiv, g->a_s_zlo, g->a_s_zhi, BM);
+           ? make_operand_map(&m.a, g->a, g->M, g->K, g->a_cin, g->a_ld, g->a_s_blk, g->batch, g->a_zdiv, g->a_s_zlo, g->a_s_zhi, BK)
+           : make_operand_map(&m.a, g->a, g->K, g->M, g->a_cin, g->a_ld, g->a_s_blk, g->batch, g->a_zdiv, g->a_s_zlo, g->a_s_zhi, BM);
   if (rc) return rc;
   rc = g->b_mn_major
-           ? make_operand_map(&tb, g->b, g->N, g->K, g->b_cin, g->b_ld, g->b_s_blk, g->batch, g->b_zdiv, g->b_s_zlo, g->b_s_zhi, BK)
-           : make_operand_map(&tb, g->b, g->K, g->N, g->b_cin, g->b_ld, g->b_s_blk, g->batch, g->b_zdiv, g->b_s_zlo, g->b_s_zhi, bn);
+           ? make_operand_map(&m.b, g->b, g->N, g->K, g->b_cin, g->b_ld, g->b_s_blk, g->batch, g->b_zdiv, g->b_s_zlo, g->b_s_zhi, BK)
+           : make_operand_map(&m.b, g->b, g->K, g->N, g->b_cin, g->b_ld, g->b_s_blk, g->batch, g->b_zdiv, g->b_s_zlo, g->b_s_zhi, bn);
   if (rc) return rc;
 
-  // TMA-store epilogue when the output is a single plain tensor (no residual / mask / atomic / table bias)
+  // TMA epilogue when the output is ONE tensor of plain 128 B-aligned rows; an optional second tensor with
+  // the same addressing (fp32 residual / bf16 mask source / bf16 P) is TMA-loaded per slab.
   int st = 0;
-  CUtensorMap to;
-  memset(&to, 0, sizeof(to));
-  if (ek == EK_LINEAR && !g->res && !(g->flags & (LVT_GEMM_MASK | LVT_GEMM_ATOMIC)) && g->bias_mod == 0 &&
-      (g->out_f32 == nullptr) != (g->out_bf16 == nullptr) && !(g->flags & (3 << 29))) {
+  const bool debug_flags = (g->flags & (3 << 29)) != 0;
+  const bool single_out = (g->out_f32 == nullptr) != (g->out_bf16 == nullptr);
+  if ((ek == EK_LINEAR || ek == EK_DS) && single_out && g->bias_mod == 0 && !debug_flags) {
     const int esize = g->out_bf16 ? 2 : 4;
     const int slab_cols = 128 / esize;
     const void* obase = g->out_bf16 ? g->out_bf16 : (void*)g->out_f32;
-    if (g->N % slab_cols == 0 && g->o_cin % slab_cols == 0 && (g->o_ld * esize) % 16 == 0 &&
-        (g->o_s_blk * esize) % 16 == 0 && (g->o_s_zlo * esize) % 16 == 0 && (g->o_s_zhi * esize) % 16 == 0 &&
-        (reinterpret_cast<uintptr_t>(obase) & 15) == 0 && (!g->bias || (reinterpret_cast<uintptr_t>(g->bias) & 15) == 0)) {
-      rc = make_operand_map(&to, obase, g->N, g->M, g->o_cin, g->o_ld, g->o_s_blk, g->batch, g->o_zdiv,
+    const bool atomic = (g->flags & LVT_GEMM_ATOMIC) != 0, mask = (g->flags & LVT_GEMM_MASK) != 0;
+    const void* cbase = nullptr;
+    int want = -1;
+    if (ek == EK_DS) { want = ST_TMA | ST_CLOAD; cbase = g->aux_bf16; }
+    else if (atomic) { if (!g->out_bf16 && !mask && !g->res) want = ST_TMA | ST_F32 | ST_REDUCE; }
+    else if (g->res && !mask) { if (g->out_f32) { want = ST_TMA | ST_F32 | ST_CLOAD; cbase = g->res; } }
+    else if (mask && !g->res) { if (g->out_bf16) { want = ST_TMA | ST_CLOAD; cbase = g->aux_bf16; } }
+    else if (!g->res && !mask) want = g->out_bf16 ? ST_TMA : (ST_TMA | ST_F32);
+    const bool aligned = g->N % slab_cols == 0 && g->o_cin % slab_cols == 0 && (g->o_ld * esize) % 16 == 0 &&
+                         (g->o_s_blk * esize) % 16 == 0 && (g->o_s_zlo * esize) % 16 == 0 &&
+                         (g->o_s_zhi * esize) % 16 == 0 && (reinterpret_cast<uintptr_t>(obase) & 15) == 0 &&
+                         (!cbase || (reinterpret_cast<uintptr_t>(cbase) & 15) == 0) &&
+                         (!g->bias || (reinterpret_cast<uintptr_t>(g->bias) & 15) == 0);
+    if (want >= 0 && aligned) {
+      rc = make_operand_map(&m.o, obase, g->N, g->M, g->o_cin, g->o_ld, g->o_s_blk, g->batch, g->o_zdiv,
                             g->o_s_zlo, g->o_s_zhi, 32, esize);
       if (rc) return rc;
-      st = g->out_bf16 ? 1 : 2;
+      if (cbase) {
+        rc = make_operand_map(&m.c, cbase, g->N, g->M, g->o_cin, g->o_ld, g->o_s_blk, g->batch, g->o_zdiv,
+                              g->o_s_zlo, g->o_s_zhi, 32, esize);
+        if (rc) return rc;
+      }
+      st = want;
     }
   }
 
   const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
   const bool amn = g->a_mn_major != 0, bmn = g->b_mn_major != 0;
-  if (ek == EK_SOFTMAX_1x16x16) return launch_gemm<256, false, false, EK_SOFTMAX_1x16x16>(ta, tb, to, p, grid, stream);
-  if (ek == EK_SOFTMAX_4x8x8) return launch_gemm<256, false, false, EK_SOFTMAX_4x8x8>(ta, tb, to, p, grid, stream);
+  if (ek == EK_SOFTMAX_1x16x16) return launch_gemm<256, false, false, EK_SOFTMAX_1x16x16>(m, p, grid, stream);
+  if (ek == EK_SOFTMAX_4x8x8) return launch_gemm<256, false, false, EK_SOFTMAX_4x8x8>(m, p, grid, stream);
   if (ek == EK_DS) {
     LVT_CHECK_ARG(!amn && !bmn, "lvt_gemm_bf16: DS mode needs K-major dO and V");
-    if (bn == 256) return launch_gemm<256, false, false, EK_DS>(ta, tb, to, p, grid, stream);
-    return launch_gemm<128, false, false, EK_DS>(ta, tb, to, p, grid, stream);
+    if (st != 0) {
+      if (bn == 256) return launch_gemm<256, false, false, EK_DS, ST_TMA | ST_CLOAD>(m, p, grid, stream);
+      return launch_gemm<128, false, false, EK_DS, ST_TMA | ST_CLOAD>(m, p, grid, stream);
+    }
+    if (bn == 256) return launch_gemm<256, false, false, EK_DS>(m, p, grid, stream);
+    return launch_gemm<128, false, false, EK_DS>(m, p, grid, stream);
   }
-  if (bn == 256) return dispatch_store<256>(ta, tb, to, p, grid, amn, bmn, st, stream);
-  return dispatch_store<128>(ta, tb, to, p, grid, amn, bmn, st, stream);
+  if (bn == 256) return dispatch_store<256>(m, p, grid, amn, bmn, st, stream);
+  return dispatch_store<128>(m, p, grid, amn, bmn, st, stream);
 }

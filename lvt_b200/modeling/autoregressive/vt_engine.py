@@ -379,8 +379,11 @@ class VTEngine:
 
     @staticmethod
     def _splits(m, n, k):
-        tiles = ((m + 127) // 128) * ((n + 127) // 128)
-        return int(max(1, min(k // 512, (2 * 148 + tiles - 1) // tiles)))
+        """split-K factor of a weight-gradient GEMM: fill the 148 SMs once with 128 x (256|128) tiles,
+        keeping at least 4 k-blocks of 64 per tile."""
+        bn = 256 if n % 256 == 0 else 128
+        tiles = ((m + 127) // 128) * ((n + bn - 1) // bn)
+        return int(max(1, min(k // 256, (148 + tiles // 2) // tiles)))
 
     def _wgrad(self, dy_ptr, ld_dy, x_ptr, ld_x, out: Operand, n_out, n_in, tokens):
         """dW[n_out, n_in] += dY[tokens, n_out]^T X[tokens, n_in] (split-K, fp32 red.add)."""
