@@ -80,6 +80,12 @@ struct SmemLayout {
   static constexpr int TOTAL = BAR_OFFSET + 256 + 1024 /*alignment slack*/;
 };
 
+LVT_DEVICE_INLINE float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 LVT_DEVICE_INLINE void red_add_v4(float* addr, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c),
                "f"(d)
@@ -535,54 +541,59 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           if (causal && c0 + i > row) v = kMasked;
           return v;
         };
-        float mx = -INFINITY;
+        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // 4 independent chains
 #pragma unroll 1
         for (int c0 = 0; c0 < 256; c0 += 32) {
           tmem_ld_32x32(taddr + c0, r);
           chunk_bias(c0);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, logit2(r[i], c0, i));
+          for (int i = 0; i < 32; ++i) m4[i & 3] = fmaxf(m4[i & 3], logit2(r[i], c0, i));
         }
-        float sum = 0.f;
+        const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+        float s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
         for (int c0 = 0; c0 < 256; c0 += 32) {
           tmem_ld_32x32(taddr + c0, r);
           chunk_bias(c0);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) sum += exp2f(logit2(r[i], c0, i) - mx);
+          for (int i = 0; i < 32; ++i) s4[i & 3] += fast_exp2(logit2(r[i], c0, i) - mx);
         }
+        const float sum = (s4[0] + s4[1]) + (s4[2] + s4[3]);
         const float inv = 1.f / sum;
         if (p.lse) p.lse[(long long)t.z * p.M + row] = (mx + log2f(sum)) * 0.6931471805599453f;
-        uint4* const stgu = reinterpret_cast<uint4*>(stg);  // 32 rows x 4 units (8 bf16 each), swizzled
-        __nv_bfloat16* const prow = p.out_bf16 + o_zbase + (long long)row_base * p.o_ld;
+        // P -> 128B-swizzled slab (32 rows x 64 bf16) -> TMA store
+        uint4* const slab = reinterpret_cast<uint4*>(stg);
+        const int o_zlo = t.z % p.o_zdiv, o_zhi = t.z / p.o_zdiv;
 #pragma unroll 1
-        for (int c0 = 0; c0 < 256; c0 += 32) {
-          tmem_ld_32x32(taddr + c0, r);
-          chunk_bias(c0);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; i += 8) {
-            float e[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) e[j] = exp2f(logit2(r[i + j], c0, i + j) - mx) * inv;
-            uint4 u;
-            u.x = pack_bf16x2(e[0], e[1]);
-            u.y = pack_bf16x2(e[2], e[3]);
-            u.z = pack_bf16x2(e[4], e[5]);
-            u.w = pack_bf16x2(e[6], e[7]);
-            stgu[stg_unit(lane, i / 8)] = u;
-          }
+        for (int c0 = 0; c0 < 256; c0 += 64) {
+          if (lane == 0) bulk_wait_group_read<0>();
           __syncwarp();
-          // coalesced store: 4 lanes x 16 B cover one 64 B row chunk
 #pragma unroll
-          for (int it = 0; it < 4; ++it) {
-            const int rl = c_row + 8 * it;
-            const uint4 u = stgu[stg_unit(rl, c_pc)];
-            *reinterpret_cast<uint4*>(prow + (long long)rl * p.o_ld + c0 + 8 * c_pc) = u;
+          for (int h = 0; h < 2; ++h) {
+            tmem_ld_32x32(taddr + c0 + 32 * h, r);
+            chunk_bias(c0 + 32 * h);
+            tmem_ld_wait();
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              float e[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) e[j] = fast_exp2(logit2(r[8 * k + j], c0 + 32 * h, 8 * k + j) - mx) * inv;
+              uint4 u;
+              u.x = pack_bf16x2(e[0], e[1]);
+              u.y = pack_bf16x2(e[2], e[3]);
+              u.z = pack_bf16x2(e[4], e[5]);
+              u.w = pack_bf16x2(e[6], e[7]);
+              slab[lane * 8 + ((4 * h + k) ^ (lane & 7))] = u;
+            }
           }
+          fence_proxy_async();
           __syncwarp();
+          if (lane == 0) {
+            tma_store_5d(&tm_o, slab, c0, row_base, 0, o_zlo, o_zhi);
+            bulk_commit_group();
+          }
         }
       }
       // this warp no longer reads the accumulator buffer
@@ -590,7 +601,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
     }
-    if ((ST & ST_TMA) != 0 && lane == 0) bulk_wait_group<0>();  // all TMA stores of this warp are complete
+    if (((ST & ST_TMA) != 0 || EK == EK_SOFTMAX_1x16x16 || EK == EK_SOFTMAX_4x8x8) && lane == 0)
+      bulk_wait_group<0>();  // all TMA stores of this warp are complete  // all TMA stores of this warp are complete
   }
 
   tc_fence_before();
@@ -887,6 +899,11 @@ extern "C" int lvt_gemm_bf16(const LvtGemm* g, void* stream_) {
 
   const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
   const bool amn = g->a_mn_major != 0, bmn = g->b_mn_major != 0;
+  if (ek == EK_SOFTMAX_1x16x16 || ek == EK_SOFTMAX_4x8x8) {
+    rc = make_operand_map(&m.o, g->out_bf16, g->N, g->M, g->o_cin, g->o_ld, g->o_s_blk, g->batch, g->o_zdiv,
+                          g->o_s_zlo, g->o_s_zhi, 32, 2);
+    if (rc) return rc;
+  }
   if (ek == EK_SOFTMAX_1x16x16) return launch_gemm<256, false, false, EK_SOFTMAX_1x16x16>(m, p, grid, stream);
   if (ek == EK_SOFTMAX_4x8x8) return launch_gemm<256, false, false, EK_SOFTMAX_4x8x8>(m, p, grid, stream);
   if (ek == EK_DS) {

@@ -187,31 +187,98 @@ attn_delta_kernel(const __nv_bfloat16* __restrict__ dO, const __nv_bfloat16* __r
 }
 
 // Gradient of the relative-position banks (get_B, vt_attention.py:169-174):
-// dbank_x[h, off] += sum_{b} sum_{i,j : off_x(i,j) == off} dS[b, h, i, j].   grid (L, H), 256 thr.
+// dbank_x[h, off] += sum_{b} sum_{i,j : off_x(i,j) == off} dS[b, h, i, j].
+// grid (L*L/2048, H, zsplit), 256 threads; a thread owns 8 consecutive keys j of one query i,
+// streams them over its batch range with 16 B loads, then bins through shared memory.
 __global__ void __launch_bounds__(256)
 relpos_bank_grad_kernel(const __nv_bfloat16* __restrict__ dS, float* __restrict__ dbt,
                         float* __restrict__ dbh, float* __restrict__ dbw, int nb, int H, int bt,
                         int bh, int bw) {
-  __shared__ float bins[256];
-  const int L = bt * bh * bw;  // == 256 == blockDim.x
-  const int i = blockIdx.x, h = blockIdx.y, j = threadIdx.x;
+  const int L = bt * bh * bw;  // == 256
+  const int h = blockIdx.y;
+  const int e0 = blockIdx.x * 2048 + threadIdx.x * 8;  // element of the L x L plane
+  const int i = e0 / L, j0 = e0 % L;
   const int nt = 2 * bt - 1, nh = 2 * bh - 1, nw = 2 * bw - 1;
-  bins[j] = 0.f;
-  __syncthreads();
-  float acc = 0.f;
-  const __nv_bfloat16* p = dS + ((size_t)h * L + i) * L + j;
-  const size_t bstride = (size_t)H * L * L;
-  for (int b = 0; b < nb; ++b) acc += __bfloat162float(p[b * bstride]);
+  const int per = (nb + gridDim.z - 1) / gridDim.z;
+  const int b0 = blockIdx.z * per, b1 = min(nb, b0 + per);
+  const size_t plane = (size_t)L * L;
+  const __nv_bfloat16* p = dS + (size_t)h * plane + e0;
+  const size_t bstride = (size_t)H * plane;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  int b = b0;
+  for (; b + 4 <= b1; b += 4) {
+    uint4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const uint4*>(p + (size_t)(b + u) * bstride);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const __nv_bfloat162* q = reinterpret_cast<const __nv_bfloat162*>(&v[u]);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 f = __bfloat1622float2(q[k]);
+        acc[2 * k] += f.x;
+        acc[2 * k + 1] += f.y;
+      }
+    }
+  }
+  for (; b < b1; ++b) {
+    const uint4 v = *reinterpret_cast<const uint4*>(p + (size_t)b * bstride);
+    const __nv_bfloat162* q = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 f = __bfloat1622float2(q[k]);
+      acc[2 * k] += f.x;
+      acc[2 * k + 1] += f.y;
+    }
+  }
+  // bin through per-warp private shared-memory bins; equal consecutive bins of a thread are merged
+  // first (8 consecutive keys share tj and, for bw >= 8, hj), and a single-entry t-bank (bt == 1)
+  // is reduced with shuffles, so same-address atomic serialisation stays small.
+  __shared__ float wbins[8][64];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int k = lane; k < 64; k += 32) wbins[warp][k] = 0.f;
+  __syncwarp();
   const int hw = bh * bw;
   const int ti = i / hw, hi = (i / bw) % bh, wi = i % bw;
-  const int tj = j / hw, hj = (j / bw) % bh, wj = j % bw;
-  atomicAdd(&bins[ti - tj + bt - 1], acc);
-  atomicAdd(&bins[nt + hi - hj + bh - 1], acc);
-  atomicAdd(&bins[nt + nh + wi - wj + bw - 1], acc);
+  float* wb = wbins[warp];
+  int prev_t = -1, prev_h = -1;
+  float run_t = 0.f, run_h = 0.f;
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const int j = j0 + u;
+    const int tj = j / hw, hj = (j / bw) % bh, wj = j % bw;
+    const int bin_t = ti - tj + bt - 1, bin_h = nt + hi - hj + bh - 1;
+    if (bin_t != prev_t) {
+      if (prev_t >= 0 && bt > 1) atomicAdd(&wb[prev_t], run_t);
+      prev_t = bin_t;
+      run_t = (bt > 1) ? 0.f : run_t;
+    }
+    run_t += acc[u];
+    if (bin_h != prev_h) {
+      if (prev_h >= 0) atomicAdd(&wb[prev_h], run_h);
+      prev_h = bin_h;
+      run_h = 0.f;
+    }
+    run_h += acc[u];
+    atomicAdd(&wb[nt + nh + wi - wj + bw - 1], acc[u]);
+  }
+  atomicAdd(&wb[prev_h], run_h);
+  if (bt > 1) {
+    atomicAdd(&wb[prev_t], run_t);
+  } else {
+    run_t = warp_sum(run_t);
+    if (lane == 0) wb[0] += run_t;
+  }
   __syncthreads();
-  if (j < nt) atomicAdd(dbt + h * nt + j, bins[j]);
-  else if (j < nt + nh) atomicAdd(dbh + h * nh + (j - nt), bins[j]);
-  else if (j < nt + nh + nw) atomicAdd(dbw + h * nw + (j - nt - nh), bins[j]);
+  const int t = threadIdx.x;
+  if (t < nt + nh + nw) {
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) v += wbins[w][t];
+    if (t < nt) atomicAdd(dbt + h * nt + t, v);
+    else if (t < nt + nh) atomicAdd(dbh + h * nh + (t - nt), v);
+    else atomicAdd(dbw + h * nw + (t - nt - nh), v);
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -635,8 +702,9 @@ extern "C" int lvt_attn_delta(const void* dO, const void* O, float* delta, int n
 extern "C" int lvt_relpos_bank_grad(const void* dS, float* dbank_t, float* dbank_h, float* dbank_w,
                                     int nb, int H, int bt, int bh, int bw, void* stream) {
   LVT_CHECK_ARG(dS && dbank_t && dbank_h && dbank_w && nb > 0, "lvt_relpos_bank_grad: bad argument");
-  LVT_CHECK_ARG(bt * bh * bw == 256 && 2 * (bt + bh + bw) - 3 <= 256, "lvt_relpos_bank_grad: block must hold 256 positions");
-  relpos_bank_grad_kernel<<<dim3(256, H), 256, 0, STREAM(stream)>>>(
+  LVT_CHECK_ARG(bt * bh * bw == 256 && 2 * (bt + bh + bw) - 3 <= 64, "lvt_relpos_bank_grad: block must hold 256 positions and <= 64 offsets");
+  const int zsplit = nb >= 16 ? 4 : 1;
+  relpos_bank_grad_kernel<<<dim3(32, H, zsplit), 256, 0, STREAM(stream)>>>(
       reinterpret_cast<const __nv_bfloat16*>(dS), dbank_t, dbank_h, dbank_w, nb, H, bt, bh, bw);
   LVT_CHECK_LAUNCH();
   lvt_count_launch(1);
