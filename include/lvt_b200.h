@@ -97,7 +97,8 @@ enum {
   LVT_GEMM_RELU = 1,       /* out = max(v, 0)                                                */
   LVT_GEMM_MASK = 2,       /* v *= (aux_bf16 > 0)  (ReLU backward)                           */
   LVT_GEMM_ATOMIC = 4,     /* out_f32 += v with red.global.add (split-K / grad accumulate)   */
-  LVT_GEMM_CAUSAL = 8      /* SOFTMAX mode: mask keys j > query i                            */
+  LVT_GEMM_CAUSAL = 8,     /* SOFTMAX mode: mask keys j > query i                            */
+  LVT_GEMM_AUX_ADD = 16    /* v += aux_bf16 (bf16 residual, ResBlock skip), before the ReLU  */
 };
 
 typedef struct LvtGemm {
@@ -126,6 +127,17 @@ typedef struct LvtGemm {
      (BlockLocalAttention.get_B, vt_attention.py:169-174); block (bt,bh,bw), bt*bh*bw == 256 */
   const float* bank_t; const float* bank_h; const float* bank_w;
   int bt, bh, bw, heads;
+  /* Implicit-GEMM convolution over NHWC bf16 activations (ResEncoder / ResDecoder convs,
+     encoder/resencoder.py:46-52, generator/resdecoder.py:48-56 and their autograd): the conv operand
+     is an activation tensor [P phases][cv_N][cv_H][cv_W][cv_C] (pixel stride cv_pix_stride elements,
+     phase stride cv_s_phase) read through per-tap shifted TMA boxes, out-of-range pixels = 0.
+       a_conv: A[m, tap*cv_C + c] = act[ph[tap]][n, h + dh[tap], w + dw[tap], c],  m = (n, h, w)
+       b_conv: B[tap*cv_C + c, k] = act[ph[tap]][n, h + dh[tap], w + dw[tap], c],  k = (n, h, w)
+               (weight gradient; needs b_mn_major = 1)                                        */
+  int a_conv, b_conv;
+  int cv_C, cv_W, cv_H, cv_N, cv_P, cv_ntaps;
+  long long cv_pix_stride, cv_s_phase;
+  signed char cv_dh[16], cv_dw[16], cv_ph[16];
 } LvtGemm;
 
 int lvt_gemm_bf16(const LvtGemm* g, void* stream);

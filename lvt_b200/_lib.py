@@ -40,6 +40,11 @@ class LvtGemm(ctypes.Structure):
         ("lse", ctypes.c_void_p), ("delta", ctypes.c_void_p),
         ("bank_t", ctypes.c_void_p), ("bank_h", ctypes.c_void_p), ("bank_w", ctypes.c_void_p),
         ("bt", ctypes.c_int), ("bh", ctypes.c_int), ("bw", ctypes.c_int), ("heads", ctypes.c_int),
+        ("a_conv", ctypes.c_int), ("b_conv", ctypes.c_int),
+        ("cv_C", ctypes.c_int), ("cv_W", ctypes.c_int), ("cv_H", ctypes.c_int), ("cv_N", ctypes.c_int),
+        ("cv_P", ctypes.c_int), ("cv_ntaps", ctypes.c_int),
+        ("cv_pix_stride", ctypes.c_longlong), ("cv_s_phase", ctypes.c_longlong),
+        ("cv_dh", ctypes.c_byte * 16), ("cv_dw", ctypes.c_byte * 16), ("cv_ph", ctypes.c_byte * 16),
     ]
 
 

@@ -60,6 +60,9 @@ struct GemmParams {
   const float* bank_h;
   const float* bank_w;
   int heads;
+  // implicit-GEMM convolution (operand = NHWC activations read through per-tap shifted TMA boxes)
+  int a_conv, b_conv, cv_C, cv_W, cv_H;
+  signed char cv_dh[16], cv_dw[16], cv_ph[16];
 };
 
 // store-path bits (template parameter ST); 0 = staged generic epilogue
@@ -177,7 +180,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           uint8_t* a_dst = smem + s * L::STAGE_BYTES;
           uint8_t* b_dst = a_dst + A_TILE_BYTES;
           if (!A_MN) {
-            tma_load_5d(a_dst, &tm_a, &full_bar[s], k0 % p.a_cin, t.m0, k0 / p.a_cin, a_zlo, a_zhi);
+            if (p.a_conv) {
+              // rows = 128 consecutive output pixels (n, h, w) of one image; k-block = 64 channels of one tap
+              const int tap = k0 / p.cv_C, c0 = k0 - tap * p.cv_C;
+              const int hw = p.cv_H * p.cv_W;
+              const int img = t.m0 / hw, h0 = (t.m0 - img * hw) / p.cv_W;
+              tma_load_5d(a_dst, &tm_a, &full_bar[s], c0, p.cv_dw[tap], h0 + p.cv_dh[tap], img, p.cv_ph[tap]);
+            } else {
+              tma_load_5d(a_dst, &tm_a, &full_bar[s], k0 % p.a_cin, t.m0, k0 / p.a_cin, a_zlo, a_zhi);
+            }
           } else {
 #pragma unroll
             for (int j = 0; j < BM / 64; ++j) {
@@ -192,8 +203,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 #pragma unroll
             for (int j = 0; j < BN / 64; ++j) {
               const int c = t.n0 + 64 * j;
-              tma_load_5d(b_dst + j * (64 * BK * 2), &tm_b, &full_bar[s], c % p.b_cin, k0, c / p.b_cin,
-                          b_zlo, b_zhi);
+              if (p.b_conv) {
+                // weight gradient: columns = (tap, channel), k-block = 64 consecutive pixels of one image
+                const int tap = c / p.cv_C, c0 = c - tap * p.cv_C;
+                const int hw = p.cv_H * p.cv_W;
+                const int img = k0 / hw, h0 = (k0 - img * hw) / p.cv_W;
+                tma_load_5d(b_dst + j * (64 * BK * 2), &tm_b, &full_bar[s], c0, p.cv_dw[tap], h0 + p.cv_dh[tap],
+                            img, p.cv_ph[tap]);
+              } else {
+                tma_load_5d(b_dst + j * (64 * BK * 2), &tm_b, &full_bar[s], c % p.b_cin, k0, c / p.b_cin,
+                            b_zlo, b_zhi);
+              }
             }
           }
         }
@@ -332,11 +352,26 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                   v[4 * k + 2] += __uint_as_float(cr[k].z); v[4 * k + 3] += __uint_as_float(cr[k].w);
                 }
               }
+              if constexpr (CLOAD && !F32) {
+                if (p.flags & LVT_GEMM_AUX_ADD) {  // bf16 residual (ResBlock skip connection)
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) {
+                    const uint32_t w[4] = {cr[4 * h + k].x, cr[4 * h + k].y, cr[4 * h + k].z, cr[4 * h + k].w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                      const float2 pf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[j]));
+                      v[8 * k + 2 * j] += pf.x;
+                      v[8 * k + 2 * j + 1] += pf.y;
+                    }
+                  }
+                }
+              }
               if (relu) {
 #pragma unroll
                 for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
               }
               if constexpr (CLOAD && !F32) {  // ReLU backward: keep where the bf16 mask source is > 0
+                if (p.flags & LVT_GEMM_MASK) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                   const uint32_t w[4] = {cr[4 * h + k].x, cr[4 * h + k].y, cr[4 * h + k].z, cr[4 * h + k].w};
@@ -346,6 +381,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                     if (!(lo != 0 && lo < 0x8000u)) v[8 * k + 2 * j] = 0.f;
                     if (!(hi != 0 && hi < 0x8000u)) v[8 * k + 2 * j + 1] = 0.f;
                   }
+                }
                 }
               }
             }
@@ -444,6 +480,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                   const float4 r4 = *reinterpret_cast<const float4*>(resp + off);
                   v.x += r4.x; v.y += r4.y; v.z += r4.z; v.w += r4.w;
                 }
+                if (flags & LVT_GEMM_AUX_ADD) {
+                  const uint2 au = *reinterpret_cast<const uint2*>(auxp + off);
+                  const float2 q0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&au.x));
+                  const float2 q1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&au.y));
+                  v.x += q0.x; v.y += q0.y; v.z += q1.x; v.w += q1.y;
+                }
                 if (flags & LVT_GEMM_RELU) {
                   v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
                 }
@@ -479,6 +521,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                   if (p.bias)
                     x += p.bias[(p.bias_mod > 0 ? (long long)((row_base + rl) % p.bias_mod) * p.N : 0) + col + e];
                   if (resp) x += resp[off + e];
+                  if (flags & LVT_GEMM_AUX_ADD) x += __bfloat162float(auxp[off + e]);
                   if (flags & LVT_GEMM_RELU) x = fmaxf(x, 0.f);
                   if ((flags & LVT_GEMM_MASK) && !(__bfloat162float(auxp[off + e]) > 0.f)) x = 0.f;
                   if (of32) {
@@ -719,6 +762,40 @@ int make_operand_map(CUtensorMap* out, const void* base, long long c_extent, lon
   return LVT_OK;
 }
 
+// NHWC activation tensor (phase, n, h, w, c) for the implicit-GEMM convolution modes:
+// box = (64 channels, W, box_h rows, 1, 1); out-of-range pixels are zero-filled by TMA (= conv padding).
+int make_conv_map(CUtensorMap* out, const void* base, int C, int W, int H, int N, int P, long long pix_stride,
+                  long long phase_stride, int box_h) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) {
+    lvt_set_error("cuTensorMapEncodeTiled driver entry point not available");
+    return LVT_ERR_CUDA;
+  }
+  cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N, (cuuint64_t)(P > 0 ? P : 1)};
+  cuuint64_t strides[4] = {(cuuint64_t)pix_stride * 2, (cuuint64_t)pix_stride * W * 2,
+                           (cuuint64_t)pix_stride * W * H * 2,
+                           (cuuint64_t)(P > 1 ? phase_stride : pix_stride * W * H * (long long)N) * 2};
+  for (int i = 0; i < 4; ++i)
+    if (strides[i] % 16 != 0) {
+      lvt_set_error("conv operand stride %d is not a multiple of 16 bytes", i);
+      return LVT_ERR_INVALID;
+    }
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) {
+    lvt_set_error("conv operand base pointer is not 16-byte aligned");
+    return LVT_ERR_INVALID;
+  }
+  cuuint32_t box[5] = {64, (cuuint32_t)W, (cuuint32_t)box_h, 1, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    lvt_set_error("cuTensorMapEncodeTiled (conv) failed with CUresult %d", (int)r);
+    return LVT_ERR_CUDA;
+  }
+  return LVT_OK;
+}
+
 struct Maps {
   CUtensorMap a, b, o, c;
 };
@@ -791,7 +868,7 @@ extern "C" int lvt_gemm_bf16(const LvtGemm* g, void* stream_) {
   LVT_CHECK_ARG(g->o_cin % 16 == 0 || g->o_cin >= g->N, "lvt_gemm_bf16: o_cin must be a multiple of 16");
   LVT_CHECK_ARG(g->o_ld % 4 == 0 && g->o_s_blk % 4 == 0 && g->o_s_zlo % 4 == 0 && g->o_s_zhi % 4 == 0,
                 "lvt_gemm_bf16: output strides must be multiples of 4 elements");
-  if (g->flags & LVT_GEMM_MASK) LVT_CHECK_ARG(g->aux_bf16, "lvt_gemm_bf16: MASK needs aux_bf16");
+  if (g->flags & (LVT_GEMM_MASK | LVT_GEMM_AUX_ADD)) LVT_CHECK_ARG(g->aux_bf16, "lvt_gemm_bf16: MASK / AUX_ADD need aux_bf16");
 
   int bn = 128;
   int ek = EK_LINEAR;
@@ -853,14 +930,40 @@ extern "C" int lvt_gemm_bf16(const LvtGemm* g, void* stream_) {
   memset(&m, 0, sizeof(m));
   int rc;
   // contiguous / strided extents per major-ness
-  rc = g->a_mn_major
-           ? make_operand_map(&m.a, g->a, g->M, g->K, g->a_cin, g->a_ld, g->a_s_blk, g->batch, g->a_zdiv, g->a_s_zlo, g->a_s_zhi, BK)
-           : make_operand_map(&m.a, g->a, g->K, g->M, g->a_cin, g->a_ld, g->a_s_blk, g->batch, g->a_zdiv, g->a_s_zlo, g->a_s_zhi, BM);
-  if (rc) return rc;
-  rc = g->b_mn_major
-           ? make_operand_map(&m.b, g->b, g->N, g->K, g->b_cin, g->b_ld, g->b_s_blk, g->batch, g->b_zdiv, g->b_s_zlo, g->b_s_zhi, BK)
-           : make_operand_map(&m.b, g->b, g->K, g->N, g->b_cin, g->b_ld, g->b_s_blk, g->batch, g->b_zdiv, g->b_s_zlo, g->b_s_zhi, bn);
-  if (rc) return rc;
+  if (g->a_conv || g->b_conv) {
+    LVT_CHECK_ARG(g->batch == 1 && g->cv_ntaps > 0 && g->cv_ntaps <= 16 && g->cv_C % 64 == 0 && g->cv_W > 0 &&
+                      128 % g->cv_W == 0 && (g->cv_H * g->cv_W) % 128 == 0 && g->cv_N > 0,
+                  "lvt_gemm_bf16: conv mode needs batch 1, <= 16 taps, C %% 64 == 0, W | 128, H*W %% 128 == 0");
+    LVT_CHECK_ARG(!(g->a_conv && g->b_conv), "lvt_gemm_bf16: only one conv operand");
+    p.a_conv = g->a_conv; p.b_conv = g->b_conv; p.cv_C = g->cv_C; p.cv_W = g->cv_W; p.cv_H = g->cv_H;
+    for (int i = 0; i < g->cv_ntaps; ++i) {
+      p.cv_dh[i] = g->cv_dh[i]; p.cv_dw[i] = g->cv_dw[i]; p.cv_ph[i] = g->cv_ph[i];
+    }
+    const long long pix = g->cv_pix_stride > 0 ? g->cv_pix_stride : g->cv_C;
+    if (g->a_conv) {
+      LVT_CHECK_ARG(!g->a_mn_major && g->K == g->cv_ntaps * g->cv_C && g->M == g->cv_N * g->cv_H * g->cv_W,
+                    "lvt_gemm_bf16: conv A needs K == ntaps*C and M == N*H*W");
+      rc = make_conv_map(&m.a, g->a, g->cv_C, g->cv_W, g->cv_H, g->cv_N, g->cv_P, pix, g->cv_s_phase, BM / g->cv_W);
+    } else {
+      LVT_CHECK_ARG(g->b_mn_major && g->N == g->cv_ntaps * g->cv_C && g->K == g->cv_N * g->cv_H * g->cv_W &&
+                        g->cv_C % bn == 0,
+                    "lvt_gemm_bf16: conv B needs MN-major, N == ntaps*C, K == N*H*W, C %% tile == 0");
+      rc = make_conv_map(&m.b, g->b, g->cv_C, g->cv_W, g->cv_H, g->cv_N, g->cv_P, pix, g->cv_s_phase, BK / g->cv_W);
+    }
+    if (rc) return rc;
+  }
+  if (!g->a_conv) {
+    rc = g->a_mn_major
+             ? make_operand_map(&m.a, g->a, g->M, g->K, g->a_cin, g->a_ld, g->a_s_blk, g->batch, g->a_zdiv, g->a_s_zlo, g->a_s_zhi, BK)
+             : make_operand_map(&m.a, g->a, g->K, g->M, g->a_cin, g->a_ld, g->a_s_blk, g->batch, g->a_zdiv, g->a_s_zlo, g->a_s_zhi, BM);
+    if (rc) return rc;
+  }
+  if (!g->b_conv) {
+    rc = g->b_mn_major
+             ? make_operand_map(&m.b, g->b, g->N, g->K, g->b_cin, g->b_ld, g->b_s_blk, g->batch, g->b_zdiv, g->b_s_zlo, g->b_s_zhi, BK)
+             : make_operand_map(&m.b, g->b, g->K, g->N, g->b_cin, g->b_ld, g->b_s_blk, g->batch, g->b_zdiv, g->b_s_zlo, g->b_s_zhi, bn);
+    if (rc) return rc;
+  }
 
   // TMA epilogue when the output is ONE tensor of plain 128 B-aligned rows; an optional second tensor with
   // the same addressing (fp32 residual / bf16 mask source / bf16 P) is TMA-loaded per slab.
@@ -871,7 +974,8 @@ extern "C" int lvt_gemm_bf16(const LvtGemm* g, void* stream_) {
     const int esize = g->out_bf16 ? 2 : 4;
     const int slab_cols = 128 / esize;
     const void* obase = g->out_bf16 ? g->out_bf16 : (void*)g->out_f32;
-    const bool atomic = (g->flags & LVT_GEMM_ATOMIC) != 0, mask = (g->flags & LVT_GEMM_MASK) != 0;
+    const bool atomic = (g->flags & LVT_GEMM_ATOMIC) != 0,
+               mask = (g->flags & (LVT_GEMM_MASK | LVT_GEMM_AUX_ADD)) != 0;
     const void* cbase = nullptr;
     int want = -1;
     if (ek == EK_DS) { want = ST_TMA | ST_CLOAD; cbase = g->aux_bf16; }

@@ -12,7 +12,7 @@ from . import _lib
 from ._lib import LvtGemm, check, ptr, stream_ptr
 
 EPI_LINEAR, EPI_SOFTMAX, EPI_DS = 0, 1, 2
-GEMM_RELU, GEMM_MASK, GEMM_ATOMIC, GEMM_CAUSAL = 1, 2, 4, 8
+GEMM_RELU, GEMM_MASK, GEMM_ATOMIC, GEMM_CAUSAL, GEMM_AUX_ADD = 1, 2, 4, 8, 16
 
 
 def _cuda_contig(t, dtype, name):
@@ -96,9 +96,24 @@ def op_mnmajor(t):
     return Operand(t.data_ptr(), t.stride(0), mn_major=True)
 
 
+@dataclass
+class ConvSpec:
+    """Implicit-GEMM convolution operand: NHWC bf16 activations [P][n][h][w][C] read through
+    per-tap shifted boxes (see `struct LvtGemm`); taps = [(dh, dw, phase), ...]."""
+    side: str                 # "a" (forward / data gradient) or "b" (weight gradient)
+    C: int
+    H: int
+    W: int
+    n: int
+    taps: list
+    P: int = 1
+    pix_stride: int = 0
+    s_phase: int = 0
+
+
 def gemm(M, N, K, a: Operand, b: Operand, out: Operand, out_f32=None, out_bf16=None, batch=1,
          splits=1, alpha=1.0, mode=EPI_LINEAR, flags=0, bias=None, bias_mod=0, res=None, aux=None,
-         lse=None, delta=None, banks=None, block=None, heads=1):
+         lse=None, delta=None, banks=None, block=None, heads=1, conv: Optional[ConvSpec] = None):
     """D[z] = epilogue(alpha * A[z] @ B[z]^T); pointers may be torch tensors or ints."""
     lib = _lib.require_device()
 
@@ -129,6 +144,12 @@ def gemm(M, N, K, a: Operand, b: Operand, out: Operand, out_f32=None, out_bf16=N
         g.bank_t, g.bank_h, g.bank_w = p(banks[0]), p(banks[1]), p(banks[2])
         g.bt, g.bh, g.bw = block
     g.heads = heads
+    if conv is not None:
+        g.a_conv, g.b_conv = int(conv.side == "a"), int(conv.side == "b")
+        g.cv_C, g.cv_W, g.cv_H, g.cv_N, g.cv_P, g.cv_ntaps = conv.C, conv.W, conv.H, conv.n, conv.P, len(conv.taps)
+        g.cv_pix_stride, g.cv_s_phase = conv.pix_stride or conv.C, conv.s_phase
+        for i, (dh, dw, ph) in enumerate(conv.taps):
+            g.cv_dh[i], g.cv_dw[i], g.cv_ph[i] = dh, dw, ph
     check(lib.lvt_gemm_bf16(ctypes.byref(g), stream_ptr()), "lvt_gemm_bf16")
 
 
