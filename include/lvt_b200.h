@@ -216,6 +216,48 @@ int lvt_cast_bf16(const float* in, void* out_bf16, long long n, void* stream);
 int lvt_permute4(const float* in, void* out, int out_is_bf16, int accumulate, const int* dims,
                  const long long* in_strides, const long long* out_strides, void* stream);
 
+/* Channels-last variants used inside the VQ-VAE engine (z_e [n*hw, num*D] fp32 as written by the
+ * last encoder GEMM): same arithmetic and index layout ([n, num, hw] int64) as lvt_vq_argmin;
+ * zq may additionally be produced as bf16 (decoder GEMM operand).                             */
+int lvt_vq_argmin_nhwc(const float* z_e, const float* codebook, int64_t* idx_out, float* zq_out,
+                       void* zq_bf16, float* counts, float* sums, int n, int num, int K, int D, int hw,
+                       void* stream);
+int lvt_vq_gather_nhwc(const int64_t* idx, const float* codebook, float* out, void* out_bf16, int n,
+                       int num, int K, int D, int hw, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * VQ-VAE edge operators (3-channel ends of ResEncoder / ResDecoder, losses)
+ * "phase-major": a 32x32 feature map stored as [hp][wp][n][16][16][C], pixel (2*h2+hp, 2*w2+wp).
+ * ---------------------------------------------------------------------------------------- */
+/* normalise (ae.py:34-36) + im2col of Conv2d(3->NF/2, k4, s2, p1) (resencoder.py:47):
+ * x fp32 NCHW [n,3,64,64] -> A bf16 [4*n*256, 64] (48 columns k=(kh*4+kw)*3+c, 16 zeros), rows in
+ * phase-major order of the 32x32 output.                                                      */
+int lvt_vqvae_in_im2col(const float* x, void* a_bf16, int n, float mean, float std, void* stream);
+/* ConvTranspose2d(C->3, k4, s2, p1) + tanh (resdecoder.py:56,68-69): act bf16 phase-major
+ * [4][n][16][16][C] (ReLU'd), w fp32 [C][3][4][4], out fp32 NCHW [n,3,64,64].                 */
+int lvt_vqvae_out_convt_fwd(const void* act_bf16, const float* w, const float* bias, float* out, int n,
+                            int C, void* stream);
+/* reconstruction loss lambda*MSE(x_tilde, (x-mean)/std) (loss.py:20, vqvae.py:79): loss += value,
+ * dpre = dL/d(pre-tanh) [n,3,64,64] (optional), dbias[3] += column sums (optional).           */
+int lvt_vqvae_recon_loss(const float* x_tilde, const float* x, float* dpre, float* loss, float* dbias,
+                         int n, float mean, float std, float lambda, void* stream);
+/* backward of the output ConvTranspose2d: dact bf16 (phase-major, ReLU-masked by act > 0) and
+ * G bf16 [n*1024, 64] with G[row, co*16+kh*4+kw] = dpre at the output pixel the tap reaches, so
+ * that dW[c][co][kh][kw] = sum_rows act[row,c] * G[row, .] is one lvt_gemm_bf16 call.         */
+int lvt_vqvae_out_convt_bwd(const void* act_bf16, const float* w, const float* dpre, void* dact_bf16,
+                            void* g_bf16, int n, int C, void* stream);
+/* commitment loss beta*MSE(z_e, zq_bar) (vqvae.py:86) + merged gradient wrt z_e:
+ * dz (bf16) = dz_st + 2*beta/numel*(z_e - zq_bar);  loss += value.                            */
+int lvt_vqvae_commit_loss(const float* z_e, const float* zq_bar, const float* dz_st, void* dz_bf16,
+                          float* loss, long long numel, float beta, void* stream);
+/* out = (a [+ b]) * (mask_src > 0), all bf16 (ReLU backward merged with a skip gradient).     */
+int lvt_relu_bwd_add(const void* a_bf16, const void* b_bf16, const void* mask_src_bf16, void* out_bf16,
+                     long long n, void* stream);
+int lvt_cast_relu_bf16(const float* in, void* out_bf16, long long n, int relu, void* stream);
+/* y*std + mean clamped to [lo, hi] (ae.py:130-139).                                           */
+int lvt_denorm_clamp(const float* in, float* out, long long n, float mean, float std, float lo, float hi,
+                     void* stream);
+
 #ifdef __cplusplus
 }
 #endif

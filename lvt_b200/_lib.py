@@ -77,6 +77,16 @@ SYMBOLS = {
     "lvt_adam_step": (_i, [_vp] * 5 + [_ll] + [_f] * 4 + [_i, _f, _vp]),
     "lvt_cast_bf16": (_i, [_vp, _vp, _ll, _vp]),
     "lvt_permute4": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),
+    "lvt_vq_argmin_nhwc": (_i, [_vp] * 7 + [_i] * 5 + [_vp]),
+    "lvt_vq_gather_nhwc": (_i, [_vp] * 4 + [_i] * 5 + [_vp]),
+    "lvt_vqvae_in_im2col": (_i, [_vp, _vp, _i, _f, _f, _vp]),
+    "lvt_vqvae_out_convt_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp]),
+    "lvt_vqvae_recon_loss": (_i, [_vp] * 5 + [_i, _f, _f, _f, _vp]),
+    "lvt_vqvae_out_convt_bwd": (_i, [_vp] * 5 + [_i, _i, _vp]),
+    "lvt_vqvae_commit_loss": (_i, [_vp] * 5 + [_ll, _f, _vp]),
+    "lvt_relu_bwd_add": (_i, [_vp] * 4 + [_ll, _vp]),
+    "lvt_cast_relu_bf16": (_i, [_vp, _vp, _ll, _i, _vp]),
+    "lvt_denorm_clamp": (_i, [_vp, _vp, _ll, _f, _f, _f, _f, _vp]),
 }
 
 

@@ -945,9 +945,8 @@ extern "C" int lvt_gemm_bf16(const LvtGemm* g, void* stream_) {
                     "lvt_gemm_bf16: conv A needs K == ntaps*C and M == N*H*W");
       rc = make_conv_map(&m.a, g->a, g->cv_C, g->cv_W, g->cv_H, g->cv_N, g->cv_P, pix, g->cv_s_phase, BM / g->cv_W);
     } else {
-      LVT_CHECK_ARG(g->b_mn_major && g->N == g->cv_ntaps * g->cv_C && g->K == g->cv_N * g->cv_H * g->cv_W &&
-                        g->cv_C % bn == 0,
-                    "lvt_gemm_bf16: conv B needs MN-major, N == ntaps*C, K == N*H*W, C %% tile == 0");
+      LVT_CHECK_ARG(g->b_mn_major && g->N == g->cv_ntaps * g->cv_C && g->K == g->cv_N * g->cv_H * g->cv_W,
+                    "lvt_gemm_bf16: conv B needs MN-major, N == ntaps*C, K == N*H*W");
       rc = make_conv_map(&m.b, g->b, g->cv_C, g->cv_W, g->cv_H, g->cv_N, g->cv_P, pix, g->cv_s_phase, BK / g->cv_W);
     }
     if (rc) return rc;

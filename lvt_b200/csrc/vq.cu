@@ -79,8 +79,9 @@ template <int D>
 __global__ void __launch_bounds__(VQ_THREADS, 1)
 vq_argmin_smem_kernel(const float* __restrict__ z_e, const float* __restrict__ codebook,
                       int64_t* __restrict__ idx_out, float* __restrict__ zq_out,
-                      float* __restrict__ counts, float* __restrict__ sums, long long total_pos,
-                      int num, int K, int hw) {
+                      __nv_bfloat16* __restrict__ zq_bf16, float* __restrict__ counts,
+                      float* __restrict__ sums, long long total_pos, int num, int K, int hw,
+                      long long pos_stride, long long ch_stride) {
   extern __shared__ float4 vq_smem4[];
   float* cb = reinterpret_cast<float*>(vq_smem4);  // [K][D]
   float* csq = cb + (size_t)K * D;                 // [K]
@@ -100,11 +101,13 @@ vq_argmin_smem_kernel(const float* __restrict__ z_e, const float* __restrict__ c
   const long long frame = p / hw;
   const int s = (int)(p - frame * hw);
   const long long C = (long long)num * D;
-  const float* xp = z_e + (frame * C + (long long)g * D) * hw + s;
+  // NCHW: pos_stride 1, ch_stride hw;  NHWC: pos_stride C, ch_stride 1 (frame stride C*hw in both)
+  const long long base = frame * C * hw + (long long)s * pos_stride + (long long)g * D * ch_stride;
+  const float* xp = z_e + base;
 
   float x[D];
 #pragma unroll
-  for (int j = 0; j < D; ++j) x[j] = __ldg(xp + (long long)j * hw);
+  for (int j = 0; j < D; ++j) x[j] = __ldg(xp + (long long)j * ch_stride);
   const float xsq = sqnorm_aten_order<D>([&](int j) { return x[j]; });
 
   float best = INFINITY;
@@ -140,10 +143,16 @@ vq_argmin_smem_kernel(const float* __restrict__ z_e, const float* __restrict__ c
 
   idx_out[(frame * num + g) * hw + s] = (int64_t)besti;
   if (zq_out) {
-    float* zp = zq_out + (frame * C + (long long)g * D) * hw + s;
+    float* zp = zq_out + base;
     const float* cr = cb + (size_t)besti * D;
 #pragma unroll
-    for (int j = 0; j < D; ++j) zp[(long long)j * hw] = cr[j];
+    for (int j = 0; j < D; ++j) zp[(long long)j * ch_stride] = cr[j];
+  }
+  if (zq_bf16) {
+    __nv_bfloat16* zp = zq_bf16 + base;
+    const float* cr = cb + (size_t)besti * D;
+#pragma unroll
+    for (int j = 0; j < D; ++j) zp[(long long)j * ch_stride] = __float2bfloat16(cr[j]);
   }
   if (counts) atomicAdd(counts + (size_t)g * K + besti, 1.f);
   if (sums) {
@@ -199,8 +208,9 @@ __global__ void vq_csq_kernel(const float* __restrict__ codebook, float* __restr
 }
 
 __global__ void vq_gather_kernel(const int64_t* __restrict__ idx, const float* __restrict__ codebook,
-                                 float* __restrict__ out, long long total_pos, int num, int K, int D,
-                                 int hw) {
+                                 float* __restrict__ out, __nv_bfloat16* __restrict__ out_bf16,
+                                 long long total_pos, int num, int K, int D, int hw, long long pos_stride,
+                                 long long ch_stride) {
   const int g = blockIdx.y;
   const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= total_pos) return;
@@ -209,8 +219,12 @@ __global__ void vq_gather_kernel(const int64_t* __restrict__ idx, const float* _
   long long code = idx[(frame * num + g) * hw + s];
   code = code < 0 ? 0 : (code >= K ? K - 1 : code);
   const float* cr = codebook + ((size_t)g * K + code) * D;
-  float* zp = out + ((frame * num + g) * (long long)D) * hw + s;
-  for (int j = 0; j < D; ++j) zp[(long long)j * hw] = __ldg(cr + j);
+  const long long base = frame * (long long)num * D * hw + (long long)s * pos_stride + (long long)g * D * ch_stride;
+  for (int j = 0; j < D; ++j) {
+    const float v = __ldg(cr + j);
+    if (out) out[base + (long long)j * ch_stride] = v;
+    if (out_bf16) out_bf16[base + (long long)j * ch_stride] = __float2bfloat16(v);
+  }
 }
 
 // EMA update for one codebook group per block (vq_embedding.py:48-59). n = sum(running_size) is
@@ -255,15 +269,15 @@ __global__ void vq_ema_kernel(float* __restrict__ codebook, float* __restrict__ 
 
 }  // namespace
 
-extern "C" int lvt_vq_argmin(const float* z_e, const float* codebook, int64_t* idx_out,
-                             float* zq_out, float* counts, float* sums, int n, int num, int K, int D,
-                             int hw, void* stream_) {
-  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+static int vq_argmin_impl(const float* z_e, const float* codebook, int64_t* idx_out, float* zq_out,
+                          void* zq_bf16, float* counts, float* sums, int n, int num, int K, int D, int hw,
+                          bool nhwc, cudaStream_t stream) {
   LVT_CHECK_ARG(n >= 0 && num > 0 && K > 0 && D > 0 && hw > 0, "lvt_vq_argmin: bad shape");
   LVT_CHECK_ARG(D % 8 == 0, "lvt_vq_argmin: D must be a multiple of 8 (got %d)", D);
   if (n == 0) return LVT_OK;
   LVT_CHECK_ARG(z_e && codebook && idx_out, "lvt_vq_argmin: null pointer");
   const long long total = (long long)n * hw;
+  const long long pos_stride = nhwc ? (long long)num * D : 1, ch_stride = nhwc ? 1 : hw;
   if (D == 64 && K % 4 == 0 && (size_t)K * D * 4 + K * 4 <= 200 * 1024) {
     const size_t smem = (size_t)K * D * 4 + (size_t)K * 4;
     static bool configured = false;
@@ -273,14 +287,16 @@ extern "C" int lvt_vq_argmin(const float* z_e, const float* codebook, int64_t* i
       configured = true;
     }
     dim3 grid(lvt_ceil_div(total, VQ_THREADS), num);
-    vq_argmin_smem_kernel<64><<<grid, VQ_THREADS, smem, stream>>>(z_e, codebook, idx_out, zq_out,
-                                                                  counts, sums, total, num, K, hw);
+    vq_argmin_smem_kernel<64><<<grid, VQ_THREADS, smem, stream>>>(
+        z_e, codebook, idx_out, zq_out, reinterpret_cast<__nv_bfloat16*>(zq_bf16), counts, sums, total, num, K, hw,
+        pos_stride, ch_stride);
     LVT_CHECK_LAUNCH();
     lvt_count_launch(1);
     return LVT_OK;
   }
-  // generic path needs |c|^2 scratch: reuse the tail of idx_out? No — keep caller-owned buffers
-  // untouched and use a small stream-ordered allocation.
+  LVT_CHECK_ARG(!nhwc && !zq_bf16, "lvt_vq_argmin: the generic (D != 64) path supports NCHW fp32 only");
+  // generic path needs |c|^2 scratch: keep caller-owned buffers untouched and use a small
+  // stream-ordered allocation.
   float* csq = nullptr;
   LVT_CHECK_CUDA(cudaMallocAsync(&csq, (size_t)num * K * sizeof(float), stream));
   vq_csq_kernel<<<lvt_ceil_div((long long)num * K, 128), 128, 0, stream>>>(codebook, csq, num * K, D);
@@ -293,18 +309,42 @@ extern "C" int lvt_vq_argmin(const float* z_e, const float* codebook, int64_t* i
   return LVT_OK;
 }
 
-extern "C" int lvt_vq_gather(const int64_t* idx, const float* codebook, float* out, int n, int num,
-                             int K, int D, int hw, void* stream_) {
-  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+extern "C" int lvt_vq_argmin(const float* z_e, const float* codebook, int64_t* idx_out,
+                             float* zq_out, float* counts, float* sums, int n, int num, int K, int D,
+                             int hw, void* stream_) {
+  return vq_argmin_impl(z_e, codebook, idx_out, zq_out, nullptr, counts, sums, n, num, K, D, hw, false,
+                        reinterpret_cast<cudaStream_t>(stream_));
+}
+
+extern "C" int lvt_vq_argmin_nhwc(const float* z_e, const float* codebook, int64_t* idx_out, float* zq_out,
+                                  void* zq_bf16, float* counts, float* sums, int n, int num, int K, int D,
+                                  int hw, void* stream_) {
+  return vq_argmin_impl(z_e, codebook, idx_out, zq_out, zq_bf16, counts, sums, n, num, K, D, hw, true,
+                        reinterpret_cast<cudaStream_t>(stream_));
+}
+
+static int vq_gather_impl(const int64_t* idx, const float* codebook, float* out, void* out_bf16, int n, int num,
+                          int K, int D, int hw, bool nhwc, cudaStream_t stream) {
   LVT_CHECK_ARG(n >= 0 && num > 0 && K > 0 && D > 0 && hw > 0, "lvt_vq_gather: bad shape");
   if (n == 0) return LVT_OK;
-  LVT_CHECK_ARG(idx && codebook && out, "lvt_vq_gather: null pointer");
+  LVT_CHECK_ARG(idx && codebook && (out || out_bf16), "lvt_vq_gather: null pointer");
   const long long total = (long long)n * hw;
   dim3 grid(lvt_ceil_div(total, 256), num);
-  vq_gather_kernel<<<grid, 256, 0, stream>>>(idx, codebook, out, total, num, K, D, hw);
+  vq_gather_kernel<<<grid, 256, 0, stream>>>(idx, codebook, out, reinterpret_cast<__nv_bfloat16*>(out_bf16), total,
+                                             num, K, D, hw, nhwc ? (long long)num * D : 1, nhwc ? 1 : hw);
   LVT_CHECK_LAUNCH();
   lvt_count_launch(1);
   return LVT_OK;
+}
+
+extern "C" int lvt_vq_gather(const int64_t* idx, const float* codebook, float* out, int n, int num,
+                             int K, int D, int hw, void* stream_) {
+  return vq_gather_impl(idx, codebook, out, nullptr, n, num, K, D, hw, false, reinterpret_cast<cudaStream_t>(stream_));
+}
+
+extern "C" int lvt_vq_gather_nhwc(const int64_t* idx, const float* codebook, float* out, void* out_bf16, int n,
+                                  int num, int K, int D, int hw, void* stream_) {
+  return vq_gather_impl(idx, codebook, out, out_bf16, n, num, K, D, hw, true, reinterpret_cast<cudaStream_t>(stream_));
 }
 
 extern "C" int lvt_vq_ema_update(float* codebook, float* running_size, float* running_sum,
