@@ -290,6 +290,46 @@ def main():
                               "note": "exact fp32 SIMT distance math (262144 FLOP/position): bound by CUDA-core "
                                       "FFMA throughput, not HBM, in this round"}
         del z, a, w, o
+        # VQ-VAE (PR-DVQVAE2) on synthetic 16-frame 64x64 clips: 32 clips = 512 frames per step
+        # (configs/vqvae/Base-VQVAE.yaml IMS_PER_BATCH 32); second half of BASELINE.json's metric.
+        try:
+            from lvt_b200.modeling.vqvae_engine import VQVAEEngine, VQVAESpec
+            nfr = 512
+            ve = VQVAEEngine(VQVAESpec(n_layers=2))
+            gq = torch.Generator().manual_seed(7)
+            init_w = {}
+            for name, shp in VQVAESpec(n_layers=2).param_shapes().items():
+                fan = 1
+                for s_ in shp[1:]:
+                    fan *= s_
+                init_w[name] = torch.randn(shp, generator=gq) / (fan ** 0.5) if len(shp) > 1 else torch.zeros(shp)
+            ve.store.load(init_w)
+            ve.load_state_dict(codebook=torch.randn(4, 512, 64, generator=gq) * 0.3,
+                               running_size=torch.full((4, 512), 5.0))
+            ve.init_optimizer(lr=3e-4, betas=(0.9, 0.9))
+            vw = ve.workspace(nfr, train=True)
+            vw.x.copy_(torch.rand((nfr, 3, 64, 64), generator=gq))
+            for _ in range(3):
+                ve.train_step(vw)
+            e0.record()
+            for _ in range(10):
+                ve.train_step(vw)
+            e1.record(); torch.cuda.synchronize()
+            t_tr = e0.elapsed_time(e1) / 10 * 1e-3
+            for _ in range(2):
+                ve.inference(vw)
+            e0.record()
+            for _ in range(10):
+                ve.inference(vw)
+            e1.record(); torch.cuda.synchronize()
+            t_inf = e0.elapsed_time(e1) / 10 * 1e-3
+            extra["vqvae"] = {"train_frames_per_s": nfr / t_tr, "train_ms_per_step": t_tr * 1e3,
+                              "inference_frames_per_s": nfr / t_inf, "frames_per_step": nfr,
+                              "train_tflops": 5.57e9 * nfr / t_tr / 1e12, "train_frac_of_bf16_peak": 5.57e9 * nfr / t_tr / 1e12 / tf_sust,
+                              "losses": vw.loss.tolist(),
+                              "note": "PR-DVQVAE2 fwd+bwd+Adam+EMA, eager launches (no CUDA graph), 5.57 GFLOP/frame"}
+        except Exception as ex:  # the DSFVT line must survive a VQ-VAE problem
+            extra["vqvae"] = {"error": repr(ex)[:300]}
 
     if rank != 0:
         return

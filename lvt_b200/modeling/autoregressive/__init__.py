@@ -1,1 +1,3 @@
-from .vt_engine import VTEngine, VTSpec, VTWorkspace  # noqa: F401
+from .vt_engine import GraphedTrainStep, VTEngine, VTSpec, VTWorkspace  # noqa: F401
+from .videotransformer import (AUTOREGRESSIVE_REGISTRY, Autoregressive, VideoTransformer,  # noqa: F401
+                               build_autoregressive)

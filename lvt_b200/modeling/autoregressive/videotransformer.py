@@ -1,0 +1,142 @@
+"""`VideoTransformer` with the reference's constructor / forward surface
+(vidgen/modeling/autoregressive/videotransformer.py:190-248, build.py:6-29), executing on VTEngine.
+Parameters / buffers carry the reference's state_dict names and shapes."""
+import logging
+
+import numpy as np
+import torch
+from torch import nn
+
+from ...utils.registry import Registry
+from ..param_tree import ParamTree, attach_store
+from .vt_engine import VTEngine, VTSpec
+
+AUTOREGRESSIVE_REGISTRY = Registry("AUTOREGRESSIVE")
+
+
+class Autoregressive(ParamTree):
+    """Base class of autoregressive models (reference autoregressive/autoregressive.py:8-27)."""
+
+
+def build_autoregressive(cfg, **kwargs):
+    """`cfg.MODEL.AUTOREGRESSIVE.NAME` -> instance (reference autoregressive/build.py:16-29)."""
+    model = AUTOREGRESSIVE_REGISTRY.get(cfg.MODEL.AUTOREGRESSIVE.NAME).from_config(cfg, **kwargs)
+    assert isinstance(model, Autoregressive)
+    logging.getLogger(__name__).info(
+        "#params in autoregressive: {}M".format(sum(p.numel() for p in model.parameters()) / 1e6))
+    return model
+
+
+@AUTOREGRESSIVE_REGISTRY.register()
+class VideoTransformer(Autoregressive):
+    @classmethod
+    def from_config(cls, cfg, **kwargs):
+        vt = cfg.MODEL.AUTOREGRESSIVE.VT
+        return cls(nc=vt.NC, nv=vt.NV, kernel_size=vt.KERNEL, stride=vt.STRIDE, d=vt.D, da=vt.DA, de=vt.DE,
+                   blocks_e=vt.BLOCKS_E, n_head_e=vt.N_HEAD_E, blocks_d=vt.BLOCKS_D, n_head_d=vt.N_HEAD_D,
+                   pad_value=vt.PAD_VALUE, share_p=vt.SHARE_P, share_embeddings=vt.SHARE_EMBEDDINGS,
+                   class_num=vt.CLASS_NUM, device=cfg.MODEL.DEVICE)
+
+    def __init__(self, nc, nv, da, de, d, blocks_e, n_head_e, kernel_size, stride, blocks_d, n_head_d, pad_value,
+                 share_p, share_embeddings, class_num, device="cuda"):
+        super().__init__()
+        self.nv = nv
+        spec = VTSpec(nc=nc, nv=nv, kernel=kernel_size, stride=stride, de=de, d=d, da=da, blocks_e=blocks_e,
+                      heads_e=n_head_e, blocks_d=blocks_d, heads_d=n_head_d, pad_value=pad_value, share_p=share_p,
+                      share_embeddings=share_embeddings, class_num=class_num)
+        object.__setattr__(self, "engine", VTEngine(spec, device))  # not a sub-module
+        attach_store(self, self.engine.store)
+        self._register_reference_buffers(spec)
+        self._reset_parameters(spec)
+
+    # buffers the reference keeps in its state_dict (vt_attention.py:24,146-167; not used by the kernels,
+    # which derive the same quantities from the block shape)
+    def _register_reference_buffers(self, spec):
+        dev = self.engine.device
+        t, h, w = spec.block
+        L = t * h * w
+        idx = torch.arange(L)
+        comp = {"dt": idx // (h * w), "dh": (idx // w) % h, "dw": idx % w}
+        for side, n in (("encoder", len(spec.blocks_e)), ("decoder", len(spec.blocks_d))):
+            n_ts = (spec.de if side == "encoder" else spec.d) // 6
+            inc = np.log(1.0e4) / n_ts
+            self.add_buffer(f"{side}.positional_encoder.inv_timescales",
+                            torch.exp(torch.arange(n_ts).float() * -inc).to(dev))
+            for i in range(n):
+                for name, c in comp.items():
+                    diff = c[:, None] - c[None, :]
+                    self.add_buffer(f"{side}.block_local_attention.{i}.{name}", (diff - diff.min()).reshape(-1).to(dev))
+                if side == "decoder":
+                    self.add_buffer(f"{side}.block_local_attention.{i}.mask",
+                                    torch.triu(torch.ones(1, 1, L, L), diagonal=1).to(dev))
+
+    @torch.no_grad()
+    def _reset_parameters(self, spec):
+        """Default initialisation of the reference modules (nn.Conv3d / nn.Linear / nn.Embedding / LayerNorm
+        defaults, xavier_normal_ for w_q/w_k/w_v/proj, zero banks, MaskedConv3d weight = ones:
+        vt_attention.py:107-111,142-144, vt_utils.py:192-193); VideoTransformerModel.init_weights then applies
+        MODEL.INIT_TYPE on top, as in the reference."""
+        for name, p in self.named_parameters():
+            if name.endswith("_bank"):
+                p.zero_()
+            elif "layer_norm.weight" in name or name.endswith("ffn.0.weight"):
+                p.fill_(1.0)
+            elif "layer_norm.bias" in name or name.endswith("ffn.0.bias"):
+                p.zero_()
+            elif ".mha.w_" in name or name.endswith("mha.proj.weight"):
+                nn.init.xavier_normal_(p)
+            elif "embed" in name:
+                p.normal_()
+            elif name == "decoder.conv.conv.weight":
+                p.fill_(1.0)
+            elif p.dim() > 1:
+                nn.init.kaiming_uniform_(p.view(p.shape[0], -1), a=5 ** 0.5)
+            else:
+                p.uniform_(-0.05, 0.05)
+        self.engine.store.p["decoder.conv.conv.weight"][:, :, -1, -1, 1:] = 0
+        self.engine.shadows_fresh = False
+
+    def load_state_dict(self, state_dict, strict=True):
+        out = super().load_state_dict(state_dict, strict=strict)
+        with torch.no_grad():
+            self.engine.store.p["decoder.conv.conv.weight"][:, :, -1, -1, 1:] = 0
+        self.engine.shadows_fresh = False
+        return out
+
+    def _stage(self, context, slc, slice_idx, ignore_mask, train):
+        eng = self.engine
+        B = context.shape[0]
+        ws = eng.workspace(B, tuple(slc.shape[2:]), tuple(context.shape[2:]), train=train)
+        eng.set_inputs(ws, context, slc, slice_idx, ignore_mask)
+        return ws
+
+    def forward(self, context, slice, slice_idx, mode="logits", pixel=None, zl=None, temp=1.0, drop_mask=None,
+                class_idx=None):
+        """context (b, nc, T, H, W), slice (b, nc, t, h, w), slice_idx (b,) int64 — as in the reference.
+        mode "logits": list of nc tensors (b, nv, t, h, w).  mode "sample_pixel": (codes (b, nc), zl)."""
+        eng, spec = self.engine, self.engine.spec
+        b = context.shape[0]
+        t, h, w = slice.shape[2:]
+        if mode == "logits":
+            ws = self._stage(context, slice, slice_idx, None, train=False)
+            eng.forward(ws, train=False, want_loss=False)
+            lg = ws.logits.view(spec.nc, b, t, h, w, spec.nv)
+            return [lg[k].permute(0, 4, 1, 2, 3).contiguous() for k in range(spec.nc)]
+        if mode == "sample_pixel":
+            ws = self._stage(context, slice, slice_idx, None, train=False)
+            if zl is None:
+                eng.encoder_forward(ws, train=False)  # cached across the pixels of one slice, like `zl`
+                zl = ws
+            eng.decoder_forward(ws, train=False)
+            ti, hi, wi = pixel
+            pos = (ti * h + hi) * w + wi
+            out = torch.zeros(b, spec.nc, dtype=torch.int64, device=ws.slice.device)
+            for k in range(spec.nc):
+                eng.predictor_forward(ws, channels=[k])
+                logits = ws.logits[k].view(b, t * h * w, spec.nv)[:, pos]
+                prob = torch.softmax(logits / temp, 1)
+                sample = torch.multinomial(prob, 1).squeeze(-1)
+                out[:, k] = sample
+                ws.slice.view(b, spec.nc, -1)[:, k, pos] = sample  # feeds the one-hot half of U[k+1]
+            return out, zl
+        raise ValueError("|mode| is invalid")

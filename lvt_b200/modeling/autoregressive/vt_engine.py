@@ -497,22 +497,16 @@ class VTEngine:
         else:
             ws.ignore.zero_()
 
-    def forward(self, ws: VTWorkspace, train=True, want_loss=True):
-        """VideoTransformer.forward(mode="logits") (videotransformer.py:232-239) [+ the CE loss of
-        meta_arch/vt.py:305-312].  Results: ws.logits [nc, M, nv] fp32, ws.loss."""
+    def _layer_ws(self, ws, i, train):
+        return ws.layers[i] if train else ws.layers[0]
+
+    def encoder_forward(self, ws: VTWorkspace, train=True):
+        """VTEncoder.forward (videotransformer.py:35-59): ws.context, ws.slice_idx -> ws.zl_bf16."""
         s, st = self.spec, self.store
         if not self.shadows_fresh:
             self.refresh_shadows()
         M, d, de, nv, nc = ws.M, s.d, s.de, s.nv, s.nc
-        t, h, w = ws.slice_shape
-        taps, offs, wp, dwp = self._live_taps(ws.slice_shape)
-        ntaps = len(taps)
-        nE, nD = len(s.blocks_e), len(s.blocks_d)
-
-        def layer(i):
-            return ws.layers[i] if train else ws.layers[0]
-
-        # ---- encoder (videotransformer.py:35-59)
+        nE = len(s.blocks_e)
         check(self.lib.lvt_vt_enc_front_fwd(ptr(ws.context), ptr(ws.slice_idx), ptr(self.enc_wt),
                                             _vp(st.pf("encoder.conv.bias")),
                                             _vp(st.pf("encoder.slice_embedding.weight")), ptr(ws.e0), ws.B, nc, nv,
@@ -522,12 +516,22 @@ class VTEngine:
              Operand(ws.x0.data_ptr(), d), out_f32=ws.x0)
         x = ws.x0
         for i in range(nE):
-            ly = layer(i)
+            ly = self._layer_ws(ws, i, train)
             y = ly.y if train else (ws.y_alt if x is ly.y else ly.y)
             self._layer_fwd(f"encoder.block_local_attention.{i}.", ws, ly, x, y, causal=False,
                             y_bf16=ws.zl_bf16 if i == nE - 1 else None)
             x = y
-        # ---- decoder (videotransformer.py:91-101)
+
+    def decoder_forward(self, ws: VTWorkspace, train=True):
+        """VTDecoder.forward (videotransformer.py:91-101): ws.slice, ws.zl_bf16 -> ws.y_final, ws.ln_y."""
+        s, st = self.spec, self.store
+        M, d, de, nv, nc = ws.M, s.d, s.de, s.nv, s.nc
+        t, h, w = ws.slice_shape
+        taps, offs, wp, dwp = self._live_taps(ws.slice_shape)
+        if not self.shadows_fresh:
+            self.refresh_shadows()
+        ntaps = len(taps)
+        nE, nD = len(s.blocks_e), len(s.blocks_d)
         check(self.lib.lvt_vt_dec_front_fwd(ptr(ws.slice), _vp(st.pf("decoder.ch_embedder.0.weight")), ptr(offs),
                                             ptr(ws.A0), ws.B, nc, nv, de, t, h, w, ntaps, stream_ptr()),
               "lvt_vt_dec_front_fwd")
@@ -537,15 +541,19 @@ class VTEngine:
              Operand(ws.y0.data_ptr(), d), out_f32=ws.y0, res=ws.y0, bias=st.pf("decoder.conv.conv.bias"))
         x = ws.y0
         for i in range(nD):
-            ly = layer(nE + i)
+            ly = self._layer_ws(ws, nE + i, train)
             y = ly.y if train else (ws.y_alt if x is ly.y else ly.y)
             self._layer_fwd(f"decoder.block_local_attention.{i}.", ws, ly, x, y, causal=True)
             x = y
         ws.y_final = x
-        # ---- channel predictor (videotransformer.py:138-160)
         self._ln_fwd(x, st.pf("ch_predictor.layer_norm.weight"), st.pf("ch_predictor.layer_norm.bias"), ws.ln_y,
                      ws.mean_p, ws.rstd_p, M)
-        for k in range(nc):
+
+    def predictor_forward(self, ws: VTWorkspace, channels=None):
+        """ChannelPredictor (videotransformer.py:144-160) for the given channels: ws.ln_y, ws.slice -> ws.logits[k]."""
+        s, st = self.spec, self.store
+        M, d, nv, nc = ws.M, s.d, s.nv, s.nc
+        for k in (range(nc) if channels is None else channels):
             ld = d + k * nv
             gemm(M, d, d, Operand(ws.ln_y.data_ptr(), d), Operand(st.pb(f"ch_predictor.U.{k}.weight"), ld),
                  Operand(ws.u.data_ptr(), d), out_f32=ws.u, bias=st.pf(f"ch_predictor.U.{k}.bias"))
@@ -554,10 +562,18 @@ class VTEngine:
                   "lvt_chpred_combine_fwd")
             gemm(M, nv, d, Operand(ws.a[k].data_ptr(), d), Operand(st.pb(f"ch_predictor.P.{k}.weight"), d),
                  Operand(ws.logits[k].data_ptr(), nv), out_f32=ws.logits[k], bias=st.pf(f"ch_predictor.P.{k}.bias"))
+
+    def forward(self, ws: VTWorkspace, train=True, want_loss=True):
+        """VideoTransformer.forward(mode="logits") (videotransformer.py:232-239) [+ the CE loss of
+        meta_arch/vt.py:305-312].  Results: ws.logits [nc, M, nv] fp32, ws.loss."""
+        s = self.spec
+        self.encoder_forward(ws, train)
+        self.decoder_forward(ws, train)
+        self.predictor_forward(ws)
         if want_loss:
             check(self.lib.lvt_cross_entropy(ptr(ws.logits), ptr(ws.slice), ptr(ws.ignore),
                                              ptr(ws.dlogits) if train else None, ptr(ws.loss), ptr(ws.count),
-                                             ws.B, nc, nv, ws.thw, stream_ptr()), "lvt_cross_entropy")
+                                             ws.B, s.nc, s.nv, ws.thw, stream_ptr()), "lvt_cross_entropy")
         return ws.loss
 
     def backward(self, ws: VTWorkspace):

@@ -221,6 +221,7 @@ class VQVAEEngine:
         w.x_tilde = e((n, 3, 64, 64), f32)
         w.recon = e((n, 3, 64, 64), f32)
         w.loss = torch.zeros((2,), dtype=f32, device=self.device)  # [reconstruction, commitment]
+        w.loss_scratch = torch.zeros((1,), dtype=f32, device=self.device)
         if train:
             w.dpre = e((n, 3, 64, 64), f32)
             w.dact32 = e((4 * M, nf // 2))
@@ -386,6 +387,8 @@ class VQVAEEngine:
         check(self.lib.lvt_vqvae_recon_loss(ptr(w.x_tilde), ptr(w.x), ptr(w.dpre), ptr(w.loss),
                                             _vp(self.store.gf(f"G.layers.{k + 3}.bias")), w.n, s.mean, s.std,
                                             s.pixel_lambda, stream_ptr()), "lvt_vqvae_recon_loss")
+        check(self.lib.lvt_vqvae_commit_loss(ptr(w.z_e), ptr(w.zq_bar), None, None, _vp(w.loss.data_ptr() + 4),
+                                             w.M * s.nf, s.beta, stream_ptr()), "lvt_vqvae_commit_loss")
 
     def backward(self, w):
         s, st = self.spec, self.store
@@ -419,7 +422,7 @@ class VQVAEEngine:
                    f32=True)
         # ---- straight-through + commitment -> gradient wrt z_e
         check(self.lib.lvt_vqvae_commit_loss(ptr(w.z_e), ptr(w.zq_bar), ptr(w.dz_st), ptr(d_out),
-                                             _vp(w.loss.data_ptr() + 4), M * nf, s.beta, stream_ptr()),
+                                             ptr(w.loss_scratch), M * nf, s.beta, stream_ptr()),
               "lvt_vqvae_commit_loss")
         # ---- encoder blocks (z_e is the un-ReLU'd output of the last block)
         if L == 0:

@@ -1,0 +1,86 @@
+"""GPU: the reference-facing Python surface (registries, build_model, forward(data, mode), Trainer, sampling)
+drives the same engines; state_dict keys equal the reference's."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+SMALL = ["MODEL.AUTOREGRESSIVE.VT.BLOCKS_E", ((1, 16, 16),) * 2, "MODEL.AUTOREGRESSIVE.VT.N_HEAD_E", (8, 8),
+         "MODEL.AUTOREGRESSIVE.VT.BLOCKS_D", ((1, 16, 16),) * 2, "MODEL.AUTOREGRESSIVE.VT.N_HEAD_D", (8, 8)]
+
+
+def test_vt_model_state_dict_and_logits_match_oracle(cuda_lib, tmp_path):
+    from lvt_b200.config.presets import preset
+    from lvt_b200.modeling import build_model
+    from oracle import lvt_oracle as O
+    cfg = preset("DSFVT", SMALL + ["OUTPUT_DIR", str(tmp_path)])
+    cfg.freeze()
+    model = build_model(cfg)
+    ocfg = O.VTConfig(blocks_e=((1, 16, 16),) * 2, heads_e=(8, 8), blocks_d=((1, 16, 16),) * 2, heads_d=(8, 8))
+    shapes = O.dsfvt_param_shapes(ocfg)
+    sd = model.model.state_dict()
+    assert {k: tuple(v.shape) for k, v in sd.items() if k in shapes} == {k: tuple(v) for k, v in shapes.items()}
+    extra = set(sd) - set(shapes)   # the reference's buffers
+    assert all(k.endswith((".dt", ".dh", ".dw", ".mask", "inv_timescales")) for k in extra), extra
+    weights = O.synth_weights(shapes, seed=1234)
+    model.model.load_state_dict(weights, strict=False)
+    # BitsEvaluator path: teacher-forced logits of a whole video (meta_arch/vt.py:230-282)
+    video = O.synth_latent_video(3, ocfg)
+    cfg2 = preset("DSFVT", SMALL + ["TEST.EVALUATORS", "BitsEvaluator", "OUTPUT_DIR", str(tmp_path)])
+    model.cfg = cfg2
+    model.train(False)
+    out = model([{"image_sequence": video}])[0]
+    assert out["logits"].shape == (4, 512, 16, 16, 16) and out["ignore_mask"][0, 0].all() and not out["ignore_mask"][0, 1].any()
+    # oracle logits for slice a = 5
+    sample = O.prepare_slice(video, (5, 0, 0), ocfg)
+    with torch.no_grad():
+        want = torch.stack(O.vt_logits(sample["context"][None], sample["slice"][None], sample["slice_idx"][None], weights, ocfg))
+    got = out["logits"][:, :, 5].cpu()            # (nc, nv, H, W)
+    want = want[:, 0, :, 0]                       # (nc, nv, h, w)
+    assert (got - want).abs().max().item() <= 2e-2 * want.abs().max().item()
+
+
+def test_trainer_runs_supervised_steps(cuda_lib, tmp_path):
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import train_net
+    from lvt_b200.config.presets import preset
+    from lvt_b200.engine import Trainer
+    for name, over in (("DSFVT", SMALL + ["SOLVER.IMS_PER_BATCH", 4]), ("PR-DVQVAE2", ["SOLVER.IMS_PER_BATCH", 8])):
+        cfg = preset(name, over + ["SOLVER.MAX_ITER", 3, "SOLVER.CHECKPOINT_PERIOD", 0, "OUTPUT_DIR", str(tmp_path / name), "SEED", 1])
+        cfg.freeze()
+        tr = Trainer(cfg, data_loader=train_net.synthetic_loader(cfg))
+        tr.train()
+        hist = tr.storage.history("total_loss")
+        assert len(hist) >= 1 and all(np.isfinite(v) for v, _ in hist)
+        assert os.path.exists(tmp_path / name / ("netG" if name == "DSFVT" else "netE") / "model_final.pth")
+
+
+def test_vqvae_model_inference_and_sampling_roundtrip(cuda_lib, tmp_path):
+    from lvt_b200.config.presets import preset
+    from lvt_b200.modeling import build_model
+    cfg = preset("PR-DVQVAE2", ["OUTPUT_DIR", str(tmp_path)])
+    cfg.freeze()
+    vq = build_model(cfg)
+    vq.train(False)
+    frames = torch.rand(5, 3, 64, 64)
+    out = vq([{"image_sequence": frames}])[0]
+    assert out["latent"].shape == (5, 4, 16, 16) and out["latent"].dtype == torch.int64
+    assert out["reconstruction"].shape == (5, 3, 64, 64)
+    assert torch.equal(vq.encode(frames.cuda()), out["latent"])
+    dec = vq.decode(out["latent"])
+    assert torch.allclose(vq.back_normalizer(dec).clamp_(0, 1), out["reconstruction"], atol=1e-6)
+    # VT sampling of one frame after 15 primed ones (vt.py:81-136), 2+2 layers
+    cfgv = preset("DSFVT", SMALL + ["TEST.EVALUATORS", "VTSampler", "TEST.VT_SAMPLER.N_PRIME", 15,
+                                    "TEST.VT_SAMPLER.NUM_SAMPLES", 1, "OUTPUT_DIR", str(tmp_path)])
+    cfgv.freeze()
+    vt = build_model(cfgv)
+    vt.train(False)
+    seq = torch.randint(0, 512, (16, 4, 16, 16))
+    torch.manual_seed(0)
+    sample = vt([{"image_sequence": seq}])[0]["samples"][0]
+    assert sample.shape == (4, 16, 16, 16)
+    assert torch.equal(sample[:, :15].cpu(), seq.transpose(0, 1)[:, :15])
+    assert int(sample.min()) >= 0 and int(sample.max()) < 512

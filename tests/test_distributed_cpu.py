@@ -1,0 +1,58 @@
+"""CPU, world_size 2 over gloo (127.0.0.1): host-side logic of the data-parallel path — rank helpers,
+in-place gradient / EMA-statistics all-reduce, per-rank batch sharding and seeding of the loader."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from lvt_b200.utils import comm
+    assert comm.get_world_size() == world and comm.get_rank() == rank and comm.is_main_process() == (rank == 0)
+    # flat-gradient all-reduce followed by the optimizer's 1/world scaling == DDP's gradient averaging
+    g = torch.full((1000,), float(rank + 1))
+    comm.all_reduce_sum_(g)
+    assert torch.equal(g, torch.full((1000,), 3.0))
+    avg = g * (1.0 / world)
+    assert torch.allclose(avg, torch.full((1000,), 1.5))
+    # EMA statistics: counts / sums are summed over ranks before the codebook update (vq_embedding.py:46-54)
+    counts = torch.zeros(4, 512)
+    counts[rank, rank] = 7.0
+    comm.all_reduce_sum_(counts)
+    assert counts[0, 0] == 7.0 and counts[1, 1] == 7.0 and counts.sum() == 14.0
+    # loader: per-rank batch = IMS_PER_BATCH / world, rank-dependent stream
+    import train_net
+    from lvt_b200.config.presets import preset
+    cfg = preset("DSFVT", ["SOLVER.IMS_PER_BATCH", 8, "SEED", 5])
+    batch = next(train_net.synthetic_loader(cfg))
+    assert len(batch) == 4 and batch[0]["context"].shape == (4, 7, 16, 16)
+    sig = torch.stack([b["slice"].sum() for b in batch]).sum().item()
+    sigs = [None, None]
+    dist.all_gather_object(sigs, sig)
+    assert sigs[0] != sigs[1]
+    comm.synchronize()
+    out.put((rank, "ok"))
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_host_logic():
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = 29000 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    got = sorted(out.get(timeout=5) for _ in range(2))
+    assert got == [(0, "ok"), (1, "ok")]

@@ -79,6 +79,8 @@ def test_vqvae_train_step_vs_oracle(cuda_lib):
     assert eng.lib.lvt_vqvae_recon_loss(w.x_tilde.data_ptr(), w.x.data_ptr(), w.dpre.data_ptr(), w.loss.data_ptr(),
                                         eng.store.gf(f"G.layers.{k + 3}.bias"), n, 0.5, 0.5, 1.0,
                                         torch.cuda.current_stream().cuda_stream) == 0
+    assert eng.lib.lvt_vqvae_commit_loss(w.z_e.data_ptr(), w.zq_bar.data_ptr(), None, None, w.loss.data_ptr() + 4,
+                                         w.M * 256, 1.0, torch.cuda.current_stream().cuda_stream) == 0
     eng.backward(w)
     torch.cuda.synchronize()
 
