@@ -17,6 +17,10 @@
 #include "common.cuh"
 
 extern void lvt_count_launch(int n);
+// tensor-core scan + exact re-rank (vq_tc.cu); returns 1 when the shape is not covered
+int lvt_vq_argmin_tc_try(const float* z_e, const float* codebook, int64_t* idx_out, float* zq_out, void* zq_bf16,
+                         float* counts, float* sums, int n, int num, int K, int D, int hw, bool nhwc,
+                         cudaStream_t stream);
 
 namespace {
 
@@ -276,6 +280,11 @@ static int vq_argmin_impl(const float* z_e, const float* codebook, int64_t* idx_
   LVT_CHECK_ARG(D % 8 == 0, "lvt_vq_argmin: D must be a multiple of 8 (got %d)", D);
   if (n == 0) return LVT_OK;
   LVT_CHECK_ARG(z_e && codebook && idx_out, "lvt_vq_argmin: null pointer");
+  {
+    const int rc = lvt_vq_argmin_tc_try(z_e, codebook, idx_out, zq_out, zq_bf16, counts, sums, n, num, K, D, hw, nhwc,
+                                        stream);
+    if (rc <= 0) return rc;  // launched (0) or failed (<0); 1 = not covered -> SIMT kernel below
+  }
   const long long total = (long long)n * hw;
   const long long pos_stride = nhwc ? (long long)num * D : 1, ch_stride = nhwc ? 1 : hw;
   if (D == 64 && K % 4 == 0 && (size_t)K * D * 4 + K * 4 <= 200 * 1024) {

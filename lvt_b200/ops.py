@@ -46,6 +46,23 @@ def vq_argmin(z_e, codebook, want_zq=False, counts=None, sums=None):
     return (idx, zq) if want_zq else idx
 
 
+def vq_argmin_nhwc(z_e, codebook, hw, want_zq=False, want_zq_bf16=False, counts=None, sums=None):
+    """Channels-last variant: z_e [n*hw, num*D] fp32 -> idx [n, num, hw] int64 (+ z_q fp32 / bf16 [n*hw, num*D])."""
+    lib = _lib.require_device()
+    _cuda_contig(z_e, torch.float32, "z_e")
+    _cuda_contig(codebook, torch.float32, "codebook")
+    M, c = z_e.shape
+    num, K, D = codebook.shape
+    assert c == num * D and M % hw == 0
+    n = M // hw
+    idx = torch.empty((n, num, hw), dtype=torch.int64, device=z_e.device)
+    zq = torch.empty_like(z_e) if want_zq else None
+    zqb = torch.empty_like(z_e, dtype=torch.bfloat16) if want_zq_bf16 else None
+    check(lib.lvt_vq_argmin_nhwc(ptr(z_e), ptr(codebook), ptr(idx), ptr(zq), ptr(zqb), ptr(counts), ptr(sums),
+                                 n, num, K, D, hw, stream_ptr()), "lvt_vq_argmin_nhwc")
+    return idx, zq, zqb
+
+
 def vq_gather(idx, codebook):
     """idx [n, num, h, w] int64 -> [n, num*D, h, w] fp32 NCHW (vq_embedding.py:92-97 + permute)."""
     lib = _lib.require_device()

@@ -94,3 +94,38 @@ def test_vq_gather_and_ema(cuda_lib):
     assert torch.allclose(rs_d.cpu(), torch.stack(rs_new), rtol=1e-5, atol=1e-6)
     assert torch.allclose(rsum_d.cpu(), torch.stack(rsum_new), rtol=1e-4, atol=1e-5)
     assert torch.allclose(cbc.cpu(), torch.stack(cb_new), rtol=2e-4, atol=1e-5)
+
+
+def test_vq_tensor_core_path_matches_exact_path_on_adversarial_codebooks(cuda_lib):
+    """The tcgen05 scan + exact re-rank must give the oracle's indices even when many codes are nearly
+    tied (near-duplicate rows, clustered codes, tiny default-init codebooks, large dynamic range)."""
+    from lvt_b200 import ops
+    from oracle import vq as ovq
+    g = torch.Generator().manual_seed(21)
+    n = 6
+    z = torch.randn((n, 256, 16, 16), generator=g) * 0.3
+    base = torch.randn((4, 512, 64), generator=g) * 0.3
+    cbs = {
+        "near_duplicates": base.clone(),
+        "clustered": (base[:, :8].repeat_interleave(64, dim=1) + 1e-3 * torch.randn((4, 512, 64), generator=g)),
+        "default_init": (torch.rand((4, 512, 64), generator=g) * 2 - 1) / 512,
+        "wide_range": base * torch.logspace(-3, 1, 512)[None, :, None],
+    }
+    cbs["near_duplicates"][:, 1::2] = cbs["near_duplicates"][:, 0::2] * (1 + 1e-6)
+    for name, cb in cbs.items():
+        idx = ops.vq_argmin(z.cuda(), cb.contiguous().cuda())
+        torch.cuda.synchronize()
+        want = ovq.vq_argmin_c(z, cb.contiguous())
+        bad = (idx.cpu() != want).sum().item()
+        assert bad == 0, f"{name}: {bad} index mismatches"
+    # EMA statistics / straight-through output through the same kernel
+    counts = torch.zeros((4, 512), device="cuda")
+    sums = torch.zeros((4, 512, 64), device="cuda")
+    cb = base.contiguous()
+    idx, zq = ops.vq_argmin(z.cuda(), cb.cuda(), want_zq=True, counts=counts, sums=sums)
+    torch.cuda.synchronize()
+    want = ovq.vq_argmin_c(z, cb)
+    assert torch.equal(idx.cpu(), want)
+    zq_want = torch.cat([cb[gg][want[:, gg]].permute(0, 3, 1, 2) for gg in range(4)], dim=1)
+    assert torch.equal(zq.cpu(), zq_want)
+    assert counts.sum().item() == n * 256 * 4
