@@ -13,7 +13,7 @@
 //   3. the reference's exact arithmetic on the candidates only (typically 1-2 of 512), lowest index
 //      wins ties  =>  bit-identical indices to the SIMT kernel / the oracle.
 // One CTA = one codebook group (its 128 KiB of -2*c stay resident), persistent over 128-position tiles;
-// warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 scan + re-rank; two 256-column TMEM buffers.
+// warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 scan + re-rank TMEM buffer 0 (codes 0-255), warps 6-9 buffer 1 (codes 256-511).
 #include <mutex>
 #include <stdlib.h>
 #include <string.h>
@@ -33,9 +33,13 @@ constexpr int A_BYTES = TM * TD * 4;        // 32 KiB
 constexpr int B_BYTES = 2 * TK * 128;       // two k-blocks of 32 fp32 (128 B rows)
 constexpr int SM_A = B_BYTES;
 constexpr int SM_C2 = SM_A + NSLOT * A_BYTES;
-constexpr int SM_BAR = SM_C2 + TK * 4;
+constexpr int LST_CAP = 16;                 // candidates kept per (position, half); more => exhaustive exact scan
+constexpr int SM_LST = SM_C2 + TK * 4;      // [LST_CAP][256] u16 candidate lists
+constexpr int SM_XMIN = SM_LST + LST_CAP * 256 * 2;  // [2][128] f32 per-half minima
+constexpr int SM_XBEST = SM_XMIN + 2 * TM * 4;       // [2][128] (d, idx) per-half winners
+constexpr int SM_BAR = SM_XBEST + 2 * TM * 8;
 constexpr int SM_TOTAL = SM_BAR + 256 + 1024;
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;             // TMA warp, MMA warp, 2 x 4 scan warps
 
 LVT_DEVICE_INLINE void tma_load_2d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
   asm volatile(
@@ -57,6 +61,7 @@ LVT_DEVICE_INLINE void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
       : "memory");
 }
 LVT_DEVICE_INLINE void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+LVT_DEVICE_INLINE void epi_bar(int id) { asm volatile("bar.sync %0, 256;" ::"r"(id) : "memory"); }
 LVT_DEVICE_INLINE float fmin3(float a, float b, float c) {
   float r;
   asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
@@ -111,6 +116,9 @@ vq_argmin_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __res
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   float* c2s = reinterpret_cast<float*>(smem + SM_C2);
+  uint16_t* lst = reinterpret_cast<uint16_t*>(smem + SM_LST);
+  float* xmin = reinterpret_cast<float*>(smem + SM_XMIN);
+  float2* xbest = reinterpret_cast<float2*>(smem + SM_XBEST);
   uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + SM_BAR);  // [NSLOT]
   uint64_t* a_empty = a_full + NSLOT;                              // [NSLOT]
   uint64_t* t_full = a_empty + NSLOT;                              // [2]
@@ -146,7 +154,7 @@ vq_argmin_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __res
 #pragma unroll
     for (int s = 0; s < NSLOT; ++s) {
       mbar_init(&a_full[s], 1);
-      mbar_init(&a_empty[s], 4);
+      mbar_init(&a_empty[s], 8);
     }
     mbar_init(&t_full[0], 1);
     mbar_init(&t_full[1], 1);
@@ -219,10 +227,13 @@ vq_argmin_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __res
     }
   } else {
     // ------------------------------------------------------------------ scan + exact re-rank
+    // Two groups of four warps; group h owns TMEM buffer h (codes h*256 .. h*256+255) of every tile.
+    const int h = (warp - 2) >> 2;
     const int q = warp & 3;
     const int m = q * 32 + lane;  // row (position) inside the tile
-    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    auto init_c2 = [&](int h) {
+    const int et = h * TM + m;    // epilogue thread id 0..255
+    const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + h * 256;
+    auto init_c2 = [&]() {
 #pragma unroll 1
       for (int c = 0; c < 8; ++c) {
         uint32_t r[32];
@@ -233,15 +244,28 @@ vq_argmin_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __res
           r[4 * i] = __float_as_uint(v.x); r[4 * i + 1] = __float_as_uint(v.y);
           r[4 * i + 2] = __float_as_uint(v.z); r[4 * i + 3] = __float_as_uint(v.w);
         }
-        tmem_st_32x32(lane_addr + h * 256 + c * 32, r);
+        tmem_st_32x32(t_addr + c * 32, r);
       }
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&t_empty[h]);
     };
-    init_c2(0);
-    init_c2(1);
+    // exact reference distance of code k (sequential fp32 FMA chain over the 64 dims, vq.cu)
+    auto exact_d = [&](const float (&x)[TD], float x2, int k) {
+      const uint8_t* brow = smem + k * 128;
+      float acc = 0.f;
+#pragma unroll
+      for (int jj = 0; jj < 16; ++jj) {
+        const float4 v = *reinterpret_cast<const float4*>(brow + (jj >> 3) * (TK * 128) + (((jj & 7) ^ (k & 7)) << 4));
+        acc = __fmaf_rn(x[4 * jj], -0.5f * v.x, acc);
+        acc = __fmaf_rn(x[4 * jj + 1], -0.5f * v.y, acc);
+        acc = __fmaf_rn(x[4 * jj + 2], -0.5f * v.z, acc);
+        acc = __fmaf_rn(x[4 * jj + 3], -0.5f * v.w, acc);
+      }
+      return __fmaf_rn(-2.f, acc, __fadd_rn(c2s[k], x2));
+    };
+    init_c2();
     int it = 0;
     for (int tile = sub; tile < num_tiles; tile += ctas_per_group, ++it) {
       const int slot = it % NSLOT;
@@ -249,93 +273,122 @@ vq_argmin_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __res
       const int frame = (int)(pos / hw), s = (int)(pos - (long long)frame * hw);
       mbar_wait(&a_full[slot], (it / NSLOT) & 1);
       // this position's 64-dim vector from the swizzled tile
-      float x[TD];
-      if (NHWC) {
-        const uint8_t* at = smem + SM_A + slot * A_BYTES + m * 128;
+      const uint8_t* at = NHWC ? smem + SM_A + slot * A_BYTES + m * 128
+                               : smem + SM_A + slot * A_BYTES + (m >> 5) * 8192 + (m & 7) * 4;
+      const int mchunk = (m & 31) >> 3;  // NCHW: 32 B chunk of the 128 B row
+      auto load_x = [&](float (&x)[TD]) {
+        if (NHWC) {
 #pragma unroll
-        for (int jj = 0; jj < 16; ++jj) {
-          const float4 v = *reinterpret_cast<const float4*>(at + (jj >> 3) * 16384 + (((jj & 7) ^ (m & 7)) << 4));
-          x[4 * jj] = v.x; x[4 * jj + 1] = v.y; x[4 * jj + 2] = v.z; x[4 * jj + 3] = v.w;
+          for (int jj = 0; jj < 16; ++jj) {
+            const float4 v = *reinterpret_cast<const float4*>(at + (jj >> 3) * 16384 + (((jj & 7) ^ (m & 7)) << 4));
+            x[4 * jj] = v.x; x[4 * jj + 1] = v.y; x[4 * jj + 2] = v.z; x[4 * jj + 3] = v.w;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < TD; ++j) x[j] = *reinterpret_cast<const float*>(at + j * 128 + ((mchunk ^ (j & 3)) << 5));
         }
-      } else {
-        const uint8_t* at = smem + SM_A + slot * A_BYTES + (m >> 5) * 8192 + (m & 7) * 4;
-        const int mchunk = (m & 31) >> 3;  // 32 B chunk of the 128 B row
-#pragma unroll
-        for (int j = 0; j < TD; ++j) x[j] = *reinterpret_cast<const float*>(at + j * 128 + ((mchunk ^ (j & 3)) << 5));
+      };
+      float x2;
+      {
+        float x[TD];
+        load_x(x);
+        x2 = sqnorm64([&](int j) { return x[j]; });
       }
-      const float x2 = sqnorm64([&](int j) { return x[j]; });
       const float E = 1.1f * 0.00390625f * sqrtf(x2 * cmax2) + 3.8146973e-6f * (x2 + cmax2);
       const float W = 2.f * E;
-      float hmin[2];
-      uint32_t mask[2][8];
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        mbar_wait(&t_full[h], it & 1);
-        tc_fence_after();
-        if (h == 1) {  // all MMAs of this tile retired and x is in registers: release the A slot
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&a_empty[slot]);
-        }
-        uint32_t r[32];
+      mbar_wait(&t_full[h], it & 1);
+      tc_fence_after();
+      // pass 1: minimum tf32 score of this half (two TMEM loads in flight per wait)
+      {
         float m0 = INFINITY, m1 = INFINITY;
 #pragma unroll 1
-        for (int c = 0; c < 8; ++c) {
-          tmem_ld_32x32(lane_addr + h * 256 + c * 32, r);
+        for (int c = 0; c < 8; c += 2) {
+          uint32_t r0[32], r1[32];
+          tmem_ld_32x32(t_addr + c * 32, r0);
+          tmem_ld_32x32(t_addr + c * 32 + 32, r1);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            m0 = fmin3(m0, __uint_as_float(r[i]), __uint_as_float(r[i + 1]));
-            m1 = fmin3(m1, __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
+          for (int i = 0; i < 32; i += 2) {
+            m0 = fmin3(m0, __uint_as_float(r0[i]), __uint_as_float(r0[i + 1]));
+            m1 = fmin3(m1, __uint_as_float(r1[i]), __uint_as_float(r1[i + 1]));
           }
         }
-        hmin[h] = fminf(m0, m1);
-        const float thr = hmin[h] + W;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          tmem_ld_32x32(lane_addr + h * 256 + c * 32, r);
-          tmem_ld_wait();
-          uint32_t w = 0;
-#pragma unroll
-          for (int i = 0; i < 32; ++i) w |= (__uint_as_float(r[i]) <= thr) ? (1u << i) : 0u;
-          mask[h][c] = w;
-          if (dbg && tile == 0 && g == 0) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) dbg[(size_t)m * TK + h * 256 + c * 32 + i] = __uint_as_float(r[i]);
-          }
-        }
-        init_c2(h);  // buffer h is free again: pre-load c2 for the next tile and hand it to the MMA warp
+        xmin[et] = fminf(m0, m1);
       }
+      epi_bar(1);
+      const float gthr = fminf(xmin[m], xmin[TM + m]) + W;
+      // pass 2: candidate list {k : s_k <= min + 2E} (increasing k), kept in shared memory
+      int cnt = 0;
+#pragma unroll 1
+      for (int c = 0; c < 8; c += 2) {
+        uint32_t r0[32], r1[32];
+        tmem_ld_32x32(t_addr + c * 32, r0);
+        tmem_ld_32x32(t_addr + c * 32 + 32, r1);
+        tmem_ld_wait();
+        uint32_t w0 = 0, w1 = 0;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          w0 |= (__uint_as_float(r0[i]) <= gthr) ? (1u << i) : 0u;
+          w1 |= (__uint_as_float(r1[i]) <= gthr) ? (1u << i) : 0u;
+        }
+        if (dbg && tile == 0 && g == 0) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            dbg[(size_t)m * TK + h * 256 + c * 32 + i] = __uint_as_float(r0[i]);
+            dbg[(size_t)m * TK + h * 256 + c * 32 + 32 + i] = __uint_as_float(r1[i]);
+          }
+        }
+        while (w0) {
+          const int b = __ffs(w0) - 1;
+          w0 &= w0 - 1;
+          if (cnt < LST_CAP) lst[cnt * 256 + et] = (uint16_t)(h * 256 + c * 32 + b);
+          ++cnt;
+        }
+        while (w1) {
+          const int b = __ffs(w1) - 1;
+          w1 &= w1 - 1;
+          if (cnt < LST_CAP) lst[cnt * 256 + et] = (uint16_t)(h * 256 + c * 32 + 32 + b);
+          ++cnt;
+        }
+      }
+      init_c2();  // buffer h is free again: pre-load c2 for the next tile and hand it to the MMA warp
+      float x[TD];
+      load_x(x);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&a_empty[slot]);  // this half's MMAs retired (t_full) and x is in registers
       // exact reference arithmetic on the candidates, increasing code index, strict < (first minimum)
-      const float gthr = fminf(hmin[0], hmin[1]) + W;
       float best = INFINITY;
       int besti = 0;
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        if (!(hmin[h] <= gthr)) continue;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          uint32_t w = mask[h][c];
-          while (w) {
-            const int b = __ffs(w) - 1;
-            w &= w - 1;
-            const int k = h * 256 + c * 32 + b;
-            const uint8_t* brow = smem + k * 128;
-            float acc = 0.f;
-#pragma unroll
-            for (int jj = 0; jj < 16; ++jj) {
-              const float4 v = *reinterpret_cast<const float4*>(brow + (jj >> 3) * (TK * 128) + (((jj & 7) ^ (k & 7)) << 4));
-              acc = __fmaf_rn(x[4 * jj], -0.5f * v.x, acc);
-              acc = __fmaf_rn(x[4 * jj + 1], -0.5f * v.y, acc);
-              acc = __fmaf_rn(x[4 * jj + 2], -0.5f * v.z, acc);
-              acc = __fmaf_rn(x[4 * jj + 3], -0.5f * v.w, acc);
-            }
-            const float d = __fmaf_rn(-2.f, acc, __fadd_rn(c2s[k], x2));
-            if (d < best) { best = d; besti = k; }
-          }
+      if (cnt <= LST_CAP) {
+        for (int i = 0; i < cnt; ++i) {
+          const int k = lst[i * 256 + et];
+          const float d = exact_d(x, x2, k);
+          if (d < best) { best = d; besti = k; }
+        }
+      } else {  // pathological codebook (dozens of near-ties): every code of this half, exactly
+        for (int k = h * 256; k < h * 256 + 256; ++k) {
+          const float d = exact_d(x, x2, k);
+          if (d < best) { best = d; besti = k; }
         }
       }
-      idx_out[((size_t)frame * num + g) * hw + s] = (int64_t)besti;
-      if (zq_out || zq_bf16) {
+      xbest[et] = make_float2(best, __int_as_float(besti));
+      epi_bar(2);
+      {
+        const float2 o = xbest[(h ^ 1) * TM + m];
+        const float od = o.x;
+        const int oi = __float_as_int(o.y);
+        // lower half wins exact ties (first minimum)
+        if (h == 0 ? (od < best) : !(best < od)) { best = od; besti = oi; }
+      }
+      if (h == 0) {
+        idx_out[((size_t)frame * num + g) * hw + s] = (int64_t)besti;
+        if (counts) atomicAdd(counts + (size_t)g * TK + besti, 1.f);
+        if (sums) {
+          float* sp = sums + ((size_t)g * TK + besti) * TD;
+#pragma unroll
+          for (int j = 0; j < TD; ++j) atomicAdd(sp + j, x[j]);
+        }
+      } else if (zq_out || zq_bf16) {
         const float* cr = cbg + (size_t)besti * TD;
         if (NHWC) {
           const size_t o = (size_t)pos * C + (size_t)g * TD;
@@ -355,12 +408,6 @@ vq_argmin_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __res
 #pragma unroll 8
           for (int j = 0; j < TD; ++j) zp[(size_t)j * hw] = __ldg(cr + j);
         }
-      }
-      if (counts) atomicAdd(counts + (size_t)g * TK + besti, 1.f);
-      if (sums) {
-        float* sp = sums + ((size_t)g * TK + besti) * TD;
-#pragma unroll
-        for (int j = 0; j < TD; ++j) atomicAdd(sp + j, x[j]);
       }
     }
     tc_fence_before();
