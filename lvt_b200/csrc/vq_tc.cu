@@ -5,15 +5,16 @@
 // FFMA-bound (1.8 % of the HBM roofline), so the 512-way scan is moved to tcgen05:
 //   1. scores  s_k = c2_k - 2 * <tf32(x), tf32(c_k)>  for all 512 codes of a group: kind::tf32 MMA,
 //      A = 128 positions x 64 dims read straight from the NCHW tensor (MN-major fp32 tile via TMA, no
-//      conversion pass), B = -2*codebook resident in shared memory, accumulator PRE-LOADED with the
-//      exact fp32 c2_k (tcgen05.st), so the epilogue never touches c2.
+//      conversion pass), B = -2*codebook resident in shared memory; an extra K-step with A = [1, 1, 0...],
+//      B = [c2_hi, c2_lo, 0...] puts c2_k into the accumulator, so the epilogue never touches c2.
 //   2. per position, the candidate set {k : s_k <= min_k s_k + 2E} with a rigorous error bound
 //      E = 1.1 * 2^-8 * |x| * max_k|c_k| + 2^-18 * (|x|^2 + max|c|^2)   (tf32 truncation of both operands,
 //      Cauchy-Schwarz; covers the tensor-core accumulation and the reference's own fp32 roundings).
 //   3. the reference's exact arithmetic on the candidates only (typically 1-2 of 512), lowest index
 //      wins ties  =>  bit-identical indices to the SIMT kernel / the oracle.
 // One CTA = one codebook group (its 128 KiB of -2*c stay resident), persistent over 128-position tiles;
-// warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 scan + re-rank TMEM buffer 0 (codes 0-255), warps 6-9 buffer 1 (codes 256-511).
+// warp 0 TMA producer, warp 1 MMA issuer, 16 scan warps in four groups of 128 codes each (two 256-column TMEM
+// buffers); candidates are compacted per warp so the exact re-rank keeps all lanes busy.
 #include <mutex>
 #include <stdlib.h>
 #include <string.h>
@@ -29,17 +30,23 @@ constexpr int TK = 512;   // codes per group
 constexpr int TD = 64;    // dims per group
 constexpr int TM = 128;   // positions per tile
 constexpr int NSLOT = 2;
+constexpr int NGRP = 4;                     // scan groups: 128 codes (TMEM columns) each
+constexpr int NEW = 4 * NGRP;               // scan warps
+constexpr int WL_CAP = 64;                  // candidates kept per warp and tile; more => exhaustive exact scan
 constexpr int A_BYTES = TM * TD * 4;        // 32 KiB
 constexpr int B_BYTES = 2 * TK * 128;       // two k-blocks of 32 fp32 (128 B rows)
 constexpr int SM_A = B_BYTES;
-constexpr int SM_C2 = SM_A + NSLOT * A_BYTES;
-constexpr int LST_CAP = 16;                 // candidates kept per (position, half); more => exhaustive exact scan
-constexpr int SM_LST = SM_C2 + TK * 4;      // [LST_CAP][256] u16 candidate lists
-constexpr int SM_XMIN = SM_LST + LST_CAP * 256 * 2;  // [2][128] f32 per-half minima
-constexpr int SM_XBEST = SM_XMIN + 2 * TM * 4;       // [2][128] (d, idx) per-half winners
-constexpr int SM_BAR = SM_XBEST + 2 * TM * 8;
+constexpr int SM_BX = SM_A + NSLOT * A_BYTES;   // 512 x 32 B rows [c2_hi, c2_lo, 0...] (SWIZZLE_32B, K-major)
+constexpr int SM_AX = SM_BX + TK * 32;          // 128 x 32 B rows [1, 1, 0...]
+constexpr int SM_C2 = SM_AX + TM * 32;          // exact fp32 c2 table
+constexpr int SM_WL = SM_C2 + TK * 4;           // [NEW][WL_CAP] u32 (row << 16 | code) candidates
+constexpr int SM_XMIN = SM_WL + NEW * WL_CAP * 4;   // [NGRP][128] per-group minima
+constexpr int SM_X2 = SM_XMIN + NGRP * TM * 4;      // [128] |x|^2, [128] window
+constexpr int SM_RB = SM_X2 + 2 * TM * 4;           // [2][128] u64 (ordered d << 32 | code) per-row winners
+constexpr int SM_WCNT = SM_RB + 2 * TM * 8;         // [NEW] candidate counters
+constexpr int SM_BAR = SM_WCNT + NEW * 4;
 constexpr int SM_TOTAL = SM_BAR + 256 + 1024;
-constexpr int TC_THREADS = 320;             // TMA warp, MMA warp, 2 x 4 scan warps
+constexpr int TC_THREADS = 64 + NEW * 32;   // TMA warp, MMA warp, 16 scan warps
 
 LVT_DEVICE_INLINE void tma_load_2d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
   asm volatile(
@@ -48,25 +55,15 @@ LVT_DEVICE_INLINE void tma_load_2d(void* smem_dst, const CUtensorMap* m, uint64_
       : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
-LVT_DEVICE_INLINE void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
-      :
-      : "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
-        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]),
-        "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]),
-        "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
-      : "memory");
-}
-LVT_DEVICE_INLINE void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-LVT_DEVICE_INLINE void epi_bar(int id) { asm volatile("bar.sync %0, 256;" ::"r"(id) : "memory"); }
+LVT_DEVICE_INLINE void epi_bar(int id) { asm volatile("bar.sync %0, 512;" ::"r"(id) : "memory"); }
 LVT_DEVICE_INLINE float fmin3(float a, float b, float c) {
   float r;
   asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
   return r;
 }
+// w |= bit when v <= thr (two instructions per score)
+#define VQ_TEST(w, v, thr, bit) \
+  asm("{\n\t.reg .pred p;\n\tsetp.le.f32 p, %1, %2;\n\t@p or.b32 %0, %0, %3;\n\t}" : "+r"(w) : "f"(v), "f"(thr), "r"(bit))
 
 // ATen-order squared norm (see vq.cu): 8-lane vectors into 4 accumulators, combined, lanes left to right
 template <typename LoadFn>
@@ -91,7 +88,8 @@ LVT_DEVICE_INLINE float sqnorm64(LoadFn ld) {
   return s;
 }
 
-// Shared-memory matrix descriptor with an explicit layout type (1 = SWIZZLE_128B_BASE32B, 2 = SWIZZLE_128B).
+// Shared-memory matrix descriptor with an explicit layout type
+// (1 = SWIZZLE_128B_BASE32B, 2 = SWIZZLE_128B, 6 = SWIZZLE_32B).
 LVT_DEVICE_INLINE uint64_t smem_desc_lt(uint32_t addr, uint32_t lbo, uint32_t sbo, uint32_t layout_type) {
   uint64_t d = 0;
   d |= (uint64_t)((addr & 0x3FFFF) >> 4);
@@ -100,6 +98,10 @@ LVT_DEVICE_INLINE uint64_t smem_desc_lt(uint32_t addr, uint32_t lbo, uint32_t sb
   d |= (uint64_t)1 << 46;
   d |= (uint64_t)layout_type << 61;
   return d;
+}
+LVT_DEVICE_INLINE uint32_t ordered_f32(float d) {  // order-preserving float -> uint map
+  const uint32_t u = __float_as_uint(d);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 
 // NHWC = true : z_e is channels-last [positions, num*64] (the VQ-VAE engine's layout): A is K-major,
@@ -113,12 +115,15 @@ vq_argmin_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __res
                     __nv_bfloat16* __restrict__ zq_bf16, float* __restrict__ counts,
                     float* __restrict__ sums, int num, int hw, int num_tiles, int ctas_per_group,
                     float* __restrict__ dbg) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps the shared address space
   float* c2s = reinterpret_cast<float*>(smem + SM_C2);
-  uint16_t* lst = reinterpret_cast<uint16_t*>(smem + SM_LST);
+  uint32_t* wl_all = reinterpret_cast<uint32_t*>(smem + SM_WL);
   float* xmin = reinterpret_cast<float*>(smem + SM_XMIN);
-  float2* xbest = reinterpret_cast<float2*>(smem + SM_XBEST);
+  float* x2s = reinterpret_cast<float*>(smem + SM_X2);
+  float* Ws = x2s + TM;
+  unsigned long long* rowbest = reinterpret_cast<unsigned long long*>(smem + SM_RB);
+  int* wcnt = reinterpret_cast<int*>(smem + SM_WCNT);
   uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + SM_BAR);  // [NSLOT]
   uint64_t* a_empty = a_full + NSLOT;                              // [NSLOT]
   uint64_t* t_full = a_empty + NSLOT;                              // [2]
@@ -133,7 +138,8 @@ vq_argmin_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __res
   const int tiles_per_frame = hw / TM;
   const int C = num * TD;
 
-  // ---- one-time setup: B = -2 * codebook[g] in the K-major 128B-swizzled UMMA layout, exact c2 table
+  // ---- one-time setup: B = -2 * codebook[g] in the K-major 128B-swizzled UMMA layout; exact c2 table; the
+  //      extra K-step operands that put c2 into the accumulator: A_x = [1, 1, 0...], B_x = [c2_hi, c2_lo, 0...]
   for (int i = threadIdx.x; i < TK * TD / 4; i += TC_THREADS) {
     const int k = i >> 4, jj = i & 15;  // code row, 16-byte chunk (4 dims) of the 64-dim row
     float4 v = __ldg(reinterpret_cast<const float4*>(cbg) + i);
@@ -147,19 +153,31 @@ vq_argmin_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __res
     const float c2 = sqnorm64([&](int j) { return __ldg(row + j); });
     c2s[k] = c2;
     cm = fmaxf(cm, c2);
+    const float hi = __uint_as_float(__float_as_uint(c2) & 0xFFFFE000u);  // tf32-exact part
+    const float lo = c2 - hi;
+    const int sw = (k >> 2) & 1;  // SWIZZLE_32B: 16 B chunk index ^= bit 2 of the row
+    *reinterpret_cast<float4*>(smem + SM_BX + k * 32 + (sw << 4)) = make_float4(hi, lo, 0.f, 0.f);
+    *reinterpret_cast<float4*>(smem + SM_BX + k * 32 + ((sw ^ 1) << 4)) = make_float4(0.f, 0.f, 0.f, 0.f);
   }
+  for (int r = threadIdx.x; r < TM; r += TC_THREADS) {
+    const int sw = (r >> 2) & 1;
+    *reinterpret_cast<float4*>(smem + SM_AX + r * 32 + (sw << 4)) = make_float4(1.f, 1.f, 0.f, 0.f);
+    *reinterpret_cast<float4*>(smem + SM_AX + r * 32 + ((sw ^ 1) << 4)) = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (int i = threadIdx.x; i < 2 * TM; i += TC_THREADS) rowbest[i] = ~0ull;
+  if (threadIdx.x < NEW) wcnt[threadIdx.x] = 0;
   cm = warp_max(cm);
   if (threadIdx.x == 0) {
     *cmax2_s = 0.f;
 #pragma unroll
     for (int s = 0; s < NSLOT; ++s) {
       mbar_init(&a_full[s], 1);
-      mbar_init(&a_empty[s], 8);
+      mbar_init(&a_empty[s], NEW);
     }
     mbar_init(&t_full[0], 1);
     mbar_init(&t_full[1], 1);
-    mbar_init(&t_empty[0], 4);
-    mbar_init(&t_empty[1], 4);
+    mbar_init(&t_empty[0], NEW / 2);
+    mbar_init(&t_empty[1], NEW / 2);
     fence_barrier_init();
     tma_prefetch_desc(&tm_x);
   }
@@ -169,7 +187,7 @@ vq_argmin_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __res
   }
   __syncthreads();
   if (lane == 0) atomicMax(reinterpret_cast<int*>(cmax2_s), __float_as_int(cm));  // cm >= 0: int order == float order
-  fence_proxy_async();  // B written through the generic proxy, read by tcgen05.mma (async proxy)
+  fence_proxy_async();  // operands written through the generic proxy, read by tcgen05.mma (async proxy)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -200,9 +218,11 @@ vq_argmin_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __res
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (kind::tf32)
     if (elect_one()) {
-      // idesc: D f32, A/B tf32, A MN-major, B K-major, N = 256, M = 128
+      // idesc: D f32, A/B tf32, A MN-major (NCHW) or K-major, B K-major, N = 256, M = 128
       constexpr uint32_t idesc = umma_idesc(TM, 256, /*tf32*/ 2, !NHWC, false);
+      constexpr uint32_t idesc_x = umma_idesc(TM, 256, /*tf32*/ 2, false, false);
       const uint32_t b_base = smem_u32(smem);
+      const uint64_t ax_desc = smem_desc_lt(smem_u32(smem + SM_AX), 16, 256, 6);
       int it = 0;
       for (int tile = sub; tile < num_tiles; tile += ctas_per_group, ++it) {
         const int slot = it % NSLOT;
@@ -210,8 +230,11 @@ vq_argmin_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __res
         const uint32_t a_base = smem_u32(smem + SM_A + slot * A_BYTES);
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-          mbar_wait(&t_empty[h], it & 1);  // scan of the previous tile done AND c2 pre-loaded
+          mbar_wait(&t_empty[h], (it & 1) ^ 1);  // scan of the previous tile's buffer h finished
           tc_fence_after();
+          // K-step 0 writes c2 (= 1*c2_hi + 1*c2_lo) into the accumulator
+          umma_tf32_ss(tmem_base + h * 256, ax_desc, smem_desc_lt(smem_u32(smem + SM_BX + h * 256 * 32), 16, 256, 6),
+                       idesc_x, 0u);
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks) {  // K = 8 per tf32 MMA
             // K-major: 32 B per K-step inside the 128 B row, next k-block after 4 steps.
@@ -219,7 +242,7 @@ vq_argmin_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __res
             const uint64_t adesc = NHWC ? smem_desc_lt(a_base + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024, 2)
                                         : smem_desc_lt(a_base + ks * 1024, 8192, 512, 1);
             const uint64_t bdesc = umma_smem_desc(b_base + (ks >> 2) * (TK * 128) + h * (256 * 128) + (ks & 3) * 32, 16, 1024);
-            umma_tf32_ss(tmem_base + h * 256, adesc, bdesc, idesc, 1u);  // accumulate onto c2
+            umma_tf32_ss(tmem_base + h * 256, adesc, bdesc, idesc, 1u);
           }
           umma_commit(&t_full[h]);
         }
@@ -227,82 +250,67 @@ vq_argmin_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __res
     }
   } else {
     // ------------------------------------------------------------------ scan + exact re-rank
-    // Two groups of four warps; group h owns TMEM buffer h (codes h*256 .. h*256+255) of every tile.
-    const int h = (warp - 2) >> 2;
-    const int q = warp & 3;
+    // Four groups of four warps; group grp scans codes grp*128 .. grp*128+127 (TMEM buffer grp/2) of every tile.
+    const int ew = warp - 2;
+    const int grp = ew >> 2;
+    const int h = grp >> 1;
+    const int q = warp & 3;       // TMEM lane quarter this warp may access
     const int m = q * 32 + lane;  // row (position) inside the tile
-    const int et = h * TM + m;    // epilogue thread id 0..255
-    const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + h * 256;
-    auto init_c2 = [&]() {
-#pragma unroll 1
-      for (int c = 0; c < 8; ++c) {
-        uint32_t r[32];
-        const float4* src = reinterpret_cast<const float4*>(c2s + h * 256 + c * 32);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 v = src[i];
-          r[4 * i] = __float_as_uint(v.x); r[4 * i + 1] = __float_as_uint(v.y);
-          r[4 * i + 2] = __float_as_uint(v.z); r[4 * i + 3] = __float_as_uint(v.w);
-        }
-        tmem_st_32x32(t_addr + c * 32, r);
-      }
-      tmem_st_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&t_empty[h]);
-    };
-    // exact reference distance of code k (sequential fp32 FMA chain over the 64 dims, vq.cu)
-    auto exact_d = [&](const float (&x)[TD], float x2, int k) {
-      const uint8_t* brow = smem + k * 128;
-      float acc = 0.f;
-#pragma unroll
-      for (int jj = 0; jj < 16; ++jj) {
-        const float4 v = *reinterpret_cast<const float4*>(brow + (jj >> 3) * (TK * 128) + (((jj & 7) ^ (k & 7)) << 4));
-        acc = __fmaf_rn(x[4 * jj], -0.5f * v.x, acc);
-        acc = __fmaf_rn(x[4 * jj + 1], -0.5f * v.y, acc);
-        acc = __fmaf_rn(x[4 * jj + 2], -0.5f * v.z, acc);
-        acc = __fmaf_rn(x[4 * jj + 3], -0.5f * v.w, acc);
-      }
-      return __fmaf_rn(-2.f, acc, __fadd_rn(c2s[k], x2));
-    };
-    init_c2();
+    const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + grp * 128;
+    uint32_t* wl = wl_all + ew * WL_CAP;
     int it = 0;
     for (int tile = sub; tile < num_tiles; tile += ctas_per_group, ++it) {
       const int slot = it % NSLOT;
       const long long pos = (long long)tile * TM + m;  // global position index (frame * hw + s)
       const int frame = (int)(pos / hw), s = (int)(pos - (long long)frame * hw);
-      mbar_wait(&a_full[slot], (it / NSLOT) & 1);
-      // this position's 64-dim vector from the swizzled tile
-      const uint8_t* at = NHWC ? smem + SM_A + slot * A_BYTES + m * 128
-                               : smem + SM_A + slot * A_BYTES + (m >> 5) * 8192 + (m & 7) * 4;
-      const int mchunk = (m & 31) >> 3;  // NCHW: 32 B chunk of the 128 B row
-      auto load_x = [&](float (&x)[TD]) {
-        if (NHWC) {
+      const uint8_t* a_tile = smem + SM_A + slot * A_BYTES;
+      // element j of row r of the (swizzled) tile
+      auto xptr = [&](int r) { return NHWC ? a_tile + r * 128 : a_tile + (r >> 5) * 8192 + (r & 7) * 4; };
+      // exact reference distance (vq.cu): sequential fp32 FMA chain over the 64 dims.  B holds -2c and
+      // fma(x, -2c, -2a) == -2 * fma(x, c, a) exactly, so  d = fl(fl(c2 + x2) - 2*dot) = fl(chain + fl(c2 + x2)).
+      auto exact_d = [&](int r, int k) {
+        const uint8_t* brow = smem + k * 128;
+        const uint8_t* xr = xptr(r);
+        const int rsw = NHWC ? (r & 7) : ((r & 31) >> 3);
+        float acc = 0.f;
 #pragma unroll
-          for (int jj = 0; jj < 16; ++jj) {
-            const float4 v = *reinterpret_cast<const float4*>(at + (jj >> 3) * 16384 + (((jj & 7) ^ (m & 7)) << 4));
-            x[4 * jj] = v.x; x[4 * jj + 1] = v.y; x[4 * jj + 2] = v.z; x[4 * jj + 3] = v.w;
+        for (int jj = 0; jj < 16; ++jj) {
+          const float4 v = *reinterpret_cast<const float4*>(brow + (jj >> 3) * (TK * 128) + (((jj & 7) ^ (k & 7)) << 4));
+          float4 xv;
+          if (NHWC) {
+            xv = *reinterpret_cast<const float4*>(xr + (jj >> 3) * 16384 + (((jj & 7) ^ rsw) << 4));
+          } else {
+            xv.x = *reinterpret_cast<const float*>(xr + (4 * jj) * 128 + ((rsw ^ 0) << 5));
+            xv.y = *reinterpret_cast<const float*>(xr + (4 * jj + 1) * 128 + ((rsw ^ 1) << 5));
+            xv.z = *reinterpret_cast<const float*>(xr + (4 * jj + 2) * 128 + ((rsw ^ 2) << 5));
+            xv.w = *reinterpret_cast<const float*>(xr + (4 * jj + 3) * 128 + ((rsw ^ 3) << 5));
           }
-        } else {
-#pragma unroll
-          for (int j = 0; j < TD; ++j) x[j] = *reinterpret_cast<const float*>(at + j * 128 + ((mchunk ^ (j & 3)) << 5));
+          acc = __fmaf_rn(xv.x, v.x, acc);
+          acc = __fmaf_rn(xv.y, v.y, acc);
+          acc = __fmaf_rn(xv.z, v.z, acc);
+          acc = __fmaf_rn(xv.w, v.w, acc);
         }
+        return __fadd_rn(acc, __fadd_rn(c2s[k], x2s[r]));
       };
-      float x2;
-      {
-        float x[TD];
-        load_x(x);
-        x2 = sqnorm64([&](int j) { return x[j]; });
+      mbar_wait(&a_full[slot], (it / NSLOT) & 1);
+      if (q == grp) {  // one warp per 32-row block computes |x|^2 and the candidate window
+        const uint8_t* xr = xptr(m);
+        const int rsw = NHWC ? (m & 7) : ((m & 31) >> 3);
+        const float x2 = sqnorm64([&](int j) {
+          return NHWC ? *reinterpret_cast<const float*>(xr + (j >> 5) * 16384 + ((((j >> 2) & 7) ^ rsw) << 4) + (j & 3) * 4)
+                      : *reinterpret_cast<const float*>(xr + j * 128 + ((rsw ^ (j & 3)) << 5));
+        });
+        const float E = 1.1f * 0.00390625f * sqrtf(x2 * cmax2) + 3.8146973e-6f * (x2 + cmax2);
+        x2s[m] = x2;
+        Ws[m] = 2.f * E;
       }
-      const float E = 1.1f * 0.00390625f * sqrtf(x2 * cmax2) + 3.8146973e-6f * (x2 + cmax2);
-      const float W = 2.f * E;
       mbar_wait(&t_full[h], it & 1);
       tc_fence_after();
-      // pass 1: minimum tf32 score of this half (two TMEM loads in flight per wait)
+      // pass 1: minimum tf32 score over this group's 128 codes
       {
         float m0 = INFINITY, m1 = INFINITY;
 #pragma unroll 1
-        for (int c = 0; c < 8; c += 2) {
+        for (int c = 0; c < 4; c += 2) {
           uint32_t r0[32], r1[32];
           tmem_ld_32x32(t_addr + c * 32, r0);
           tmem_ld_32x32(t_addr + c * 32 + 32, r1);
@@ -313,14 +321,13 @@ vq_argmin_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __res
             m1 = fmin3(m1, __uint_as_float(r1[i]), __uint_as_float(r1[i + 1]));
           }
         }
-        xmin[et] = fminf(m0, m1);
+        xmin[grp * TM + m] = fminf(m0, m1);
       }
       epi_bar(1);
-      const float gthr = fminf(xmin[m], xmin[TM + m]) + W;
-      // pass 2: candidate list {k : s_k <= min + 2E} (increasing k), kept in shared memory
-      int cnt = 0;
+      const float gthr = fminf(fminf(xmin[m], xmin[TM + m]), fminf(xmin[2 * TM + m], xmin[3 * TM + m])) + Ws[m];
+      // pass 2: candidates {k : s_k <= min + 2E} appended to this warp's (row, code) list
 #pragma unroll 1
-      for (int c = 0; c < 8; c += 2) {
+      for (int c = 0; c < 4; c += 2) {
         uint32_t r0[32], r1[32];
         tmem_ld_32x32(t_addr + c * 32, r0);
         tmem_ld_32x32(t_addr + c * 32 + 32, r1);
@@ -328,87 +335,91 @@ vq_argmin_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __res
         uint32_t w0 = 0, w1 = 0;
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          w0 |= (__uint_as_float(r0[i]) <= gthr) ? (1u << i) : 0u;
-          w1 |= (__uint_as_float(r1[i]) <= gthr) ? (1u << i) : 0u;
+          VQ_TEST(w0, __uint_as_float(r0[i]), gthr, 1u << i);
+          VQ_TEST(w1, __uint_as_float(r1[i]), gthr, 1u << i);
         }
         if (dbg && tile == 0 && g == 0) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            dbg[(size_t)m * TK + h * 256 + c * 32 + i] = __uint_as_float(r0[i]);
-            dbg[(size_t)m * TK + h * 256 + c * 32 + 32 + i] = __uint_as_float(r1[i]);
+            dbg[(size_t)m * TK + grp * 128 + c * 32 + i] = __uint_as_float(r0[i]);
+            dbg[(size_t)m * TK + grp * 128 + c * 32 + 32 + i] = __uint_as_float(r1[i]);
           }
         }
         while (w0) {
           const int b = __ffs(w0) - 1;
           w0 &= w0 - 1;
-          if (cnt < LST_CAP) lst[cnt * 256 + et] = (uint16_t)(h * 256 + c * 32 + b);
-          ++cnt;
+          const int p = atomicAdd(&wcnt[ew], 1);
+          if (p < WL_CAP) wl[p] = ((uint32_t)m << 16) | (uint32_t)(grp * 128 + c * 32 + b);
         }
         while (w1) {
           const int b = __ffs(w1) - 1;
           w1 &= w1 - 1;
-          if (cnt < LST_CAP) lst[cnt * 256 + et] = (uint16_t)(h * 256 + c * 32 + 32 + b);
-          ++cnt;
+          const int p = atomicAdd(&wcnt[ew], 1);
+          if (p < WL_CAP) wl[p] = ((uint32_t)m << 16) | (uint32_t)(grp * 128 + c * 32 + 32 + b);
         }
       }
-      init_c2();  // buffer h is free again: pre-load c2 for the next tile and hand it to the MMA warp
-      float x[TD];
-      load_x(x);
+      tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&a_empty[slot]);  // this half's MMAs retired (t_full) and x is in registers
-      // exact reference arithmetic on the candidates, increasing code index, strict < (first minimum)
-      float best = INFINITY;
-      int besti = 0;
-      if (cnt <= LST_CAP) {
-        for (int i = 0; i < cnt; ++i) {
-          const int k = lst[i * 256 + et];
-          const float d = exact_d(x, x2, k);
-          if (d < best) { best = d; besti = k; }
+      if (lane == 0) mbar_arrive(&t_empty[h]);  // TMEM buffer h may be overwritten by the next tile's MMAs
+      // exact reference arithmetic on the candidates, all lanes busy; winner per row = min (d, code)
+      unsigned long long* rb = rowbest + (it & 1) * TM;
+      const int n = wcnt[ew];
+      if (n <= WL_CAP) {
+        for (int e = lane; e < n; e += 32) {
+          const uint32_t ent = wl[e];
+          const int r = ent >> 16, k = ent & 0xFFFF;
+          atomicMin(&rb[r], ((unsigned long long)ordered_f32(exact_d(r, k)) << 32) | (unsigned)k);
         }
-      } else {  // pathological codebook (dozens of near-ties): every code of this half, exactly
-        for (int k = h * 256; k < h * 256 + 256; ++k) {
-          const float d = exact_d(x, x2, k);
-          if (d < best) { best = d; besti = k; }
-        }
+      } else {  // pathological codebook (dozens of near-ties): every code of this group for this warp's rows
+        for (int k = grp * 128; k < grp * 128 + 128; ++k)
+          atomicMin(&rb[m], ((unsigned long long)ordered_f32(exact_d(m, k)) << 32) | (unsigned)k);
       }
-      xbest[et] = make_float2(best, __int_as_float(besti));
+      __syncwarp();
+      if (lane == 0) wcnt[ew] = 0;
       epi_bar(2);
-      {
-        const float2 o = xbest[(h ^ 1) * TM + m];
-        const float od = o.x;
-        const int oi = __float_as_int(o.y);
-        // lower half wins exact ties (first minimum)
-        if (h == 0 ? (od < best) : !(best < od)) { best = od; besti = oi; }
-      }
-      if (h == 0) {
+      const int besti = (int)(rb[m] & 0xFFFFFFFFull);
+      if (grp == 0) {
         idx_out[((size_t)frame * num + g) * hw + s] = (int64_t)besti;
+      } else if (grp == 1) {
+        if (zq_out || zq_bf16) {
+          const float* cr = cbg + (size_t)besti * TD;
+          if (NHWC) {
+            const size_t o = (size_t)pos * C + (size_t)g * TD;
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj) {
+              const float4 v = __ldg(reinterpret_cast<const float4*>(cr) + jj);
+              if (zq_out) *reinterpret_cast<float4*>(zq_out + o + 4 * jj) = v;
+              if (zq_bf16) {
+                uint2 u;
+                u.x = pack_bf16x2(v.x, v.y);
+                u.y = pack_bf16x2(v.z, v.w);
+                *reinterpret_cast<uint2*>(zq_bf16 + o + 4 * jj) = u;
+              }
+            }
+          } else {
+            float* zp = zq_out + ((size_t)frame * C + (size_t)g * TD) * hw + s;
+#pragma unroll 8
+            for (int j = 0; j < TD; ++j) zp[(size_t)j * hw] = __ldg(cr + j);
+          }
+        }
+      } else if (grp == 2) {
         if (counts) atomicAdd(counts + (size_t)g * TK + besti, 1.f);
         if (sums) {
           float* sp = sums + ((size_t)g * TK + besti) * TD;
-#pragma unroll
-          for (int j = 0; j < TD; ++j) atomicAdd(sp + j, x[j]);
-        }
-      } else if (zq_out || zq_bf16) {
-        const float* cr = cbg + (size_t)besti * TD;
-        if (NHWC) {
-          const size_t o = (size_t)pos * C + (size_t)g * TD;
-#pragma unroll
-          for (int jj = 0; jj < 16; ++jj) {
-            const float4 v = __ldg(reinterpret_cast<const float4*>(cr) + jj);
-            if (zq_out) *reinterpret_cast<float4*>(zq_out + o + 4 * jj) = v;
-            if (zq_bf16) {
-              uint2 u;
-              u.x = pack_bf16x2(v.x, v.y);
-              u.y = pack_bf16x2(v.z, v.w);
-              *reinterpret_cast<uint2*>(zq_bf16 + o + 4 * jj) = u;
-            }
-          }
-        } else {
-          float* zp = zq_out + ((size_t)frame * C + (size_t)g * TD) * hw + s;
+          const uint8_t* xr = xptr(m);
+          const int rsw = NHWC ? (m & 7) : ((m & 31) >> 3);
 #pragma unroll 8
-          for (int j = 0; j < TD; ++j) zp[(size_t)j * hw] = __ldg(cr + j);
+          for (int j = 0; j < TD; ++j) {
+            const float xv = NHWC ? *reinterpret_cast<const float*>(xr + (j >> 5) * 16384 + ((((j >> 2) & 7) ^ rsw) << 4) + (j & 3) * 4)
+                                  : *reinterpret_cast<const float*>(xr + j * 128 + ((rsw ^ (j & 3)) << 5));
+            atomicAdd(sp + j, xv);
+          }
         }
+      } else {
+        rowbest[((it + 1) & 1) * TM + m] = ~0ull;  // last read before this tile's first barrier
       }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&a_empty[slot]);
     }
     tc_fence_before();
   }
