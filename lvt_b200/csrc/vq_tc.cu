@@ -32,20 +32,22 @@ constexpr int TM = 128;   // positions per tile
 constexpr int NSLOT = 2;
 constexpr int NGRP = 4;                     // scan groups: 128 codes (TMEM columns) each
 constexpr int NEW = 4 * NGRP;               // scan warps
-constexpr int WL_CAP = 64;                  // candidates kept per warp and tile; more => exhaustive exact scan
+constexpr int WL_CAP = 512;                 // candidates kept per tile; more => exhaustive exact scan
 constexpr int A_BYTES = TM * TD * 4;        // 32 KiB
 constexpr int B_BYTES = 2 * TK * 128;       // two k-blocks of 32 fp32 (128 B rows)
 constexpr int SM_A = B_BYTES;
 constexpr int SM_BX = SM_A + NSLOT * A_BYTES;   // 512 x 32 B rows [c2_hi, c2_lo, 0...] (SWIZZLE_32B, K-major)
 constexpr int SM_AX = SM_BX + TK * 32;          // 128 x 32 B rows [1, 1, 0...]
 constexpr int SM_C2 = SM_AX + TM * 32;          // exact fp32 c2 table
-constexpr int SM_WL = SM_C2 + TK * 4;           // [NEW][WL_CAP] u32 (row << 16 | code) candidates
-constexpr int SM_XMIN = SM_WL + NEW * WL_CAP * 4;   // [NGRP][128] per-group minima
-constexpr int SM_X2 = SM_XMIN + NGRP * TM * 4;      // [128] |x|^2, [128] window
-constexpr int SM_RB = SM_X2 + 2 * TM * 4;           // [2][128] u64 (ordered d << 32 | code) per-row winners
-constexpr int SM_WCNT = SM_RB + 2 * TM * 8;         // [NEW] candidate counters
-constexpr int SM_BAR = SM_WCNT + NEW * 4;
+constexpr int SM_WL = SM_C2 + TK * 4;           // [WL_CAP] u32 (row << 16 | code) candidates of the tile
+constexpr int SM_XMIN = SM_WL + WL_CAP * 4;     // [NGRP][128] per-group minima
+constexpr int SM_X2 = SM_XMIN + NGRP * TM * 4;      // [128] |x|^2, [8][128] its per-vector-lane partial sums
+constexpr int SM_RB = SM_X2 + 9 * TM * 4;           // [2][128] u64 (ordered d << 32 | code) per-row winners
+constexpr int SM_WCNT = SM_RB + 2 * TM * 8;         // candidate counter
+constexpr int SM_RCNT = SM_WCNT + 64;               // [128] candidates per row
+constexpr int SM_BAR = SM_RCNT + TM * 4;
 constexpr int SM_TOTAL = SM_BAR + 256 + 1024;
+static_assert(SM_TOTAL <= 232448, "shared memory budget");
 constexpr int TC_THREADS = 64 + NEW * 32;   // TMA warp, MMA warp, 16 scan warps
 
 LVT_DEVICE_INLINE void tma_load_2d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
@@ -114,16 +116,17 @@ vq_argmin_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __res
                     int64_t* __restrict__ idx_out, float* __restrict__ zq_out,
                     __nv_bfloat16* __restrict__ zq_bf16, float* __restrict__ counts,
                     float* __restrict__ sums, int num, int hw, int num_tiles, int ctas_per_group,
-                    float* __restrict__ dbg) {
+                    float* __restrict__ dbg, unsigned* __restrict__ clk) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps the shared address space
   float* c2s = reinterpret_cast<float*>(smem + SM_C2);
   uint32_t* wl_all = reinterpret_cast<uint32_t*>(smem + SM_WL);
   float* xmin = reinterpret_cast<float*>(smem + SM_XMIN);
   float* x2s = reinterpret_cast<float*>(smem + SM_X2);
-  float* Ws = x2s + TM;
+  float* lsum = x2s + TM;
   unsigned long long* rowbest = reinterpret_cast<unsigned long long*>(smem + SM_RB);
   int* wcnt = reinterpret_cast<int*>(smem + SM_WCNT);
+  int* rowcnt = reinterpret_cast<int*>(smem + SM_RCNT);
   uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + SM_BAR);  // [NSLOT]
   uint64_t* a_empty = a_full + NSLOT;                              // [NSLOT]
   uint64_t* t_full = a_empty + NSLOT;                              // [2]
@@ -137,6 +140,7 @@ vq_argmin_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __res
   const float* cbg = codebook + (size_t)g * TK * TD;
   const int tiles_per_frame = hw / TM;
   const int C = num * TD;
+#define VQ_CLK(who, ev) do { if (clk && blockIdx.x == 0 && it < 24 && lane == 0) clk[(it * 4 + (who)) * 16 + (ev)] = (unsigned)clock(); } while (0)
 
   // ---- one-time setup: B = -2 * codebook[g] in the K-major 128B-swizzled UMMA layout; exact c2 table; the
   //      extra K-step operands that put c2 into the accumulator: A_x = [1, 1, 0...], B_x = [c2_hi, c2_lo, 0...]
@@ -165,7 +169,8 @@ vq_argmin_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __res
     *reinterpret_cast<float4*>(smem + SM_AX + r * 32 + ((sw ^ 1) << 4)) = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   for (int i = threadIdx.x; i < 2 * TM; i += TC_THREADS) rowbest[i] = ~0ull;
-  if (threadIdx.x < NEW) wcnt[threadIdx.x] = 0;
+  if (threadIdx.x == 0) *wcnt = 0;
+  if (threadIdx.x < TM) rowcnt[threadIdx.x] = 0;
   cm = warp_max(cm);
   if (threadIdx.x == 0) {
     *cmax2_s = 0.f;
@@ -227,10 +232,12 @@ vq_argmin_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __res
       for (int tile = sub; tile < num_tiles; tile += ctas_per_group, ++it) {
         const int slot = it % NSLOT;
         mbar_wait(&a_full[slot], (it / NSLOT) & 1);
+        VQ_CLK(0, 0);
         const uint32_t a_base = smem_u32(smem + SM_A + slot * A_BYTES);
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           mbar_wait(&t_empty[h], (it & 1) ^ 1);  // scan of the previous tile's buffer h finished
+          VQ_CLK(0, 1 + h);
           tc_fence_after();
           // K-step 0 writes c2 (= 1*c2_hi + 1*c2_lo) into the accumulator
           umma_tf32_ss(tmem_base + h * 256, ax_desc, smem_desc_lt(smem_u32(smem + SM_BX + h * 256 * 32), 16, 256, 6),
@@ -251,21 +258,27 @@ vq_argmin_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __res
   } else {
     // ------------------------------------------------------------------ scan + exact re-rank
     // Four groups of four warps; group grp scans codes grp*128 .. grp*128+127 (TMEM buffer grp/2) of every tile.
+    // A row whose window holds a single code needs no re-rank at all (that code is the exact argmin).
     const int ew = warp - 2;
     const int grp = ew >> 2;
     const int h = grp >> 1;
     const int q = warp & 3;       // TMEM lane quarter this warp may access
     const int m = q * 32 + lane;  // row (position) inside the tile
+    const int et = ew * 32 + lane;  // scan thread id 0..511
     const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + grp * 128;
-    uint32_t* wl = wl_all + ew * WL_CAP;
+    uint32_t* wl = wl_all;
     int it = 0;
     for (int tile = sub; tile < num_tiles; tile += ctas_per_group, ++it) {
       const int slot = it % NSLOT;
-      const long long pos = (long long)tile * TM + m;  // global position index (frame * hw + s)
-      const int frame = (int)(pos / hw), s = (int)(pos - (long long)frame * hw);
+      const uint32_t pos = (uint32_t)tile * TM + m;  // global position index (frame * hw + s) < 2^31
+      const uint32_t frame = pos / (uint32_t)hw, s = pos - frame * (uint32_t)hw;
       const uint8_t* a_tile = smem + SM_A + slot * A_BYTES;
       // element j of row r of the (swizzled) tile
       auto xptr = [&](int r) { return NHWC ? a_tile + r * 128 : a_tile + (r >> 5) * 8192 + (r & 7) * 4; };
+      auto xelem = [&](const uint8_t* xr, int rsw, int j) {
+        return NHWC ? *reinterpret_cast<const float*>(xr + (j >> 5) * 16384 + ((((j >> 2) & 7) ^ rsw) << 4) + (j & 3) * 4)
+                    : *reinterpret_cast<const float*>(xr + j * 128 + ((rsw ^ (j & 3)) << 5));
+      };
       // exact reference distance (vq.cu): sequential fp32 FMA chain over the 64 dims.  B holds -2c and
       // fma(x, -2c, -2a) == -2 * fma(x, c, a) exactly, so  d = fl(fl(c2 + x2) - 2*dot) = fl(chain + fl(c2 + x2)).
       auto exact_d = [&](int r, int k) {
@@ -292,20 +305,32 @@ vq_argmin_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __res
         }
         return __fadd_rn(acc, __fadd_rn(c2s[k], x2s[r]));
       };
+      const int who = ew == 0 ? 1 : (ew == 12 ? 2 : (ew == 5 ? 3 : -1));
+#define VQ_ECLK(ev) do { if (who > 0) VQ_CLK(who, ev); } while (0)
+      VQ_ECLK(0);
       mbar_wait(&a_full[slot], (it / NSLOT) & 1);
-      if (q == grp) {  // one warp per 32-row block computes |x|^2 and the candidate window
+      VQ_ECLK(1);
+      {
+        // |x|^2 in ATen's order (vq.cu) = sum over the 8 vector lanes l (left to right) of
+        // ((a0+a1)+a2)+a3, a_j = x[8j+l]^2 + x[8(j+4)+l]^2.  The four threads of a row take two lanes each.
         const uint8_t* xr = xptr(m);
         const int rsw = NHWC ? (m & 7) : ((m & 31) >> 3);
-        const float x2 = sqnorm64([&](int j) {
-          return NHWC ? *reinterpret_cast<const float*>(xr + (j >> 5) * 16384 + ((((j >> 2) & 7) ^ rsw) << 4) + (j & 3) * 4)
-                      : *reinterpret_cast<const float*>(xr + j * 128 + ((rsw ^ (j & 3)) << 5));
-        });
-        const float E = 1.1f * 0.00390625f * sqrtf(x2 * cmax2) + 3.8146973e-6f * (x2 + cmax2);
-        x2s[m] = x2;
-        Ws[m] = 2.f * E;
+#pragma unroll
+        for (int ll = 0; ll < 2; ++ll) {
+          const int l = 2 * grp + ll;
+          float a[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float x0 = xelem(xr, rsw, 8 * j + l), x1 = xelem(xr, rsw, 8 * (j + 4) + l);
+            a[j] = __fadd_rn(__fmul_rn(x0, x0), __fmul_rn(x1, x1));
+          }
+          lsum[l * TM + m] = __fadd_rn(__fadd_rn(__fadd_rn(a[0], a[1]), a[2]), a[3]);
+        }
       }
+      VQ_ECLK(2);
       mbar_wait(&t_full[h], it & 1);
       tc_fence_after();
+      VQ_ECLK(3);
       // pass 1: minimum tf32 score over this group's 128 codes
       {
         float m0 = INFINITY, m1 = INFINITY;
@@ -323,10 +348,18 @@ vq_argmin_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __res
         }
         xmin[grp * TM + m] = fminf(m0, m1);
       }
+      VQ_ECLK(4);
       epi_bar(1);
-      const float gthr = fminf(fminf(xmin[m], xmin[TM + m]), fminf(xmin[2 * TM + m], xmin[3 * TM + m])) + Ws[m];
-      // pass 2: candidates {k : s_k <= min + 2E} appended to this warp's (row, code) list
-#pragma unroll 1
+      VQ_ECLK(5);
+      float x2 = lsum[m];
+#pragma unroll
+      for (int l = 1; l < 8; ++l) x2 = __fadd_rn(x2, lsum[l * TM + m]);
+      const float E = 1.1f * 0.00390625f * sqrtf(x2 * cmax2) + 3.8146973e-6f * (x2 + cmax2);
+      if (grp == 0) x2s[m] = x2;
+      const float gthr = fminf(fminf(xmin[m], xmin[TM + m]), fminf(xmin[2 * TM + m], xmin[3 * TM + m])) + 2.f * E;
+      // pass 2: candidates {k : s_k <= min + 2E}
+      uint32_t w[4];
+#pragma unroll
       for (int c = 0; c < 4; c += 2) {
         uint32_t r0[32], r1[32];
         tmem_ld_32x32(t_addr + c * 32, r0);
@@ -338,6 +371,8 @@ vq_argmin_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __res
           VQ_TEST(w0, __uint_as_float(r0[i]), gthr, 1u << i);
           VQ_TEST(w1, __uint_as_float(r1[i]), gthr, 1u << i);
         }
+        w[c] = w0;
+        w[c + 1] = w1;
         if (dbg && tile == 0 && g == 0) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
@@ -345,38 +380,59 @@ vq_argmin_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __res
             dbg[(size_t)m * TK + grp * 128 + c * 32 + 32 + i] = __uint_as_float(r1[i]);
           }
         }
-        while (w0) {
-          const int b = __ffs(w0) - 1;
-          w0 &= w0 - 1;
-          const int p = atomicAdd(&wcnt[ew], 1);
-          if (p < WL_CAP) wl[p] = ((uint32_t)m << 16) | (uint32_t)(grp * 128 + c * 32 + b);
-        }
-        while (w1) {
-          const int b = __ffs(w1) - 1;
-          w1 &= w1 - 1;
-          const int p = atomicAdd(&wcnt[ew], 1);
-          if (p < WL_CAP) wl[p] = ((uint32_t)m << 16) | (uint32_t)(grp * 128 + c * 32 + 32 + b);
-        }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&t_empty[h]);  // TMEM buffer h may be overwritten by the next tile's MMAs
-      // exact reference arithmetic on the candidates, all lanes busy; winner per row = min (d, code)
+      {
+        // one shared-memory atomic per warp: exclusive scan of the lanes' candidate counts
+        const int c = __popc(w[0]) + __popc(w[1]) + __popc(w[2]) + __popc(w[3]);
+        int incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int v = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += v;
+        }
+        int base = 0;
+        if (lane == 31 && incl > 0) base = atomicAdd(wcnt, incl);
+        base = __shfl_sync(0xffffffffu, base, 31);
+        if (c) {
+          atomicAdd(&rowcnt[m], c);
+          int p = base + incl - c;
+          const uint32_t ent0 = ((uint32_t)m << 16) | (uint32_t)(grp * 128);
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc) {
+            uint32_t ww = w[cc];
+            while (ww) {
+              const int b = __ffs(ww) - 1;
+              ww &= ww - 1;
+              if (p < WL_CAP) wl[p] = ent0 + cc * 32 + b;
+              ++p;
+            }
+          }
+        }
+      }
+      VQ_ECLK(6);
+      // exact reference arithmetic on the candidates, spread over all scan threads; winner per row = min (d, code)
+      epi_bar(2);
+      VQ_ECLK(7);
       unsigned long long* rb = rowbest + (it & 1) * TM;
-      const int n = wcnt[ew];
+      const int n = *wcnt;  // candidates of the tile
       if (n <= WL_CAP) {
-        for (int e = lane; e < n; e += 32) {
+        for (int e = et; e < n; e += NEW * 32) {
           const uint32_t ent = wl[e];
           const int r = ent >> 16, k = ent & 0xFFFF;
-          atomicMin(&rb[r], ((unsigned long long)ordered_f32(exact_d(r, k)) << 32) | (unsigned)k);
+          if (rowcnt[r] == 1) rb[r] = (unsigned long long)k;  // the only code inside the window IS the exact argmin
+          else atomicMin(&rb[r], ((unsigned long long)ordered_f32(exact_d(r, k)) << 32) | (unsigned)k);
         }
-      } else {  // pathological codebook (dozens of near-ties): every code of this group for this warp's rows
+      } else {  // pathological codebook (dozens of near-ties per row): every code, exactly
         for (int k = grp * 128; k < grp * 128 + 128; ++k)
           atomicMin(&rb[m], ((unsigned long long)ordered_f32(exact_d(m, k)) << 32) | (unsigned)k);
       }
-      __syncwarp();
-      if (lane == 0) wcnt[ew] = 0;
-      epi_bar(2);
+      VQ_ECLK(8);
+      epi_bar(3);
+      VQ_ECLK(9);
+      if (et == 0) *wcnt = 0;  // next appends come after the next tile's barrier 1
       const int besti = (int)(rb[m] & 0xFFFFFFFFull);
       if (grp == 0) {
         idx_out[((size_t)frame * num + g) * hw + s] = (int64_t)besti;
@@ -409,15 +465,13 @@ vq_argmin_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __res
           const uint8_t* xr = xptr(m);
           const int rsw = NHWC ? (m & 7) : ((m & 31) >> 3);
 #pragma unroll 8
-          for (int j = 0; j < TD; ++j) {
-            const float xv = NHWC ? *reinterpret_cast<const float*>(xr + (j >> 5) * 16384 + ((((j >> 2) & 7) ^ rsw) << 4) + (j & 3) * 4)
-                                  : *reinterpret_cast<const float*>(xr + j * 128 + ((rsw ^ (j & 3)) << 5));
-            atomicAdd(sp + j, xv);
-          }
+          for (int j = 0; j < TD; ++j) atomicAdd(sp + j, xelem(xr, rsw, j));
         }
       } else {
         rowbest[((it + 1) & 1) * TM + m] = ~0ull;  // last read before this tile's first barrier
+        rowcnt[m] = 0;                             // next increments come after the next tile's barrier 1
       }
+      VQ_ECLK(10);
       __syncwarp();
       if (lane == 0) mbar_arrive(&a_empty[slot]);
     }
@@ -449,6 +503,8 @@ PFN_encodeTiled encode_fn() {
 }  // namespace
 
 static float* g_dbg_scores = nullptr;
+static unsigned* g_dbg_clk = nullptr;
+extern "C" void lvt_dbg_vq_clock(unsigned* p) { g_dbg_clk = p; }  // debugging aid: per-tile timeline of CTA 0
 extern "C" void lvt_dbg_vq_scores(float* p) { g_dbg_scores = p; }  // debugging aid: dump tile 0 / group 0 scores
 
 // Returns LVT_OK after launching, or 1 when the shape is not covered (caller falls back to the SIMT kernel).
@@ -461,7 +517,7 @@ int lvt_vq_argmin_tc_try(const float* z_e, const float* codebook, int64_t* idx_o
     disabled = (e && e[0] == '1') ? 1 : 0;
   }
   const long long positions = (long long)n * hw;
-  if (disabled || K != TK || D != TD || n <= 0) return 1;
+  if (disabled || K != TK || D != TD || n <= 0 || positions >= (1ll << 31)) return 1;
   if (nhwc ? (positions % TM != 0) : (hw % TM != 0 || zq_bf16 != nullptr)) return 1;
   if ((reinterpret_cast<uintptr_t>(z_e) & 15) != 0 || (reinterpret_cast<uintptr_t>(codebook) & 15) != 0) return 1;
   PFN_encodeTiled enc = encode_fn();
@@ -500,10 +556,10 @@ int lvt_vq_argmin_tc_try(const float* z_e, const float* codebook, int64_t* idx_o
   if (nhwc)
     vq_argmin_tc_kernel<true><<<per_group * num, TC_THREADS, SM_TOTAL, stream>>>(
         tm, codebook, idx_out, zq_out, reinterpret_cast<__nv_bfloat16*>(zq_bf16), counts, sums, num, hw, num_tiles,
-        per_group, g_dbg_scores);
+        per_group, g_dbg_scores, g_dbg_clk);
   else
     vq_argmin_tc_kernel<false><<<per_group * num, TC_THREADS, SM_TOTAL, stream>>>(
-        tm, codebook, idx_out, zq_out, nullptr, counts, sums, num, hw, num_tiles, per_group, g_dbg_scores);
+        tm, codebook, idx_out, zq_out, nullptr, counts, sums, num, hw, num_tiles, per_group, g_dbg_scores, g_dbg_clk);
   LVT_CHECK_LAUNCH();
   lvt_count_launch(1);
   return LVT_OK;
