@@ -112,6 +112,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="slices per GPU")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="DSFVT step only: skip the per-kernel figures and the CPU baseline")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -251,7 +252,7 @@ def main():
 
     # ---------------- per-kernel roofline figures (rank 0, timed alone)
     extra = {}
-    if rank == 0:
+    if rank == 0 and not args.quick:
         from lvt_b200 import ops
         from lvt_b200.ops import Operand
         M, d, N = B * 256, 512, 3072
@@ -333,7 +334,7 @@ def main():
 
     if rank != 0:
         return
-    cpu = cpu_reference_arm(2, 1, batch=8)
+    cpu = cpu_reference_arm(2, 1, batch=8) if not args.quick else {k: None for k in ("value", "unit", "cores", "kind", "sample")}
     step_flops = USEFUL_FLOP_PER_SAMPLE * B  # per GPU
     achieved = step_flops / (ms * 1e-3) / 1e12
     line = {

@@ -99,8 +99,11 @@ def load():
         raise LvtError(
             f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; "
             "g.build()'` (or `make -C lvt_b200/csrc`). lvt_b200 has no CPU / PyTorch fallback.")
-    lib = ctypes.CDLL(LIB_PATH)
+    override = os.environ.get("LVT_B200_LIB")  # A/B timing of an older build (tools/ only)
+    lib = ctypes.CDLL(override or LIB_PATH)
     for name, (res, args) in SYMBOLS.items():
+        if override and not hasattr(lib, name):
+            continue
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args

@@ -5,6 +5,7 @@
 // instruction descriptor follow the PTX ISA tables (the same fields CuTe's
 // cute/arch/mma_sm100_desc.hpp names) and are spelled out below.
 #pragma once
+#include <string.h>
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -55,6 +56,39 @@ void lvt_set_error(const char* fmt, ...);
       return LVT_ERR_CUDA;                                                                \
     }                                                                                     \
   } while (0)
+
+// ----------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL): consecutive kernels of one stream (or of a captured CUDA graph)
+// overlap the next grid's launch + prologue with the previous grid's tail.  Every kernel launched through
+// lvt_launch() calls pdl_launch_dependents() first and pdl_wait() before its first access to global memory
+// (griddepcontrol.wait returns when the prerequisite grid has completed and flushed), so data dependencies
+// between neighbours are unchanged.  The launch attribute is only set when LVT_PDL=1 (see lvt_pdl_enabled()).
+// ----------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_prologue() {
+  pdl_launch_dependents();
+  pdl_wait();
+}
+bool lvt_pdl_enabled();
+template <typename... P, typename... A>
+static inline cudaError_t lvt_launch(void (*kern)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                     A&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = lvt_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<P>(args)...);
+}
+#endif
 
 static inline int lvt_ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 

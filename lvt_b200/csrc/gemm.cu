@@ -62,8 +62,10 @@ struct GemmParams {
   int heads;
   // implicit-GEMM convolution (operand = NHWC activations read through per-tap shifted TMA boxes)
   int a_conv, b_conv, cv_C, cv_W, cv_H;
-  signed char cv_dh[16], cv_dw[16], cv_ph[16];
+  // per-tap offsets packed 4 bits each (value + 8): no dynamically indexed parameter arrays -> no stack copy
+  unsigned long long cv_dh_pk, cv_dw_pk, cv_ph_pk;
 };
+LVT_DEVICE_INLINE int cv_tap(unsigned long long pk, int tap) { return (int)((pk >> (4 * tap)) & 15ull) - 8; }
 
 // store-path bits (template parameter ST); 0 = staged generic epilogue
 constexpr int ST_TMA = 1;     // epilogue writes 128 B-row slabs to smem and stores them with TMA
@@ -137,6 +139,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  pdl_launch_dependents();  // the next kernel's CTAs may be scheduled as soon as SMs free up
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_a);
@@ -162,6 +165,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();  // everything above overlapped the previous kernel's tail; its results are visible from here on
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -171,6 +175,38 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         const TileCoord t = decode_tile(p, tile, BN);
         const int a_zlo = t.z % p.a_zdiv, a_zhi = t.z / p.a_zdiv;
         const int b_zlo = t.z % p.b_zdiv, b_zhi = t.z / p.b_zdiv;
+        if (!(p.a_conv | p.b_conv)) {  // plain operands: keep this loop free of the conv address math
+          for (int it = 0; it < t.num_kb; ++it, ++kiter) {
+            const int s = kiter % STAGES;
+            const uint32_t ph = (kiter / STAGES) & 1;
+            const int k0 = (t.kb_begin + it) * BK;
+            mbar_wait(&empty_bar[s], ph ^ 1);
+            mbar_arrive_expect_tx(&full_bar[s], L::STAGE_BYTES);
+            uint8_t* a_dst = smem + s * L::STAGE_BYTES;
+            uint8_t* b_dst = a_dst + A_TILE_BYTES;
+            if (!A_MN) {
+              tma_load_5d(a_dst, &tm_a, &full_bar[s], k0 % p.a_cin, t.m0, k0 / p.a_cin, a_zlo, a_zhi);
+            } else {
+  #pragma unroll
+              for (int j = 0; j < BM / 64; ++j) {
+                const int c = t.m0 + 64 * j;
+                tma_load_5d(a_dst + j * (64 * BK * 2), &tm_a, &full_bar[s], c % p.a_cin, k0, c / p.a_cin,
+                            a_zlo, a_zhi);
+              }
+            }
+            if (!B_MN) {
+              tma_load_5d(b_dst, &tm_b, &full_bar[s], k0 % p.b_cin, t.n0, k0 / p.b_cin, b_zlo, b_zhi);
+            } else {
+  #pragma unroll
+              for (int j = 0; j < BN / 64; ++j) {
+                const int c = t.n0 + 64 * j;
+                tma_load_5d(b_dst + j * (64 * BK * 2), &tm_b, &full_bar[s], c % p.b_cin, k0, c / p.b_cin,
+                            b_zlo, b_zhi);
+              }
+            }
+          }
+          continue;
+        }
         for (int it = 0; it < t.num_kb; ++it, ++kiter) {
           const int s = kiter % STAGES;
           const uint32_t ph = (kiter / STAGES) & 1;
@@ -185,7 +221,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
               const int tap = k0 / p.cv_C, c0 = k0 - tap * p.cv_C;
               const int hw = p.cv_H * p.cv_W;
               const int img = t.m0 / hw, h0 = (t.m0 - img * hw) / p.cv_W;
-              tma_load_5d(a_dst, &tm_a, &full_bar[s], c0, p.cv_dw[tap], h0 + p.cv_dh[tap], img, p.cv_ph[tap]);
+              tma_load_5d(a_dst, &tm_a, &full_bar[s], c0, cv_tap(p.cv_dw_pk, tap), h0 + cv_tap(p.cv_dh_pk, tap), img, cv_tap(p.cv_ph_pk, tap));
             } else {
               tma_load_5d(a_dst, &tm_a, &full_bar[s], k0 % p.a_cin, t.m0, k0 / p.a_cin, a_zlo, a_zhi);
             }
@@ -208,8 +244,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 const int tap = c / p.cv_C, c0 = c - tap * p.cv_C;
                 const int hw = p.cv_H * p.cv_W;
                 const int img = k0 / hw, h0 = (k0 - img * hw) / p.cv_W;
-                tma_load_5d(b_dst + j * (64 * BK * 2), &tm_b, &full_bar[s], c0, p.cv_dw[tap], h0 + p.cv_dh[tap],
-                            img, p.cv_ph[tap]);
+                tma_load_5d(b_dst + j * (64 * BK * 2), &tm_b, &full_bar[s], c0, cv_tap(p.cv_dw_pk, tap),
+                            h0 + cv_tap(p.cv_dh_pk, tap), img, cv_tap(p.cv_ph_pk, tap));
               } else {
                 tma_load_5d(b_dst + j * (64 * BK * 2), &tm_b, &full_bar[s], c % p.b_cin, k0, c / p.b_cin,
                             b_zlo, b_zhi);
@@ -809,8 +845,7 @@ int launch_gemm(const Maps& m, const GemmParams& p, int grid, cudaStream_t strea
     LVT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     configured = true;
   }
-  kern<<<grid, NUM_THREADS, L::TOTAL, stream>>>(m.a, m.b, m.o, m.c, p);
-  LVT_CHECK_LAUNCH();
+  LVT_CHECK_CUDA(lvt_launch(kern, dim3(grid), dim3(NUM_THREADS), L::TOTAL, stream, m.a, m.b, m.o, m.c, p));
   lvt_count_launch(1);
   return LVT_OK;
 }
@@ -937,7 +972,11 @@ extern "C" int lvt_gemm_bf16(const LvtGemm* g, void* stream_) {
     LVT_CHECK_ARG(!(g->a_conv && g->b_conv), "lvt_gemm_bf16: only one conv operand");
     p.a_conv = g->a_conv; p.b_conv = g->b_conv; p.cv_C = g->cv_C; p.cv_W = g->cv_W; p.cv_H = g->cv_H;
     for (int i = 0; i < g->cv_ntaps; ++i) {
-      p.cv_dh[i] = g->cv_dh[i]; p.cv_dw[i] = g->cv_dw[i]; p.cv_ph[i] = g->cv_ph[i];
+      LVT_CHECK_ARG(g->cv_dh[i] >= -8 && g->cv_dh[i] < 8 && g->cv_dw[i] >= -8 && g->cv_dw[i] < 8 && g->cv_ph[i] >= 0 &&
+                        g->cv_ph[i] < 8, "lvt_gemm_bf16: conv tap offsets must lie in [-8, 8), phases in [0, 8)");
+      p.cv_dh_pk |= (unsigned long long)(g->cv_dh[i] + 8) << (4 * i);
+      p.cv_dw_pk |= (unsigned long long)(g->cv_dw[i] + 8) << (4 * i);
+      p.cv_ph_pk |= (unsigned long long)(g->cv_ph[i] + 8) << (4 * i);
     }
     const long long pix = g->cv_pix_stride > 0 ? g->cv_pix_stride : g->cv_C;
     if (g->a_conv) {

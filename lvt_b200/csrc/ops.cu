@@ -33,6 +33,7 @@ __global__ void __launch_bounds__(256)
 ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
               const float* __restrict__ beta, __nv_bfloat16* __restrict__ y,
               float* __restrict__ mean, float* __restrict__ rstd, int M, float eps) {
+  pdl_prologue();
   constexpr int d = V4 * 128;
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -76,6 +77,7 @@ ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
               const float* __restrict__ gamma, const float* __restrict__ dres,
               float* __restrict__ dx, __nv_bfloat16* __restrict__ dx_bf16,
               float* __restrict__ dgamma, float* __restrict__ dbeta, int M) {
+  pdl_prologue();
   constexpr int d = V4 * 128;
   __shared__ float s_red[8][d + 4];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -136,6 +138,7 @@ ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
 __global__ void __launch_bounds__(256)
 colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, int M, int N,
                    long long ld, int rows_per_block) {
+  pdl_prologue();
   __shared__ float s[8][64];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = blockIdx.x * 64 + tx * 2;
@@ -165,6 +168,7 @@ colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out,
 __global__ void __launch_bounds__(256)
 attn_delta_kernel(const __nv_bfloat16* __restrict__ dO, const __nv_bfloat16* __restrict__ O,
                   float* __restrict__ delta, int nb, int H, int L, int da) {
+  pdl_prologue();
   const long long wid = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   const long long total = (long long)nb * L * H;
@@ -194,6 +198,7 @@ __global__ void __launch_bounds__(256)
 relpos_bank_grad_kernel(const __nv_bfloat16* __restrict__ dS, float* __restrict__ dbt,
                         float* __restrict__ dbh, float* __restrict__ dbw, int nb, int H, int bt,
                         int bh, int bw) {
+  pdl_prologue();
   const int L = bt * bh * bw;  // == 256
   const int h = blockIdx.y;
   const int e0 = blockIdx.x * 2048 + threadIdx.x * 8;  // element of the L x L plane
@@ -295,6 +300,7 @@ enc_front_fwd_kernel(const int64_t* __restrict__ ctx, const int64_t* __restrict_
                      const float* __restrict__ wt, const float* __restrict__ bias,
                      const float* __restrict__ slice_emb, __nv_bfloat16* __restrict__ out,
                      EncFrontDims D) {
+  pdl_prologue();
   const long long pos = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   const long long per = (long long)D.to * D.ho * D.wo;
@@ -329,6 +335,7 @@ __global__ void __launch_bounds__(256)
 enc_front_bwd_kernel(const int64_t* __restrict__ ctx, const int64_t* __restrict__ slice_idx,
                      const float* __restrict__ dout, float* __restrict__ dwt,
                      float* __restrict__ dslice_emb, EncFrontDims D) {
+  pdl_prologue();
   const long long pos = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   const long long per = (long long)D.to * D.ho * D.wo;
@@ -368,6 +375,7 @@ struct DecFrontDims {
 __global__ void __launch_bounds__(256)
 dec_front_fwd_kernel(const int64_t* __restrict__ slc, const float* __restrict__ emb,
                      const int* __restrict__ taps, __nv_bfloat16* __restrict__ out, DecFrontDims D) {
+  pdl_prologue();
   const long long wid = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   const int thw = D.t * D.h * D.w;
@@ -401,6 +409,7 @@ dec_front_fwd_kernel(const int64_t* __restrict__ slc, const float* __restrict__ 
 __global__ void __launch_bounds__(256)
 dec_front_bwd_kernel(const int64_t* __restrict__ slc, const float* __restrict__ dA,
                      const int* __restrict__ taps, float* __restrict__ demb_tab, DecFrontDims D) {
+  pdl_prologue();
   const long long m = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   const int thw = D.t * D.h * D.w;
@@ -434,6 +443,7 @@ __global__ void __launch_bounds__(256)
 chpred_combine_fwd_kernel(const float* __restrict__ u, const float* __restrict__ ut,
                           const int64_t* __restrict__ slc, __nv_bfloat16* __restrict__ a, int M,
                           int nc, int nv, int d, int thw, int k) {
+  pdl_prologue();
   const long long m = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (m >= M) return;
@@ -453,6 +463,7 @@ chpred_combine_fwd_kernel(const float* __restrict__ u, const float* __restrict__
 __global__ void __launch_bounds__(256)
 chpred_combine_bwd_kernel(const __nv_bfloat16* __restrict__ du, const int64_t* __restrict__ slc,
                           float* __restrict__ dut, int M, int nc, int nv, int d, int thw, int k) {
+  pdl_prologue();
   const long long m = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (m >= M) return;
@@ -473,6 +484,7 @@ chpred_combine_bwd_kernel(const __nv_bfloat16* __restrict__ du, const int64_t* _
 // cnt[0] = number of valid rows (the ignore mask is shared by all channels).
 // ------------------------------------------------------------------------------------------
 __global__ void count_valid_kernel(const uint8_t* __restrict__ ignore, int n, int* __restrict__ cnt) {
+  pdl_prologue();
   int c = 0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
     c += ignore[i] ? 0 : 1;
@@ -486,6 +498,7 @@ cross_entropy_kernel(const float* __restrict__ logits, const int64_t* __restrict
                      const uint8_t* __restrict__ ignore, const int* __restrict__ cnt,
                      __nv_bfloat16* __restrict__ dlogits, float* __restrict__ loss, int M, int nc,
                      int thw) {
+  pdl_prologue();
   constexpr int nv = V4 * 128;
   __shared__ float s_loss[8];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -553,6 +566,7 @@ __global__ void __launch_bounds__(256)
 rmsprop_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ sq,
                float* __restrict__ buf, __nv_bfloat16* __restrict__ pb, long long n4, float lr,
                float alpha, float momentum, float eps, float gscale) {
+  pdl_prologue();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
        i += (long long)gridDim.x * blockDim.x) {
     float4 P = ld4(p + 4 * i), G = ld4(g + 4 * i), S = ld4(sq + 4 * i), Bf = ld4(buf + 4 * i);
@@ -574,6 +588,7 @@ __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
             float* __restrict__ v, __nv_bfloat16* __restrict__ pb, long long n4, float lr,
             float beta1, float beta2, float eps, float bc1, float rsqrt_bc2, float gscale) {
+  pdl_prologue();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
        i += (long long)gridDim.x * blockDim.x) {
     float4 P = ld4(p + 4 * i), G = ld4(g + 4 * i), Mm = ld4(m + 4 * i), V = ld4(v + 4 * i);
@@ -593,6 +608,7 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
 
 __global__ void __launch_bounds__(256)
 cast_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n4) {
+  pdl_prologue();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
        i += (long long)gridDim.x * blockDim.x) {
     const float4 v = ld4(in + 4 * i);
@@ -608,6 +624,7 @@ struct Permute4 {
 template <bool BF16, bool ACC>
 __global__ void __launch_bounds__(256)
 permute4_kernel(const float* __restrict__ in, void* __restrict__ out, Permute4 P, long long total) {
+  pdl_prologue();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     long long r = i;
@@ -644,8 +661,8 @@ extern "C" int lvt_layernorm_fwd(const float* x, const float* gamma, const float
   LVT_CHECK_ARG(x && gamma && beta && y_bf16 && mean && rstd && M > 0, "lvt_layernorm_fwd: bad argument");
   LVT_CHECK_ARG(d % 128 == 0, "lvt_layernorm_fwd: d must be a multiple of 128");
   int rc = dispatch_v4(d / 128, [&](auto v4) {
-    ln_fwd_kernel<decltype(v4)::value><<<lvt_ceil_div(M, 8), 256, 0, STREAM(stream)>>>(
-        x, gamma, beta, reinterpret_cast<__nv_bfloat16*>(y_bf16), mean, rstd, M, eps);
+    LVT_CHECK_CUDA(lvt_launch(ln_fwd_kernel<decltype(v4)::value>, dim3(lvt_ceil_div(M, 8)), dim3(256), 0, STREAM(stream), 
+        x, gamma, beta, reinterpret_cast<__nv_bfloat16*>(y_bf16), mean, rstd, M, eps));
     return LVT_OK;
   });
   if (rc) return rc;
@@ -663,9 +680,9 @@ extern "C" int lvt_layernorm_bwd(const float* dy, const float* x, const float* m
   int rc = dispatch_v4(d / 128, [&](auto v4) {
     constexpr int V4 = decltype(v4)::value;
     if constexpr (V4 <= 4) {
-      ln_bwd_kernel<V4><<<blocks, 256, 0, STREAM(stream)>>>(dy, x, mean, rstd, gamma, dres, dx_f32,
+      LVT_CHECK_CUDA(lvt_launch(ln_bwd_kernel<V4>, dim3(blocks), dim3(256), 0, STREAM(stream), dy, x, mean, rstd, gamma, dres, dx_f32,
                                                            reinterpret_cast<__nv_bfloat16*>(dx_bf16),
-                                                           dgamma, dbeta, M);
+                                                           dgamma, dbeta, M));
     }
     return LVT_OK;
   });
@@ -681,8 +698,8 @@ extern "C" int lvt_colsum_bf16(const void* x, float* out, int M, int N, long lon
   int ysplit = max(1, min(lvt_ceil_div(M, 64), (kSMs * 4) / strips));
   const int rows_per_block = lvt_ceil_div(M, ysplit);
   ysplit = lvt_ceil_div(M, rows_per_block);
-  colsum_bf16_kernel<<<dim3(strips, ysplit), 256, 0, STREAM(stream)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(x), out, M, N, ld, rows_per_block);
+  LVT_CHECK_CUDA(lvt_launch(colsum_bf16_kernel, dim3(dim3(strips, ysplit)), dim3(256), 0, STREAM(stream), 
+      reinterpret_cast<const __nv_bfloat16*>(x), out, M, N, ld, rows_per_block));
   LVT_CHECK_LAUNCH();
   lvt_count_launch(1);
   return LVT_OK;
@@ -692,8 +709,8 @@ extern "C" int lvt_attn_delta(const void* dO, const void* O, float* delta, int n
                               void* stream) {
   LVT_CHECK_ARG(dO && O && delta && nb > 0 && da % 4 == 0, "lvt_attn_delta: bad argument");
   const long long warps = (long long)nb * L * H;
-  attn_delta_kernel<<<lvt_ceil_div(warps, 8), 256, 0, STREAM(stream)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(dO), reinterpret_cast<const __nv_bfloat16*>(O), delta, nb, H, L, da);
+  LVT_CHECK_CUDA(lvt_launch(attn_delta_kernel, dim3(lvt_ceil_div(warps, 8)), dim3(256), 0, STREAM(stream), 
+      reinterpret_cast<const __nv_bfloat16*>(dO), reinterpret_cast<const __nv_bfloat16*>(O), delta, nb, H, L, da));
   LVT_CHECK_LAUNCH();
   lvt_count_launch(1);
   return LVT_OK;
@@ -704,8 +721,8 @@ extern "C" int lvt_relpos_bank_grad(const void* dS, float* dbank_t, float* dbank
   LVT_CHECK_ARG(dS && dbank_t && dbank_h && dbank_w && nb > 0, "lvt_relpos_bank_grad: bad argument");
   LVT_CHECK_ARG(bt * bh * bw == 256 && 2 * (bt + bh + bw) - 3 <= 64, "lvt_relpos_bank_grad: block must hold 256 positions and <= 64 offsets");
   const int zsplit = nb >= 16 ? 4 : 1;
-  relpos_bank_grad_kernel<<<dim3(32, H, zsplit), 256, 0, STREAM(stream)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(dS), dbank_t, dbank_h, dbank_w, nb, H, bt, bh, bw);
+  LVT_CHECK_CUDA(lvt_launch(relpos_bank_grad_kernel, dim3(dim3(32, H, zsplit)), dim3(256), 0, STREAM(stream), 
+      reinterpret_cast<const __nv_bfloat16*>(dS), dbank_t, dbank_h, dbank_w, nb, H, bt, bh, bw));
   LVT_CHECK_LAUNCH();
   lvt_count_launch(1);
   return LVT_OK;
@@ -732,8 +749,8 @@ extern "C" int lvt_vt_enc_front_fwd(const int64_t* context, const int64_t* slice
   int rc = enc_dims(&D, B, nc, nv, de, ctx_shape, kernel, stride, pad_value);
   if (rc) return rc;
   const long long npos = (long long)B * D.to * D.ho * D.wo;
-  enc_front_fwd_kernel<<<lvt_ceil_div(npos, 8), 256, 0, STREAM(stream)>>>(
-      context, slice_idx, wt, bias, slice_emb, reinterpret_cast<__nv_bfloat16*>(out_bf16), D);
+  LVT_CHECK_CUDA(lvt_launch(enc_front_fwd_kernel, dim3(lvt_ceil_div(npos, 8)), dim3(256), 0, STREAM(stream), 
+      context, slice_idx, wt, bias, slice_emb, reinterpret_cast<__nv_bfloat16*>(out_bf16), D));
   LVT_CHECK_LAUNCH();
   lvt_count_launch(1);
   return LVT_OK;
@@ -748,8 +765,8 @@ extern "C" int lvt_vt_enc_front_bwd(const int64_t* context, const int64_t* slice
   int rc = enc_dims(&D, B, nc, nv, de, ctx_shape, kernel, stride, pad_value);
   if (rc) return rc;
   const long long npos = (long long)B * D.to * D.ho * D.wo;
-  enc_front_bwd_kernel<<<lvt_ceil_div(npos, 8), 256, 0, STREAM(stream)>>>(context, slice_idx, dout, dwt,
-                                                                        dslice_emb, D);
+  LVT_CHECK_CUDA(lvt_launch(enc_front_bwd_kernel, dim3(lvt_ceil_div(npos, 8)), dim3(256), 0, STREAM(stream), context, slice_idx, dout, dwt,
+                                                                        dslice_emb, D));
   LVT_CHECK_LAUNCH();
   lvt_count_launch(1);
   return LVT_OK;
@@ -761,8 +778,8 @@ extern "C" int lvt_vt_dec_front_fwd(const int64_t* slc, const float* emb, const 
   LVT_CHECK_ARG(slc && emb && taps && out_bf16 && B > 0 && ntaps > 0 && de % 4 == 0, "lvt_vt_dec_front_fwd: bad argument");
   DecFrontDims D{B, nc, nv, de, t, h, w, ntaps};
   const long long warps = (long long)B * t * h * w * ntaps;
-  dec_front_fwd_kernel<<<lvt_ceil_div(warps, 8), 256, 0, STREAM(stream)>>>(
-      slc, emb, taps, reinterpret_cast<__nv_bfloat16*>(out_bf16), D);
+  LVT_CHECK_CUDA(lvt_launch(dec_front_fwd_kernel, dim3(lvt_ceil_div(warps, 8)), dim3(256), 0, STREAM(stream), 
+      slc, emb, taps, reinterpret_cast<__nv_bfloat16*>(out_bf16), D));
   LVT_CHECK_LAUNCH();
   lvt_count_launch(1);
   return LVT_OK;
@@ -773,7 +790,7 @@ extern "C" int lvt_vt_dec_front_bwd(const int64_t* slc, const float* dA, const i
                                     void* stream) {
   LVT_CHECK_ARG(slc && dA && taps && demb && B > 0 && ntaps > 0 && de % 4 == 0, "lvt_vt_dec_front_bwd: bad argument");
   DecFrontDims D{B, nc, nv, de, t, h, w, ntaps};
-  dec_front_bwd_kernel<<<lvt_ceil_div((long long)B * t * h * w, 8), 256, 0, STREAM(stream)>>>(slc, dA, taps, demb, D);
+  LVT_CHECK_CUDA(lvt_launch(dec_front_bwd_kernel, dim3(lvt_ceil_div((long long)B * t * h * w, 8)), dim3(256), 0, STREAM(stream), slc, dA, taps, demb, D));
   LVT_CHECK_LAUNCH();
   lvt_count_launch(1);
   return LVT_OK;
@@ -782,8 +799,8 @@ extern "C" int lvt_vt_dec_front_bwd(const int64_t* slc, const float* dA, const i
 extern "C" int lvt_chpred_combine_fwd(const float* u, const float* ut, const int64_t* slc, void* a_bf16,
                                       int M, int nc, int nv, int d, int thw, int k, void* stream) {
   LVT_CHECK_ARG(u && slc && a_bf16 && (k == 0 || ut) && M > 0 && d % 4 == 0 && k >= 0 && k < nc, "lvt_chpred_combine_fwd: bad argument");
-  chpred_combine_fwd_kernel<<<lvt_ceil_div(M, 8), 256, 0, STREAM(stream)>>>(
-      u, ut, slc, reinterpret_cast<__nv_bfloat16*>(a_bf16), M, nc, nv, d, thw, k);
+  LVT_CHECK_CUDA(lvt_launch(chpred_combine_fwd_kernel, dim3(lvt_ceil_div(M, 8)), dim3(256), 0, STREAM(stream), 
+      u, ut, slc, reinterpret_cast<__nv_bfloat16*>(a_bf16), M, nc, nv, d, thw, k));
   LVT_CHECK_LAUNCH();
   lvt_count_launch(1);
   return LVT_OK;
@@ -794,8 +811,8 @@ extern "C" int lvt_chpred_combine_bwd(const void* du_bf16, const int64_t* slc, f
   LVT_CHECK_ARG(du_bf16 && slc && M > 0 && d % 4 == 0 && k >= 0 && k < nc, "lvt_chpred_combine_bwd: bad argument");
   if (k == 0) return LVT_OK;
   LVT_CHECK_ARG(dut, "lvt_chpred_combine_bwd: null dut");
-  chpred_combine_bwd_kernel<<<lvt_ceil_div(M, 8), 256, 0, STREAM(stream)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(du_bf16), slc, dut, M, nc, nv, d, thw, k);
+  LVT_CHECK_CUDA(lvt_launch(chpred_combine_bwd_kernel, dim3(lvt_ceil_div(M, 8)), dim3(256), 0, STREAM(stream), 
+      reinterpret_cast<const __nv_bfloat16*>(du_bf16), slc, dut, M, nc, nv, d, thw, k));
   LVT_CHECK_LAUNCH();
   lvt_count_launch(1);
   return LVT_OK;
@@ -809,10 +826,10 @@ extern "C" int lvt_cross_entropy(const float* logits, const int64_t* slc, const 
   const int M = B * thw;
   LVT_CHECK_CUDA(cudaMemsetAsync(count_scratch, 0, sizeof(int), STREAM(stream)));
   LVT_CHECK_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), STREAM(stream)));
-  count_valid_kernel<<<min(lvt_ceil_div(M, 256), kSMs), 256, 0, STREAM(stream)>>>(ignore, M, count_scratch);
+  LVT_CHECK_CUDA(lvt_launch(count_valid_kernel, dim3(min(lvt_ceil_div(M, 256), kSMs)), dim3(256), 0, STREAM(stream), ignore, M, count_scratch));
   int rc = dispatch_v4(nv / 128, [&](auto v4) {
-    cross_entropy_kernel<decltype(v4)::value><<<lvt_ceil_div((long long)nc * M, 8), 256, 0, STREAM(stream)>>>(
-        logits, slc, ignore, count_scratch, reinterpret_cast<__nv_bfloat16*>(dlogits_bf16), loss, M, nc, thw);
+    LVT_CHECK_CUDA(lvt_launch(cross_entropy_kernel<decltype(v4)::value>, dim3(lvt_ceil_div((long long)nc * M, 8)), dim3(256), 0, STREAM(stream), 
+        logits, slc, ignore, count_scratch, reinterpret_cast<__nv_bfloat16*>(dlogits_bf16), loss, M, nc, thw));
     return LVT_OK;
   });
   if (rc) return rc;
@@ -827,8 +844,8 @@ extern "C" int lvt_rmsprop_step(float* p, const float* g, float* sq, float* buf,
                                 float lr, float alpha, float momentum, float eps, float grad_scale,
                                 void* stream) {
   LVT_CHECK_ARG(p && g && sq && buf && n > 0 && n % 4 == 0, "lvt_rmsprop_step: bad argument (n must be a multiple of 4)");
-  rmsprop_kernel<<<flat_grid(n / 4), 256, 0, STREAM(stream)>>>(p, g, sq, buf, reinterpret_cast<__nv_bfloat16*>(p_bf16),
-                                                              n / 4, lr, alpha, momentum, eps, grad_scale);
+  LVT_CHECK_CUDA(lvt_launch(rmsprop_kernel, dim3(flat_grid(n / 4)), dim3(256), 0, STREAM(stream), p, g, sq, buf, reinterpret_cast<__nv_bfloat16*>(p_bf16),
+                                                              n / 4, lr, alpha, momentum, eps, grad_scale));
   LVT_CHECK_LAUNCH();
   lvt_count_launch(1);
   return LVT_OK;
@@ -838,9 +855,9 @@ extern "C" int lvt_adam_step(float* p, const float* g, float* m, float* v, void*
                              float beta1, float beta2, float eps, int step, float grad_scale, void* stream) {
   LVT_CHECK_ARG(p && g && m && v && n > 0 && n % 4 == 0 && step >= 1, "lvt_adam_step: bad argument");
   const double bc1 = 1.0 - pow((double)beta1, step), bc2 = 1.0 - pow((double)beta2, step);
-  adam_kernel<<<flat_grid(n / 4), 256, 0, STREAM(stream)>>>(p, g, m, v, reinterpret_cast<__nv_bfloat16*>(p_bf16), n / 4,
+  LVT_CHECK_CUDA(lvt_launch(adam_kernel, dim3(flat_grid(n / 4)), dim3(256), 0, STREAM(stream), p, g, m, v, reinterpret_cast<__nv_bfloat16*>(p_bf16), n / 4,
                                                            lr, beta1, beta2, eps, (float)bc1,
-                                                           (float)(1.0 / sqrt(bc2)), grad_scale);
+                                                           (float)(1.0 / sqrt(bc2)), grad_scale));
   LVT_CHECK_LAUNCH();
   lvt_count_launch(1);
   return LVT_OK;
@@ -848,7 +865,7 @@ extern "C" int lvt_adam_step(float* p, const float* g, float* m, float* v, void*
 
 extern "C" int lvt_cast_bf16(const float* in, void* out_bf16, long long n, void* stream) {
   LVT_CHECK_ARG(in && out_bf16 && n > 0 && n % 4 == 0, "lvt_cast_bf16: bad argument");
-  cast_bf16_kernel<<<flat_grid(n / 4), 256, 0, STREAM(stream)>>>(in, reinterpret_cast<__nv_bfloat16*>(out_bf16), n / 4);
+  LVT_CHECK_CUDA(lvt_launch(cast_bf16_kernel, dim3(flat_grid(n / 4)), dim3(256), 0, STREAM(stream), in, reinterpret_cast<__nv_bfloat16*>(out_bf16), n / 4));
   LVT_CHECK_LAUNCH();
   lvt_count_launch(1);
   return LVT_OK;
@@ -866,9 +883,9 @@ extern "C" int lvt_permute4(const float* in, void* out, int out_is_bf16, int acc
   }
   LVT_CHECK_ARG(total > 0, "lvt_permute4: empty");
   const int grid = (int)min((long long)kSMs * 8, (total + 255) / 256);
-  if (out_is_bf16) permute4_kernel<true, false><<<grid, 256, 0, STREAM(stream)>>>(in, out, P, total);
-  else if (accumulate) permute4_kernel<false, true><<<grid, 256, 0, STREAM(stream)>>>(in, out, P, total);
-  else permute4_kernel<false, false><<<grid, 256, 0, STREAM(stream)>>>(in, out, P, total);
+  if (out_is_bf16) LVT_CHECK_CUDA(lvt_launch(permute4_kernel<true, false>, dim3(grid), dim3(256), 0, STREAM(stream), in, out, P, total));
+  else if (accumulate) LVT_CHECK_CUDA(lvt_launch(permute4_kernel<false, true>, dim3(grid), dim3(256), 0, STREAM(stream), in, out, P, total));
+  else LVT_CHECK_CUDA(lvt_launch(permute4_kernel<false, false>, dim3(grid), dim3(256), 0, STREAM(stream), in, out, P, total));
   LVT_CHECK_LAUNCH();
   lvt_count_launch(1);
   return LVT_OK;
