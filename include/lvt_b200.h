@@ -98,7 +98,10 @@ enum {
   LVT_GEMM_MASK = 2,       /* v *= (aux_bf16 > 0)  (ReLU backward)                           */
   LVT_GEMM_ATOMIC = 4,     /* out_f32 += v with red.global.add (split-K / grad accumulate)   */
   LVT_GEMM_CAUSAL = 8,     /* SOFTMAX mode: mask keys j > query i                            */
-  LVT_GEMM_AUX_ADD = 16    /* v += aux_bf16 (bf16 residual, ResBlock skip), before the ReLU  */
+  LVT_GEMM_AUX_ADD = 16,   /* v += aux_bf16 (bf16 residual, ResBlock skip), before the ReLU  */
+  LVT_GEMM_ROWDOT = 32     /* rowdot[...] = sum over each rd_block columns of v * aux_bf16: the softmax-backward
+                              row term delta = rowsum(dO * O) (vt_attention.py:75-80) produced by the GEMM
+                              that computes dO; bf16 output, batch == 1                          */
 };
 
 typedef struct LvtGemm {
@@ -138,6 +141,9 @@ typedef struct LvtGemm {
   int cv_C, cv_W, cv_H, cv_N, cv_P, cv_ntaps;
   long long cv_pix_stride, cv_s_phase;
   signed char cv_dh[16], cv_dw[16], cv_ph[16];
+  /* LVT_GEMM_ROWDOT: rowdot[((m / rd_L) * (N / rd_block) + n / rd_block) * rd_L + m % rd_L]
+     (= delta[sequence, head, position] for rd_block = da, rd_L = block length)                 */
+  float* rowdot; int rd_block, rd_L;
 } LvtGemm;
 
 int lvt_gemm_bf16(const LvtGemm* g, void* stream);

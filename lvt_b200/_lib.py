@@ -45,6 +45,7 @@ class LvtGemm(ctypes.Structure):
         ("cv_P", ctypes.c_int), ("cv_ntaps", ctypes.c_int),
         ("cv_pix_stride", ctypes.c_longlong), ("cv_s_phase", ctypes.c_longlong),
         ("cv_dh", ctypes.c_byte * 16), ("cv_dw", ctypes.c_byte * 16), ("cv_ph", ctypes.c_byte * 16),
+        ("rowdot", ctypes.c_void_p), ("rd_block", ctypes.c_int), ("rd_L", ctypes.c_int),
     ]
 
 

@@ -60,6 +60,8 @@ struct GemmParams {
   const float* bank_h;
   const float* bank_w;
   int heads;
+  float* rowdot;  // LVT_GEMM_ROWDOT
+  int rd_block, rd_L;
   // implicit-GEMM convolution (operand = NHWC activations read through per-tap shifted TMA boxes)
   int a_conv, b_conv, cv_C, cv_W, cv_H;
   // per-tap offsets packed 4 bits each (value + 8): no dynamically indexed parameter arrays -> no stack copy
@@ -324,6 +326,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         const float alpha = p.alpha;
         const bool relu = (p.flags & LVT_GEMM_RELU) != 0;
         const int ncols = min(BN, p.N - t.n0);
+        float rd_acc = 0.f;  // LVT_GEMM_ROWDOT: running sum over the current block of rd_block columns
+        (void)rd_acc;
         float dl = 0.f;
         if constexpr (EK == EK_DS) dl = (row_base + lane < p.M) ? p.delta[(long long)t.z * p.M + row_base + lane] : 0.f;
         auto issue_c = [&](int c0) {
@@ -389,6 +393,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 }
               }
               if constexpr (CLOAD && !F32) {
+                if (p.flags & LVT_GEMM_ROWDOT) {  // delta = rowsum(dO * O): this lane's row of both
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) {
+                    const uint32_t w[4] = {cr[4 * h + k].x, cr[4 * h + k].y, cr[4 * h + k].z, cr[4 * h + k].w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                      const float2 pf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[j]));
+                      rd_acc = fmaf(v[8 * k + 2 * j], pf.x, rd_acc);
+                      rd_acc = fmaf(v[8 * k + 2 * j + 1], pf.y, rd_acc);
+                    }
+                  }
+                }
                 if (p.flags & LVT_GEMM_AUX_ADD) {  // bf16 residual (ResBlock skip connection)
 #pragma unroll
                   for (int k = 0; k < 4; ++k) {
@@ -437,6 +453,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 slab[lane * 8 + (k ^ (lane & 7))] =
                     make_uint4(__float_as_uint(v[4 * k]), __float_as_uint(v[4 * k + 1]),
                                __float_as_uint(v[4 * k + 2]), __float_as_uint(v[4 * k + 3]));
+            }
+          }
+          if constexpr (CLOAD && !F32 && EK == EK_LINEAR) {
+            if ((p.flags & LVT_GEMM_ROWDOT) && (col0 + SLAB_COLS) % p.rd_block == 0) {  // block of columns complete
+              const int row = row_base + lane;
+              if (row < p.M) {
+                const int seq = row / p.rd_L;
+                p.rowdot[((long long)seq * (p.N / p.rd_block) + col0 / p.rd_block) * p.rd_L + (row - seq * p.rd_L)] = rd_acc;
+              }
+              rd_acc = 0.f;
             }
           }
           fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA (async proxy)
@@ -904,6 +930,11 @@ extern "C" int lvt_gemm_bf16(const LvtGemm* g, void* stream_) {
   LVT_CHECK_ARG(g->o_ld % 4 == 0 && g->o_s_blk % 4 == 0 && g->o_s_zlo % 4 == 0 && g->o_s_zhi % 4 == 0,
                 "lvt_gemm_bf16: output strides must be multiples of 4 elements");
   if (g->flags & (LVT_GEMM_MASK | LVT_GEMM_AUX_ADD)) LVT_CHECK_ARG(g->aux_bf16, "lvt_gemm_bf16: MASK / AUX_ADD need aux_bf16");
+  if (g->flags & LVT_GEMM_ROWDOT)
+    LVT_CHECK_ARG(g->aux_bf16 && g->rowdot && g->out_bf16 && !g->out_f32 && !g->res && g->batch == 1 && splits == 1 &&
+                      g->mode == LVT_EPI_LINEAR && (g->rd_block == 64 || g->rd_block == 128) && g->N % g->rd_block == 0 &&
+                      g->rd_L > 0 && g->M % g->rd_L == 0,
+                  "lvt_gemm_bf16: ROWDOT needs aux_bf16, rowdot, a single bf16 output, batch 1, rd_block in {64, 128} dividing N, rd_L | M");
 
   int bn = 128;
   int ek = EK_LINEAR;
@@ -960,6 +991,7 @@ extern "C" int lvt_gemm_bf16(const LvtGemm* g, void* stream_) {
   p.lse = g->lse; p.delta = g->delta;
   p.bank_t = g->bank_t; p.bank_h = g->bank_h; p.bank_w = g->bank_w;
   p.heads = g->heads > 0 ? g->heads : 1;
+  p.rowdot = g->rowdot; p.rd_block = g->rd_block; p.rd_L = g->rd_L;
 
   Maps m;
   memset(&m, 0, sizeof(m));
@@ -1013,7 +1045,7 @@ extern "C" int lvt_gemm_bf16(const LvtGemm* g, void* stream_) {
     const int slab_cols = 128 / esize;
     const void* obase = g->out_bf16 ? g->out_bf16 : (void*)g->out_f32;
     const bool atomic = (g->flags & LVT_GEMM_ATOMIC) != 0,
-               mask = (g->flags & (LVT_GEMM_MASK | LVT_GEMM_AUX_ADD)) != 0;
+               mask = (g->flags & (LVT_GEMM_MASK | LVT_GEMM_AUX_ADD | LVT_GEMM_ROWDOT)) != 0;
     const void* cbase = nullptr;
     int want = -1;
     if (ek == EK_DS) { want = ST_TMA | ST_CLOAD; cbase = g->aux_bf16; }
@@ -1039,6 +1071,8 @@ extern "C" int lvt_gemm_bf16(const LvtGemm* g, void* stream_) {
     }
   }
 
+  LVT_CHECK_ARG(!(g->flags & LVT_GEMM_ROWDOT) || st == (ST_TMA | ST_CLOAD),
+                "lvt_gemm_bf16: ROWDOT needs 128-byte aligned bf16 output / aux rows (TMA epilogue)");
   const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
   const bool amn = g->a_mn_major != 0, bmn = g->b_mn_major != 0;
   if (ek == EK_SOFTMAX_1x16x16 || ek == EK_SOFTMAX_4x8x8) {

@@ -448,11 +448,10 @@ class VTEngine:
         # ---- attention output projection
         dhb = ws.dh_bf16.data_ptr()
         self._wgrad(dhb, d, ly.o.data_ptr(), H * da, Operand(st.gf(prefix + "mha.proj.weight"), H * da), d, H * da, M)
+        # dO = dh Wproj; its epilogue also emits delta[seq, head, i] = rowsum(dO * O) (softmax backward row term)
         gemm(M, H * da, d, Operand(dhb, d), Operand(st.pb(prefix + "mha.proj.weight"), H * da, mn_major=True),
-             Operand(ws.do.data_ptr(), H * da), out_bf16=ws.do)
+             Operand(ws.do.data_ptr(), H * da), out_bf16=ws.do, aux=ly.o, rowdot=ws.delta, rd_block=da, rd_L=L)
         # ---- softmax attention backward
-        check(self.lib.lvt_attn_delta(ptr(ws.do), ptr(ly.o), ptr(ws.delta), ws.nseq, H, L, da, stream_ptr()),
-              "lvt_attn_delta")
         P_k = Operand(ly.P.data_ptr(), L, zdiv=1, s_zhi=L * L)
         P_mn = Operand(ly.P.data_ptr(), L, mn_major=True, zdiv=1, s_zhi=L * L)
         do_k = Operand(ws.do.data_ptr(), H * da, cin=da, zdiv=H, s_zlo=da, s_zhi=L * H * da)

@@ -12,7 +12,7 @@ from . import _lib
 from ._lib import LvtGemm, check, ptr, stream_ptr
 
 EPI_LINEAR, EPI_SOFTMAX, EPI_DS = 0, 1, 2
-GEMM_RELU, GEMM_MASK, GEMM_ATOMIC, GEMM_CAUSAL, GEMM_AUX_ADD = 1, 2, 4, 8, 16
+GEMM_RELU, GEMM_MASK, GEMM_ATOMIC, GEMM_CAUSAL, GEMM_AUX_ADD, GEMM_ROWDOT = 1, 2, 4, 8, 16, 32
 
 
 def _cuda_contig(t, dtype, name):
@@ -130,7 +130,8 @@ class ConvSpec:
 
 def gemm(M, N, K, a: Operand, b: Operand, out: Operand, out_f32=None, out_bf16=None, batch=1,
          splits=1, alpha=1.0, mode=EPI_LINEAR, flags=0, bias=None, bias_mod=0, res=None, aux=None,
-         lse=None, delta=None, banks=None, block=None, heads=1, conv: Optional[ConvSpec] = None):
+         lse=None, delta=None, banks=None, block=None, heads=1, conv: Optional[ConvSpec] = None,
+         rowdot=None, rd_block=0, rd_L=0):
     """D[z] = epilogue(alpha * A[z] @ B[z]^T); pointers may be torch tensors or ints."""
     lib = _lib.require_device()
 
@@ -167,6 +168,9 @@ def gemm(M, N, K, a: Operand, b: Operand, out: Operand, out_f32=None, out_bf16=N
         g.cv_pix_stride, g.cv_s_phase = conv.pix_stride or conv.C, conv.s_phase
         for i, (dh, dw, ph) in enumerate(conv.taps):
             g.cv_dh[i], g.cv_dw[i], g.cv_ph[i] = dh, dw, ph
+    if rowdot is not None:
+        g.rowdot, g.rd_block, g.rd_L = p(rowdot), rd_block, rd_L
+        g.flags |= GEMM_ROWDOT
     check(lib.lvt_gemm_bf16(ctypes.byref(g), stream_ptr()), "lvt_gemm_bf16")
 
 

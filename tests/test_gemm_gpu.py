@@ -202,3 +202,22 @@ def test_attention_via_gemm(cuda_lib, block, causal):
     dP = torch.einsum("bhid,bhjd->bhij", dOh, v)
     want = P.float().cpu() * (dP - delta.cpu()[..., None])
     _close(dS.cpu(), want, 1e-2)
+
+
+@pytest.mark.parametrize("M,N,K,blk,L", [(512, 1024, 512, 128, 256), (768, 384, 256, 128, 256), (256, 256, 128, 64, 128)])
+def test_gemm_rowdot_epilogue(cuda_lib, M, N, K, blk, L):
+    """LVT_GEMM_ROWDOT: delta[seq, head, i] = sum over the head's columns of (A B^T) * aux — the softmax
+    backward row term rowsum(dO * O) (vt_attention.py:75-80) fused into the GEMM that produces dO."""
+    from lvt_b200 import ops
+    a, b = _rand((M, K), 21), _rand((N, K), 22, 0.05)
+    aux = _rand((M, N), 23)
+    want_o = a.float() @ b.float().t()
+    H = N // blk
+    want_d = (want_o * aux.float()).view(M // L, L, H, blk).sum(-1).permute(0, 2, 1).contiguous()  # [seq, head, L]
+    out = torch.zeros((M, N), device="cuda", dtype=torch.bfloat16)
+    delta = torch.full((M // L, H, L), float("nan"), device="cuda")
+    ops.gemm(M, N, K, ops.op_kmajor(a), ops.op_kmajor(b), ops.Operand(out.data_ptr(), N), out_bf16=out, aux=aux,
+             rowdot=delta, rd_block=blk, rd_L=L)
+    torch.cuda.synchronize()
+    _close(out, want_o, 6e-3)
+    _close(delta, want_d, 1e-4)
