@@ -240,6 +240,8 @@ class VTEngine:
         self.dut = [None] + [torch.zeros_like(self.ut[k]) for k in range(1, s.nc)]
         self._taps_cache = {}
         self.conv_wp = None  # packed masked-conv weight, depends on the slice shape (live taps)
+        self._side = torch.cuda.Stream()  # parameter-gradient stream of the backward pass
+        self._side_pending = False
         self.shadows_fresh = False
 
     # ------------------------------------------------------------------ parameters
@@ -427,27 +429,51 @@ class VTEngine:
         gemm(M, d, d, Operand(ly.a1.data_ptr(), d), Operand(st.pb(prefix + "ffn.3.weight"), d),
              Operand(_vp(y).value, d), out_f32=y, out_bf16=y_bf16, bias=st.pf(prefix + "ffn.3.bias"), res=ly.h)
 
+    # Weight / bias / bank gradients are leaves of the backward graph: they go to a second stream so that
+    # their CTAs fill the tails of the dgrad chain's kernels (and vice versa) instead of queueing behind them.
+    def _side_begin(self):
+        """side stream waits for everything issued so far on the main stream"""
+        self._side.wait_stream(torch.cuda.current_stream())
+        self._side_pending = True
+        return torch.cuda.stream(self._side)
+
+    def _side_join(self):
+        # (only when the side stream holds work forked from this stream: during CUDA-graph capture a wait on a
+        # stream outside the capture would cross the capture boundary)
+        if self._side_pending:
+            torch.cuda.current_stream().wait_stream(self._side)
+            self._side_pending = False
+
     def _layer_bwd(self, prefix, ws: VTWorkspace, ly: _Layer, x, dy, dy_bf16, dx, dx_bf16):
-        """dy (fp32 + bf16 copy) = gradient wrt the layer output; writes dx (fp32 + bf16)."""
+        """dy (fp32 + bf16 copy) = gradient wrt the layer output; writes dx (fp32 + bf16).
+        Main stream: the data-gradient chain.  Side stream: parameter gradients (they only meet again in the
+        optimizer); the scratch buffers they read (dy_bf16, dz1, dh_bf16, dS, dqkv) are protected by a join at
+        the start of the next layer and before this layer's final LayerNorm backward overwrites dy_bf16."""
         s, st = self.spec, self.store
         M, d, H, da, L = ws.M, s.d, s.H, s.da, 256
         nz = ws.nseq * H
         scale = 1.0 / math.sqrt(da)
         dyb = _vp(dy_bf16).value
+        self._side_join()  # previous layer's parameter gradients no longer read the scratch buffers
         # ---- FFN
-        self._colsum(dyb, st.gf(prefix + "ffn.3.bias"), M, d)
-        self._wgrad(dyb, d, ly.a1.data_ptr(), d, Operand(st.gf(prefix + "ffn.3.weight"), d), d, d, M)
+        with self._side_begin():
+            self._colsum(dyb, st.gf(prefix + "ffn.3.bias"), M, d)
+            self._wgrad(dyb, d, ly.a1.data_ptr(), d, Operand(st.gf(prefix + "ffn.3.weight"), d), d, d, M)
+            ev_dy_read = torch.cuda.Event()
+            ev_dy_read.record()
         gemm(M, d, d, Operand(dyb, d), Operand(st.pb(prefix + "ffn.3.weight"), d, mn_major=True),
              Operand(ws.dz1.data_ptr(), d), out_bf16=ws.dz1, aux=ly.a1, flags=ops.GEMM_MASK)
-        self._colsum(ws.dz1, st.gf(prefix + "ffn.1.bias"), M, d)
-        self._wgrad(ws.dz1.data_ptr(), d, ly.ln2.data_ptr(), d, Operand(st.gf(prefix + "ffn.1.weight"), d), d, d, M)
+        with self._side_begin():
+            self._colsum(ws.dz1, st.gf(prefix + "ffn.1.bias"), M, d)
+            self._wgrad(ws.dz1.data_ptr(), d, ly.ln2.data_ptr(), d, Operand(st.gf(prefix + "ffn.1.weight"), d), d, d, M)
         gemm(M, d, d, Operand(ws.dz1.data_ptr(), d), Operand(st.pb(prefix + "ffn.1.weight"), d, mn_major=True),
              Operand(ws.dln.data_ptr(), d), out_f32=ws.dln)
         self._ln_bwd(ws.dln, ly.h, ly.mean2, ly.rstd2, st.pf(prefix + "ffn.0.weight"), dy, ws.dh, ws.dh_bf16,
                      st.gf(prefix + "ffn.0.weight"), st.gf(prefix + "ffn.0.bias"), M)
         # ---- attention output projection
         dhb = ws.dh_bf16.data_ptr()
-        self._wgrad(dhb, d, ly.o.data_ptr(), H * da, Operand(st.gf(prefix + "mha.proj.weight"), H * da), d, H * da, M)
+        with self._side_begin():
+            self._wgrad(dhb, d, ly.o.data_ptr(), H * da, Operand(st.gf(prefix + "mha.proj.weight"), H * da), d, H * da, M)
         # dO = dh Wproj; its epilogue also emits delta[seq, head, i] = rowsum(dO * O) (softmax backward row term)
         gemm(M, H * da, d, Operand(dhb, d), Operand(st.pb(prefix + "mha.proj.weight"), H * da, mn_major=True),
              Operand(ws.do.data_ptr(), H * da), out_bf16=ws.do, aux=ly.o, rowdot=ws.delta, rd_block=da, rd_L=L)
@@ -465,23 +491,26 @@ class VTEngine:
         # dS = P * (dO V^T - delta)
         gemm(L, L, da, do_k, self._qkv_op(qkv, 2, False, L), dS_k, out_bf16=ws.dS, batch=nz, mode=ops.EPI_DS,
              aux=ly.P, delta=ws.delta)
+        with self._side_begin():
+            check(self.lib.lvt_relpos_bank_grad(ptr(ws.dS), _vp(st.gf(prefix + "dt_bank")),
+                                                _vp(st.gf(prefix + "dh_bank")), _vp(st.gf(prefix + "dw_bank")),
+                                                ws.nseq, H, s.block[0], s.block[1], s.block[2], stream_ptr()),
+                  "lvt_relpos_bank_grad")
         # dQ = scale * dS K ; dK = scale * dS^T Q
         gemm(L, da, L, dS_k, self._qkv_op(qkv, 1, True, L), out_blk(0), out_bf16=out_blk(0).data, batch=nz,
              alpha=scale)
         gemm(L, da, L, dS_mn, self._qkv_op(qkv, 0, True, L), out_blk(1), out_bf16=out_blk(1).data, batch=nz,
              alpha=scale)
-        check(self.lib.lvt_relpos_bank_grad(ptr(ws.dS), _vp(st.gf(prefix + "dt_bank")),
-                                            _vp(st.gf(prefix + "dh_bank")), _vp(st.gf(prefix + "dw_bank")),
-                                            ws.nseq, H, s.block[0], s.block[1], s.block[2], stream_ptr()),
-              "lvt_relpos_bank_grad")
         # ---- QKV projection
-        gemm(d, 3 * H * da, M, Operand(ly.ln1.data_ptr(), d, mn_major=True),
-             Operand(dqkv, 3 * H * da, mn_major=True),
-             Operand(st.gf(prefix + "mha.w_q"), da, cin=da, s_blk=d * da), out_f32=st.gf(prefix + "mha.w_q"),
-             splits=self._splits(d, 3 * H * da, M), flags=ops.GEMM_ATOMIC)
+        with self._side_begin():
+            gemm(d, 3 * H * da, M, Operand(ly.ln1.data_ptr(), d, mn_major=True),
+                 Operand(dqkv, 3 * H * da, mn_major=True),
+                 Operand(st.gf(prefix + "mha.w_q"), da, cin=da, s_blk=d * da), out_f32=st.gf(prefix + "mha.w_q"),
+                 splits=self._splits(d, 3 * H * da, M), flags=ops.GEMM_ATOMIC)
         gemm(M, d, 3 * H * da, Operand(dqkv, 3 * H * da),
              Operand(st.pb(prefix + "mha.w_q"), da, mn_major=False, cin=da, s_blk=d * da),
              Operand(ws.dln.data_ptr(), d), out_f32=ws.dln)
+        torch.cuda.current_stream().wait_event(ev_dy_read)  # dx_bf16 may alias dy_bf16
         self._ln_bwd(ws.dln, x, ly.mean1, ly.rstd1, st.pf(prefix + "mha.layer_norm.weight"), ws.dh, dx, dx_bf16,
                      st.gf(prefix + "mha.layer_norm.weight"), st.gf(prefix + "mha.layer_norm.bias"), M)
 
@@ -608,6 +637,7 @@ class VTEngine:
             ly = ws.layers[nE + i]
             x = ws.layers[nE + i - 1].y if i > 0 else ws.y0
             self._layer_bwd(f"decoder.block_local_attention.{i}.", ws, ly, x, ws.dy, ws.dy_bf16, ws.dy, ws.dy_bf16)
+        self._side_join()
         # ---- decoder front: y0 = conv(emb) + posenc + bias + zl Wlp^T
         dyb = ws.dy_bf16.data_ptr()
         self._colsum(dyb, st.gf("decoder.conv.conv.bias"), M, d)
@@ -629,6 +659,7 @@ class VTEngine:
             first = i == nE - 1
             self._layer_bwd(f"encoder.block_local_attention.{i}.", ws, ly, x, ws.dh if first else ws.dy,
                             ws.dh_bf16 if first else ws.dy_bf16, ws.dy, ws.dy_bf16)
+        self._side_join()
         # ---- encoder front: x0 = e0 Wlp_e^T ; e0 = gather-sum + bias + slice_emb
         dxb = ws.dy_bf16.data_ptr()
         self._wgrad(dxb, d, ws.e0.data_ptr(), de, Operand(st.gf("encoder.linear_projector.weight"), de), d, de, M)
