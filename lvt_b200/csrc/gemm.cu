@@ -76,14 +76,17 @@ constexpr int ST_REDUCE = 4;  // cp.reduce.async.bulk (+=) instead of a plain st
 constexpr int ST_CLOAD = 8;   // a second tensor with the output's addressing is TMA-loaded per slab:
                               // fp32 residual (added), bf16 ReLU-mask source, or bf16 P of the DS epilogue
 
-template <int BN, int ST>
+template <int BN, int ST, int EK = EK_LINEAR>
 struct SmemLayout {
+  static constexpr bool SOFTMAX = EK == EK_SOFTMAX_1x16x16 || EK == EK_SOFTMAX_4x8x8;
   static constexpr int B_TILE_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
-  static constexpr int STAGES = (BN == 256 ? 4 : 6) - ((ST & ST_CLOAD) ? 1 : 0);
+  // (the attention-probability kernel has K = da = 128: two k-blocks per tile; three stages keep 1.5 tiles in flight)
+  static constexpr int STAGES = SOFTMAX ? 3 : (BN == 256 ? 4 : 6) - ((ST & ST_CLOAD) ? 1 : 0);
   static constexpr int STG_PER_WARP = (ST & ST_CLOAD) ? 2 * STG_BYTES_PER_WARP : STG_BYTES_PER_WARP;
   static constexpr int STG_OFFSET = STAGES * STAGE_BYTES;
-  static constexpr int BAR_OFFSET = STG_OFFSET + NUM_EPI_WARPS * STG_PER_WARP;
+  static constexpr int XCHG_OFFSET = STG_OFFSET + NUM_EPI_WARPS * STG_PER_WARP;  // [2][2][128] fp32 row max / row sum
+  static constexpr int BAR_OFFSET = XCHG_OFFSET + (SOFTMAX ? 2048 : 0);
   static constexpr int TOTAL = BAR_OFFSET + 256 + 1024 /*alignment slack*/;
 };
 
@@ -126,8 +129,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                  const __grid_constant__ CUtensorMap tm_o, const __grid_constant__ CUtensorMap tm_c,
                  const GemmParams p) {
-  using L = SmemLayout<BN, ST>;
+  using L = SmemLayout<BN, ST, EK>;
   constexpr int STAGES = L::STAGES;
+  constexpr bool SOFTMAX = L::SOFTMAX;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte alignment
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -153,8 +157,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     }
     mbar_init(&tmem_full_bar[0], 1);
     mbar_init(&tmem_full_bar[1], 1);
-    mbar_init(&tmem_empty_bar[0], 4);  // one arrive per epilogue warp of the group
-    mbar_init(&tmem_empty_bar[1], 4);
+    mbar_init(&tmem_empty_bar[0], SOFTMAX ? 8 : 4);  // one arrive per epilogue warp working on the buffer
+    mbar_init(&tmem_empty_bar[1], SOFTMAX ? 8 : 4);
 #pragma unroll
     for (int w = 0; w < NUM_EPI_WARPS; ++w) mbar_init(&c_bar[w], 1);
     fence_barrier_init();
@@ -299,6 +303,117 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     // coalesced mapping inside a 32-row x 16-col chunk: 4 lanes cover one row (4 x 16 B)
     const int c_row = lane >> 2;    // + 8 * it
     const int c_pc = lane & 3;      // 16-byte piece -> columns 4*c_pc .. 4*c_pc+3
+    if constexpr (SOFTMAX) {
+      // -------- attention probabilities: all 8 warps work on every tile; the two warps of a lane quarter own
+      // one query row each per lane and 128 of the 256 keys.  ONE pass over TMEM: the 128 logits stay in
+      // registers, the accumulator buffer is handed back at once, row max / row sum are exchanged through smem.
+      // v = alpha*acc + B[head, i, j]; causal: j > i -> -1e4 (vt_attention.py:63-74); the relative-position bias
+      // is separable, so each thread keeps its row's bank slices in registers:
+      // B[i, j] = bt[tj] + bh[hj] + bw[wj]  (get_B, vt_attention.py:169-174).
+      constexpr int BT = EK == EK_SOFTMAX_1x16x16 ? 1 : 4;
+      constexpr int BH = EK == EK_SOFTMAX_1x16x16 ? 16 : 8;
+      constexpr int BW = EK == EK_SOFTMAX_1x16x16 ? 16 : 8;
+      static_assert(BN == 256 || !SOFTMAX, "softmax epilogue needs BN == 256");
+      const int half = ew >> 2;    // which 128 keys
+      float* const xchg = reinterpret_cast<float*>(smem + L::XCHG_OFFSET);
+      float* const x_own_max = xchg + half * 128 + q * 32 + lane;
+      float* const x_oth_max = xchg + (half ^ 1) * 128 + q * 32 + lane;
+      float* const x_own_sum = x_own_max + 256;
+      float* const x_oth_sum = x_oth_max + 256;
+      const float kLog2e = 1.4426950408889634f;
+      const bool causal = (p.flags & LVT_GEMM_CAUSAL) != 0;
+      const float a2 = p.alpha * kLog2e;
+      const float kMasked = -1e4f * kLog2e;
+      uint4* const slab = reinterpret_cast<uint4*>(stg);
+      uint32_t titer = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++titer) {
+        const TileCoord t = decode_tile(p, tile, BN);
+        const uint32_t buf = titer & 1;
+        const uint32_t taddr = tmem_base + buf * BN + (static_cast<uint32_t>(q * 32) << 16) + half * 128;
+        const int row_base = t.m0 + q * 32;
+        const int row = row_base + lane;  // 0..255 inside the block (M == 256)
+        const int head = t.z % p.heads;
+        const int ti = row / (BH * BW), hi = (row / BW) % BH, wi = row % BW;
+        // bank slices of this row for the 128 keys of this half, pre-scaled into the log2 domain:
+        // key k = half*128 + kk -> tj = k / (BH*BW), hj = (k / BW) % BH, wj = k % BW
+        constexpr int TJN = (BH * BW <= 128) ? 128 / (BH * BW) : 1;  // distinct tj inside a half
+        constexpr int HJN = (128 / BW < BH) ? 128 / BW : BH;         // distinct hj inside a half
+        float btl[TJN], bhl[HJN], bw[BW];
+#pragma unroll
+        for (int x = 0; x < TJN; ++x) {
+          const int tj = (half * 128) / (BH * BW) + x;
+          btl[x] = kLog2e * __ldg(p.bank_t + head * (2 * BT - 1) + (ti - tj + BT - 1));
+        }
+#pragma unroll
+        for (int y = 0; y < HJN; ++y) {
+          const int hj = ((half * 128) / BW + y) % BH;
+          bhl[y] = kLog2e * __ldg(p.bank_h + head * (2 * BH - 1) + (hi - hj + BH - 1));
+        }
+#pragma unroll
+        for (int x = 0; x < BW; ++x) bw[x] = kLog2e * __ldg(p.bank_w + head * (2 * BW - 1) + (wi - x + BW - 1));
+        mbar_wait(&tmem_full_bar[buf], (titer >> 1) & 1);
+        tc_fence_after();
+        // all four accumulator loads in flight at once; the logits replace the raw accumulators in place
+        uint32_t racc[128];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tmem_ld_32x32(taddr + 32 * c, *reinterpret_cast<uint32_t(*)[32]>(&racc[32 * c]));
+        tmem_ld_wait();
+        float* const l = reinterpret_cast<float*>(racc);  // logits in the log2 domain: (alpha*acc + B) * log2(e)
+        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+        for (int kk = 0; kk < 128; ++kk) {
+          const float bias = (btl[(kk / (BH * BW)) % TJN] + bhl[(kk / BW) % HJN]) + bw[kk % BW];
+          float v = __uint_as_float(racc[kk]) * a2 + bias;
+          if (causal && half * 128 + kk > row) v = kMasked;
+          racc[kk] = __float_as_uint(v);
+          m4[kk & 3] = fmaxf(m4[kk & 3], v);
+        }
+        // the accumulator buffer may be overwritten by the MMAs of the tile after next
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+        float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+        *x_own_max = mx;
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+        mx = fmaxf(mx, *x_oth_max);
+        float s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int i = 0; i < 128; ++i) {
+          l[i] = fast_exp2(l[i] - mx);
+          s4[i & 3] += l[i];
+        }
+        float sum = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+        *x_own_sum = sum;
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+        sum += *x_oth_sum;
+        const float inv = 1.f / sum;
+        if (p.lse && half == 0) p.lse[(long long)t.z * p.M + row] = (mx + log2f(sum)) * 0.6931471805599453f;
+        // P -> 128B-swizzled slab (32 rows x 64 bf16) -> TMA store
+        const int o_zlo = t.z % p.o_zdiv, o_zhi = t.z / p.o_zdiv;
+#pragma unroll
+        for (int sl = 0; sl < 2; ++sl) {
+          if (lane == 0) bulk_wait_group_read<0>();  // the previous store of this warp has drained the slab
+          __syncwarp();
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const float* e = l + 64 * sl + 8 * k;
+            uint4 u;
+            u.x = pack_bf16x2(e[0] * inv, e[1] * inv);
+            u.y = pack_bf16x2(e[2] * inv, e[3] * inv);
+            u.z = pack_bf16x2(e[4] * inv, e[5] * inv);
+            u.w = pack_bf16x2(e[6] * inv, e[7] * inv);
+            slab[lane * 8 + (k ^ (lane & 7))] = u;
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_5d(&tm_o, slab, half * 128 + 64 * sl, row_base, 0, o_zlo, o_zhi);
+            bulk_commit_group();
+          }
+        }
+      }
+      if (lane == 0) bulk_wait_group<0>();  // all TMA stores of this warp are complete
+    } else {
     uint32_t titer = grp;
     uint32_t c_phase = 0;  // parity of this warp's C-slab barrier
     (void)c_phase;
@@ -597,117 +712,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           }
           __syncwarp();
         }
-      } else {
-        // -------- attention probabilities: one thread owns one query row and all 256 keys
-        // v = alpha*acc + B[head, i, j]; causal: j > i -> -1e4 (vt_attention.py:63-74); the
-        // relative-position bias is separable, so each thread keeps its row's bank slices in
-        // registers: B[i, j] = bt[tj] + bh[hj] + bw[wj]  (get_B, vt_attention.py:169-174).
-        constexpr int BT = EK == EK_SOFTMAX_1x16x16 ? 1 : 4;
-        constexpr int BH = EK == EK_SOFTMAX_1x16x16 ? 16 : 8;
-        constexpr int BW = EK == EK_SOFTMAX_1x16x16 ? 16 : 8;
-        static_assert(BN == 256 || EK == EK_LINEAR || EK == EK_DS, "softmax epilogue needs BN == 256");
-        constexpr int NH = 32 / BW;  // distinct key-h values inside one 32-column chunk
-        const int row = row_base + lane;  // 0..255 inside the block (M == 256)
-        const int head = t.z % p.heads;
-        const int ti = row / (BH * BW), hi = (row / BW) % BH, wi = row % BW;
-        const float kLog2e = 1.4426950408889634f;
-        // bank slices of this row, pre-scaled into the log2 domain
-        float bt[BT], bh[BH], bw[BW];
-#pragma unroll
-        for (int x = 0; x < BT; ++x) bt[x] = kLog2e * __ldg(p.bank_t + head * (2 * BT - 1) + (ti - x + BT - 1));
-#pragma unroll
-        for (int x = 0; x < BH; ++x) bh[x] = kLog2e * __ldg(p.bank_h + head * (2 * BH - 1) + (hi - x + BH - 1));
-#pragma unroll
-        for (int x = 0; x < BW; ++x) bw[x] = kLog2e * __ldg(p.bank_w + head * (2 * BW - 1) + (wi - x + BW - 1));
-        const bool causal = (p.flags & LVT_GEMM_CAUSAL) != 0;
-        const float a2 = p.alpha * kLog2e;
-        const float kMasked = -1e4f * kLog2e;
-        uint32_t r[32];
-        float cb[NH];  // bt[tj] + bh[hj] for the key-h values of the current chunk
-        auto chunk_bias = [&](int c0) {
-          const int tjv = c0 / (BH * BW);
-          const int hbase = (c0 / BW) % BH;
-          float bts = bt[0];
-#pragma unroll
-          for (int x = 1; x < BT; ++x)
-            if (tjv == x) bts = bt[x];
-#pragma unroll
-          for (int y = 0; y < NH; ++y) {
-            float v = bh[y];
-#pragma unroll
-            for (int hb = NH; hb < BH; hb += NH)
-              if (hbase == hb) v = bh[hb + y];
-            cb[y] = v + bts;
-          }
-        };
-        // logit in the log2 domain: (alpha*acc + B) * log2(e); i = column inside the chunk
-        auto logit2 = [&](uint32_t acc, int c0, int i) -> float {
-          float v = __uint_as_float(acc) * a2 + (cb[i / BW] + bw[i % BW]);
-          if (causal && c0 + i > row) v = kMasked;
-          return v;
-        };
-        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // 4 independent chains
-#pragma unroll 1
-        for (int c0 = 0; c0 < 256; c0 += 32) {
-          tmem_ld_32x32(taddr + c0, r);
-          chunk_bias(c0);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) m4[i & 3] = fmaxf(m4[i & 3], logit2(r[i], c0, i));
-        }
-        const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
-        float s4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 1
-        for (int c0 = 0; c0 < 256; c0 += 32) {
-          tmem_ld_32x32(taddr + c0, r);
-          chunk_bias(c0);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) s4[i & 3] += fast_exp2(logit2(r[i], c0, i) - mx);
-        }
-        const float sum = (s4[0] + s4[1]) + (s4[2] + s4[3]);
-        const float inv = 1.f / sum;
-        if (p.lse) p.lse[(long long)t.z * p.M + row] = (mx + log2f(sum)) * 0.6931471805599453f;
-        // P -> 128B-swizzled slab (32 rows x 64 bf16) -> TMA store
-        uint4* const slab = reinterpret_cast<uint4*>(stg);
-        const int o_zlo = t.z % p.o_zdiv, o_zhi = t.z / p.o_zdiv;
-#pragma unroll 1
-        for (int c0 = 0; c0 < 256; c0 += 64) {
-          if (lane == 0) bulk_wait_group_read<0>();
-          __syncwarp();
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            tmem_ld_32x32(taddr + c0 + 32 * h, r);
-            chunk_bias(c0 + 32 * h);
-            tmem_ld_wait();
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              float e[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j) e[j] = fast_exp2(logit2(r[8 * k + j], c0 + 32 * h, 8 * k + j) - mx) * inv;
-              uint4 u;
-              u.x = pack_bf16x2(e[0], e[1]);
-              u.y = pack_bf16x2(e[2], e[3]);
-              u.z = pack_bf16x2(e[4], e[5]);
-              u.w = pack_bf16x2(e[6], e[7]);
-              slab[lane * 8 + ((4 * h + k) ^ (lane & 7))] = u;
-            }
-          }
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) {
-            tma_store_5d(&tm_o, slab, c0, row_base, 0, o_zlo, o_zhi);
-            bulk_commit_group();
-          }
-        }
       }
       // this warp no longer reads the accumulator buffer
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
     }
-    if (((ST & ST_TMA) != 0 || EK == EK_SOFTMAX_1x16x16 || EK == EK_SOFTMAX_4x8x8) && lane == 0)
-      bulk_wait_group<0>();  // all TMA stores of this warp are complete  // all TMA stores of this warp are complete
+    if ((ST & ST_TMA) != 0 && lane == 0) bulk_wait_group<0>();  // all TMA stores of this warp are complete
+    }  // !SOFTMAX
   }
 
   tc_fence_before();
@@ -864,7 +876,7 @@ struct Maps {
 
 template <int BN, bool A_MN, bool B_MN, int EK, int ST = 0>
 int launch_gemm(const Maps& m, const GemmParams& p, int grid, cudaStream_t stream) {
-  using L = SmemLayout<BN, ST>;
+  using L = SmemLayout<BN, ST, EK>;
   auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, EK, ST>;
   static bool configured = false;
   if (!configured) {

@@ -385,7 +385,8 @@ class VTEngine:
         keeping at least 4 k-blocks of 64 per tile."""
         bn = 256 if n % 256 == 0 else 128
         tiles = ((m + 127) // 128) * ((n + bn - 1) // bn)
-        return int(max(1, min(k // 256, (148 + tiles // 2) // tiles)))
+        # never more than 148 CTAs: the kernel is persistent, a 149th tile would double the time of one SM
+        return int(max(1, min(k // 256, 148 // tiles)))
 
     def _wgrad(self, dy_ptr, ld_dy, x_ptr, ld_x, out: Operand, n_out, n_in, tokens):
         """dW[n_out, n_in] += dY[tokens, n_out]^T X[tokens, n_in] (split-K, fp32 red.add)."""

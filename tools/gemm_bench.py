@@ -50,7 +50,7 @@ tests = {
     "ffn": (lambda: ops.gemm(M, d, d, Operand(x.data_ptr(), d), Operand(w.data_ptr(), d), Operand(o1.data_ptr(), d), out_bf16=o1), 2.0 * M * d * d),
     "proj": (lambda: ops.gemm(M, d, 2 * d, Operand(x2.data_ptr(), 2 * d), Operand(wp.data_ptr(), 2 * d), Operand(of.data_ptr(), d), out_f32=of, res=of), 2.0 * M * d * 2 * d),
     "ffn_dgrad": (lambda: ops.gemm(M, d, d, Operand(x.data_ptr(), d), Operand(w.data_ptr(), d, mn_major=True), Operand(of.data_ptr(), d), out_f32=of), 2.0 * M * d * d),
-    "ffn_wgrad": (lambda: ops.gemm(d, d, M, Operand(x.data_ptr(), d, mn_major=True), Operand(o1.data_ptr(), d, mn_major=True), Operand(gw.data_ptr(), d), out_f32=gw, splits=32, flags=ops.GEMM_ATOMIC), 2.0 * M * d * d),
+    "ffn_wgrad": (lambda: ops.gemm(d, d, M, Operand(x.data_ptr(), d, mn_major=True), Operand(o1.data_ptr(), d, mn_major=True), Operand(gw.data_ptr(), d), out_f32=gw, splits=int(os.environ.get('WGRAD_SPLITS', 18)), flags=ops.GEMM_ATOMIC), 2.0 * M * d * d),
     "qkv_wgrad": (lambda: ops.gemm(d, 3072, M, Operand(x.data_ptr(), d, mn_major=True), Operand(o3.data_ptr(), 3072, mn_major=True), Operand(gq.data_ptr(), da, cin=da, s_blk=d * da), out_f32=gq, splits=6, flags=ops.GEMM_ATOMIC), 2.0 * M * 3072 * d),
     "pv": (lambda: ops.gemm(L, da, L, Operand(P.data_ptr(), L, zdiv=1, s_zhi=L * L), qkv_op(o3, 2, True), Operand(x2.data_ptr(), H * da, cin=da, zdiv=H, s_zlo=da, s_zhi=L * H * da), out_bf16=x2, batch=nb * H), 2.0 * nb * H * L * L * da),
     "softmax": (lambda: ops.gemm(L, L, da, qkv_op(o3, 0, False), qkv_op(o3, 1, False), Operand(P.data_ptr(), L, zdiv=1, s_zhi=L * L), out_bf16=P, batch=nb * H, alpha=0.088, mode=ops.EPI_SOFTMAX, flags=ops.GEMM_CAUSAL, banks=banks, block=(1, 16, 16), heads=H), 2.0 * nb * H * L * L * da),
