@@ -140,3 +140,60 @@ class VideoTransformer(Autoregressive):
                 ws.slice.view(b, spec.nc, -1)[:, k, pos] = sample  # feeds the one-hot half of U[k+1]
             return out, zl
         raise ValueError("|mode| is invalid")
+
+    @torch.no_grad()
+    def sample_slice(self, context, slice, slice_idx, prime_mask=None, temp=1.0, use_graph=True):
+        """Every non-primed position of one slice in raster order — the inner loops of
+        VideoTransformerModel.sample_video (meta_arch/vt.py:107-134) around mode "sample_pixel"
+        (videotransformer.py:161-185, 240-246): encoder once per slice, then per position the masked decoder pass and
+        the channel-by-channel multinomial draw.  The per-position step reads its position from a device scalar, so
+        it is captured ONCE in a CUDA graph and replayed (no host work between the ~100 launches of a step).
+        Returns the completed slice (b, nc, t, h, w) int64."""
+        eng, spec = self.engine, self.engine.spec
+        b = context.shape[0]
+        t, h, w = slice.shape[2:]
+        thw = t * h * w
+        ws = self._stage(context, slice, slice_idx, None, train=False)
+        eng.encoder_forward(ws, train=False)
+        primed = torch.zeros(thw, dtype=torch.bool) if prime_mask is None else prime_mask.reshape(-1).cpu()
+        todo = [p for p in range(thw) if not bool(primed[p])]
+        if not todo:
+            return ws.slice.view(b, spec.nc, t, h, w).clone()
+        # the graph only references the workspace's static buffers, so it is captured once per (workspace, temp)
+        cache = self.__dict__.setdefault("_sample_graphs", {})
+        key = (id(ws), float(temp))
+        if key in cache:
+            graph, pos_t, step = cache[key]
+            if not use_graph:
+                graph = None
+        else:
+            pos_t = torch.full((1,), todo[0], dtype=torch.int64, device=ws.slice.device)
+            codes = ws.slice.view(b, spec.nc, thw)
+
+            def step():
+                eng.decoder_forward(ws, train=False)
+                for k in range(spec.nc):
+                    eng.predictor_forward(ws, channels=[k])
+                    logits = ws.logits[k].view(b, thw, spec.nv).index_select(1, pos_t).squeeze(1)
+                    sample = torch.multinomial(torch.softmax(logits / temp, 1), 1)            # (b, 1)
+                    codes[:, k].scatter_(1, pos_t.expand(b, 1), sample)  # feeds the one-hot half of U[k+1] and the next steps
+
+            graph = None
+            if use_graph:
+                pos_t.fill_(todo[0])
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    step()  # eager warm-up (kernel attributes, TMA maps, cached tables); position todo[0] is redrawn below
+                torch.cuda.current_stream().wait_stream(side)
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    step()
+                cache[key] = (graph, pos_t, step)
+        for p in todo:
+            pos_t.fill_(p)
+            if graph is not None:
+                graph.replay()
+            else:
+                step()
+        return ws.slice.view(b, spec.nc, t, h, w).clone()

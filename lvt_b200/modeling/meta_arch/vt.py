@@ -1,6 +1,8 @@
 """VideoTransformerModel: the reference's meta-architecture surface (vidgen/modeling/meta_arch/vt.py:21-328)
 on top of the B200 engine: forward(data: list[dict], mode), sample_video(s), calculate_logits_for_entire_video,
 configure_optimizers_and_checkpointers, wrap_parallel."""
+import os
+
 import numpy as np
 import torch
 from torch import nn
@@ -41,6 +43,8 @@ class VideoTransformerModel(nn.Module):
         self.model = build_autoregressive(cfg)
         self.init_weights(self.model, cfg.MODEL.INIT_TYPE)
         self.vis_period = cfg.VIS_PERIOD
+        # LVT_SAMPLER_GRAPH=0: the reference's per-pixel Python loop (eager launches, eager RNG stream)
+        self.sampler_graph = os.environ.get("LVT_SAMPLER_GRAPH", "1") != "0"
         self.model.engine.grad_hook = None
         self._anchor = torch.zeros(1, device=self.device, requires_grad=True)
 
@@ -174,15 +178,19 @@ class VideoTransformerModel(nn.Module):
             context = ss_shift(video.masked_fill(~vmask, pad_value), a, b, c, st, sh, sw, T, H, W, *kernel,
                                pad_value=pad_value)
             sidx = torch.full((B,), slice_idx, dtype=torch.int64, device=self.device)
-            zl = None
-            for ti in range(t):
-                for hi in range(h):
-                    for wi in range(w):
-                        if bool(prime_slice[ti, hi, wi]):
-                            continue
-                        pred, zl = self.model(context, slc, sidx, mode="sample_pixel", pixel=(ti, hi, wi), zl=zl,
-                                              temp=temp, class_idx=class_idx)
-                        slc[:, :, ti, hi, wi] = pred
+            if self.sampler_graph:
+                # same loops, one CUDA-graph replay per position (VideoTransformer.sample_slice)
+                slc = self.model.sample_slice(context, slc, sidx, prime_slice, temp=temp)
+            else:
+                zl = None
+                for ti in range(t):
+                    for hi in range(h):
+                        for wi in range(w):
+                            if bool(prime_slice[ti, hi, wi]):
+                                continue
+                            pred, zl = self.model(context, slc, sidx, mode="sample_pixel", pixel=(ti, hi, wi), zl=zl,
+                                                  temp=temp, class_idx=class_idx)
+                            slc[:, :, ti, hi, wi] = pred
             video[:, :, a::st, b::sh, c::sw] = slc
         return video
 

@@ -84,3 +84,24 @@ def test_vqvae_model_inference_and_sampling_roundtrip(cuda_lib, tmp_path):
     assert sample.shape == (4, 16, 16, 16)
     assert torch.equal(sample[:, :15].cpu(), seq.transpose(0, 1)[:, :15])
     assert int(sample.min()) >= 0 and int(sample.max()) < 512
+
+
+def test_graph_sampler_matches_per_pixel_loop(cuda_lib, tmp_path):
+    """VideoTransformer.sample_slice (one CUDA-graph replay per position) against the reference-shaped per-pixel
+    loop (vt.py:107-134): at temperature -> 0 the multinomial draw is the argmax of identical logits, so the sampled
+    frame must be identical code for code."""
+    from lvt_b200.config.presets import preset
+    from lvt_b200.modeling import build_model
+    cfgv = preset("DSFVT", SMALL + ["TEST.EVALUATORS", "VTSampler", "OUTPUT_DIR", str(tmp_path)])
+    cfgv.freeze()
+    vt = build_model(cfgv)
+    vt.train(False)
+    video = torch.randint(0, 512, (1, 4, 16, 16, 16)).cuda()
+    video[:, :, 15:] = 0
+    outs = []
+    for graph in (True, False):
+        vt.sampler_graph = graph
+        torch.manual_seed(0)
+        outs.append(vt.sample_video(video.clone(), temp=1e-4, n_prime=15).cpu())
+    assert torch.equal(outs[0], outs[1])
+    assert torch.equal(outs[0][:, :, :15], video[:, :, :15].cpu())

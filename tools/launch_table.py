@@ -1,18 +1,29 @@
-"""Summarise an `ncu --metrics gpu__time_duration.sum --csv` launch list per kernel."""
+"""Summarise an `ncu --metrics gpu__time_duration.sum[,dram__bytes_read.sum,dram__bytes_write.sum] --csv` launch
+list per kernel: time share, launches, average duration and (when captured) DRAM traffic."""
 import collections, csv, re, sys
 path = sys.argv[1]
 top = int(sys.argv[2]) if len(sys.argv) > 2 else 25
 with open(path) as f:
     lines = [l for l in f if not l.startswith('==')]
-agg = collections.OrderedDict(); tot = 0
+SCALE = {'ns': 1e-3, 'us': 1.0, 'usecond': 1.0, 'ms': 1e3, 'msecond': 1e3, 'nsecond': 1e-3, 'second': 1e6,
+         'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
+agg = collections.OrderedDict()
+tot_t = tot_b = 0.0
+ids = set()
 for row in csv.DictReader(lines):
     name = row['Kernel Name']
-    t = float(row['Metric Value'].replace(',', ''))
-    if row['Metric Unit'] == 'ns': t /= 1000
-    elif row['Metric Unit'] == 'ms': t *= 1000
+    val = float(row['Metric Value'].replace(',', '')) * SCALE.get(row['Metric Unit'], 1.0)
     m = re.search(r'gemm_bf16_kernel<([^>]*)>', name)
     key = ('gemm<' + m.group(1).replace('(int)', '').replace('(bool)', '') + '>') if m else re.sub(r'\(.*', '', name)[-44:]
-    a = agg.setdefault(key, [0, 0.0]); a[0] += 1; a[1] += t; tot += t
-for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:top]:
-    print(f"{t/1000:8.3f} ms {100*t/tot:5.1f}%  n={n:4d} avg {t/n:8.1f} us  {k}")
-print(f"total {tot/1000:.3f} ms over {sum(v[0] for v in agg.values())} launches")
+    a = agg.setdefault(key, [set(), 0.0, 0.0])
+    a[0].add(row['ID'])
+    ids.add(row['ID'])
+    if row['Metric Name'] == 'gpu__time_duration.sum':
+        a[1] += val; tot_t += val
+    elif row['Metric Name'].startswith('dram__bytes'):
+        a[2] += val; tot_b += val
+for k, (n, t, b) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:top]:
+    extra = f"  dram {b/1e6:9.1f} MB ({b/1e3/max(t,1e-9):6.0f} GB/s)" if tot_b else ""
+    print(f"{t/1000:8.3f} ms {100*t/tot_t:5.1f}%  n={len(n):4d} avg {t/len(n):8.1f} us  {k}{extra}")
+print(f"total {tot_t/1000:.3f} ms over {len(ids)} launches" + (f"; DRAM traffic {tot_b/1e9:.2f} GB = {tot_b/1e3/tot_t:.0f} GB/s "
+      f"averaged over the summed kernel time" if tot_b else ""))
