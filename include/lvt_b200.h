@@ -239,19 +239,19 @@ int lvt_vq_gather_nhwc(const int64_t* idx, const float* codebook, float* out, vo
  * x fp32 NCHW [n,3,64,64] -> A bf16 [4*n*256, 64] (48 columns k=(kh*4+kw)*3+c, 16 zeros), rows in
  * phase-major order of the 32x32 output.                                                      */
 int lvt_vqvae_in_im2col(const float* x, void* a_bf16, int n, float mean, float std, void* stream);
-/* ConvTranspose2d(C->3, k4, s2, p1) + tanh (resdecoder.py:56,68-69): act bf16 phase-major
- * [4][n][16][16][C] (ReLU'd), w fp32 [C][3][4][4], out fp32 NCHW [n,3,64,64].                 */
-int lvt_vqvae_out_convt_fwd(const void* act_bf16, const float* w, const float* bias, float* out, int n,
-                            int C, void* stream);
+/* ConvTranspose2d(C->3, k4, s2, p1) + tanh (resdecoder.py:56,68-69), second half: the contraction over the C
+ * input channels is one lvt_gemm_bf16 call Y[row, (kh*4+kw)*3+co] = sum_c act[row,c] * w[c][co][kh][kw] over the
+ * phase-major 32x32 input pixels; this entry gathers the 2x2 (input pixel, tap) pairs of every output pixel, adds
+ * the bias and applies tanh.  y fp32 [4*n*256, 64], out fp32 NCHW [n,3,64,64].                  */
+int lvt_vqvae_out_col2im_tanh(const float* y, const float* bias, float* out, int n, void* stream);
 /* reconstruction loss lambda*MSE(x_tilde, (x-mean)/std) (loss.py:20, vqvae.py:79): loss += value,
  * dpre = dL/d(pre-tanh) [n,3,64,64] (optional), dbias[3] += column sums (optional).           */
 int lvt_vqvae_recon_loss(const float* x_tilde, const float* x, float* dpre, float* loss, float* dbias,
                          int n, float mean, float std, float lambda, void* stream);
-/* backward of the output ConvTranspose2d: dact bf16 (phase-major, ReLU-masked by act > 0) and
- * G bf16 [n*1024, 64] with G[row, co*16+kh*4+kw] = dpre at the output pixel the tap reaches, so
- * that dW[c][co][kh][kw] = sum_rows act[row,c] * G[row, .] is one lvt_gemm_bf16 call.         */
-int lvt_vqvae_out_convt_bwd(const void* act_bf16, const float* w, const float* dpre, void* dact_bf16,
-                            void* g_bf16, int n, int C, void* stream);
+/* backward of the output ConvTranspose2d, first half: G bf16 [n*1024, 64] with
+ * G[row, co*16+kh*4+kw] = dpre at the output pixel the tap reaches (0 outside), so that both
+ * dW[c][co][kh][kw] = sum_rows act[row,c] * G[row, .] and dact = relu'(act) * (G @ w^T) are lvt_gemm_bf16 calls. */
+int lvt_vqvae_out_convt_g(const float* dpre, void* g_bf16, int n, void* stream);
 /* commitment loss beta*MSE(z_e, zq_bar) (vqvae.py:86) + merged gradient wrt z_e:
  * dz (bf16) = dz_st + 2*beta/numel*(z_e - zq_bar);  loss += value.                            */
 int lvt_vqvae_commit_loss(const float* z_e, const float* zq_bar, const float* dz_st, void* dz_bf16,

@@ -45,20 +45,19 @@ in_im2col_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ A, int
   }
 }
 
-// ConvTranspose2d(C -> 3, k4, s2, p1) + tanh on a phase-major 32x32 input (already ReLU'd).
-// One warp per output pixel; lanes split the C channels; w: [C][3][4][4] fp32.
-// out: fp32 NCHW [n, 3, 64, 64].  Output row oy = 2Q+py takes kh = py+1 (mod 2): iy = Q + (py+1-kh)/2.
-template <int C>
+// ConvTranspose2d(C -> 3, k4, s2, p1) + tanh, second half.  The contraction over the C input channels is a
+// tensor-core GEMM Y[row, (kh*4+kw)*3 + co] = sum_c act[row, c] * w[c][co][kh][kw] over the phase-major 32x32
+// input pixels (rows); this kernel gathers, per OUTPUT pixel, the 2 x 2 (input pixel, tap) pairs that reach it:
+// output row oy = 2Q+py takes kh = (py+1)%2 + 2a from input row iy = Q + (py+1-kh)/2.
+// Y fp32 [4*n*256, 64]; out fp32 NCHW [n, 3, 64, 64].
 __global__ void __launch_bounds__(256)
-out_convt_fwd_kernel(const __nv_bfloat16* __restrict__ act, const float* __restrict__ w,
-                     const float* __restrict__ bias, float* __restrict__ out, int n) {
-  const long long wid = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (wid >= (long long)n * 4096) return;
-  const int img = (int)(wid >> 12);
-  const int oy = (int)((wid >> 6) & 63), ox = (int)(wid & 63);
+out_col2im_tanh_kernel(const float* __restrict__ Y, const float* __restrict__ bias, float* __restrict__ out, int n) {
+  const long long pix = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (pix >= (long long)n * 4096) return;
+  const int img = (int)(pix >> 12);
+  const int oy = (int)((pix >> 6) & 63), ox = (int)(pix & 63);
   const int py = oy & 1, px = ox & 1, Q = oy >> 1, R = ox >> 1;
-  float acc[3] = {0.f, 0.f, 0.f};
+  float acc[3] = {bias[0], bias[1], bias[2]};
 #pragma unroll
   for (int a = 0; a < 2; ++a) {
     const int kh = (py + 1) % 2 + 2 * a;
@@ -70,22 +69,15 @@ out_convt_fwd_kernel(const __nv_bfloat16* __restrict__ act, const float* __restr
       const int ix = R + (px + 1 - kw) / 2;
       if (ix < 0 || ix >= 32) continue;
       const int phase = (iy & 1) * 2 + (ix & 1);
-      const __nv_bfloat16* ap = act + ((((long long)phase * n + img) * 16 + (iy >> 1)) * 16 + (ix >> 1)) * C;
-      for (int c = lane; c < C; c += 32) {
-        const float v = __bfloat162float(ap[c]);
-        const float* wp = w + (long long)c * 48 + kh * 4 + kw;
-        acc[0] += v * wp[0];
-        acc[1] += v * wp[16];
-        acc[2] += v * wp[32];
-      }
+      const long long row = (((long long)phase * n + img) * 16 + (iy >> 1)) * 16 + (ix >> 1);
+      const float* yp = Y + row * 64 + (kh * 4 + kw) * 3;
+      acc[0] += yp[0];
+      acc[1] += yp[1];
+      acc[2] += yp[2];
     }
   }
 #pragma unroll
-  for (int co = 0; co < 3; ++co) acc[co] = warp_sum(acc[co]);
-  if (lane < 3) {
-    const float v = lane == 0 ? acc[0] : (lane == 1 ? acc[1] : acc[2]);
-    out[(((long long)img * 3 + lane) * 64 + oy) * 64 + ox] = tanhf(v + bias[lane]);
-  }
+  for (int co = 0; co < 3; ++co) out[(((long long)img * 3 + co) * 64 + oy) * 64 + ox] = tanhf(acc[co]);
 }
 
 // dpre[n,3,64,64] = dL/d(pre-tanh) for the reconstruction MSE (loss.py:20, vqvae.py:79):
@@ -131,60 +123,32 @@ recon_loss_kernel(const float* __restrict__ xt, const float* __restrict__ x, flo
   }
 }
 
-// Backward of the output ConvTranspose2d wrt its (phase-major, ReLU'd) input.
-// One warp per INPUT pixel of the 32x32 grid; lanes split channels.  For input (iy, ix) and tap
-// (kh, kw) the output pixel is (2*iy - 1 + kh, 2*ix - 1 + kw).
-//   dact[c]  = relu'(act[c]) * sum_{co,kh,kw} dpre[co, oy, ox] * w[c][co][kh][kw]     (bf16, phase-major)
-//   G[row, co*16 + kh*4 + kw] = dpre[co, oy, ox] (bf16, 48 columns + 16 zeros): the weight gradient is
-//   then the tensor-core GEMM dw[c][k] = sum_rows act[row, c] * G[row, k] (no atomics).
-template <int C>
+// Backward of the output ConvTranspose2d, first half: G[row, co*16 + kh*4 + kw] = dpre[co, oy, ox] at the
+// output pixel (2*iy - 1 + kh, 2*ix - 1 + kw) that tap (kh, kw) of input pixel `row` reaches (0 outside the
+// image; bf16, 48 columns + 16 zeros; rows in the phase-major order of the 32x32 input).  Both gradients are
+// then tensor-core GEMMs:  dW[c][k] = sum_rows act[row, c] * G[row, k]  and
+// dact[row, c] = relu'(act[row, c]) * sum_k G[row, k] * w[c][k].
 __global__ void __launch_bounds__(256)
-out_convt_bwd_kernel(const __nv_bfloat16* __restrict__ act, const float* __restrict__ w,
-                     const float* __restrict__ dpre, __nv_bfloat16* __restrict__ dact,
-                     __nv_bfloat16* __restrict__ G, int n) {
-  __shared__ float s_w[C * 48];
-  for (int i = threadIdx.x; i < C * 48; i += 256) s_w[i] = w[i];
-  __syncthreads();
-  const int lane = threadIdx.x & 31;
-  const long long total = (long long)n * 1024;
-  for (long long wid = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); wid < total; wid += (long long)gridDim.x * 8) {
-    // phase-major enumeration so that reads / writes of act / dact are contiguous per warp
-    const int pos = (int)(wid & 255);
-    const long long r2 = wid >> 8;
-    const int img = (int)(r2 % n), phase = (int)(r2 / n);
-    const int iy = 2 * (pos >> 4) + (phase >> 1), ix = 2 * (pos & 15) + (phase & 1);
-    float g[48];  // dpre of the 16 taps x 3 channels this input pixel feeds (0 outside the image)
+out_convt_g_kernel(const float* __restrict__ dpre, __nv_bfloat16* __restrict__ G, int n) {
+  const long long t = (long long)blockIdx.x * 256 + threadIdx.x;  // one thread = one row and two columns
+  const long long row = t >> 5;
+  if (row >= (long long)n * 1024) return;
+  const int k0 = (int)(t & 31) * 2;
+  const int pos = (int)(row & 255);
+  const long long r2 = row >> 8;
+  const int img = (int)(r2 % n), phase = (int)(r2 / n);
+  const int iy = 2 * (pos >> 4) + (phase >> 1), ix = 2 * (pos & 15) + (phase & 1);
+  float v[2] = {0.f, 0.f};
 #pragma unroll
-    for (int kh = 0; kh < 4; ++kh) {
-      const int oy = 2 * iy - 1 + kh;
-#pragma unroll
-      for (int kw = 0; kw < 4; ++kw) {
-        const int ox = 2 * ix - 1 + kw;
-        const bool ok = oy >= 0 && oy < 64 && ox >= 0 && ox < 64;
-#pragma unroll
-        for (int co = 0; co < 3; ++co)
-          g[co * 16 + kh * 4 + kw] = ok ? __ldg(dpre + (((long long)img * 3 + co) * 64 + oy) * 64 + ox) : 0.f;
-      }
-    }
-    if (G) {
-      // lanes 0..23 write two of the 48 values each, lanes 24..31 the zero padding
-      float v0 = 0.f, v1 = 0.f;
-#pragma unroll
-      for (int k = 0; k < 48; k += 2) {
-        if (lane == k / 2) { v0 = g[k]; v1 = g[k + 1]; }
-      }
-      reinterpret_cast<__nv_bfloat162*>(G + wid * 64)[lane] = __floats2bfloat162_rn(v0, v1);
-    }
-    const long long base = wid * C;
-    for (int c = lane; c < C; c += 32) {
-      const float a = __bfloat162float(act[base + c]);
-      const float* wp = s_w + c * 48;
-      float s = 0.f;
-#pragma unroll
-      for (int k = 0; k < 48; ++k) s += g[k] * wp[k];
-      dact[base + c] = __float2bfloat16(a > 0.f ? s : 0.f);
+  for (int e = 0; e < 2; ++e) {
+    const int k = k0 + e;
+    if (k < 48) {
+      const int co = k >> 4, kh = (k >> 2) & 3, kw = k & 3;
+      const int oy = 2 * iy - 1 + kh, ox = 2 * ix - 1 + kw;
+      if (oy >= 0 && oy < 64 && ox >= 0 && ox < 64) v[e] = __ldg(dpre + (((long long)img * 3 + co) * 64 + oy) * 64 + ox);
     }
   }
+  reinterpret_cast<__nv_bfloat162*>(G)[t] = __floats2bfloat162_rn(v[0], v[1]);
 }
 
 // Commitment loss + gradient wrt z_e, merged with the straight-through gradient (vqvae.py:75,86;
@@ -259,12 +223,9 @@ extern "C" int lvt_vqvae_in_im2col(const float* x, void* a_bf16, int n, float me
   return LVT_OK;
 }
 
-extern "C" int lvt_vqvae_out_convt_fwd(const void* act_bf16, const float* w, const float* bias, float* out, int n,
-                                       int C, void* stream) {
-  LVT_CHECK_ARG(act_bf16 && w && bias && out && n > 0, "lvt_vqvae_out_convt_fwd: bad argument");
-  LVT_CHECK_ARG(C == 128, "lvt_vqvae_out_convt_fwd: C must be 128 (NF/2 of the shipped configs)");
-  out_convt_fwd_kernel<128><<<lvt_ceil_div((long long)n * 4096, 8), 256, 0, STREAM(stream)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(act_bf16), w, bias, out, n);
+extern "C" int lvt_vqvae_out_col2im_tanh(const float* y, const float* bias, float* out, int n, void* stream) {
+  LVT_CHECK_ARG(y && bias && out && n > 0, "lvt_vqvae_out_col2im_tanh: bad argument");
+  out_col2im_tanh_kernel<<<lvt_ceil_div((long long)n * 4096, 256), 256, 0, STREAM(stream)>>>(y, bias, out, n);
   LVT_CHECK_LAUNCH();
   lvt_count_launch(1);
   return LVT_OK;
@@ -281,15 +242,10 @@ extern "C" int lvt_vqvae_recon_loss(const float* x_tilde, const float* x, float*
   return LVT_OK;
 }
 
-extern "C" int lvt_vqvae_out_convt_bwd(const void* act_bf16, const float* w, const float* dpre, void* dact_bf16,
-                                       void* g_bf16, int n, int C, void* stream) {
-  LVT_CHECK_ARG(act_bf16 && w && dpre && dact_bf16 && n > 0, "lvt_vqvae_out_convt_bwd: bad argument");
-  LVT_CHECK_ARG(C == 128, "lvt_vqvae_out_convt_bwd: C must be 128");
-  const long long warps = (long long)n * 1024;
-  const int blocks = (int)(warps / 8 < 148 * 8 ? (warps + 7) / 8 : 148 * 8);
-  out_convt_bwd_kernel<128><<<blocks > 0 ? blocks : 1, 256, 0, STREAM(stream)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(act_bf16), w, dpre, reinterpret_cast<__nv_bfloat16*>(dact_bf16),
-      reinterpret_cast<__nv_bfloat16*>(g_bf16), n);
+extern "C" int lvt_vqvae_out_convt_g(const float* dpre, void* g_bf16, int n, void* stream) {
+  LVT_CHECK_ARG(dpre && g_bf16 && n > 0, "lvt_vqvae_out_convt_g: bad argument");
+  out_convt_g_kernel<<<lvt_ceil_div((long long)n * 1024 * 32, 256), 256, 0, STREAM(stream)>>>(
+      dpre, reinterpret_cast<__nv_bfloat16*>(g_bf16), n);
   LVT_CHECK_LAUNCH();
   lvt_count_launch(1);
   return LVT_OK;

@@ -108,6 +108,9 @@ class VQVAEEngine:
         self.ct1_grad = z((4, nf // 2, 4 * nf))
         self.ct1_dg = z((nf, 16 * (nf // 2)), bf16)       # as Conv2d(k4,s2,p1): [ci][16 taps * co]
         self.dw_out = z((nf // 2, 64))                    # output ConvT weight gradient scratch [c][48 (+16)]
+        # output ConvTranspose2d(nf/2 -> 3) weight [c][co][kh][kw] as GEMM operands (rows beyond 48 stay zero)
+        self.w_out_fwd = z((64, nf // 2), bf16)           # [(kh*4+kw)*3 + co][c]
+        self.w_out_dg = z((nf // 2, 64), bf16)            # [c][co*16 + kh*4 + kw]
         self._ws = {}
         self.shadows_fresh = False
         self.opt = None
@@ -162,6 +165,10 @@ class VQVAEEngine:
                     self._permute4(st.pf(wct) + 4 * t, self.ct1_fwd[ph * 2 + pw].data_ptr() + 2 * j * ci, True, False,
                                    (co, ci, 1, 1), (16, co * 16, 0, 0), (4 * ci, 1, 0, 0))
         self._permute4(st.pf(wct), self.ct1_dg, True, False, (ci, 16, co, 1), (co * 16, 1, 16, 0), (16 * co, co, 1, 0))
+        wo = st.pf(f"G.layers.{self.kG + 3}.weight")      # [c][3][16]
+        c2 = nf // 2
+        self._permute4(wo, self.w_out_fwd, True, False, (16, 3, c2, 1), (1, 16, 48, 0), (3 * c2, c2, 1, 0))
+        self._permute4(wo, self.w_out_dg, True, False, (c2, 48, 1, 1), (48, 1, 0, 0), (64, 1, 0, 0))
         self.shadows_fresh = True
 
     def _fold_packed_grads(self):
@@ -218,6 +225,7 @@ class VQVAEEngine:
         w.gr = [e((M, nf)) for _ in range(L + 1)]       # decoder block inputs; gr[L] = ReLU'd decoder trunk output
         w.gh = [e((M, rc)) for _ in range(L)]
         w.act32 = e((4 * M, nf // 2))
+        w.Y = torch.empty((4 * M, 64), dtype=f32, device=self.device)  # output ConvT partial sums per input pixel
         w.x_tilde = e((n, 3, 64, 64), f32)
         w.recon = e((n, 3, 64, 64), f32)
         w.loss = torch.zeros((2,), dtype=f32, device=self.device)  # [reconstruction, commitment]
@@ -349,9 +357,12 @@ class VQVAEEngine:
                 p = ph * 2 + pw
                 self._conv(w.gr[L], nf, n, self.ct1_fwd[p], 4 * nf, nf // 2, w.act32[p * M:(p + 1) * M],
                            st.pf(f"G.layers.{k + 1}.bias"), shifts)
-        check(self.lib.lvt_vqvae_out_convt_fwd(ptr(w.act32), _vp(st.pf(f"G.layers.{k + 3}.weight")),
-                                               _vp(st.pf(f"G.layers.{k + 3}.bias")), ptr(w.x_tilde), n, nf // 2,
-                                               stream_ptr()), "lvt_vqvae_out_convt_fwd")
+        # output ConvTranspose2d(nf/2 -> 3) + tanh: channel contraction on the tensor cores, then the 2x2 tap gather
+        c2 = nf // 2
+        gemm(4 * M, 64, c2, Operand(w.act32.data_ptr(), c2), Operand(self.w_out_fwd.data_ptr(), c2),
+             Operand(w.Y.data_ptr(), 64), out_f32=w.Y)
+        check(self.lib.lvt_vqvae_out_col2im_tanh(ptr(w.Y), _vp(st.pf(f"G.layers.{k + 3}.bias")), ptr(w.x_tilde), n,
+                                                 stream_ptr()), "lvt_vqvae_out_col2im_tanh")
 
     def inference(self, w):
         """AutoEncoderModel.forward(mode='inference') (ae.py:120-147): x in [0,1] -> recon in [0,1], latent."""
@@ -374,12 +385,20 @@ class VQVAEEngine:
     # ------------------------------------------------------------------ training
     def forward_train(self, w, allreduce=None):
         """compute_supervised_loss (vqvae.py:66-91): losses in w.loss = [reconstruction, commitment(after bwd)]."""
-        s = self.spec
-        self.encode(w)
-        self.quantize(w, train=True)
+        self._forward_train_a(w)
         if allreduce is not None:
             allreduce(w.counts)
             allreduce(w.sums)
+        self._forward_train_b(w)
+
+    def _forward_train_a(self, w):
+        """encoder + codebook search with the OLD codebook; per-code counts / sums of this rank"""
+        self.encode(w)
+        self.quantize(w, train=True)
+
+    def _forward_train_b(self, w):
+        """EMA codebook update (after the cross-rank sum), decoder, losses"""
+        s = self.spec
         self.ema_update(w)
         self.decode(w)
         w.loss.zero_()
@@ -396,8 +415,9 @@ class VQVAEEngine:
         k = self.kG
         self._zero_packed_grads()
         # ---- output ConvTranspose2d + tanh
-        check(self.lib.lvt_vqvae_out_convt_bwd(ptr(w.act32), _vp(st.pf(f"G.layers.{k + 3}.weight")), ptr(w.dpre),
-                                               ptr(w.dact32), ptr(w.G), n, nf // 2, stream_ptr()), "lvt_vqvae_out_convt_bwd")
+        check(self.lib.lvt_vqvae_out_convt_g(ptr(w.dpre), ptr(w.G), n, stream_ptr()), "lvt_vqvae_out_convt_g")
+        gemm(4 * M, nf // 2, 64, Operand(w.G.data_ptr(), 64), Operand(self.w_out_dg.data_ptr(), 64),
+             Operand(w.dact32.data_ptr(), nf // 2), out_bf16=w.dact32, aux=w.act32, flags=ops.GEMM_MASK)
         self._wgrad_plain(w.act32, nf // 2, w.G, 64, 4 * M, self.dw_out)
         # ---- ConvTranspose2d(nf -> nf/2)
         self._colsum(w.dact32, st.gf(f"G.layers.{k + 1}.bias"), 4 * M, nf // 2)
@@ -476,3 +496,74 @@ class VQVAEEngine:
             allreduce(self.store.grad)
         self.optimizer_step(1.0 / world_size)
         return w.loss
+
+
+class GraphedVQVAEStep:
+    """The VQ-VAE train step (compute_supervised_loss + backward + Adam, trainer.py:79-87) with its ~250 launches
+    captured in CUDA graphs: [zero-grad, encoder, codebook search] (all-reduce of the EMA counts / sums when
+    world_size > 1, vq_embedding.py:44-59) [EMA update, decoder, losses, backward] (all-reduce of the flat gradient)
+    Adam (eager: its bias correction depends on the step count) [weight re-layout]."""
+
+    def __init__(self, engine: "VQVAEEngine", w, world_size=1, allreduce=None):
+        self.engine, self.w, self.world_size, self.allreduce = engine, w, world_size, allreduce
+        self.graphs = None
+
+    def _seg_a(self):
+        self.engine.store.grad.zero_()
+        self.engine._forward_train_a(self.w)
+
+    def _seg_b(self):
+        self.engine._forward_train_b(self.w)
+        self.engine.backward(self.w)
+
+    def _adam(self):
+        eng = self.engine
+        o, st = eng.opt, eng.store
+        o["step"] += 1
+        check(eng.lib.lvt_adam_step(ptr(st.master), ptr(st.grad), ptr(eng.opt_m), ptr(eng.opt_v), ptr(st.shadow),
+                                    st.numel, o["lr"], o["betas"][0], o["betas"][1], o["eps"], o["step"],
+                                    1.0 / self.world_size, stream_ptr()), "lvt_adam_step")
+
+    def _refresh(self):
+        self.engine.refresh_shadows(cast=False)
+
+    def _eager(self):
+        self._seg_a()
+        if self.allreduce is not None:
+            self.allreduce(self.w.counts)
+            self.allreduce(self.w.sums)
+        self._seg_b()
+        if self.allreduce is not None:
+            self.allreduce(self.engine.store.grad)
+        self._adam()
+        self._refresh()
+
+    def capture(self, warmup=2):
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):  # eager warm-up: kernel attributes, TMA maps
+                self._eager()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        segs = [self._seg_a, self._seg_b] if self.allreduce is not None else [lambda: (self._seg_a(), self._seg_b())]
+        self.graphs = []
+        for seg in segs + [self._refresh]:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                seg()
+            self.graphs.append(g)
+        torch.cuda.synchronize()
+
+    def step(self):
+        if self.allreduce is not None:
+            self.graphs[0].replay()
+            self.allreduce(self.w.counts)
+            self.allreduce(self.w.sums)
+            self.graphs[1].replay()
+            self.allreduce(self.engine.store.grad)
+        else:
+            self.graphs[0].replay()
+        self._adam()
+        self.graphs[-1].replay()
+        return self.w.loss

@@ -109,3 +109,41 @@ def test_vqvae_train_step_vs_oracle(cuda_lib):
     torch.cuda.synchronize()
     delta = (eng.store.master - before).abs().max().item()
     assert 0 < delta <= 3e-4 * 1.001
+
+
+def test_vqvae_graphed_step_matches_eager(cuda_lib):
+    """GraphedVQVAEStep (CUDA-graph replay of forward + EMA + backward, Adam outside) against the eager
+    train_step on identical state: same code indices, same losses and parameters after 3 steps (up to the
+    summation order of the atomically accumulated weight gradients)."""
+    from lvt_b200.modeling.vqvae_engine import GraphedVQVAEStep, VQVAEEngine, VQVAESpec
+    n, L = 8, 2
+    cfg, we, wg, x, cb, z_ref = _setup(n, L)
+    runs = []
+    for graphed in (False, True):
+        eng = VQVAEEngine(VQVAESpec(n_layers=L))
+        eng.load_state_dict(we, wg, cb, running_size=torch.full((4, 512), 5.0), running_sum=cb * 5.0)
+        eng.init_optimizer()
+        w = eng.workspace(n, train=True)
+        w.x.copy_(x)
+        losses = []
+        if graphed:
+            stepper = GraphedVQVAEStep(eng, w)
+            state = (eng.store.master.clone(), eng.codebook.clone(), eng.running_size.clone(), eng.running_sum.clone())
+            stepper.capture(warmup=1)
+            # the warm-up step moved the state: restore it so that both runs start from the same point
+            eng.store.master.copy_(state[0]); eng.codebook.copy_(state[1])
+            eng.running_size.copy_(state[2]); eng.running_sum.copy_(state[3])
+            eng.opt_m.zero_(); eng.opt_v.zero_(); eng.opt["step"] = 0
+            eng.refresh_shadows()
+            for _ in range(3):
+                losses.append(stepper.step().clone())
+        else:
+            for _ in range(3):
+                losses.append(eng.train_step(w).clone())
+        torch.cuda.synchronize()
+        runs.append((torch.stack(losses).cpu(), eng.store.master.cpu().clone(), w.idx.cpu().clone(), eng.codebook.cpu().clone()))
+    (l0, m0, i0, c0), (l1, m1, i1, c1) = runs
+    assert torch.allclose(l0, l1, rtol=1e-2, atol=1e-4), (l0, l1)  # near-tie index flips move the small commitment term
+    assert (i0 != i1).float().mean().item() <= 1e-3      # identical up to near-ties after drifting weights
+    assert torch.allclose(c0, c1, rtol=1e-3, atol=1e-5)
+    assert (m0 - m1).abs().max().item() <= 3 * 3e-4      # Adam moves a weight by at most lr per step
