@@ -231,6 +231,30 @@ __global__ void vq_gather_kernel(const int64_t* __restrict__ idx, const float* _
   }
 }
 
+// channels-last variant: 16 threads per position, one float4 of the code row each -> 256 B contiguous per position
+__global__ void __launch_bounds__(256)
+vq_gather_nhwc_kernel(const int64_t* __restrict__ idx, const float* __restrict__ codebook, float* __restrict__ out,
+                      __nv_bfloat16* __restrict__ out_bf16, long long total_pos, int num, int K, int hw) {
+  const int g = blockIdx.y;
+  const long long t = (long long)blockIdx.x * 256 + threadIdx.x;
+  const long long p = t >> 4;
+  if (p >= total_pos) return;
+  const int j4 = (int)(t & 15);
+  const long long frame = p / hw;
+  const int s = (int)(p - frame * hw);
+  long long code = idx[(frame * num + g) * hw + s];
+  code = code < 0 ? 0 : (code >= K ? K - 1 : code);
+  const float4 v = __ldg(reinterpret_cast<const float4*>(codebook + ((size_t)g * K + code) * 64) + j4);
+  const long long o = (p * num + g) * 64 + 4 * j4;
+  if (out) *reinterpret_cast<float4*>(out + o) = v;
+  if (out_bf16) {
+    uint2 u;
+    u.x = pack_bf16x2(v.x, v.y);
+    u.y = pack_bf16x2(v.z, v.w);
+    *reinterpret_cast<uint2*>(out_bf16 + o) = u;
+  }
+}
+
 // EMA update for one codebook group per block (vq_embedding.py:48-59). n = sum(running_size) is
 // reduced in a fixed order inside the block, so the update is deterministic.
 __global__ void vq_ema_kernel(float* __restrict__ codebook, float* __restrict__ running_size,
@@ -288,15 +312,38 @@ vq_ema_stats_kernel(const float* __restrict__ z_e, const int64_t* __restrict__ i
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long p0 = (long long)blockIdx.x * chunk;
   const long long p1 = p0 + chunk < total ? p0 + chunk : total;
-  for (long long pos = p0 + warp; pos < p1; pos += 8) {
-    const long long frame = pos / hw, sp = pos - frame * hw;
-    const int k = (int)idx[(frame * num + g) * hw + sp];
-    const float* x = z_e + (ch_stride == 1 ? pos * pos_stride + (long long)g * 64
-                                           : (frame * num * 64 + (long long)g * 64) * hw + sp);
-    const float x0 = x[(2 * lane) * ch_stride], x1 = x[(2 * lane + 1) * ch_stride];
-    atomicAdd(&s_acc[k * 64 + 2 * lane], x0);
-    atomicAdd(&s_acc[k * 64 + 2 * lane + 1], x1);
-    if (lane == 0) atomicAdd(&s_cnt[k], 1.f);
+  constexpr int U = 4;  // positions in flight per warp: index and row loads of all U issue before the first atomic
+  for (long long pb = p0 + warp; pb < p1; pb += 8 * U) {
+    int kk[U];
+    float x0[U], x1[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long pos = pb + 8 * u;
+      kk[u] = -1;
+      if (pos < p1) {
+        const long long frame = pos / hw, sp = pos - frame * hw;
+        kk[u] = (int)idx[(frame * num + g) * hw + sp];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long pos = pb + 8 * u;
+      x0[u] = x1[u] = 0.f;
+      if (kk[u] >= 0) {
+        const long long frame = pos / hw, sp = pos - frame * hw;
+        const float* x = z_e + (ch_stride == 1 ? pos * pos_stride + (long long)g * 64
+                                               : (frame * num * 64 + (long long)g * 64) * hw + sp);
+        x0[u] = x[(2 * lane) * ch_stride];
+        x1[u] = x[(2 * lane + 1) * ch_stride];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (kk[u] < 0) continue;  // warp-uniform
+      atomicAdd(&s_acc[kk[u] * 64 + 2 * lane], x0[u]);
+      atomicAdd(&s_acc[kk[u] * 64 + 2 * lane + 1], x1[u]);
+      if (lane == 0) atomicAdd(&s_cnt[kk[u]], 1.f);
+    }
   }
   __syncthreads();
   for (int k = warp; k < K; k += 8) {
@@ -402,6 +449,14 @@ static int vq_gather_impl(const int64_t* idx, const float* codebook, float* out,
   if (n == 0) return LVT_OK;
   LVT_CHECK_ARG(idx && codebook && (out || out_bf16), "lvt_vq_gather: null pointer");
   const long long total = (long long)n * hw;
+  if (nhwc && D == 64) {
+    dim3 grid16(lvt_ceil_div(total * 16, 256), num);
+    vq_gather_nhwc_kernel<<<grid16, 256, 0, stream>>>(idx, codebook, out, reinterpret_cast<__nv_bfloat16*>(out_bf16), total,
+                                                      num, K, hw);
+    LVT_CHECK_LAUNCH();
+    lvt_count_launch(1);
+    return LVT_OK;
+  }
   dim3 grid(lvt_ceil_div(total, 256), num);
   vq_gather_kernel<<<grid, 256, 0, stream>>>(idx, codebook, out, reinterpret_cast<__nv_bfloat16*>(out_bf16), total,
                                              num, K, D, hw, nhwc ? (long long)num * D : 1, nhwc ? 1 : hw);
