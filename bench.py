@@ -112,6 +112,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="slices per GPU")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true", help="one gradient all-reduce after the backward instead of two overlapped buckets")
     ap.add_argument("--quick", action="store_true", help="DSFVT step only: skip the per-kernel figures and the CPU baseline")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -189,7 +190,7 @@ def main():
     if world > 1:
         def allreduce(flat):
             dist.all_reduce(flat)
-    stepper = GraphedTrainStep(eng, ws, world_size=world, allreduce=allreduce)
+    stepper = GraphedTrainStep(eng, ws, world_size=world, allreduce=allreduce, overlap=not args.no_overlap)
     if args.no_graph:
         def one_step():
             eng.zero_grad(); eng.forward(ws, train=True); eng.backward(ws)

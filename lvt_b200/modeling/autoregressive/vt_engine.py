@@ -318,13 +318,17 @@ class VTEngine:
         for key, (taps, offs, wp, dwp) in self._taps_cache.items():
             dwp.zero_()
 
-    def _fold_special_grads(self, slice_shape):
-        """re-laid-out gradients -> master gradient layout (+=)."""
+    def _fold_special_grads_enc(self):
+        """re-laid-out gradients -> master gradient layout (+=): encoder one-hot conv."""
         s, st = self.spec, self.store
         ktaps = s.kernel[0] * s.kernel[1] * s.kernel[2]
         self._permute4(self.enc_dwt, st.gf("encoder.conv.weight"), False, True,
                        (s.nc, ktaps, s.nv, s.de), (ktaps * s.nv * s.de, s.nv * s.de, s.de, 1),
                        (s.nv * ktaps, 1, ktaps, s.nc * s.nv * ktaps))
+
+    def _fold_special_grads_dec(self, slice_shape):
+        """... one-hot half of the predictor's U[k], live taps of the masked conv."""
+        s, st = self.spec, self.store
         for k in range(1, s.nc):
             ld = s.d + k * s.nv
             self._permute4(self.dut[k], st.gf(f"ch_predictor.U.{k}.weight") + 4 * s.d, False, True,
@@ -607,6 +611,17 @@ class VTEngine:
 
     def backward(self, ws: VTWorkspace):
         """Gradient of ws.loss wrt every parameter, ACCUMULATED into the flat gradient buffer."""
+        self.backward_decoder(ws)
+        self.backward_encoder(ws)
+
+    def grad_buckets(self):
+        """The flat gradient as two contiguous buckets in the order the backward completes them:
+        [decoder + channel predictor] (final after backward_decoder), [encoder] (final after backward_encoder)."""
+        off = self.store.offsets["decoder.ch_embedder.0.weight"]
+        return self.store.grad[off:], self.store.grad[:off]
+
+    def backward_decoder(self, ws: VTWorkspace):
+        """Channel predictor, decoder stack, decoder front; leaves d(loss)/d(zl) in ws.dh / ws.dh_bf16."""
         s, st = self.spec, self.store
         M, d, de, nv, nc = ws.M, s.d, s.de, s.nv, s.nc
         t, h, w = ws.slice_shape
@@ -653,6 +668,13 @@ class VTEngine:
         # (written to the dh buffers: the GEMM may not overwrite its own A operand)
         gemm(M, d, d, Operand(dyb, d), Operand(st.pb("decoder.linear_projector.weight"), d, mn_major=True),
              Operand(ws.dh.data_ptr(), d), out_f32=ws.dh, out_bf16=ws.dh_bf16)
+        self._fold_special_grads_dec(ws.slice_shape)
+
+    def backward_encoder(self, ws: VTWorkspace):
+        """Encoder stack and encoder front (gradient entering through ws.dh / ws.dh_bf16)."""
+        s, st = self.spec, self.store
+        M, d, de, nv, nc = ws.M, s.d, s.de, s.nv, s.nc
+        nE = len(s.blocks_e)
         # ---- encoder stack
         for i in reversed(range(nE)):
             ly = ws.layers[i]
@@ -671,7 +693,7 @@ class VTEngine:
                                             _vp(st.gf("encoder.slice_embedding.weight")), ws.B, nc, nv, de,
                                             _i3(ws.ctx_shape), _i3(s.kernel), _i3(s.stride), s.pad_value,
                                             stream_ptr()), "lvt_vt_enc_front_bwd")
-        self._fold_special_grads(ws.slice_shape)
+        self._fold_special_grads_enc()
 
     # ------------------------------------------------------------------ optimizer
     def init_optimizer(self, name="rmsprop", lr=2e-5, alpha=0.95, momentum=0.9, eps=1e-8, betas=(0.9, 0.9)):
@@ -708,16 +730,20 @@ class VTEngine:
 class GraphedTrainStep:
     """The DSFVT train step (zero_grad + forward + backward [+ gradient all-reduce] + optimizer)
     captured once into CUDA graphs and replayed: one host launch per step instead of ~700.
-    With world_size > 1 the flat fp32 gradient is summed across ranks with one NCCL all-reduce
-    between the two graphs (reference: DDP over self.model, meta_arch/vt.py:61-63) and averaged
-    by the optimizer kernel's grad_scale."""
+    With world_size > 1 the flat fp32 gradient is summed across ranks in two buckets (reference: DDP over
+    self.model, meta_arch/vt.py:61-63): the decoder + predictor bucket is reduced on a communication stream
+    WHILE the encoder half of the backward runs, the encoder bucket after it; the optimizer kernel's
+    grad_scale averages."""
 
-    def __init__(self, engine: VTEngine, ws: VTWorkspace, world_size=1, allreduce=None):
+    def __init__(self, engine: VTEngine, ws: VTWorkspace, world_size=1, allreduce=None, overlap=True):
         self.engine, self.ws = engine, ws
         self.world_size = world_size
         self.allreduce = allreduce
-        self.g_fb = None
+        self.overlap = overlap  # False: one all-reduce of the whole flat gradient after the backward
+        self.g_fb = None     # zero-grad + forward + backward (decoder half only when world_size > 1)
+        self.g_enc = None    # encoder half of the backward (world_size > 1)
         self.g_opt = None
+        self.comm = torch.cuda.Stream() if allreduce is not None else None
         self.launches_per_step = 0
 
     def _fwd_bwd(self):
@@ -725,8 +751,30 @@ class GraphedTrainStep:
         self.engine.forward(self.ws, train=True)
         self.engine.backward(self.ws)
 
+    def _fwd_bwd_dec(self):
+        self.engine.zero_grad()
+        self.engine.forward(self.ws, train=True)
+        self.engine.backward_decoder(self.ws)
+
     def _opt(self):
         self.engine.optimizer_step(grad_scale=1.0 / self.world_size)
+
+    def _reduce_overlapped(self, run_encoder_backward):
+        """bucket 0 (decoder + predictor gradients) on the communication stream during the encoder backward"""
+        if not self.overlap:
+            run_encoder_backward()
+            self.allreduce(self.engine.store.grad)
+            return
+        main = torch.cuda.current_stream()
+        b_dec, b_enc = self.engine.grad_buckets()
+        self.comm.wait_stream(main)
+        with torch.cuda.stream(self.comm):
+            self.allreduce(b_dec)
+        run_encoder_backward()
+        self.comm.wait_stream(main)
+        with torch.cuda.stream(self.comm):
+            self.allreduce(b_enc)
+        main.wait_stream(self.comm)
 
     def capture(self, warmup=2):
         eng = self.engine
@@ -734,19 +782,25 @@ class GraphedTrainStep:
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(warmup):  # eager warm-up: sets kernel attributes, builds TMA maps
-                self._fwd_bwd()
                 if self.allreduce is not None:
-                    self.allreduce(eng.store.grad)
+                    self._fwd_bwd_dec()
+                    self._reduce_overlapped(lambda: eng.backward_encoder(self.ws))
+                else:
+                    self._fwd_bwd()
                 self._opt()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         n0 = _lib.launch_count()
         self.g_fb = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.g_fb):
-            self._fwd_bwd()
-        if self.allreduce is None:
-            # single rank: optimizer joins the same graph region
-            pass
+            if self.allreduce is not None:
+                self._fwd_bwd_dec()
+            else:
+                self._fwd_bwd()
+        if self.allreduce is not None:
+            self.g_enc = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.g_enc):
+                eng.backward_encoder(self.ws)
         self.g_opt = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.g_opt):
             self._opt()
@@ -756,6 +810,6 @@ class GraphedTrainStep:
     def step(self):
         self.g_fb.replay()
         if self.allreduce is not None:
-            self.allreduce(self.engine.store.grad)
+            self._reduce_overlapped(self.g_enc.replay)
         self.g_opt.replay()
         return self.ws.loss

@@ -1,1 +1,1 @@
-for i in 1 2 3; do timeout 900 python -m pytest tests/test_vqvae_gpu.py -x -q -k graphed 2>&1 | grep -E "^E|passed|failed" | head -8; done
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 6000 -c 1500 --csv --log-file gpurun_out/r01d_sampler_launches.csv python tools/sampler_bench.py > /dev/null 2>&1

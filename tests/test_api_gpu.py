@@ -105,3 +105,25 @@ def test_graph_sampler_matches_per_pixel_loop(cuda_lib, tmp_path):
         outs.append(vt.sample_video(video.clone(), temp=1e-4, n_prime=15).cpu())
     assert torch.equal(outs[0], outs[1])
     assert torch.equal(outs[0][:, :, :15], video[:, :, :15].cpu())
+
+
+def test_codes_extractor_round_trip(cuda_lib, tmp_path):
+    """VQ-VAE -> latent tree -> loader: batched extraction writes exactly the codes VQVAEModel.encode
+    returns, in the reference's on-disk format, and the transformer's loader reads them back."""
+    from lvt_b200.config.presets import preset
+    from lvt_b200.data import extract_codes, get_latent_video_paths, load_latent_video
+    from lvt_b200.modeling import build_model
+    cfg = preset("PR-DVQVAE2", ["OUTPUT_DIR", str(tmp_path)])
+    cfg.freeze()
+    vq = build_model(cfg)
+    vq.train(False)
+    g = torch.Generator().manual_seed(3)
+    videos = [{"image_sequence": torch.rand((6, 3, 64, 64), generator=g), "video_idx": i} for i in range(5)]
+    assert extract_codes(vq, videos, "bair_test", str(tmp_path / "inference"), videos_per_batch=2) == {"latents": {}}
+    entries = get_latent_video_paths(str(tmp_path / "inference" / "bair_test"))
+    assert len(entries) == 5
+    for e in entries:
+        i = int(os.path.basename(e["video_path"]).split("_")[1])
+        got = load_latent_video(e, -1)
+        want = vq.encode(videos[i]["image_sequence"].cuda()).cpu()
+        assert got.shape == (6, 4, 16, 16) and torch.equal(got, want)

@@ -3,8 +3,9 @@
 
     python tools/train_net.py --config-file <reference yaml | preset name> [--num-gpus N] [--eval-only] KEY VALUE ...
 
-Datasets are out of scope: batches come from the synthetic generators of
-lvt_b200.data unless a loader is supplied programmatically (Trainer(cfg, data_loader))."""
+Batches come from the synthetic generators of lvt_b200.data, or — for the video transformer — from a tree of latent
+codes in the reference's on-disk format when LVT_LATENT_ROOT=<dir> is set (written by the CodesExtractor,
+lvt_b200.data.latents); a loader can also be supplied programmatically (Trainer(cfg, data_loader))."""
 import os
 import random
 import sys
@@ -57,7 +58,13 @@ def synthetic_loader(cfg):
 
 def main(args):
     cfg = setup(args)
-    trainer = Trainer(cfg, data_loader=synthetic_loader(cfg))
+    latent_root = os.environ.get("LVT_LATENT_ROOT")
+    if latent_root and cfg.MODEL.META_ARCHITECTURE == "VideoTransformerModel":
+        from lvt_b200.data import latent_slice_loader
+        loader = latent_slice_loader(cfg, latent_root)
+    else:
+        loader = synthetic_loader(cfg)
+    trainer = Trainer(cfg, data_loader=loader)
     trainer.resume_or_load(resume=args.resume)
     if args.eval_only:
         model = trainer.model
