@@ -144,6 +144,12 @@ typedef struct LvtGemm {
   /* LVT_GEMM_ROWDOT: rowdot[((m / rd_L) * (N / rd_block) + n / rd_block) * rd_L + m % rd_L]
      (= delta[sequence, head, position] for rd_block = da, rd_L = block length)                 */
   float* rowdot; int rd_block, rd_L;
+  /* LVT_EPI_SOFTMAX with v != NULL: fused attention forward (vt_attention.py:61-81).  After the softmax the same
+     kernel computes O[z] = P[z] @ V[z] with P taken from shared memory: V[z] is [N keys][o2_n] (keys = rows, like
+     an MN-major B operand), O goes to o2_bf16 [M, o2_n] (o2_n = da = 128).  out_bf16 (P, needed by the backward)
+     becomes optional.                                                                              */
+  const void* v; int v_cin, v_zdiv; long long v_ld, v_s_zlo, v_s_zhi;
+  void* o2_bf16; int o2_n, o2_cin, o2_zdiv; long long o2_ld, o2_s_zlo, o2_s_zhi;
 } LvtGemm;
 
 int lvt_gemm_bf16(const LvtGemm* g, void* stream);

@@ -46,6 +46,10 @@ class LvtGemm(ctypes.Structure):
         ("cv_pix_stride", ctypes.c_longlong), ("cv_s_phase", ctypes.c_longlong),
         ("cv_dh", ctypes.c_byte * 16), ("cv_dw", ctypes.c_byte * 16), ("cv_ph", ctypes.c_byte * 16),
         ("rowdot", ctypes.c_void_p), ("rd_block", ctypes.c_int), ("rd_L", ctypes.c_int),
+        ("v", ctypes.c_void_p), ("v_cin", ctypes.c_int), ("v_zdiv", ctypes.c_int),
+        ("v_ld", ctypes.c_longlong), ("v_s_zlo", ctypes.c_longlong), ("v_s_zhi", ctypes.c_longlong),
+        ("o2_bf16", ctypes.c_void_p), ("o2_n", ctypes.c_int), ("o2_cin", ctypes.c_int), ("o2_zdiv", ctypes.c_int),
+        ("o2_ld", ctypes.c_longlong), ("o2_s_zlo", ctypes.c_longlong), ("o2_s_zhi", ctypes.c_longlong),
     ]
 
 

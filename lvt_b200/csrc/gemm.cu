@@ -730,6 +730,295 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   }
 }
 
+
+// ----------------------------------------------------------------------------------------
+// Fused attention forward for one 256-token block per (sequence, head):
+//   S = Q K^T (tcgen05, 128 x 256 tile, K = da = 128)  ->  P = softmax(alpha*S + B [causal -1e4])  ->  O = P V
+// (ScaledDotProductAttention.forward, vt_attention.py:61-81, with the bias of BlockLocalAttention.get_B).
+// P never leaves the SM between the softmax and the second MMA: the epilogue warps write it as the
+// 128B-swizzled K-major A operand (4 k-blocks of 128 rows x 64 keys) straight into shared memory, the same bytes
+// are TMA-stored to HBM for the backward (optional).  Saves the P re-read of a separate P V GEMM and one launch.
+//   warp 0: TMA producer (Q, K tile; V tile)        warp 1: MMA issuer (QK^T of tile i+1 is issued before PV of tile i)
+//   warps 2-9: softmax + O epilogue; the two warps of a lane quarter own one query row per lane and 128 keys each
+// TMEM: S at columns [0, 256), O at [256, 384).
+// ----------------------------------------------------------------------------------------
+struct AttnSmem {
+  static constexpr int Q_OFF = 0;                  // 2 k-blocks x (128 rows x 128 B)
+  static constexpr int K_OFF = 32768;              // 2 k-blocks x (256 rows x 128 B)
+  static constexpr int V_OFF = 98304;              // 4 key-blocks x 2 x (64 keys x 128 B)   (MN-major B operand)
+  static constexpr int P_OFF = 163840;             // 4 key-blocks x (128 rows x 128 B)      (K-major A operand)
+  static constexpr int XCHG_OFF = 229376;          // [2][2][128] fp32
+  static constexpr int BAR_OFF = XCHG_OFF + 2048;
+  static constexpr int TOTAL = BAR_OFF + 256;
+};
+static_assert(AttnSmem::TOTAL <= 232448, "attention forward: shared memory budget");
+
+template <int EK>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_p,
+                const __grid_constant__ CUtensorMap tm_o, const GemmParams p, int v_cin, int v_zdiv, int o2_cin,
+                int o2_zdiv, int store_p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  using A = AttnSmem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + A::BAR_OFF);
+  uint64_t* qk_full = bars + 0;
+  uint64_t* qk_empty = bars + 1;
+  uint64_t* s_full = bars + 2;
+  uint64_t* s_empty = bars + 3;
+  uint64_t* v_full = bars + 4;
+  uint64_t* p_full = bars + 5;
+  uint64_t* pv_done = bars + 6;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 8);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    if ((smem_u32(smem) & 1023u) != 0) {
+      printf("lvt_b200: attention forward needs 1024-byte aligned dynamic shared memory\n");
+      __trap();
+    }
+    tma_prefetch_desc(&tm_q);
+    tma_prefetch_desc(&tm_k);
+    tma_prefetch_desc(&tm_v);
+    mbar_init(qk_full, 1);
+    mbar_init(qk_empty, 1);
+    mbar_init(s_full, 1);
+    mbar_init(s_empty, NUM_EPI_WARPS);
+    mbar_init(v_full, 1);
+    mbar_init(p_full, NUM_EPI_WARPS);
+    mbar_init(pv_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr_smem, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (elect_one()) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+        const TileCoord t = decode_tile(p, tile, 256);
+        const int a_zlo = t.z % p.a_zdiv, a_zhi = t.z / p.a_zdiv;
+        const int b_zlo = t.z % p.b_zdiv, b_zhi = t.z / p.b_zdiv;
+        mbar_wait(qk_empty, (it & 1) ^ 1);  // QK^T of the previous tile has consumed the operands
+        mbar_arrive_expect_tx(qk_full, 98304);
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb) {
+          const int k0 = kb * BK;
+          tma_load_5d(smem + A::Q_OFF + kb * 16384, &tm_q, qk_full, k0 % p.a_cin, t.m0, k0 / p.a_cin, a_zlo, a_zhi);
+          tma_load_5d(smem + A::K_OFF + kb * 32768, &tm_k, qk_full, k0 % p.b_cin, 0, k0 / p.b_cin, b_zlo, b_zhi);
+        }
+        const int v_zlo = t.z % v_zdiv, v_zhi = t.z / v_zdiv;
+        mbar_wait(pv_done, (it & 1) ^ 1);   // P V of the previous tile has consumed V
+        mbar_arrive_expect_tx(v_full, 65536);
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb) {
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const int c = 64 * j;
+            tma_load_5d(smem + A::V_OFF + kb * 16384 + j * 8192, &tm_v, v_full, c % v_cin, kb * BK, c / v_cin, v_zlo,
+                        v_zhi);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (elect_one()) {
+      constexpr uint32_t idesc_qk = umma_idesc(BM, 256, /*bf16*/ 1, false, false);
+      constexpr uint32_t idesc_pv = umma_idesc(BM, 128, /*bf16*/ 1, false, true);
+      const uint32_t q_base = smem_u32(smem + A::Q_OFF), k_base = smem_u32(smem + A::K_OFF);
+      const uint32_t v_base = smem_u32(smem + A::V_OFF), p_base = smem_u32(smem + A::P_OFF);
+      auto issue_qk = [&](uint32_t it) {
+        mbar_wait(qk_full, it & 1);
+        mbar_wait(s_empty, (it & 1) ^ 1);  // the softmax warps hold the previous S in registers
+        tc_fence_after();
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb) {
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4)
+            umma_bf16_ss(tmem_base, umma_smem_desc(q_base + kb * 16384 + k4 * 32, 16, 1024),
+                         umma_smem_desc(k_base + kb * 32768 + k4 * 32, 16, 1024), idesc_qk, (kb | k4) ? 1u : 0u);
+        }
+        umma_commit(qk_empty);
+        umma_commit(s_full);
+      };
+      const int my_tiles = blockIdx.x < p.total_tiles ? (p.total_tiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+      if (my_tiles > 0) issue_qk(0);
+      for (int it = 0; it < my_tiles; ++it) {
+        if (it + 1 < my_tiles) issue_qk(it + 1);  // next tile's scores while this tile's softmax runs
+        mbar_wait(v_full, it & 1);
+        mbar_wait(p_full, it & 1);               // P of this tile is in shared memory (and O of the previous one was read)
+        tc_fence_after();
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb) {
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4)
+            umma_bf16_ss(tmem_base + 256, umma_smem_desc(p_base + kb * 16384 + k4 * 32, 16, 1024),
+                         umma_smem_desc(v_base + kb * 16384 + k4 * 2048, 8192, 1024), idesc_pv, (kb | k4) ? 1u : 0u);
+        }
+        umma_commit(pv_done);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax + O epilogue
+    constexpr int BT = EK == EK_SOFTMAX_1x16x16 ? 1 : 4;
+    constexpr int BH = EK == EK_SOFTMAX_1x16x16 ? 16 : 8;
+    constexpr int BW = EK == EK_SOFTMAX_1x16x16 ? 16 : 8;
+    constexpr int TJN = (BH * BW <= 128) ? 128 / (BH * BW) : 1;
+    constexpr int HJN = (128 / BW < BH) ? 128 / BW : BH;
+    const int ew = warp - 2;
+    const int q = warp & 3;      // TMEM lane quarter
+    const int half = ew >> 2;    // which 128 keys (softmax) / which 64 output columns (O)
+    float* const xchg = reinterpret_cast<float*>(smem + A::XCHG_OFF);
+    float* const x_own_max = xchg + half * 128 + q * 32 + lane;
+    float* const x_oth_max = xchg + (half ^ 1) * 128 + q * 32 + lane;
+    float* const x_own_sum = x_own_max + 256;
+    float* const x_oth_sum = x_oth_max + 256;
+    const float kLog2e = 1.4426950408889634f;
+    const bool causal = (p.flags & LVT_GEMM_CAUSAL) != 0;
+    const float a2 = p.alpha * kLog2e;
+    const float kMasked = -1e4f * kLog2e;
+    // this warp's two P slabs: key-blocks 2*half and 2*half + 1, rows 32q .. 32q+31 of the A operand
+    uint4* const slab0 = reinterpret_cast<uint4*>(smem + A::P_OFF + (2 * half) * 16384 + q * 4096);
+    uint4* const slab1 = reinterpret_cast<uint4*>(smem + A::P_OFF + (2 * half + 1) * 16384 + q * 4096);
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const TileCoord t = decode_tile(p, tile, 256);
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + half * 128;
+      const int row_base = t.m0 + q * 32;
+      const int row = row_base + lane;
+      const int head = t.z % p.heads;
+      const int ti = row / (BH * BW), hi = (row / BW) % BH, wi = row % BW;
+      float btl[TJN], bhl[HJN], bw[BW];
+#pragma unroll
+      for (int x = 0; x < TJN; ++x) {
+        const int tj = (half * 128) / (BH * BW) + x;
+        btl[x] = kLog2e * __ldg(p.bank_t + head * (2 * BT - 1) + (ti - tj + BT - 1));
+      }
+#pragma unroll
+      for (int y = 0; y < HJN; ++y) {
+        const int hj = ((half * 128) / BW + y) % BH;
+        bhl[y] = kLog2e * __ldg(p.bank_h + head * (2 * BH - 1) + (hi - hj + BH - 1));
+      }
+#pragma unroll
+      for (int x = 0; x < BW; ++x) bw[x] = kLog2e * __ldg(p.bank_w + head * (2 * BW - 1) + (wi - x + BW - 1));
+      mbar_wait(s_full, it & 1);
+      tc_fence_after();
+      uint32_t racc[128];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_ld_32x32(taddr + 32 * c, *reinterpret_cast<uint32_t(*)[32]>(&racc[32 * c]));
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_empty);  // S may be overwritten by the next tile's QK^T
+      float* const l = reinterpret_cast<float*>(racc);
+      float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+      for (int kk = 0; kk < 128; ++kk) {
+        const float bias = (btl[(kk / (BH * BW)) % TJN] + bhl[(kk / BW) % HJN]) + bw[kk % BW];
+        float v = __uint_as_float(racc[kk]) * a2 + bias;
+        if (causal && half * 128 + kk > row) v = kMasked;
+        racc[kk] = __float_as_uint(v);
+        m4[kk & 3] = fmaxf(m4[kk & 3], v);
+      }
+      float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+      *x_own_max = mx;
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+      mx = fmaxf(mx, *x_oth_max);
+      float s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int i = 0; i < 128; ++i) {
+        l[i] = fast_exp2(l[i] - mx);
+        s4[i & 3] += l[i];
+      }
+      float sum = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+      *x_own_sum = sum;
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+      sum += *x_oth_sum;
+      const float inv = 1.f / sum;
+      if (p.lse && half == 0) p.lse[(long long)t.z * p.M + row] = (mx + log2f(sum)) * 0.6931471805599453f;
+      // P slabs (the previous tile's P V has completed: this warp waited for pv_done in its O epilogue; its own
+      // TMA stores out of the slabs must have finished reading)
+      if (lane == 0) bulk_wait_group_read<0>();
+      __syncwarp();
+#pragma unroll
+      for (int sl = 0; sl < 2; ++sl) {
+        uint4* const slab = sl ? slab1 : slab0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float* e = l + 64 * sl + 8 * k;
+          uint4 u;
+          u.x = pack_bf16x2(e[0] * inv, e[1] * inv);
+          u.y = pack_bf16x2(e[2] * inv, e[3] * inv);
+          u.z = pack_bf16x2(e[4] * inv, e[5] * inv);
+          u.w = pack_bf16x2(e[6] * inv, e[7] * inv);
+          slab[lane * 8 + (k ^ (lane & 7))] = u;
+        }
+      }
+      fence_proxy_async();  // generic-proxy writes -> visible to tcgen05.mma and to the TMA store
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(p_full);
+        if (store_p) {
+          const int o_zlo = t.z % p.o_zdiv, o_zhi = t.z / p.o_zdiv;
+          tma_store_5d(&tm_p, slab0, half * 128, row_base, 0, o_zlo, o_zhi);
+          tma_store_5d(&tm_p, slab1, half * 128 + 64, row_base, 0, o_zlo, o_zhi);
+          bulk_commit_group();
+        }
+      }
+      // O = P V: 64 of the 128 output columns per warp
+      mbar_wait(pv_done, it & 1);
+      tc_fence_after();
+      {
+        uint32_t r0[32], r1[32];
+        const uint32_t taddr_o = tmem_base + 256 + (static_cast<uint32_t>(q * 32) << 16) + half * 64;
+        tmem_ld_32x32(taddr_o, r0);
+        tmem_ld_32x32(taddr_o + 32, r1);
+        tmem_ld_wait();
+        if (lane == 0) bulk_wait_group_read<0>();  // the P stores have drained slab0
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          uint4 u;
+          u.x = pack_bf16x2(__uint_as_float(r0[8 * k]), __uint_as_float(r0[8 * k + 1]));
+          u.y = pack_bf16x2(__uint_as_float(r0[8 * k + 2]), __uint_as_float(r0[8 * k + 3]));
+          u.z = pack_bf16x2(__uint_as_float(r0[8 * k + 4]), __uint_as_float(r0[8 * k + 5]));
+          u.w = pack_bf16x2(__uint_as_float(r0[8 * k + 6]), __uint_as_float(r0[8 * k + 7]));
+          slab0[lane * 8 + (k ^ (lane & 7))] = u;
+          u.x = pack_bf16x2(__uint_as_float(r1[8 * k]), __uint_as_float(r1[8 * k + 1]));
+          u.y = pack_bf16x2(__uint_as_float(r1[8 * k + 2]), __uint_as_float(r1[8 * k + 3]));
+          u.z = pack_bf16x2(__uint_as_float(r1[8 * k + 4]), __uint_as_float(r1[8 * k + 5]));
+          u.w = pack_bf16x2(__uint_as_float(r1[8 * k + 6]), __uint_as_float(r1[8 * k + 7]));
+          slab0[lane * 8 + ((4 + k) ^ (lane & 7))] = u;
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          const int col = half * 64;
+          tma_store_5d(&tm_o, slab0, col % o2_cin, row_base, col / o2_cin, t.z % o2_zdiv, t.z / o2_zdiv);
+          bulk_commit_group();
+        }
+      }
+    }
+    if (lane == 0) bulk_wait_group<0>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 // ----------------------------------------------------------------------------------------
 // host: TMA descriptor construction (driver entry point fetched at run time: no -lcuda)
 // ----------------------------------------------------------------------------------------
@@ -930,7 +1219,7 @@ extern "C" int lvt_gemm_bf16(const LvtGemm* g, void* stream_) {
   LVT_CHECK_ARG(g->M > 0 && g->N > 0 && g->K > 0 && g->batch > 0, "lvt_gemm_bf16: bad shape %dx%dx%d batch %d",
                 g->M, g->N, g->K, g->batch);
   LVT_CHECK_ARG(g->a && g->b, "lvt_gemm_bf16: null operand");
-  LVT_CHECK_ARG(g->out_f32 || g->out_bf16, "lvt_gemm_bf16: no output");
+  LVT_CHECK_ARG(g->out_f32 || g->out_bf16 || (g->mode == LVT_EPI_SOFTMAX && g->v), "lvt_gemm_bf16: no output");
   int splits = g->splits > 0 ? g->splits : 1;
   LVT_CHECK_ARG(splits == 1 || ((g->flags & LVT_GEMM_ATOMIC) && !g->out_bf16 && g->mode == LVT_EPI_LINEAR),
                 "lvt_gemm_bf16: split-K needs LVT_GEMM_ATOMIC fp32 output only");
@@ -951,8 +1240,13 @@ extern "C" int lvt_gemm_bf16(const LvtGemm* g, void* stream_) {
   int bn = 128;
   int ek = EK_LINEAR;
   if (g->mode == LVT_EPI_SOFTMAX) {
-    LVT_CHECK_ARG(g->N == 256 && g->out_bf16 && g->bank_t && g->bank_h && g->bank_w && g->M == 256 && g->heads > 0,
+    LVT_CHECK_ARG(g->N == 256 && (g->out_bf16 || g->v) && g->bank_t && g->bank_h && g->bank_w && g->M == 256 && g->heads > 0,
                   "lvt_gemm_bf16: SOFTMAX mode needs M == N == 256, banks and out_bf16");
+    if (g->v)
+      LVT_CHECK_ARG(g->K == 128 && g->o2_bf16 && g->o2_n == 128 && g->v_cin > 0 && g->v_zdiv > 0 && g->o2_cin >= 64 &&
+                        g->o2_cin % 64 == 0 && g->o2_zdiv > 0 && g->a_cin % 64 == 0 && g->b_cin % 64 == 0 &&
+                        g->v_cin % 64 == 0,
+                    "lvt_gemm_bf16: fused attention forward needs K == o2_n == 128, o2_bf16 and 64-aligned blockings");
     if (g->bt == 1 && g->bh == 16 && g->bw == 16) ek = EK_SOFTMAX_1x16x16;
     else if (g->bt == 4 && g->bh == 8 && g->bw == 8) ek = EK_SOFTMAX_4x8x8;
     else {
@@ -1087,10 +1381,34 @@ extern "C" int lvt_gemm_bf16(const LvtGemm* g, void* stream_) {
                 "lvt_gemm_bf16: ROWDOT needs 128-byte aligned bf16 output / aux rows (TMA epilogue)");
   const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
   const bool amn = g->a_mn_major != 0, bmn = g->b_mn_major != 0;
-  if (ek == EK_SOFTMAX_1x16x16 || ek == EK_SOFTMAX_4x8x8) {
+  if ((ek == EK_SOFTMAX_1x16x16 || ek == EK_SOFTMAX_4x8x8) && g->out_bf16) {
     rc = make_operand_map(&m.o, g->out_bf16, g->N, g->M, g->o_cin, g->o_ld, g->o_s_blk, g->batch, g->o_zdiv,
                           g->o_s_zlo, g->o_s_zhi, 32, 2);
     if (rc) return rc;
+  }
+  if ((ek == EK_SOFTMAX_1x16x16 || ek == EK_SOFTMAX_4x8x8) && g->v) {
+    // fused attention forward: V as an MN-major B operand (64-key boxes), O through its own store map
+    CUtensorMap tm_v, tm_o2;
+    rc = make_operand_map(&tm_v, g->v, g->o2_n, g->N, g->v_cin, g->v_ld, 0, g->batch, g->v_zdiv, g->v_s_zlo, g->v_s_zhi, BK);
+    if (rc) return rc;
+    rc = make_operand_map(&tm_o2, g->o2_bf16, g->o2_n, g->M, g->o2_cin, g->o2_ld, 0, g->batch, g->o2_zdiv, g->o2_s_zlo,
+                          g->o2_s_zhi, 32, 2);
+    if (rc) return rc;
+    if (!g->out_bf16) m.o = tm_o2;  // unused placeholder (store_p == 0)
+    auto launch = [&](auto kern) -> int {
+      static bool configured[2] = {false, false};
+      const int which = ek == EK_SOFTMAX_1x16x16 ? 0 : 1;
+      if (!configured[which]) {
+        LVT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem::TOTAL));
+        configured[which] = true;
+      }
+      LVT_CHECK_CUDA(lvt_launch(kern, dim3(grid), dim3(NUM_THREADS), AttnSmem::TOTAL, stream, m.a, m.b, tm_v, m.o, tm_o2,
+                                p, g->v_cin, g->v_zdiv, g->o2_cin, g->o2_zdiv, g->out_bf16 ? 1 : 0));
+      lvt_count_launch(1);
+      return LVT_OK;
+    };
+    if (ek == EK_SOFTMAX_1x16x16) return launch(attn_fwd_kernel<EK_SOFTMAX_1x16x16>);
+    return launch(attn_fwd_kernel<EK_SOFTMAX_4x8x8>);
   }
   if (ek == EK_SOFTMAX_1x16x16) return launch_gemm<256, false, false, EK_SOFTMAX_1x16x16>(m, p, grid, stream);
   if (ek == EK_SOFTMAX_4x8x8) return launch_gemm<256, false, false, EK_SOFTMAX_4x8x8>(m, p, grid, stream);

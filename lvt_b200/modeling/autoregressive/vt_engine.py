@@ -16,6 +16,7 @@ No torch op runs on this path; torch owns the device memory and the stream only.
 """
 import ctypes
 import math
+import os
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -26,6 +27,7 @@ from ..._lib import check, ptr, stream_ptr
 from ...ops import Operand, gemm
 
 LN_EPS = 1e-5
+_SPLIT_ATTN = os.environ.get("LVT_SPLIT_ATTN", "0") == "1"
 _ALIGN = 64  # elements; keeps every parameter 256 B (fp32) / 128 B (bf16) aligned for TMA
 
 
@@ -404,7 +406,7 @@ class VTEngine:
         return Operand(buf_ptr + 2 * which * s.H * s.da, ld, mn_major=mn, cin=s.da, zdiv=s.H, s_zlo=s.da,
                        s_zhi=L * ld)
 
-    def _layer_fwd(self, prefix, ws: VTWorkspace, ly: _Layer, x, y, causal, y_bf16=None):
+    def _layer_fwd(self, prefix, ws: VTWorkspace, ly: _Layer, x, y, causal, y_bf16=None, keep_p=True):
         s, st = self.spec, self.store
         M, d, H, da, L = ws.M, s.d, s.H, s.da, 256
         nz = ws.nseq * H
@@ -414,15 +416,23 @@ class VTEngine:
         gemm(M, 3 * H * da, d, Operand(ly.ln1.data_ptr(), d),
              Operand(st.pb(prefix + "mha.w_q"), da, mn_major=True, cin=da, s_blk=d * da),
              Operand(ly.qkv.data_ptr(), 3 * H * da), out_bf16=ly.qkv)
-        # P = softmax(QK^T/sqrt(da) + B [causal -1e4]) (vt_attention.py:63-79), O = P V (:80)
+        # P = softmax(QK^T/sqrt(da) + B [causal -1e4]) (vt_attention.py:63-79) and O = P V (:80) in ONE kernel: P goes
+        # to the second MMA through shared memory; it is written to HBM only when a backward will read it
         banks = (st.pf(prefix + "dt_bank"), st.pf(prefix + "dh_bank"), st.pf(prefix + "dw_bank"))
-        gemm(L, L, da, self._qkv_op(ly.qkv.data_ptr(), 0, False, L), self._qkv_op(ly.qkv.data_ptr(), 1, False, L),
-             Operand(ly.P.data_ptr(), L, zdiv=1, s_zhi=L * L), out_bf16=ly.P, batch=nz,
-             alpha=1.0 / math.sqrt(da), mode=ops.EPI_SOFTMAX, flags=ops.GEMM_CAUSAL if causal else 0,
-             banks=banks, block=s.block, heads=H)
-        gemm(L, da, L, Operand(ly.P.data_ptr(), L, zdiv=1, s_zhi=L * L), self._qkv_op(ly.qkv.data_ptr(), 2, True, L),
-             Operand(ly.o.data_ptr(), H * da, cin=da, zdiv=H, s_zlo=da, s_zhi=L * H * da), out_bf16=ly.o,
-             batch=nz)
+        if _SPLIT_ATTN:  # A/B timing aid: the two-kernel form (softmax GEMM, then P V GEMM)
+            gemm(L, L, da, self._qkv_op(ly.qkv.data_ptr(), 0, False, L), self._qkv_op(ly.qkv.data_ptr(), 1, False, L),
+                 Operand(ly.P.data_ptr(), L, zdiv=1, s_zhi=L * L), out_bf16=ly.P, batch=nz,
+                 alpha=1.0 / math.sqrt(da), mode=ops.EPI_SOFTMAX, flags=ops.GEMM_CAUSAL if causal else 0,
+                 banks=banks, block=s.block, heads=H)
+            gemm(L, da, L, Operand(ly.P.data_ptr(), L, zdiv=1, s_zhi=L * L), self._qkv_op(ly.qkv.data_ptr(), 2, True, L),
+                 Operand(ly.o.data_ptr(), H * da, cin=da, zdiv=H, s_zlo=da, s_zhi=L * H * da), out_bf16=ly.o,
+                 batch=nz)
+        else:
+            gemm(L, L, da, self._qkv_op(ly.qkv.data_ptr(), 0, False, L), self._qkv_op(ly.qkv.data_ptr(), 1, False, L),
+                 Operand(ly.P.data_ptr(), L, zdiv=1, s_zhi=L * L), out_bf16=ly.P if keep_p else None, batch=nz,
+                 alpha=1.0 / math.sqrt(da), mode=ops.EPI_SOFTMAX, flags=ops.GEMM_CAUSAL if causal else 0,
+                 banks=banks, block=s.block, heads=H, v=self._qkv_op(ly.qkv.data_ptr(), 2, True, L),
+                 o2=Operand(ly.o.data_ptr(), H * da, cin=da, zdiv=H, s_zlo=da, s_zhi=L * H * da), o2_n=da)
         # output projection + residual (:127-128)
         gemm(M, d, H * da, Operand(ly.o.data_ptr(), H * da), Operand(st.pb(prefix + "mha.proj.weight"), H * da),
              Operand(ly.h.data_ptr(), d), out_f32=ly.h, res=x)
@@ -552,7 +562,7 @@ class VTEngine:
             ly = self._layer_ws(ws, i, train)
             y = ly.y if train else (ws.y_alt if x is ly.y else ly.y)
             self._layer_fwd(f"encoder.block_local_attention.{i}.", ws, ly, x, y, causal=False,
-                            y_bf16=ws.zl_bf16 if i == nE - 1 else None)
+                            y_bf16=ws.zl_bf16 if i == nE - 1 else None, keep_p=train)
             x = y
 
     def decoder_forward(self, ws: VTWorkspace, train=True):
@@ -576,7 +586,7 @@ class VTEngine:
         for i in range(nD):
             ly = self._layer_ws(ws, nE + i, train)
             y = ly.y if train else (ws.y_alt if x is ly.y else ly.y)
-            self._layer_fwd(f"decoder.block_local_attention.{i}.", ws, ly, x, y, causal=True)
+            self._layer_fwd(f"decoder.block_local_attention.{i}.", ws, ly, x, y, causal=True, keep_p=train)
             x = y
         ws.y_final = x
         self._ln_fwd(x, st.pf("ch_predictor.layer_norm.weight"), st.pf("ch_predictor.layer_norm.bias"), ws.ln_y,

@@ -131,7 +131,7 @@ class ConvSpec:
 def gemm(M, N, K, a: Operand, b: Operand, out: Operand, out_f32=None, out_bf16=None, batch=1,
          splits=1, alpha=1.0, mode=EPI_LINEAR, flags=0, bias=None, bias_mod=0, res=None, aux=None,
          lse=None, delta=None, banks=None, block=None, heads=1, conv: Optional[ConvSpec] = None,
-         rowdot=None, rd_block=0, rd_L=0):
+         rowdot=None, rd_block=0, rd_L=0, v: Optional[Operand] = None, o2: Optional[Operand] = None, o2_n=0):
     """D[z] = epilogue(alpha * A[z] @ B[z]^T); pointers may be torch tensors or ints."""
     lib = _lib.require_device()
 
@@ -168,6 +168,10 @@ def gemm(M, N, K, a: Operand, b: Operand, out: Operand, out_f32=None, out_bf16=N
         g.cv_pix_stride, g.cv_s_phase = conv.pix_stride or conv.C, conv.s_phase
         for i, (dh, dw, ph) in enumerate(conv.taps):
             g.cv_dh[i], g.cv_dw[i], g.cv_ph[i] = dh, dw, ph
+    if v is not None:  # fused attention forward: O = softmax(...) @ V in the same kernel
+        g.v, g.v_cin, g.v_zdiv, g.v_ld, g.v_s_zlo, g.v_s_zhi = v.data, v.cin or o2_n, v.zdiv, v.ld, v.s_zlo, v.s_zhi
+        g.o2_bf16, g.o2_n, g.o2_cin, g.o2_zdiv = o2.data, o2_n, o2.cin or o2_n, o2.zdiv
+        g.o2_ld, g.o2_s_zlo, g.o2_s_zhi = o2.ld, o2.s_zlo, o2.s_zhi
     if rowdot is not None:
         g.rowdot, g.rd_block, g.rd_L = p(rowdot), rd_block, rd_L
         g.flags |= GEMM_ROWDOT

@@ -221,3 +221,40 @@ def test_gemm_rowdot_epilogue(cuda_lib, M, N, K, blk, L):
     torch.cuda.synchronize()
     _close(out, want_o, 6e-3)
     _close(delta, want_d, 1e-4)
+
+
+@pytest.mark.parametrize("block,causal,store_p", [((1, 16, 16), True, True), ((1, 16, 16), False, False),
+                                                   ((4, 8, 8), True, True)])
+@pytest.mark.parametrize("Bsz", [1, 5])
+def test_fused_attention_forward(cuda_lib, block, causal, store_p, Bsz):
+    """LVT_EPI_SOFTMAX with V: P = softmax(QK^T/sqrt(da) + B [mask]) and O = P V in ONE kernel (P handed to the
+    second MMA through shared memory), against fp32 torch on the same bf16 inputs; P optional."""
+    from lvt_b200 import ops
+    H, da, L = 8, 128, 256
+    M = Bsz * L
+    qkv = _rand((M, 3 * H * da), 31, 0.5)
+    g = torch.Generator().manual_seed(32)
+    banks = [torch.randn(H, 2 * n - 1, generator=g) * 0.5 for n in block]
+    banks_d = [b.cuda().contiguous() for b in banks]
+    qf = qkv.float().cpu().view(Bsz, L, 3, H, da)
+    q, k, v = [qf[:, :, i].permute(0, 2, 1, 3) for i in range(3)]
+    p_ref, lse_ref, o_ref = _attn_ref(q, k, v, banks, block, causal)
+    ld = 3 * H * da
+    P = torch.full((Bsz, H, L, L), float("nan"), device="cuda", dtype=torch.bfloat16)
+    O = torch.full((M, H * da), float("nan"), device="cuda", dtype=torch.bfloat16)
+
+    def qkv_op(which, mn):
+        return ops.Operand(qkv.data_ptr() + 2 * which * H * da, ld, mn_major=mn, cin=da, zdiv=H,
+                           s_zlo=da, s_zhi=L * ld)
+
+    for _ in range(2):  # twice: the persistent pipeline must leave no stale state behind
+        ops.gemm(L, L, da, qkv_op(0, False), qkv_op(1, False),
+                 ops.Operand(P.data_ptr(), L, zdiv=1, s_zhi=L * L), out_bf16=P if store_p else None, batch=Bsz * H,
+                 alpha=1.0 / math.sqrt(da), mode=ops.EPI_SOFTMAX, flags=ops.GEMM_CAUSAL if causal else 0,
+                 banks=banks_d, block=block, heads=H, v=qkv_op(2, True),
+                 o2=ops.Operand(O.data_ptr(), H * da, cin=da, zdiv=H, s_zlo=da, s_zhi=L * H * da), o2_n=da)
+    torch.cuda.synchronize()
+    if store_p:
+        assert (P.float().cpu() - p_ref).abs().max().item() < 4e-3
+    o_want = o_ref.permute(0, 2, 1, 3).reshape(M, H * da)
+    _close(O.cpu(), o_want, 1e-2)

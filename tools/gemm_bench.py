@@ -55,6 +55,8 @@ tests = {
     "pv": (lambda: ops.gemm(L, da, L, Operand(P.data_ptr(), L, zdiv=1, s_zhi=L * L), qkv_op(o3, 2, True), Operand(x2.data_ptr(), H * da, cin=da, zdiv=H, s_zlo=da, s_zhi=L * H * da), out_bf16=x2, batch=nb * H), 2.0 * nb * H * L * L * da),
     "softmax": (lambda: ops.gemm(L, L, da, qkv_op(o3, 0, False), qkv_op(o3, 1, False), Operand(P.data_ptr(), L, zdiv=1, s_zhi=L * L), out_bf16=P, batch=nb * H, alpha=0.088, mode=ops.EPI_SOFTMAX, flags=ops.GEMM_CAUSAL, banks=banks, block=(1, 16, 16), heads=H), 2.0 * nb * H * L * L * da),
 }
+tests["attn_fused"] = (lambda: ops.gemm(L, L, da, qkv_op(o3, 0, False), qkv_op(o3, 1, False), Operand(P.data_ptr(), L, zdiv=1, s_zhi=L * L), out_bf16=P, batch=nb * H, alpha=0.088, mode=ops.EPI_SOFTMAX, flags=ops.GEMM_CAUSAL, banks=banks, block=(1, 16, 16), heads=H, v=qkv_op(o3, 2, True), o2=Operand(x2.data_ptr(), H * da, cin=da, zdiv=H, s_zlo=da, s_zhi=L * H * da), o2_n=da), 4.0 * nb * H * L * L * da)
+tests["attn_fused_nop"] = (lambda: ops.gemm(L, L, da, qkv_op(o3, 0, False), qkv_op(o3, 1, False), Operand(P.data_ptr(), L, zdiv=1, s_zhi=L * L), out_bf16=None, batch=nb * H, alpha=0.088, mode=ops.EPI_SOFTMAX, flags=ops.GEMM_CAUSAL, banks=banks, block=(1, 16, 16), heads=H, v=qkv_op(o3, 2, True), o2=Operand(x2.data_ptr(), H * da, cin=da, zdiv=H, s_zlo=da, s_zhi=L * H * da), o2_n=da), 4.0 * nb * H * L * L * da)
 DBG = int(os.environ.get("GEMM_DBG", "0"))
 if DBG:
     tests["qkv"] = (lambda: ops.gemm(M, 3072, d, Operand(x.data_ptr(), d), Operand(wq.data_ptr(), da, mn_major=True, cin=da, s_blk=d * da), Operand(o3.data_ptr(), 3072), out_bf16=o3, flags=DBG), 2.0 * M * 3072 * d)
