@@ -166,6 +166,10 @@ int lvt_layernorm_fwd(const float* x, const float* gamma, const float* beta, voi
 int lvt_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd,
                       const float* gamma, const float* dres, float* dx_f32, void* dx_bf16,
                       float* dgamma, float* dbeta, int M, int d, void* stream);
+/* same with dy in bf16 (as written by the GEMM that produced it: halves that round trip).     */
+int lvt_layernorm_bwd_bf16dy(const void* dy_bf16, const float* x, const float* mean, const float* rstd,
+                             const float* gamma, const float* dres, float* dx_f32, void* dx_bf16,
+                             float* dgamma, float* dbeta, int M, int d, void* stream);
 /* out[n] += sum_m x[m*ld + n], x bf16 (bias gradients of nn.Linear / Conv3d).                */
 int lvt_colsum_bf16(const void* x, float* out, int M, int N, long long ld, void* stream);
 /* delta[b,h,i] = sum_d dO[b*L+i, h*da+d] * O[b*L+i, h*da+d] (softmax backward row term of

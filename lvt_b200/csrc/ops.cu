@@ -70,9 +70,10 @@ ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
 
 // LayerNorm backward. dx = dres + rstd*(g - mean(g) - xhat*mean(g*xhat)), g = dy*gamma.
 // dgamma/dbeta: per-warp register partials over a strided set of rows, block reduce, atomics.
-template <int V4>
+// DYB: dy arrives as bf16 (written by the GEMM that produced it) instead of fp32.
+template <int V4, bool DYB>
 __global__ void __launch_bounds__(256)
-ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+ln_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x,
               const float* __restrict__ mean, const float* __restrict__ rstd,
               const float* __restrict__ gamma, const float* __restrict__ dres,
               float* __restrict__ dx, __nv_bfloat16* __restrict__ dx_bf16,
@@ -91,13 +92,21 @@ ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
   for (int row = blockIdx.x * 8 + warp; row < M; row += gridDim.x * 8) {
     const float mu = mean[row], rs = rstd[row];
     const float* xr = x + (size_t)row * d;
-    const float* dyr = dy + (size_t)row * d;
     float4 xh[V4], g[V4];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < V4; ++i) {
       const int c = (i * 32 + lane) * 4;
-      const float4 xv = ld4(xr + c), dv = ld4(dyr + c);
+      const float4 xv = ld4(xr + c);
+      float4 dv;
+      if constexpr (DYB) {
+        const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(dy_) + (size_t)row * d + c);
+        const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+        const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+        dv = make_float4(lo.x, lo.y, hi.x, hi.y);
+      } else {
+        dv = ld4(reinterpret_cast<const float*>(dy_) + (size_t)row * d + c);
+      }
       xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
       g[i] = make_float4(dv.x * gm[i].x, dv.y * gm[i].y, dv.z * gm[i].z, dv.w * gm[i].w);
       s1 += (g[i].x + g[i].y) + (g[i].z + g[i].w);
@@ -671,25 +680,39 @@ extern "C" int lvt_layernorm_fwd(const float* x, const float* gamma, const float
   return LVT_OK;
 }
 
-extern "C" int lvt_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd,
-                                 const float* gamma, const float* dres, float* dx_f32, void* dx_bf16,
-                                 float* dgamma, float* dbeta, int M, int d, void* stream) {
+static int layernorm_bwd_impl(const void* dy, bool dy_bf16, const float* x, const float* mean, const float* rstd,
+                              const float* gamma, const float* dres, float* dx_f32, void* dx_bf16, float* dgamma,
+                              float* dbeta, int M, int d, void* stream) {
   LVT_CHECK_ARG(dy && x && mean && rstd && gamma && dgamma && dbeta && M > 0, "lvt_layernorm_bwd: bad argument");
   LVT_CHECK_ARG(d % 128 == 0 && d <= 512, "lvt_layernorm_bwd: d must be 128, 256 or 512");
   const int blocks = min(lvt_ceil_div(M, 8), kSMs * 4);
   int rc = dispatch_v4(d / 128, [&](auto v4) {
     constexpr int V4 = decltype(v4)::value;
     if constexpr (V4 <= 4) {
-      LVT_CHECK_CUDA(lvt_launch(ln_bwd_kernel<V4>, dim3(blocks), dim3(256), 0, STREAM(stream), dy, x, mean, rstd, gamma, dres, dx_f32,
-                                                           reinterpret_cast<__nv_bfloat16*>(dx_bf16),
-                                                           dgamma, dbeta, M));
+      if (dy_bf16)
+        LVT_CHECK_CUDA(lvt_launch(ln_bwd_kernel<V4, true>, dim3(blocks), dim3(256), 0, STREAM(stream), dy, x, mean, rstd,
+                                  gamma, dres, dx_f32, reinterpret_cast<__nv_bfloat16*>(dx_bf16), dgamma, dbeta, M));
+      else
+        LVT_CHECK_CUDA(lvt_launch(ln_bwd_kernel<V4, false>, dim3(blocks), dim3(256), 0, STREAM(stream), dy, x, mean, rstd,
+                                  gamma, dres, dx_f32, reinterpret_cast<__nv_bfloat16*>(dx_bf16), dgamma, dbeta, M));
     }
     return LVT_OK;
   });
   if (rc) return rc;
-  LVT_CHECK_LAUNCH();
   lvt_count_launch(1);
   return LVT_OK;
+}
+
+extern "C" int lvt_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd,
+                                 const float* gamma, const float* dres, float* dx_f32, void* dx_bf16,
+                                 float* dgamma, float* dbeta, int M, int d, void* stream) {
+  return layernorm_bwd_impl(dy, false, x, mean, rstd, gamma, dres, dx_f32, dx_bf16, dgamma, dbeta, M, d, stream);
+}
+
+extern "C" int lvt_layernorm_bwd_bf16dy(const void* dy_bf16, const float* x, const float* mean, const float* rstd,
+                                        const float* gamma, const float* dres, float* dx_f32, void* dx_bf16,
+                                        float* dgamma, float* dbeta, int M, int d, void* stream) {
+  return layernorm_bwd_impl(dy_bf16, true, x, mean, rstd, gamma, dres, dx_f32, dx_bf16, dgamma, dbeta, M, d, stream);
 }
 
 extern "C" int lvt_colsum_bf16(const void* x, float* out, int M, int N, long long ld, void* stream) {

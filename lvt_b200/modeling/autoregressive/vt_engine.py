@@ -212,6 +212,7 @@ class VTWorkspace:
             self.dlogits = e((nc, M, nv), bf16)
             self.du = e((M, d), bf16)
             self.dln = e((M, d), f32)
+            self.dln_bf16 = e((M, d), bf16)  # gradient wrt a LayerNorm output, as the dgrad GEMM writes it
             self.dy, self.dy_bf16 = e((M, d), f32), e((M, d), bf16)
             self.dh, self.dh_bf16 = e((M, d), f32), e((M, d), bf16)
             self.dz1 = e((M, d), bf16)
@@ -378,7 +379,8 @@ class VTEngine:
                                          LN_EPS, stream_ptr()), "lvt_layernorm_fwd")
 
     def _ln_bwd(self, dy, x, mean, rstd, g, dres, dx, dxb, dg, db, M):
-        check(self.lib.lvt_layernorm_bwd(_vp(dy), _vp(x), _vp(mean), _vp(rstd), _vp(g), _vp(dres), _vp(dx),
+        fn = self.lib.lvt_layernorm_bwd_bf16dy if getattr(dy, "dtype", None) == torch.bfloat16 else self.lib.lvt_layernorm_bwd
+        check(fn(_vp(dy), _vp(x), _vp(mean), _vp(rstd), _vp(g), _vp(dres), _vp(dx),
                                          _vp(dxb), _vp(dg), _vp(db), M, self.spec.d, stream_ptr()),
               "lvt_layernorm_bwd")
 
@@ -482,8 +484,8 @@ class VTEngine:
             self._colsum(ws.dz1, st.gf(prefix + "ffn.1.bias"), M, d)
             self._wgrad(ws.dz1.data_ptr(), d, ly.ln2.data_ptr(), d, Operand(st.gf(prefix + "ffn.1.weight"), d), d, d, M)
         gemm(M, d, d, Operand(ws.dz1.data_ptr(), d), Operand(st.pb(prefix + "ffn.1.weight"), d, mn_major=True),
-             Operand(ws.dln.data_ptr(), d), out_f32=ws.dln)
-        self._ln_bwd(ws.dln, ly.h, ly.mean2, ly.rstd2, st.pf(prefix + "ffn.0.weight"), dy, ws.dh, ws.dh_bf16,
+             Operand(ws.dln_bf16.data_ptr(), d), out_bf16=ws.dln_bf16)
+        self._ln_bwd(ws.dln_bf16, ly.h, ly.mean2, ly.rstd2, st.pf(prefix + "ffn.0.weight"), dy, ws.dh, ws.dh_bf16,
                      st.gf(prefix + "ffn.0.weight"), st.gf(prefix + "ffn.0.bias"), M)
         # ---- attention output projection
         dhb = ws.dh_bf16.data_ptr()
@@ -524,9 +526,9 @@ class VTEngine:
                  splits=self._splits(d, 3 * H * da, M), flags=ops.GEMM_ATOMIC)
         gemm(M, d, 3 * H * da, Operand(dqkv, 3 * H * da),
              Operand(st.pb(prefix + "mha.w_q"), da, mn_major=False, cin=da, s_blk=d * da),
-             Operand(ws.dln.data_ptr(), d), out_f32=ws.dln)
+             Operand(ws.dln_bf16.data_ptr(), d), out_bf16=ws.dln_bf16)
         torch.cuda.current_stream().wait_event(ev_dy_read)  # dx_bf16 may alias dy_bf16
-        self._ln_bwd(ws.dln, x, ly.mean1, ly.rstd1, st.pf(prefix + "mha.layer_norm.weight"), ws.dh, dx, dx_bf16,
+        self._ln_bwd(ws.dln_bf16, x, ly.mean1, ly.rstd1, st.pf(prefix + "mha.layer_norm.weight"), ws.dh, dx, dx_bf16,
                      st.gf(prefix + "mha.layer_norm.weight"), st.gf(prefix + "mha.layer_norm.bias"), M)
 
     # ------------------------------------------------------------------ whole network
