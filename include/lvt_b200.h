@@ -147,7 +147,9 @@ typedef struct LvtGemm {
   /* LVT_EPI_SOFTMAX with v != NULL: fused attention forward (vt_attention.py:61-81).  After the softmax the same
      kernel computes O[z] = P[z] @ V[z] with P taken from shared memory: V[z] is [N keys][o2_n] (keys = rows, like
      an MN-major B operand), O goes to o2_bf16 [M, o2_n] (o2_n = da = 128).  out_bf16 (P, needed by the backward)
-     becomes optional.                                                                              */
+     becomes optional.
+     LVT_EPI_DS with v != NULL: first half of the attention backward in one kernel: dS (out_bf16) as before and
+     dQ[z] = alpha * dS[z] @ K[z] with K passed as `v`, dQ as `o2_bf16`; alpha is applied to dQ only.            */
   const void* v; int v_cin, v_zdiv; long long v_ld, v_s_zlo, v_s_zhi;
   void* o2_bf16; int o2_n, o2_cin, o2_zdiv; long long o2_ld, o2_s_zlo, o2_s_zhi;
 } LvtGemm;

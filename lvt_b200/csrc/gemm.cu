@@ -753,11 +753,14 @@ struct AttnSmem {
 };
 static_assert(AttnSmem::TOTAL <= 232448, "attention forward: shared memory budget");
 
+// EK == EK_DS turns the same pipeline into the first half of the attention BACKWARD:
+//   dP = dO V^T (first MMA)  ->  dS = P * (dP - delta) (P TMA-loaded into the slabs, overwritten in place)  ->
+//   dQ = alpha * dS K (second MMA, K as the MN-major operand); dS is TMA-stored for the dK GEMM and the bank gradient.
 template <int EK>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                 const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_p,
-                const __grid_constant__ CUtensorMap tm_o, const GemmParams p, int v_cin, int v_zdiv, int o2_cin,
+                const __grid_constant__ CUtensorMap tm_o, const __grid_constant__ CUtensorMap tm_c, const GemmParams p, int v_cin, int v_zdiv, int o2_cin,
                 int o2_zdiv, int store_p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   using A = AttnSmem;
@@ -769,7 +772,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   uint64_t* v_full = bars + 4;
   uint64_t* p_full = bars + 5;
   uint64_t* pv_done = bars + 6;
+  uint64_t* c_bar = bars + 16;  // [NUM_EPI_WARPS] P slab loads (EK_DS)
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 8);
+  constexpr bool BWD = EK == EK_DS;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -787,6 +792,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     mbar_init(v_full, 1);
     mbar_init(p_full, NUM_EPI_WARPS);
     mbar_init(pv_done, 1);
+#pragma unroll
+    for (int w = 0; w < NUM_EPI_WARPS; ++w) mbar_init(&c_bar[w], 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -868,9 +875,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     }
   } else {
     // ------------------------------------------------------------------ softmax + O epilogue
-    constexpr int BT = EK == EK_SOFTMAX_1x16x16 ? 1 : 4;
-    constexpr int BH = EK == EK_SOFTMAX_1x16x16 ? 16 : 8;
-    constexpr int BW = EK == EK_SOFTMAX_1x16x16 ? 16 : 8;
+    constexpr int BT = EK == EK_SOFTMAX_4x8x8 ? 4 : 1;
+    constexpr int BH = EK == EK_SOFTMAX_4x8x8 ? 8 : 16;
+    constexpr int BW = EK == EK_SOFTMAX_4x8x8 ? 8 : 16;
     constexpr int TJN = (BH * BW <= 128) ? 128 / (BH * BW) : 1;
     constexpr int HJN = (128 / BW < BH) ? 128 / BW : BH;
     const int ew = warp - 2;
@@ -894,6 +901,46 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + half * 128;
       const int row_base = t.m0 + q * 32;
       const int row = row_base + lane;
+      if constexpr (BWD) {
+        // P slabs of this tile -> the slabs (the previous tile's second MMA is complete: this warp waited for pv_done
+        // in its dQ epilogue; its own TMA stores out of the slabs must have finished reading)
+        const int o_zlo = t.z % p.o_zdiv, o_zhi = t.z / p.o_zdiv;
+        if (lane == 0) {
+          bulk_wait_group_read<0>();
+          mbar_arrive_expect_tx(&c_bar[ew], 8192);
+          tma_load_5d(slab0, &tm_c, &c_bar[ew], half * 128, row_base, 0, o_zlo, o_zhi);
+          tma_load_5d(slab1, &tm_c, &c_bar[ew], half * 128 + 64, row_base, 0, o_zlo, o_zhi);
+        }
+        const float dl = p.delta[(long long)t.z * p.M + row];
+        mbar_wait(s_full, it & 1);
+        tc_fence_after();
+        mbar_wait(&c_bar[ew], it & 1);
+#pragma unroll
+        for (int sl = 0; sl < 2; ++sl) {
+          uint4* const slab = sl ? slab1 : slab0;
+          uint32_t r0[32], r1[32];
+          tmem_ld_32x32(taddr + 64 * sl, r0);
+          tmem_ld_32x32(taddr + 64 * sl + 32, r1);
+          tmem_ld_wait();
+          if (sl == 1) {  // the whole accumulator row is in registers: dP may be overwritten by the next tile
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(s_empty);
+          }
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const uint32_t* acc = k < 4 ? &r0[8 * k] : &r1[8 * (k - 4)];
+            uint4 pu = slab[lane * 8 + (k ^ (lane & 7))];
+            uint32_t w[4] = {pu.x, pu.y, pu.z, pu.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 pf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[j]));
+              w[j] = pack_bf16x2(pf.x * (__uint_as_float(acc[2 * j]) - dl), pf.y * (__uint_as_float(acc[2 * j + 1]) - dl));
+            }
+            slab[lane * 8 + (k ^ (lane & 7))] = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+        }
+      } else {
       const int head = t.z % p.heads;
       const int ti = row / (BH * BW), hi = (row / BW) % BH, wi = row % BW;
       float btl[TJN], bhl[HJN], bw[BW];
@@ -962,6 +1009,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           slab[lane * 8 + (k ^ (lane & 7))] = u;
         }
       }
+      }
       fence_proxy_async();  // generic-proxy writes -> visible to tcgen05.mma and to the TMA store
       tc_fence_before();
       __syncwarp();
@@ -983,6 +1031,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         tmem_ld_32x32(taddr_o, r0);
         tmem_ld_32x32(taddr_o + 32, r1);
         tmem_ld_wait();
+        if constexpr (BWD) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            r0[i] = __float_as_uint(__uint_as_float(r0[i]) * p.alpha);
+            r1[i] = __float_as_uint(__uint_as_float(r1[i]) * p.alpha);
+          }
+        }
         if (lane == 0) bulk_wait_group_read<0>();  // the P stores have drained slab0
         __syncwarp();
 #pragma unroll
@@ -1259,6 +1314,10 @@ extern "C" int lvt_gemm_bf16(const LvtGemm* g, void* stream_) {
     bn = 256;
   } else if (g->mode == LVT_EPI_DS) {
     LVT_CHECK_ARG(g->out_bf16 && g->aux_bf16 && g->delta, "lvt_gemm_bf16: DS mode needs out_bf16, aux_bf16 (P) and delta");
+    if (g->v)
+      LVT_CHECK_ARG(g->v_cin > 0 && g->v_zdiv > 0 && g->o2_cin >= 64 && g->o2_cin % 64 == 0 && g->o2_zdiv > 0 &&
+                        g->a_cin % 64 == 0 && g->b_cin % 64 == 0 && g->v_cin % 64 == 0,
+                    "lvt_gemm_bf16: fused dS/dQ needs 64-aligned operand blockings");
     ek = EK_DS;
     bn = (g->N % 256 == 0) ? 256 : 128;
   } else {
@@ -1386,8 +1445,13 @@ extern "C" int lvt_gemm_bf16(const LvtGemm* g, void* stream_) {
                           g->o_s_zlo, g->o_s_zhi, 32, 2);
     if (rc) return rc;
   }
-  if ((ek == EK_SOFTMAX_1x16x16 || ek == EK_SOFTMAX_4x8x8) && g->v) {
-    // fused attention forward: V as an MN-major B operand (64-key boxes), O through its own store map
+  if (g->v && g->mode != LVT_EPI_LINEAR) {
+    // fused attention kernels: the second operand (V forward / K backward) as an MN-major B operand (64-key
+    // boxes), the second output (O / dQ) through its own store map
+    if (ek == EK_DS)
+      LVT_CHECK_ARG(st == (ST_TMA | ST_CLOAD) && g->N == 256 && g->M == 256 && g->K == 128 && g->o2_bf16 && g->o2_n == 128 &&
+                        !amn && !bmn,
+                    "lvt_gemm_bf16: fused dS/dQ needs M == N == 256, K == 128, K-major dO and V, aligned P / dS rows");
     CUtensorMap tm_v, tm_o2;
     rc = make_operand_map(&tm_v, g->v, g->o2_n, g->N, g->v_cin, g->v_ld, 0, g->batch, g->v_zdiv, g->v_s_zlo, g->v_s_zhi, BK);
     if (rc) return rc;
@@ -1395,20 +1459,21 @@ extern "C" int lvt_gemm_bf16(const LvtGemm* g, void* stream_) {
                           g->o2_s_zhi, 32, 2);
     if (rc) return rc;
     if (!g->out_bf16) m.o = tm_o2;  // unused placeholder (store_p == 0)
-    auto launch = [&](auto kern) -> int {
-      static bool configured[2] = {false, false};
-      const int which = ek == EK_SOFTMAX_1x16x16 ? 0 : 1;
+    if (ek != EK_DS) m.c = m.o;     // unused placeholder
+    auto launch = [&](auto kern, int which) -> int {
+      static bool configured[3] = {false, false, false};
       if (!configured[which]) {
         LVT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem::TOTAL));
         configured[which] = true;
       }
       LVT_CHECK_CUDA(lvt_launch(kern, dim3(grid), dim3(NUM_THREADS), AttnSmem::TOTAL, stream, m.a, m.b, tm_v, m.o, tm_o2,
-                                p, g->v_cin, g->v_zdiv, g->o2_cin, g->o2_zdiv, g->out_bf16 ? 1 : 0));
+                                m.c, p, g->v_cin, g->v_zdiv, g->o2_cin, g->o2_zdiv, g->out_bf16 ? 1 : 0));
       lvt_count_launch(1);
       return LVT_OK;
     };
-    if (ek == EK_SOFTMAX_1x16x16) return launch(attn_fwd_kernel<EK_SOFTMAX_1x16x16>);
-    return launch(attn_fwd_kernel<EK_SOFTMAX_4x8x8>);
+    if (ek == EK_SOFTMAX_1x16x16) return launch(attn_fwd_kernel<EK_SOFTMAX_1x16x16>, 0);
+    if (ek == EK_SOFTMAX_4x8x8) return launch(attn_fwd_kernel<EK_SOFTMAX_4x8x8>, 1);
+    return launch(attn_fwd_kernel<EK_DS>, 2);
   }
   if (ek == EK_SOFTMAX_1x16x16) return launch_gemm<256, false, false, EK_SOFTMAX_1x16x16>(m, p, grid, stream);
   if (ek == EK_SOFTMAX_4x8x8) return launch_gemm<256, false, false, EK_SOFTMAX_4x8x8>(m, p, grid, stream);

@@ -505,17 +505,16 @@ class VTEngine:
         out_blk = lambda which: self._qkv_op(dqkv, which, False, L)  # noqa: E731
         # dV = P^T dO
         gemm(L, da, L, P_mn, do_mn, out_blk(2), out_bf16=out_blk(2).data, batch=nz)
-        # dS = P * (dO V^T - delta)
+        # dS = P * (dO V^T - delta) and dQ = scale * dS K in ONE kernel (dS reaches the second MMA through shared
+        # memory; it is still written out for the dK GEMM and the bank gradient)
         gemm(L, L, da, do_k, self._qkv_op(qkv, 2, False, L), dS_k, out_bf16=ws.dS, batch=nz, mode=ops.EPI_DS,
-             aux=ly.P, delta=ws.delta)
+             aux=ly.P, delta=ws.delta, alpha=scale, v=self._qkv_op(qkv, 1, True, L), o2=out_blk(0), o2_n=da)
         with self._side_begin():
             check(self.lib.lvt_relpos_bank_grad(ptr(ws.dS), _vp(st.gf(prefix + "dt_bank")),
                                                 _vp(st.gf(prefix + "dh_bank")), _vp(st.gf(prefix + "dw_bank")),
                                                 ws.nseq, H, s.block[0], s.block[1], s.block[2], stream_ptr()),
                   "lvt_relpos_bank_grad")
-        # dQ = scale * dS K ; dK = scale * dS^T Q
-        gemm(L, da, L, dS_k, self._qkv_op(qkv, 1, True, L), out_blk(0), out_bf16=out_blk(0).data, batch=nz,
-             alpha=scale)
+        # dK = scale * dS^T Q
         gemm(L, da, L, dS_mn, self._qkv_op(qkv, 0, True, L), out_blk(1), out_bf16=out_blk(1).data, batch=nz,
              alpha=scale)
         # ---- QKV projection

@@ -258,3 +258,41 @@ def test_fused_attention_forward(cuda_lib, block, causal, store_p, Bsz):
         assert (P.float().cpu() - p_ref).abs().max().item() < 4e-3
     o_want = o_ref.permute(0, 2, 1, 3).reshape(M, H * da)
     _close(O.cpu(), o_want, 1e-2)
+
+
+@pytest.mark.parametrize("Bsz", [1, 3])
+def test_fused_attention_backward_ds_dq(cuda_lib, Bsz):
+    """LVT_EPI_DS with K as second operand: dS = P * (dO V^T - delta) and dQ = scale * dS K in ONE kernel
+    (dS handed to the second MMA through shared memory), against fp32 torch on the same bf16 inputs."""
+    from lvt_b200 import ops
+    H, da, L = 8, 128, 256
+    M = Bsz * L
+    scale = 1.0 / math.sqrt(da)
+    qkv = _rand((M, 3 * H * da), 41, 0.5)
+    dO = _rand((M, H * da), 42)
+    g = torch.Generator().manual_seed(43)
+    P = torch.softmax(torch.randn((Bsz, H, L, L), generator=g) * 2.0, -1).to(torch.bfloat16).cuda()
+    delta = (torch.randn((Bsz, H, L), generator=g) * 0.5).cuda()
+    ld = 3 * H * da
+
+    def qkv_op(buf, which, mn):
+        return ops.Operand(buf.data_ptr() + 2 * which * H * da, ld, mn_major=mn, cin=da, zdiv=H,
+                           s_zlo=da, s_zhi=L * ld)
+
+    dS = torch.full((Bsz, H, L, L), float("nan"), device="cuda", dtype=torch.bfloat16)
+    dqkv = torch.full((M, ld), float("nan"), device="cuda", dtype=torch.bfloat16)
+    for _ in range(2):
+        ops.gemm(L, L, da, ops.Operand(dO.data_ptr(), H * da, cin=da, zdiv=H, s_zlo=da, s_zhi=L * H * da),
+                 qkv_op(qkv, 2, False), ops.Operand(dS.data_ptr(), L, zdiv=1, s_zhi=L * L), out_bf16=dS,
+                 batch=Bsz * H, mode=ops.EPI_DS, aux=P, delta=delta, alpha=scale,
+                 v=qkv_op(qkv, 1, True), o2=qkv_op(dqkv, 0, False), o2_n=da)
+    torch.cuda.synchronize()
+    qf = qkv.float().cpu().view(Bsz, L, 3, H, da)
+    k, v = [qf[:, :, i].permute(0, 2, 1, 3) for i in (1, 2)]       # [B,H,L,da]
+    dOh = dO.float().cpu().view(Bsz, L, H, da).permute(0, 2, 1, 3)
+    dP = torch.einsum("bhid,bhjd->bhij", dOh, v)
+    want_dS = P.float().cpu() * (dP - delta.cpu()[..., None])
+    _close(dS.cpu(), want_dS, 1e-2)
+    want_dQ = scale * torch.einsum("bhij,bhjd->bhid", dS.float().cpu(), k)   # from the bf16 dS the kernel used
+    got_dQ = dqkv.float().cpu().view(Bsz, L, 3, H, da)[:, :, 0].permute(0, 2, 1, 3)
+    _close(got_dQ, want_dQ, 1e-2)
