@@ -225,7 +225,7 @@ def test_gemm_rowdot_epilogue(cuda_lib, M, N, K, blk, L):
 
 @pytest.mark.parametrize("block,causal,store_p", [((1, 16, 16), True, True), ((1, 16, 16), False, False),
                                                    ((4, 8, 8), True, True)])
-@pytest.mark.parametrize("Bsz", [1, 5])
+@pytest.mark.parametrize("Bsz", [1, 5, 40])  # 40 x 8 heads x 2 tiles = 640 tiles: several tiles per persistent CTA
 def test_fused_attention_forward(cuda_lib, block, causal, store_p, Bsz):
     """LVT_EPI_SOFTMAX with V: P = softmax(QK^T/sqrt(da) + B [mask]) and O = P V in ONE kernel (P handed to the
     second MMA through shared memory), against fp32 torch on the same bf16 inputs; P optional."""
@@ -260,7 +260,7 @@ def test_fused_attention_forward(cuda_lib, block, causal, store_p, Bsz):
     _close(O.cpu(), o_want, 1e-2)
 
 
-@pytest.mark.parametrize("Bsz", [1, 3])
+@pytest.mark.parametrize("Bsz", [1, 3, 40])  # 40: several tiles per persistent CTA
 def test_fused_attention_backward_ds_dq(cuda_lib, Bsz):
     """LVT_EPI_DS with K as second operand: dS = P * (dO V^T - delta) and dQ = scale * dS K in ONE kernel
     (dS handed to the second MMA through shared memory), against fp32 torch on the same bf16 inputs."""
