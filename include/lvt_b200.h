@@ -149,7 +149,9 @@ typedef struct LvtGemm {
      an MN-major B operand), O goes to o2_bf16 [M, o2_n] (o2_n = da = 128).  out_bf16 (P, needed by the backward)
      becomes optional.
      LVT_EPI_DS with v != NULL: first half of the attention backward in one kernel: dS (out_bf16) as before and
-     dQ[z] = alpha * dS[z] @ K[z] with K passed as `v`, dQ as `o2_bf16`; alpha is applied to dQ only.            */
+     dQ[z] = alpha * dS[z] @ K[z] with K passed as `v`, dQ as `o2_bf16`; alpha is applied to dQ only.  If bank_t/h/w
+     are set (block (1,16,16)) they are the dt/dh/dw_bank GRADIENT buffers [heads, 2*bx-1], accumulated (+=) from dS
+     in the epilogue (BlockLocalAttention.get_B, vt_attention.py:169-174).                                     */
   const void* v; int v_cin, v_zdiv; long long v_ld, v_s_zlo, v_s_zhi;
   void* o2_bf16; int o2_n, o2_cin, o2_zdiv; long long o2_ld, o2_s_zlo, o2_s_zhi;
 } LvtGemm;

@@ -749,7 +749,8 @@ struct AttnSmem {
   static constexpr int P_OFF = 163840;             // 4 key-blocks x (128 rows x 128 B)      (K-major A operand)
   static constexpr int XCHG_OFF = 229376;          // [2][2][128] fp32
   static constexpr int BAR_OFF = XCHG_OFF + 2048;
-  static constexpr int TOTAL = BAR_OFF + 256;
+  static constexpr int BINS_OFF = BAR_OFF + 256;   // [2][64] fp32 bank-gradient bins (backward)
+  static constexpr int TOTAL = BINS_OFF + 512;
 };
 static_assert(AttnSmem::TOTAL <= 232448, "attention forward: shared memory budget");
 
@@ -761,7 +762,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                 const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_p,
                 const __grid_constant__ CUtensorMap tm_o, const __grid_constant__ CUtensorMap tm_c, const GemmParams p, int v_cin, int v_zdiv, int o2_cin,
-                int o2_zdiv, int store_p) {
+                int o2_zdiv, int store_p, int bank_fused) {
   extern __shared__ __align__(1024) uint8_t smem[];
   using A = AttnSmem;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + A::BAR_OFF);
@@ -775,6 +776,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   uint64_t* c_bar = bars + 16;  // [NUM_EPI_WARPS] P slab loads (EK_DS)
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 8);
   constexpr bool BWD = EK == EK_DS;
+  float* const bank_bins = reinterpret_cast<float*>(smem + AttnSmem::BINS_OFF);  // [2][64] (EK_DS, fused bank gradient)
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -796,6 +798,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     for (int w = 0; w < NUM_EPI_WARPS; ++w) mbar_init(&c_bar[w], 1);
     fence_barrier_init();
   }
+  if (threadIdx.x < 128) bank_bins[threadIdx.x] = 0.f;
   if (warp == 1) {
     tmem_alloc(tmem_ptr_smem, 512);
     tmem_relinquish();
@@ -901,6 +904,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + half * 128;
       const int row_base = t.m0 + q * 32;
       const int row = row_base + lane;
+      float rs_h[8], cs_w[16];  // bank-gradient partial sums of this row (EK_DS)
+      (void)rs_h;
+      (void)cs_w;
       if constexpr (BWD) {
         // P slabs of this tile -> the slabs (the previous tile's second MMA is complete: this warp waited for pv_done
         // in its dQ epilogue; its own TMA stores out of the slabs must have finished reading)
@@ -912,6 +918,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           tma_load_5d(slab1, &tm_c, &c_bar[ew], half * 128 + 64, row_base, 0, o_zlo, o_zhi);
         }
         const float dl = p.delta[(long long)t.z * p.M + row];
+        // relative-position bank gradient of block (1,16,16) (get_B, vt_attention.py:169-174): this row's sums of
+        // dS over the 16 key columns of each of its 8 key rows (-> dh_bank) and over the 8 key rows per column (-> dw_bank)
+#pragma unroll
+        for (int y = 0; y < 8; ++y) rs_h[y] = 0.f;
+#pragma unroll
+        for (int x = 0; x < 16; ++x) cs_w[x] = 0.f;
         mbar_wait(s_full, it & 1);
         tc_fence_after();
         mbar_wait(&c_bar[ew], it & 1);
@@ -935,7 +947,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const float2 pf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[j]));
-              w[j] = pack_bf16x2(pf.x * (__uint_as_float(acc[2 * j]) - dl), pf.y * (__uint_as_float(acc[2 * j + 1]) - dl));
+              const float v0 = pf.x * (__uint_as_float(acc[2 * j]) - dl), v1 = pf.y * (__uint_as_float(acc[2 * j + 1]) - dl);
+              w[j] = pack_bf16x2(v0, v1);
+              rs_h[4 * sl + (k >> 1)] += v0 + v1;        // key (half*128 + 64 sl + 8 k + 2 j + e) = (hj, wj)
+              cs_w[8 * (k & 1) + 2 * j] += v0;
+              cs_w[8 * (k & 1) + 2 * j + 1] += v1;
             }
             slab[lane * 8 + (k ^ (lane & 7))] = make_uint4(w[0], w[1], w[2], w[3]);
           }
@@ -1020,6 +1036,43 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           tma_store_5d(&tm_p, slab0, half * 128, row_base, 0, o_zlo, o_zhi);
           tma_store_5d(&tm_p, slab1, half * 128 + 64, row_base, 0, o_zlo, o_zhi);
           bulk_commit_group();
+        }
+      }
+      if constexpr (BWD) {
+        if (bank_fused) {
+          // fills the wait for the second MMA: warp / CTA reduction of the bank partial sums, one flush per tile
+          float* const bins = bank_bins + (it & 1) * 64;  // [0,31) dh, [31,62) dw, [62] dt
+          const int hi = (row >> 4) & 15, wi = row & 15;
+          float tot = 0.f;
+#pragma unroll
+          for (int y = 0; y < 8; ++y) {
+            float v = rs_h[y];
+            tot += v;
+            v += __shfl_xor_sync(0xffffffffu, v, 8);
+            v += __shfl_xor_sync(0xffffffffu, v, 4);
+            v += __shfl_xor_sync(0xffffffffu, v, 2);
+            v += __shfl_xor_sync(0xffffffffu, v, 1);
+            if ((lane & 15) == 0) atomicAdd(&bins[hi - (half * 8 + y) + 15], v);
+          }
+#pragma unroll
+          for (int x = 0; x < 16; ++x) {
+            const float v = cs_w[x] + __shfl_xor_sync(0xffffffffu, cs_w[x], 16);
+            if (lane < 16) atomicAdd(&bins[31 + wi - x + 15], v);  // distinct bins across the 16 lanes
+          }
+          tot = warp_sum(tot);
+          if (lane == 0) atomicAdd(&bins[62], tot);
+          asm volatile("bar.sync 5, 256;" ::: "memory");  // the 8 epilogue warps
+          if (ew == 0) {
+            const int head = t.z % p.heads;
+#pragma unroll
+            for (int i = lane; i < 63; i += 32) {
+              const float v = bins[i];
+              bins[i] = 0.f;  // this buffer is added to again two tiles from now, after the next barrier
+              float* dst = i < 31 ? const_cast<float*>(p.bank_h) + head * 31 + i
+                                  : (i < 62 ? const_cast<float*>(p.bank_w) + head * 31 + (i - 31) : const_cast<float*>(p.bank_t) + head);
+              atomicAdd(dst, v);
+            }
+          }
         }
       }
       // O = P V: 64 of the 128 output columns per warp
@@ -1460,6 +1513,11 @@ extern "C" int lvt_gemm_bf16(const LvtGemm* g, void* stream_) {
     if (rc) return rc;
     if (!g->out_bf16) m.o = tm_o2;  // unused placeholder (store_p == 0)
     if (ek != EK_DS) m.c = m.o;     // unused placeholder
+    // EK_DS with bank pointers: they are the dt/dh/dw_bank GRADIENTS, accumulated in the epilogue (block (1,16,16))
+    const int bank_fused = (ek == EK_DS && g->bank_t && g->bank_h && g->bank_w) ? 1 : 0;
+    if (bank_fused)
+      LVT_CHECK_ARG(g->bt == 1 && g->bh == 16 && g->bw == 16 && g->heads > 0,
+                    "lvt_gemm_bf16: the fused bank gradient covers attention block (1,16,16) only");
     auto launch = [&](auto kern, int which) -> int {
       static bool configured[3] = {false, false, false};
       if (!configured[which]) {
@@ -1467,7 +1525,7 @@ extern "C" int lvt_gemm_bf16(const LvtGemm* g, void* stream_) {
         configured[which] = true;
       }
       LVT_CHECK_CUDA(lvt_launch(kern, dim3(grid), dim3(NUM_THREADS), AttnSmem::TOTAL, stream, m.a, m.b, tm_v, m.o, tm_o2,
-                                m.c, p, g->v_cin, g->v_zdiv, g->o2_cin, g->o2_zdiv, g->out_bf16 ? 1 : 0));
+                                m.c, p, g->v_cin, g->v_zdiv, g->o2_cin, g->o2_zdiv, g->out_bf16 ? 1 : 0, bank_fused));
       lvt_count_launch(1);
       return LVT_OK;
     };

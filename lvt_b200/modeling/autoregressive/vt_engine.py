@@ -507,13 +507,17 @@ class VTEngine:
         gemm(L, da, L, P_mn, do_mn, out_blk(2), out_bf16=out_blk(2).data, batch=nz)
         # dS = P * (dO V^T - delta) and dQ = scale * dS K in ONE kernel (dS reaches the second MMA through shared
         # memory; it is still written out for the dK GEMM and the bank gradient)
+        # (for block (1,16,16) the same epilogue also accumulates the dt/dh/dw_bank gradients from dS)
+        fused_bank = tuple(s.block) == (1, 16, 16)
+        gbanks = (st.gf(prefix + "dt_bank"), st.gf(prefix + "dh_bank"), st.gf(prefix + "dw_bank"))
         gemm(L, L, da, do_k, self._qkv_op(qkv, 2, False, L), dS_k, out_bf16=ws.dS, batch=nz, mode=ops.EPI_DS,
-             aux=ly.P, delta=ws.delta, alpha=scale, v=self._qkv_op(qkv, 1, True, L), o2=out_blk(0), o2_n=da)
-        with self._side_begin():
-            check(self.lib.lvt_relpos_bank_grad(ptr(ws.dS), _vp(st.gf(prefix + "dt_bank")),
-                                                _vp(st.gf(prefix + "dh_bank")), _vp(st.gf(prefix + "dw_bank")),
-                                                ws.nseq, H, s.block[0], s.block[1], s.block[2], stream_ptr()),
-                  "lvt_relpos_bank_grad")
+             aux=ly.P, delta=ws.delta, alpha=scale, v=self._qkv_op(qkv, 1, True, L), o2=out_blk(0), o2_n=da,
+             banks=gbanks if fused_bank else None, block=s.block, heads=H)
+        if not fused_bank:
+            with self._side_begin():
+                check(self.lib.lvt_relpos_bank_grad(ptr(ws.dS), _vp(gbanks[0]), _vp(gbanks[1]), _vp(gbanks[2]),
+                                                    ws.nseq, H, s.block[0], s.block[1], s.block[2], stream_ptr()),
+                      "lvt_relpos_bank_grad")
         # dK = scale * dS^T Q
         gemm(L, da, L, dS_mn, self._qkv_op(qkv, 0, True, L), out_blk(1), out_bf16=out_blk(1).data, batch=nz,
              alpha=scale)

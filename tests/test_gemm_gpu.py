@@ -281,11 +281,14 @@ def test_fused_attention_backward_ds_dq(cuda_lib, Bsz):
 
     dS = torch.full((Bsz, H, L, L), float("nan"), device="cuda", dtype=torch.bfloat16)
     dqkv = torch.full((M, ld), float("nan"), device="cuda", dtype=torch.bfloat16)
-    for _ in range(2):
+    block = (1, 16, 16)
+    gbanks = [torch.full((H, 2 * n - 1), 1.0, device="cuda") for n in block]   # accumulated into (+=)
+    for rep in range(2):
         ops.gemm(L, L, da, ops.Operand(dO.data_ptr(), H * da, cin=da, zdiv=H, s_zlo=da, s_zhi=L * H * da),
                  qkv_op(qkv, 2, False), ops.Operand(dS.data_ptr(), L, zdiv=1, s_zhi=L * L), out_bf16=dS,
                  batch=Bsz * H, mode=ops.EPI_DS, aux=P, delta=delta, alpha=scale,
-                 v=qkv_op(qkv, 1, True), o2=qkv_op(dqkv, 0, False), o2_n=da)
+                 v=qkv_op(qkv, 1, True), o2=qkv_op(dqkv, 0, False), o2_n=da,
+                 banks=gbanks if rep == 1 else None, block=block, heads=H)   # second launch: fused bank gradient too
     torch.cuda.synchronize()
     qf = qkv.float().cpu().view(Bsz, L, 3, H, da)
     k, v = [qf[:, :, i].permute(0, 2, 1, 3) for i in (1, 2)]       # [B,H,L,da]
@@ -296,3 +299,13 @@ def test_fused_attention_backward_ds_dq(cuda_lib, Bsz):
     want_dQ = scale * torch.einsum("bhij,bhjd->bhid", dS.float().cpu(), k)   # from the bf16 dS the kernel used
     got_dQ = dqkv.float().cpu().view(Bsz, L, 3, H, da)[:, :, 0].permute(0, 2, 1, 3)
     _close(got_dQ, want_dQ, 1e-2)
+    # bank gradients (BlockLocalAttention.get_B, vt_attention.py:169-174) from the same dS, on top of the initial 1.0
+    bt, bh, bw = block
+    banks = [torch.zeros(H, 2 * n - 1, requires_grad=True) for n in block]
+    i = torch.arange(L)
+    t, h, w = i // (bh * bw), (i // bw) % bh, i % bw
+    B = (banks[0][:, t[:, None] - t[None, :] + bt - 1] + banks[1][:, h[:, None] - h[None, :] + bh - 1]
+         + banks[2][:, w[:, None] - w[None, :] + bw - 1])
+    (B[None] * want_dS).sum().backward()
+    for got, b in zip(gbanks, banks):
+        _close(got.cpu() - 1.0, b.grad, 2e-3 if b.shape[1] > 1 else 1.0)   # (H, 1) dt bank: sum of all dS, pure cancellation
