@@ -104,6 +104,88 @@ def cpu_reference_arm(steps, warmup, batch=8):
                       f"{torch.get_num_threads()} threads", "ms_per_step": dt * 1e3}
 
 
+def vqvae_main(args, rank, world, local_rank):
+    """BASELINE.json config 3: PR-DVQVAE2 training on synthetic 16-frame 64x64 clips, data-parallel: 32 clips = 512
+    frames per GPU and step (weak scaling), EMA counts / sums and the flat gradient summed over ranks with NCCL
+    (vq_embedding.py:44-59, ae.py:69-73); CUDA-graph replay, max over ranks."""
+    import torch
+    from lvt_b200 import _lib
+    from lvt_b200.modeling.vqvae_engine import GraphedVQVAEStep, VQVAEEngine, VQVAESpec
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    _lib.require_device()
+    _, _, tf_sust, peak_src = measured_peaks()
+    nfr = 512
+    spec = VQVAESpec(n_layers=2)
+    ve = VQVAEEngine(spec)
+    gq = torch.Generator().manual_seed(7)
+    init_w = {}
+    for name, shp in spec.param_shapes().items():
+        fan = 1
+        for s_ in shp[1:]:
+            fan *= s_
+        init_w[name] = torch.randn(shp, generator=gq) / (fan ** 0.5) if len(shp) > 1 else torch.zeros(shp)
+    ve.store.load(init_w)
+    ve.load_state_dict(codebook=torch.randn(4, 512, 64, generator=gq) * 0.3, running_size=torch.full((4, 512), 5.0))
+    ve.init_optimizer(lr=3e-4, betas=(0.9, 0.9))
+    vw = ve.workspace(nfr, train=True)
+    host = torch.rand((nfr, 3, 64, 64), generator=torch.Generator().manual_seed(100 + rank)).pin_memory()
+    vw.x.copy_(host)
+    allreduce = (lambda t: dist.all_reduce(t)) if world > 1 else None
+    step = GraphedVQVAEStep(ve, vw, world_size=world, allreduce=allreduce)
+    step.capture(warmup=2)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        step.step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step.step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / args.steps
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(args.steps):   # end to end: frames from pinned host memory in, the two losses out, every step
+        vw.x.copy_(host, non_blocking=True)
+        step.step()
+        _ = vw.loss.tolist()
+    e1.record()
+    barrier()
+    ms_e2e = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3) / args.steps
+    if dist is not None:
+        t = torch.tensor([ms, ms_e2e], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = t.tolist()
+    if rank == 0:
+        n_gpus = max(1, world)
+        tf = 5.57e9 * nfr / (ms * 1e-3) / 1e12
+        print(json.dumps({
+            "metric": "VQ-VAE frames/sec (PR-DVQVAE2 train step)", "value": nfr * n_gpus / (ms * 1e-3), "unit": "frames/s",
+            "n_gpus": n_gpus, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "PR-DVQVAE2 training on synthetic 16-frame 64x64 clips, 32 clips (512 frames) per GPU "
+                                   "and step, Adam + EMA codebook, data-parallel", "parallelism": f"dp{n_gpus}",
+                       "l2": "512 frames of activations (> 1 GB) exceed the 126 MB L2; no explicit flush"},
+            "losses": vw.loss.tolist(),
+            "e2e": {"value": nfr * n_gpus / (ms_e2e * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": int(host.numel() * 4),
+                    "d2h_bytes_per_step": 8, "ms_per_step": ms_e2e},
+            "roofline": {"bound": "tensor", "achieved": tf, "peak": tf_sust, "unit": "TFLOP/s", "frac": tf / tf_sust,
+                         "traffic": None, "peak_source": peak_src,
+                         "kernel": "gemm_bf16_kernel implicit-GEMM convolutions: 5.57 GFLOP per frame fwd+bwd / step time, per GPU"}}))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -113,6 +195,9 @@ def main():
     ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="slices per GPU")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="one gradient all-reduce after the backward instead of two overlapped buckets")
+    ap.add_argument("--workload", default="dsfvt", choices=["dsfvt", "vqvae"],
+                    help="dsfvt (default, the headline line) | vqvae: PR-DVQVAE2 data-parallel training, frames/s "
+                         "(BASELINE.json config 3)")
     ap.add_argument("--quick", action="store_true", help="DSFVT step only: skip the per-kernel figures and the CPU baseline")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -125,6 +210,8 @@ def main():
               "l2": "working set per step (>5 GB activations + 0.6 GB weights/optimizer state) exceeds the "
                     "126 MB L2; no explicit flush"}
 
+    if args.workload == "vqvae" and args.impl == "ours":
+        return vqvae_main(args, rank, world, local_rank)
     if args.impl == "reference":
         if rank != 0:
             return
