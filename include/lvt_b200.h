@@ -222,6 +222,12 @@ int lvt_chpred_combine_bwd(const void* du_bf16, const int64_t* slice, float* dut
 int lvt_cross_entropy(const float* logits, const int64_t* slice, const uint8_t* ignore,
                       void* dlogits_bf16, float* loss, int* count_scratch, int B, int nc, int nv,
                       int thw, void* stream);
+/* One channel of ChannelPredictor.sample (videotransformer.py:161-185) at position *pos of every sequence:
+ * slice[b, k, *pos] = argmax_i softmax(logits[b*thw + *pos, :] / temp)_i / q_exp[b, i]  with q_exp ~ Exp(1) drawn by the
+ * caller — the arithmetic of torch.multinomial(probs, 1), so both consume the same random stream.  logits fp32
+ * [B*thw, nv]; slice int64 [B, nc, thw]; pos: ONE int64 in device memory (graph replay with a moving position). */
+int lvt_vt_sample_pixel(const float* logits, const float* q_exp, const int64_t* pos, int64_t* slice, int B,
+                        int thw, int nv, int nc, int k, float temp, void* stream);
 /* torch.optim.RMSprop / Adam steps (solver/build.py:62-72) over flat fp32 buffers of n elements
  * (n % 4 == 0), gradients pre-multiplied by grad_scale; p_bf16 (optional) receives the bf16
  * shadow copy the GEMMs read.                                                               */

@@ -62,6 +62,7 @@ SYMBOLS = {
     "lvt_device_check": (_i, []),
     "lvt_launch_count": (_ll, []),
     "lvt_launch_count_reset": (None, []),
+    "lvt_vt_sample_pixel": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp]),
     "lvt_vq_argmin": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "lvt_vq_ema_update": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _d, _d, _vp]),
     "lvt_vq_gather": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),

@@ -1376,6 +1376,11 @@ extern "C" int lvt_gemm_bf16(const LvtGemm* g, void* stream_) {
   } else {
     LVT_CHECK_ARG(g->mode == LVT_EPI_LINEAR, "lvt_gemm_bf16: unknown epilogue mode %d", g->mode);
     bn = (g->N % 256 == 0) ? 256 : 128;
+    // latency-bound small problems (a few output tiles, e.g. the M = 256 GEMMs of the sampler): 128-wide tiles
+    // give twice the CTAs and six instead of four k-blocks in flight per CTA
+    if (bn == 256 && g->N % 128 == 0 &&
+        (long long)((g->M + BM - 1) / BM) * (g->N / 256) * g->batch * (g->splits > 0 ? g->splits : 1) <= 37)
+      bn = 128;
   }
 
   GemmParams p;

@@ -661,6 +661,64 @@ int dispatch_v4(int n128, F f) {
   }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// One channel of ChannelPredictor.sample (videotransformer.py:161-185): categorical draw from
+// softmax(logits / temp) at ONE position per sequence, written straight into the slice buffer.
+// Same arithmetic as torch.multinomial(softmax(.), 1) on CUDA: argmax_i p_i / q_i with q ~ Exp(1) drawn by
+// the caller (torch's generator, so both paths consume the same random stream); first index wins ties.
+// One block per sequence; pos is read from device memory (CUDA-graph replay with a moving position).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+sample_pixel_kernel(const float* __restrict__ logits, const float* __restrict__ q, const int64_t* __restrict__ pos_ptr,
+                    int64_t* __restrict__ slc, int thw, int nv, int nc, int k, float inv_temp) {
+  pdl_prologue();
+  __shared__ float s_f[8];
+  __shared__ int s_i[8];
+  const int b = blockIdx.x;
+  const int pos = (int)pos_ptr[0];
+  const float* row = logits + ((long long)b * thw + pos) * nv;
+  const float* qr = q + (long long)b * nv;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float mx = -INFINITY;
+  for (int i = threadIdx.x; i < nv; i += 256) mx = fmaxf(mx, row[i] * inv_temp);
+  mx = warp_max(mx);
+  if (lane == 0) s_f[warp] = mx;
+  __syncthreads();
+  mx = s_f[0];
+#pragma unroll
+  for (int w = 1; w < 8; ++w) mx = fmaxf(mx, s_f[w]);
+  __syncthreads();
+  float sum = 0.f;
+  for (int i = threadIdx.x; i < nv; i += 256) sum += expf(row[i] * inv_temp - mx);
+  sum = warp_sum(sum);
+  if (lane == 0) s_f[warp] = sum;
+  __syncthreads();
+  sum = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) sum += s_f[w];
+  __syncthreads();
+  float best = -INFINITY;
+  int besti = 0x7fffffff;
+  for (int i = threadIdx.x; i < nv; i += 256) {
+    const float v = (expf(row[i] * inv_temp - mx) / sum) / qr[i];
+    if (v > best) { best = v; besti = i; }  // ascending i per thread: the first maximum is kept
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+    if (ov > best || (ov == best && oi < besti)) { best = ov; besti = oi; }
+  }
+  if (lane == 0) { s_f[warp] = best; s_i[warp] = besti; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w)
+      if (s_f[w] > best || (s_f[w] == best && s_i[w] < besti)) { best = s_f[w]; besti = s_i[w]; }
+    slc[((long long)b * nc + k) * thw + pos] = besti;
+  }
+}
+
 }  // namespace
 
 #define STREAM(s) reinterpret_cast<cudaStream_t>(s)
@@ -910,6 +968,16 @@ extern "C" int lvt_permute4(const float* in, void* out, int out_is_bf16, int acc
   else if (accumulate) LVT_CHECK_CUDA(lvt_launch(permute4_kernel<false, true>, dim3(grid), dim3(256), 0, STREAM(stream), in, out, P, total));
   else LVT_CHECK_CUDA(lvt_launch(permute4_kernel<false, false>, dim3(grid), dim3(256), 0, STREAM(stream), in, out, P, total));
   LVT_CHECK_LAUNCH();
+  lvt_count_launch(1);
+  return LVT_OK;
+}
+
+extern "C" int lvt_vt_sample_pixel(const float* logits, const float* q_exp, const int64_t* pos, int64_t* slice, int B,
+                                   int thw, int nv, int nc, int k, float temp, void* stream) {
+  LVT_CHECK_ARG(logits && q_exp && pos && slice && B > 0 && thw > 0 && nv > 0 && k >= 0 && k < nc && temp > 0.f,
+                "lvt_vt_sample_pixel: bad argument");
+  LVT_CHECK_CUDA(lvt_launch(sample_pixel_kernel, dim3(B), dim3(256), 0, STREAM(stream), logits, q_exp, pos, slice, thw, nv, nc, k,
+                            1.f / temp));
   lvt_count_launch(1);
   return LVT_OK;
 }

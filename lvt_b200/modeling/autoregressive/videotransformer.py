@@ -5,6 +5,8 @@ import logging
 
 import numpy as np
 import torch
+
+from ..._lib import check, ptr, stream_ptr
 from torch import nn
 
 from ...utils.registry import Registry
@@ -168,15 +170,19 @@ class VideoTransformer(Autoregressive):
                 graph = None
         else:
             pos_t = torch.full((1,), todo[0], dtype=torch.int64, device=ws.slice.device)
-            codes = ws.slice.view(b, spec.nc, thw)
+            q_exp = torch.empty((b, spec.nv), dtype=torch.float32, device=ws.slice.device)
 
             def step():
                 eng.decoder_forward(ws, train=False)
                 for k in range(spec.nc):
                     eng.predictor_forward(ws, channels=[k])
-                    logits = ws.logits[k].view(b, thw, spec.nv).index_select(1, pos_t).squeeze(1)
-                    sample = torch.multinomial(torch.softmax(logits / temp, 1), 1)            # (b, 1)
-                    codes[:, k].scatter_(1, pos_t.expand(b, 1), sample)  # feeds the one-hot half of U[k+1] and the next steps
+                    # torch.multinomial(softmax(logits / temp), 1) == argmax(probs / q), q ~ Exp(1): q from torch's
+                    # generator (same random stream as the reference's call), the rest in one kernel that writes
+                    # the code into the slice buffer (it feeds the one-hot half of U[k+1] and the next positions)
+                    q_exp.exponential_(1)
+                    check(eng.lib.lvt_vt_sample_pixel(ptr(ws.logits[k]), ptr(q_exp), ptr(pos_t), ptr(ws.slice), b, thw,
+                                                      spec.nv, spec.nc, k, float(temp), stream_ptr()),
+                          "lvt_vt_sample_pixel")
 
             graph = None
             if use_graph:

@@ -43,7 +43,8 @@ class VideoTransformerModel(nn.Module):
         self.model = build_autoregressive(cfg)
         self.init_weights(self.model, cfg.MODEL.INIT_TYPE)
         self.vis_period = cfg.VIS_PERIOD
-        # LVT_SAMPLER_GRAPH=0: the reference's per-pixel Python loop (eager launches, eager RNG stream)
+        # LVT_SAMPLER_GRAPH=0: the reference's per-pixel Python loop (eager launches, eager RNG stream);
+        # sampler_graph = "eager": the fused per-position step without graph capture (eager RNG stream)
         self.sampler_graph = os.environ.get("LVT_SAMPLER_GRAPH", "1") != "0"
         self.model.engine.grad_hook = None
         self._anchor = torch.zeros(1, device=self.device, requires_grad=True)
@@ -180,7 +181,8 @@ class VideoTransformerModel(nn.Module):
             sidx = torch.full((B,), slice_idx, dtype=torch.int64, device=self.device)
             if self.sampler_graph:
                 # same loops, one CUDA-graph replay per position (VideoTransformer.sample_slice)
-                slc = self.model.sample_slice(context, slc, sidx, prime_slice, temp=temp)
+                slc = self.model.sample_slice(context, slc, sidx, prime_slice, temp=temp,
+                                              use_graph=self.sampler_graph != "eager")
             else:
                 zl = None
                 for ti in range(t):
