@@ -465,9 +465,9 @@ def main():
         "gpu_launches_per_step": int(launches_per_step),
         "clocks": clocks,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": tf_sust, "unit": "TFLOP/s",
-                     "frac": achieved / tf_sust, "traffic": 30.61e9, "peak_source": peak_src,
+                     "frac": achieved / tf_sust, "traffic": 27.49e9, "peak_source": peak_src,
                      "traffic_note": "DRAM bytes of one whole step (all launches), ncu dram__bytes_read+write, "
-                                     "profiles/r01c_step_launches.txt; achieved / peak are per step too",
+                                     "profiles/r01f_step_launches.csv (first 433 launches); achieved / peak are per step too",
                      "kernel": "gemm_bf16_kernel (tcgen05) — whole-step useful FLOPs / step time, per GPU",
                      "kernels": extra},
         "cpu_baseline": {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")},
