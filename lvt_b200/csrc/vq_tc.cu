@@ -279,16 +279,19 @@ vq_argmin_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __res
         return NHWC ? *reinterpret_cast<const float*>(xr + (j >> 5) * 16384 + ((((j >> 2) & 7) ^ rsw) << 4) + (j & 3) * 4)
                     : *reinterpret_cast<const float*>(xr + j * 128 + ((rsw ^ (j & 3)) << 5));
       };
-      // exact reference distance (vq.cu): sequential fp32 FMA chain over the 64 dims.  B holds -2c and
-      // fma(x, -2c, -2a) == -2 * fma(x, c, a) exactly, so  d = fl(fl(c2 + x2) - 2*dot) = fl(chain + fl(c2 + x2)).
+      // exact reference distance (vq.cu): sequential fp32 FMA chain over the 64 dims, d = fl(fl(c2 + x2) - 2*dot).
+      // The code row comes from global memory (L1 / L2 resident, 16 independent 16-byte loads issued up front):
+      // while the re-rank runs the next tile's MMAs take most of the shared-memory bandwidth.
       auto exact_d = [&](int r, int k) {
-        const uint8_t* brow = smem + k * 128;
+        const float4* crow = reinterpret_cast<const float4*>(cbg + (size_t)k * TD);
+        float4 cv[16];
+#pragma unroll
+        for (int jj = 0; jj < 16; ++jj) cv[jj] = __ldg(crow + jj);
         const uint8_t* xr = xptr(r);
         const int rsw = NHWC ? (r & 7) : ((r & 31) >> 3);
         float acc = 0.f;
 #pragma unroll
         for (int jj = 0; jj < 16; ++jj) {
-          const float4 v = *reinterpret_cast<const float4*>(brow + (jj >> 3) * (TK * 128) + (((jj & 7) ^ (k & 7)) << 4));
           float4 xv;
           if (NHWC) {
             xv = *reinterpret_cast<const float4*>(xr + (jj >> 3) * 16384 + (((jj & 7) ^ rsw) << 4));
@@ -298,12 +301,12 @@ vq_argmin_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __res
             xv.z = *reinterpret_cast<const float*>(xr + (4 * jj + 2) * 128 + ((rsw ^ 2) << 5));
             xv.w = *reinterpret_cast<const float*>(xr + (4 * jj + 3) * 128 + ((rsw ^ 3) << 5));
           }
-          acc = __fmaf_rn(xv.x, v.x, acc);
-          acc = __fmaf_rn(xv.y, v.y, acc);
-          acc = __fmaf_rn(xv.z, v.z, acc);
-          acc = __fmaf_rn(xv.w, v.w, acc);
+          acc = __fmaf_rn(xv.x, cv[jj].x, acc);
+          acc = __fmaf_rn(xv.y, cv[jj].y, acc);
+          acc = __fmaf_rn(xv.z, cv[jj].z, acc);
+          acc = __fmaf_rn(xv.w, cv[jj].w, acc);
         }
-        return __fadd_rn(acc, __fadd_rn(c2s[k], x2s[r]));
+        return __fadd_rn(-2.f * acc, __fadd_rn(c2s[k], x2s[r]));  // -2 * acc is exact
       };
       const int who = ew == 0 ? 1 : (ew == 12 ? 2 : (ew == 5 ? 3 : -1));
 #define VQ_ECLK(ev) do { if (who > 0) VQ_CLK(who, ev); } while (0)
