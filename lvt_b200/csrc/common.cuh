@@ -60,7 +60,8 @@ void lvt_set_error(const char* fmt, ...);
 // ----------------------------------------------------------------------------------------
 // Programmatic dependent launch (PDL): consecutive kernels of one stream (or of a captured CUDA graph)
 // overlap the next grid's launch + prologue with the previous grid's tail.  Every kernel launched through
-// lvt_launch() calls pdl_launch_dependents() first and pdl_wait() before its first access to global memory
+// lvt_launch() calls pdl_wait() before its first access to global memory; the persistent GEMM kernels call
+// pdl_launch_dependents() when they start their LAST tile, so only the next grid's launch latency and prologue overlap the tail
 // (griddepcontrol.wait returns when the prerequisite grid has completed and flushed), so data dependencies
 // between neighbours are unchanged.  The launch attribute is only set when LVT_PDL=1 (see lvt_pdl_enabled()).
 // ----------------------------------------------------------------------------------------
@@ -68,7 +69,8 @@ void lvt_set_error(const char* fmt, ...);
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_prologue() {
-  pdl_launch_dependents();
+  // elementwise kernels only wait: an early launch_dependents would let the next grid's CTAs sit on thread / register
+  // slots of the waves of THIS grid that have not started yet (measured: the step got slower)
   pdl_wait();
 }
 bool lvt_pdl_enabled();

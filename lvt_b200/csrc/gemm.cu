@@ -145,7 +145,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  pdl_launch_dependents();  // the next kernel's CTAs may be scheduled as soon as SMs free up
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_a);
@@ -269,6 +268,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++titer) {
         const TileCoord t = decode_tile(p, tile, BN);
         const uint32_t buf = titer & 1;
+        if (tile + (int)gridDim.x >= p.total_tiles) pdl_launch_dependents();  // last tile of this CTA (PDL, see common.cuh)
         mbar_wait(&tmem_empty_bar[buf], ((titer >> 1) & 1) ^ 1);  // epilogue drained this buffer
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + buf * BN;
@@ -807,6 +807,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -863,6 +864,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       if (my_tiles > 0) issue_qk(0);
       for (int it = 0; it < my_tiles; ++it) {
         if (it + 1 < my_tiles) issue_qk(it + 1);  // next tile's scores while this tile's softmax runs
+        else pdl_launch_dependents();
         mbar_wait(v_full, it & 1);
         mbar_wait(p_full, it & 1);               // P of this tile is in shared memory (and O of the previous one was read)
         tc_fence_after();
