@@ -225,9 +225,41 @@ int lvt_cross_entropy(const float* logits, const int64_t* slice, const uint8_t* 
 /* One channel of ChannelPredictor.sample (videotransformer.py:161-185) at position *pos of every sequence:
  * slice[b, k, *pos] = argmax_i softmax(logits[b*thw + *pos, :] / temp)_i / q_exp[b, i]  with q_exp ~ Exp(1) drawn by the
  * caller — the arithmetic of torch.multinomial(probs, 1), so both consume the same random stream.  logits fp32
- * [B*thw, nv]; slice int64 [B, nc, thw]; pos: ONE int64 in device memory (graph replay with a moving position). */
+ * [B*logit_rows, nv] with logit_rows == thw (full pass) or 1 (one row per sequence, incremental pass); slice int64
+ * [B, nc, thw]; pos: ONE int64 in device memory (graph replay with a moving position).                          */
 int lvt_vt_sample_pixel(const float* logits, const float* q_exp, const int64_t* pos, int64_t* slice, int B,
-                        int thw, int nv, int nc, int k, float temp, void* stream);
+                        int thw, int nv, int nc, int k, float temp, int logit_rows, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Incremental (K/V-cached) decoding step of the sampler (meta_arch/vt.py:107-134 recomputes the whole decoder
+ * pass per position): skinny B-row products against bf16 weights, B <= 16.  *pos = current position.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct LvtRowsLinear {
+  int B, N, K;
+  const void* x; long long x_ldb, x_pos_mul; int x_bf16;   /* row b at x + b*x_ldb + (*pos)*x_pos_mul (elements) */
+  const float* ln_gamma; const float* ln_beta; float ln_eps; /* optional LayerNorm of the row first              */
+  int round_in;                                             /* round the input row to bf16 (as the full pass)  */
+  const void* w_bf16; long long w_ld;                       /* W [N, K] rows (nn.Linear layout), bf16          */
+  const float* bias;                                        /* optional [N]                                    */
+  const float* res; long long res_ldb, res_pos_mul;         /* optional residual row                           */
+  const float* gtab; const int64_t* slice; int g_count, nv, nc, thw;
+                       /* out[b,n] += sum_{j<g_count} gtab[(j*nv + slice[b,j,*pos])*N + n] (one-hot half of U[k]) */
+  int relu, round_out;
+  float* out; long long out_ldb;
+  const int64_t* pos;
+} LvtRowsLinear;
+/* out[b, :] = epi([LN](x[b, :]) @ W^T) */
+int lvt_rows_linear(const LvtRowsLinear* a, void* stream);
+/* q | k | v of row *pos from w_q|w_k|w_v [3H, d, da] (vt_attention.py:98-104,120-124) with the pre-LayerNorm fused:
+ * q -> q_out fp32 [B, H*da]; k, v -> caches bf16 [B, H, L, da] at row *pos.                                   */
+int lvt_rows_qkv(const float* x, const float* ln_gamma, const float* ln_beta, float eps, const void* w_bf16,
+                 float* q_out, void* k_cache_bf16, void* v_cache_bf16, const int64_t* pos, int B, int H, int d,
+                 int da, int L, void* stream);
+/* o[b, h, :] = softmax(q k^T * scale + B[h, *pos, :] [keys after *pos: -1e4]) v over the cached rows
+ * (vt_attention.py:61-81,169-174).                                                                           */
+int lvt_attn_row(const float* q, const void* k_cache_bf16, const void* v_cache_bf16, const float* bank_t,
+                 const float* bank_h, const float* bank_w, int bt, int bh, int bw, const int64_t* pos, float scale,
+                 float* o, int B, int H, int L, int da, void* stream);
 /* torch.optim.RMSprop / Adam steps (solver/build.py:62-72) over flat fp32 buffers of n elements
  * (n % 4 == 0), gradients pre-multiplied by grad_scale; p_bf16 (optional) receives the bf16
  * shadow copy the GEMMs read.                                                               */

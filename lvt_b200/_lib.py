@@ -53,6 +53,24 @@ class LvtGemm(ctypes.Structure):
     ]
 
 
+class LvtRowsLinear(ctypes.Structure):
+    """Mirror of `struct LvtRowsLinear` (include/lvt_b200.h)."""
+    _fields_ = [
+        ("B", ctypes.c_int), ("N", ctypes.c_int), ("K", ctypes.c_int),
+        ("x", ctypes.c_void_p), ("x_ldb", ctypes.c_longlong), ("x_pos_mul", ctypes.c_longlong), ("x_bf16", ctypes.c_int),
+        ("ln_gamma", ctypes.c_void_p), ("ln_beta", ctypes.c_void_p), ("ln_eps", ctypes.c_float),
+        ("round_in", ctypes.c_int),
+        ("w_bf16", ctypes.c_void_p), ("w_ld", ctypes.c_longlong),
+        ("bias", ctypes.c_void_p),
+        ("res", ctypes.c_void_p), ("res_ldb", ctypes.c_longlong), ("res_pos_mul", ctypes.c_longlong),
+        ("gtab", ctypes.c_void_p), ("slice", ctypes.c_void_p), ("g_count", ctypes.c_int), ("nv", ctypes.c_int),
+        ("nc", ctypes.c_int), ("thw", ctypes.c_int),
+        ("relu", ctypes.c_int), ("round_out", ctypes.c_int),
+        ("out", ctypes.c_void_p), ("out_ldb", ctypes.c_longlong),
+        ("pos", ctypes.c_void_p),
+    ]
+
+
 _vp, _i, _ll, _d, _f = (ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_double,
                         ctypes.c_float)
 # symbol -> (restype, argtypes); one entry per function include/lvt_b200.h declares
@@ -62,7 +80,10 @@ SYMBOLS = {
     "lvt_device_check": (_i, []),
     "lvt_launch_count": (_ll, []),
     "lvt_launch_count_reset": (None, []),
-    "lvt_vt_sample_pixel": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp]),
+    "lvt_vt_sample_pixel": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _vp]),
+    "lvt_rows_linear": (_i, [_vp, _vp]),
+    "lvt_rows_qkv": (_i, [_vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "lvt_attn_row": (_i, [_vp] * 6 + [_i, _i, _i, _vp, _f, _vp, _i, _i, _i, _i, _vp]),
     "lvt_vq_argmin": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "lvt_vq_ema_update": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _d, _d, _vp]),
     "lvt_vq_gather": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),

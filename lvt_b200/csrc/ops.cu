@@ -671,13 +671,14 @@ int dispatch_v4(int n128, F f) {
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 sample_pixel_kernel(const float* __restrict__ logits, const float* __restrict__ q, const int64_t* __restrict__ pos_ptr,
-                    int64_t* __restrict__ slc, int thw, int nv, int nc, int k, float inv_temp) {
+                    int64_t* __restrict__ slc, int thw, int nv, int nc, int k, float inv_temp, int logit_rows) {
   pdl_prologue();
   __shared__ float s_f[8];
   __shared__ int s_i[8];
   const int b = blockIdx.x;
   const int pos = (int)pos_ptr[0];
-  const float* row = logits + ((long long)b * thw + pos) * nv;
+  // logits: [B * thw, nv] (full pass, logit_rows == thw) or one row per sequence (incremental pass, logit_rows == 1)
+  const float* row = logits + ((long long)b * logit_rows + (logit_rows > 1 ? pos : 0)) * nv;
   const float* qr = q + (long long)b * nv;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float mx = -INFINITY;
@@ -973,11 +974,12 @@ extern "C" int lvt_permute4(const float* in, void* out, int out_is_bf16, int acc
 }
 
 extern "C" int lvt_vt_sample_pixel(const float* logits, const float* q_exp, const int64_t* pos, int64_t* slice, int B,
-                                   int thw, int nv, int nc, int k, float temp, void* stream) {
-  LVT_CHECK_ARG(logits && q_exp && pos && slice && B > 0 && thw > 0 && nv > 0 && k >= 0 && k < nc && temp > 0.f,
+                                   int thw, int nv, int nc, int k, float temp, int logit_rows, void* stream) {
+  LVT_CHECK_ARG(logits && q_exp && pos && slice && B > 0 && thw > 0 && nv > 0 && k >= 0 && k < nc && temp > 0.f &&
+                    (logit_rows == thw || logit_rows == 1),
                 "lvt_vt_sample_pixel: bad argument");
   LVT_CHECK_CUDA(lvt_launch(sample_pixel_kernel, dim3(B), dim3(256), 0, STREAM(stream), logits, q_exp, pos, slice, thw, nv, nc, k,
-                            1.f / temp));
+                            1.f / temp, logit_rows));
   lvt_count_launch(1);
   return LVT_OK;
 }

@@ -144,13 +144,15 @@ class VideoTransformer(Autoregressive):
         raise ValueError("|mode| is invalid")
 
     @torch.no_grad()
-    def sample_slice(self, context, slice, slice_idx, prime_mask=None, temp=1.0, use_graph=True):
+    def sample_slice(self, context, slice, slice_idx, prime_mask=None, temp=1.0, use_graph=True, incremental=None):
         """Every non-primed position of one slice in raster order — the inner loops of
         VideoTransformerModel.sample_video (meta_arch/vt.py:107-134) around mode "sample_pixel"
-        (videotransformer.py:161-185, 240-246): encoder once per slice, then per position the masked decoder pass and
-        the channel-by-channel multinomial draw.  The per-position step reads its position from a device scalar, so
-        it is captured ONCE in a CUDA graph and replayed (no host work between the ~100 launches of a step).
+        (videotransformer.py:161-185, 240-246): encoder once per slice, then per position the masked decoder and the
+        channel-by-channel multinomial draw.  The per-position step reads its position from a device scalar, so it is
+        captured ONCE in a CUDA graph and replayed.  incremental (default for <= 16 sequences): one ROW per sequence
+        goes through the decoder against cached keys / values (IncrementalDecoder) instead of the full 256-token pass.
         Returns the completed slice (b, nc, t, h, w) int64."""
+        from .incremental import MAX_ROWS, IncrementalDecoder
         eng, spec = self.engine, self.engine.spec
         b = context.shape[0]
         t, h, w = slice.shape[2:]
@@ -161,45 +163,60 @@ class VideoTransformer(Autoregressive):
         todo = [p for p in range(thw) if not bool(primed[p])]
         if not todo:
             return ws.slice.view(b, spec.nc, t, h, w).clone()
-        # the graph only references the workspace's static buffers, so it is captured once per (workspace, temp)
+        if incremental is None:
+            incremental = b <= 8  # measured: 0.50 vs 0.61 ms/position at b = 1, break-even near b = 8
+        assert not incremental or b <= MAX_ROWS
         cache = self.__dict__.setdefault("_sample_graphs", {})
-        key = (id(ws), float(temp))
-        if key in cache:
-            graph, pos_t, step = cache[key]
+        key = (id(ws), float(temp), bool(incremental))
+        if key not in cache:
+            if incremental:
+                dec = IncrementalDecoder(eng, ws)
+                pos_t = dec.pos
+                steps = {"sample": lambda: dec.sample_row(temp), "fill": dec.decode_row}
+            else:
+                dec = None
+                pos_t = torch.zeros(1, dtype=torch.int64, device=ws.slice.device)
+                q_exp = torch.empty((b, spec.nv), dtype=torch.float32, device=ws.slice.device)
+
+                def full_step():
+                    eng.decoder_forward(ws, train=False)
+                    for k in range(spec.nc):
+                        eng.predictor_forward(ws, channels=[k])
+                        # torch.multinomial(softmax(logits / temp), 1) == argmax(probs / q), q ~ Exp(1): q from torch's
+                        # generator (same random stream as the reference's call), the rest in one kernel that writes
+                        # the code into the slice buffer (it feeds the one-hot half of U[k+1] and the next positions)
+                        q_exp.exponential_(1)
+                        check(eng.lib.lvt_vt_sample_pixel(ptr(ws.logits[k]), ptr(q_exp), ptr(pos_t), ptr(ws.slice), b, thw,
+                                                          spec.nv, spec.nc, k, float(temp), thw, stream_ptr()),
+                              "lvt_vt_sample_pixel")
+                steps = {"sample": full_step}
+            cache[key] = {"dec": dec, "pos": pos_t, "steps": steps, "graphs": {}}
+        entry = cache[key]
+        dec, pos_t = entry["dec"], entry["pos"]
+        if dec is not None:
+            dec.begin_slice()
+
+        def run(kind, p):
+            pos_t.fill_(p)
             if not use_graph:
-                graph = None
-        else:
-            pos_t = torch.full((1,), todo[0], dtype=torch.int64, device=ws.slice.device)
-            q_exp = torch.empty((b, spec.nv), dtype=torch.float32, device=ws.slice.device)
-
-            def step():
-                eng.decoder_forward(ws, train=False)
-                for k in range(spec.nc):
-                    eng.predictor_forward(ws, channels=[k])
-                    # torch.multinomial(softmax(logits / temp), 1) == argmax(probs / q), q ~ Exp(1): q from torch's
-                    # generator (same random stream as the reference's call), the rest in one kernel that writes
-                    # the code into the slice buffer (it feeds the one-hot half of U[k+1] and the next positions)
-                    q_exp.exponential_(1)
-                    check(eng.lib.lvt_vt_sample_pixel(ptr(ws.logits[k]), ptr(q_exp), ptr(pos_t), ptr(ws.slice), b, thw,
-                                                      spec.nv, spec.nc, k, float(temp), stream_ptr()),
-                          "lvt_vt_sample_pixel")
-
-            graph = None
-            if use_graph:
-                pos_t.fill_(todo[0])
+                entry["steps"][kind]()
+                return
+            if kind not in entry["graphs"]:
                 side = torch.cuda.Stream()
                 side.wait_stream(torch.cuda.current_stream())
                 with torch.cuda.stream(side):
-                    step()  # eager warm-up (kernel attributes, TMA maps, cached tables); position todo[0] is redrawn below
+                    entry["steps"][kind]()  # eager warm-up (kernel attributes, TMA maps, cached tables); redone below
                 torch.cuda.current_stream().wait_stream(side)
-                graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(graph):
-                    step()
-                cache[key] = (graph, pos_t, step)
-        for p in todo:
-            pos_t.fill_(p)
-            if graph is not None:
-                graph.replay()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    entry["steps"][kind]()
+                entry["graphs"][kind] = g
+            entry["graphs"][kind].replay()
+
+        for p in range(todo[-1] + 1):
+            if bool(primed[p]):
+                if dec is not None:
+                    run("fill", p)  # given position: only its keys / values are needed by the later rows
             else:
-                step()
+                run("sample", p)
         return ws.slice.view(b, spec.nc, t, h, w).clone()

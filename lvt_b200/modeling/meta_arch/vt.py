@@ -182,7 +182,8 @@ class VideoTransformerModel(nn.Module):
             if self.sampler_graph:
                 # same loops, one CUDA-graph replay per position (VideoTransformer.sample_slice)
                 slc = self.model.sample_slice(context, slc, sidx, prime_slice, temp=temp,
-                                              use_graph=self.sampler_graph != "eager")
+                                              use_graph=self.sampler_graph != "eager",
+                                              incremental=getattr(self.model, "sample_incremental", None))
             else:
                 zl = None
                 for ti in range(t):

@@ -98,6 +98,7 @@ def test_graph_sampler_matches_per_pixel_loop(cuda_lib, tmp_path):
     vt.train(False)
     video = torch.randint(0, 512, (1, 4, 16, 16, 16)).cuda()
     video[:, :, 15:] = 0
+    vt.model.sample_incremental = False   # the full-pass step: bitwise the logits of the per-pixel loop
     outs = []
     for graph in (True, False):
         vt.sampler_graph = graph
@@ -142,6 +143,7 @@ def test_fused_sampling_step_consumes_torch_multinomial_stream(cuda_lib, tmp_pat
     video = torch.randint(0, 512, (2, 4, 16, 16, 16)).cuda()
     video[:, :, 15:] = 0
     outs = []
+    vt.model.sample_incremental = False
     for mode in ("eager", False):
         vt.sampler_graph = mode
         torch.manual_seed(123)
@@ -149,3 +151,54 @@ def test_fused_sampling_step_consumes_torch_multinomial_stream(cuda_lib, tmp_pat
     same = (outs[0] == outs[1]).float().mean().item()
     assert same >= 0.999, same   # (a differing code would change everything after it)
     assert len(torch.unique(outs[0][:, :, 15])) > 100   # really sampling, not an argmax
+
+
+@pytest.mark.parametrize("block,kernel,stride,vshape", [((1, 16, 16), (7, 1, 1), (16, 1, 1), (16, 16, 16)),
+                                                        ((4, 8, 8), (5, 3, 3), (4, 2, 2), (16, 16, 16))])
+def test_incremental_decoder_matches_full_pass(cuda_lib, block, kernel, stride, vshape):
+    """IncrementalDecoder (one row per sequence against cached keys / values, csrc/sampler.cu) reproduces the
+    teacher-forced logits of the full 256-token pass at every position and channel: max |diff| <= 1e-2 of the logit
+    scale (bf16 roundings at the same places; only the summation order differs)."""
+    from oracle import lvt_oracle as O
+    from lvt_b200.modeling.autoregressive import VTEngine, VTSpec
+    from lvt_b200.modeling.autoregressive.incremental import IncrementalDecoder
+    layers, batch = 2, 3
+    blocks = (block,) * layers
+    cfg = O.VTConfig(kernel=kernel, stride=stride, video_shape=vshape, blocks_e=blocks, heads_e=(8,) * layers,
+                     blocks_d=blocks, heads_d=(8,) * layers)
+    weights = O.synth_weights(O.dsfvt_param_shapes(cfg), seed=77)
+    context, slc, slice_idx, ignore = O.synth_vt_batch(batch, seed=9, cfg=cfg)
+    eng = VTEngine(VTSpec(kernel=kernel, stride=stride, blocks_e=blocks, heads_e=(8,) * layers, blocks_d=blocks,
+                          heads_d=(8,) * layers))
+    eng.load_state_dict(weights)
+    ws = eng.workspace(batch, cfg.slice_shape, tuple(context.shape[2:]), train=False)
+    eng.set_inputs(ws, context, slc, slice_idx, None)
+    eng.forward(ws, train=False, want_loss=False)
+    full = ws.logits.clone().view(cfg.nc, batch, ws.thw, cfg.nv)
+    dec = IncrementalDecoder(eng, ws)
+    dec.begin_slice()
+    scale = full.abs().max().item()
+    worst = 0.0
+    for p in range(ws.thw):
+        dec.pos.fill_(p)
+        dec.decode_row()
+        for k in range(cfg.nc):
+            dec.channel_logits(k)
+            worst = max(worst, (dec.logits - full[k][:, p]).abs().max().item())
+    assert worst <= 1e-2 * scale, (worst, scale)
+
+
+def test_incremental_sampler_runs_and_respects_priming(cuda_lib, tmp_path):
+    from lvt_b200.config.presets import preset
+    from lvt_b200.modeling import build_model
+    cfgv = preset("DSFVT", SMALL + ["TEST.EVALUATORS", "VTSampler", "OUTPUT_DIR", str(tmp_path)])
+    cfgv.freeze()
+    vt = build_model(cfgv)
+    vt.train(False)
+    video = torch.randint(0, 512, (2, 4, 16, 16, 16)).cuda()
+    video[:, :, 14:] = 0
+    torch.manual_seed(5)
+    out = vt.sample_video(video.clone(), temp=1.0, n_prime=14).cpu()      # two sampled frames, graph replay
+    assert torch.equal(out[:, :, :14], video[:, :, :14].cpu())
+    assert int(out.min()) >= 0 and int(out.max()) < 512
+    assert len(torch.unique(out[:, :, 14:])) > 100
