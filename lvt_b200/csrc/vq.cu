@@ -300,25 +300,26 @@ __global__ void vq_ema_kernel(float* __restrict__ codebook, float* __restrict__ 
 // sums[g,k,:] += sum of the z_e rows assigned to code k.  One CTA = one codebook group and a contiguous chunk
 // of positions; the K x 64 sums are privatised in shared memory (conflict-free: lane l owns dims 2l, 2l+1), so
 // global memory sees one vectorised red.add per touched row and CTA instead of 64 scalar atomics per position.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 vq_ema_stats_kernel(const float* __restrict__ z_e, const int64_t* __restrict__ idx, float* __restrict__ counts,
                     float* __restrict__ sums, long long total, int num, int K, int hw, long long pos_stride,
                     long long ch_stride, int chunk) {
   extern __shared__ float s_acc[];  // [K][64] sums, then [K] counts
   float* s_cnt = s_acc + (size_t)K * 64;
   const int g = blockIdx.y;
-  for (int i = threadIdx.x; i < K * 65; i += 256) s_acc[i] = 0.f;
+  const int nw = blockDim.x >> 5;  // warps per block (few, large blocks: every block flushes K x 64 sums at the end)
+  for (int i = threadIdx.x; i < K * 65; i += blockDim.x) s_acc[i] = 0.f;
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long p0 = (long long)blockIdx.x * chunk;
   const long long p1 = p0 + chunk < total ? p0 + chunk : total;
   constexpr int U = 4;  // positions in flight per warp: index and row loads of all U issue before the first atomic
-  for (long long pb = p0 + warp; pb < p1; pb += 8 * U) {
+  for (long long pb = p0 + warp; pb < p1; pb += (long long)nw * U) {
     int kk[U];
     float x0[U], x1[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const long long pos = pb + 8 * u;
+      const long long pos = pb + (long long)nw * u;
       kk[u] = -1;
       if (pos < p1) {
         const long long frame = pos / hw, sp = pos - frame * hw;
@@ -327,7 +328,7 @@ vq_ema_stats_kernel(const float* __restrict__ z_e, const int64_t* __restrict__ i
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const long long pos = pb + 8 * u;
+      const long long pos = pb + (long long)nw * u;
       x0[u] = x1[u] = 0.f;
       if (kk[u] >= 0) {
         const long long frame = pos / hw, sp = pos - frame * hw;
@@ -346,7 +347,7 @@ vq_ema_stats_kernel(const float* __restrict__ z_e, const int64_t* __restrict__ i
     }
   }
   __syncthreads();
-  for (int k = warp; k < K; k += 8) {
+  for (int k = warp; k < K; k += nw) {
     const float c = s_cnt[k];
     if (c == 0.f) continue;  // warp-uniform
     if (lane == 0 && counts) atomicAdd(counts + (size_t)g * K + k, c);
@@ -384,11 +385,11 @@ static int vq_argmin_impl(const float* z_e, const float* codebook, int64_t* idx_
           LVT_CHECK_CUDA(cudaFuncSetAttribute(vq_ema_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
           configured = true;
         }
-        int per_group = 148 / num > 0 ? 148 / num : 1;
+        int per_group = 74 / num > 0 ? 74 / num : 1;  // 1024-thread blocks, half as many flushes
         int chunk = (int)((total + per_group - 1) / per_group);
         if (chunk < 256) chunk = 256;
         dim3 grid(lvt_ceil_div(total, chunk), num);
-        vq_ema_stats_kernel<<<grid, 256, smem, stream>>>(z_e, idx_out, counts, sums, total, num, K, hw,
+        vq_ema_stats_kernel<<<grid, 1024, smem, stream>>>(z_e, idx_out, counts, sums, total, num, K, hw,
                                                          nhwc ? (long long)num * D : 1, nhwc ? 1 : hw, chunk);
         LVT_CHECK_LAUNCH();
         lvt_count_launch(1);
