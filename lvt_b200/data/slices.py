@@ -91,3 +91,50 @@ def synthetic_vt_batch(batch, seed, kernel=(7, 1, 1), stride=(16, 1, 1), n_prime
                               sample_abc(stride, video_shape[0], n_prime, rng), kernel, stride, n_prime, pad_value)
                for i in range(batch)]
     return tuple(torch.stack([s[k] for s in samples], 0) for k in ("context", "slice", "slice_idx", "ignore_mask"))
+
+
+def prepare_slices_batched(videos, abc, kernel, stride, n_prime, pad_value=-1):
+    """Batched, device-side form of `prepare_slices` (dataset_mapper.py:113-149): one gather per output tensor
+    instead of per-sample Python loops, on whatever device `videos` lives (a latent dataset resident in HBM needs no
+    DataLoader workers).  videos (B, T, nc, H, W) integer codes, abc (B, 3) integer slice offsets ->
+    context (B, nc, Tc, Hc, Wc) int64, slice (B, nc, t, h, w) int64, slice_idx (B,) int64, ignore_mask (B, 1, t, h, w) bool,
+    identical to stacking prepare_slices over the batch.
+
+    Derivation of the context window (ss_shift, vt_utils.py:104-128): along an axis of size S with stride s, kernel k and
+    offset o the window starts at source index o - k//2 and has (S//s - 1)*s + k entries; an entry is visible iff its
+    source position lies inside the video and belongs to a slice generated before (a, b, c) in raster order
+    (visible_abc_mask, vt_utils.py:48-57), otherwise it holds pad_value."""
+    v = torch.as_tensor(videos)
+    dev = v.device
+    abc = torch.as_tensor(abc, device=dev).long()
+    B, T, nc, H, W = v.shape
+    (st, sh, sw), (kt, kh, kw) = stride, kernel
+    assert T % st == 0 and H % sh == 0 and W % sw == 0
+    t, h, w = T // st, H // sh, W // sw
+    a, b, c = abc[:, 0], abc[:, 1], abc[:, 2]
+    ar = lambda n: torch.arange(n, device=dev)  # noqa: E731
+    # ---- slice: video[bi, a + ts*st, :, b + hs*sh, c + ws*sw]
+    ti = (a[:, None] + ar(t)[None] * st)                      # (B, t)
+    hi = (b[:, None] + ar(h)[None] * sh)
+    wi = (c[:, None] + ar(w)[None] * sw)
+    bi = ar(B)[:, None, None, None]
+    slc = v[bi, ti[:, :, None, None], :, hi[:, None, :, None], wi[:, None, None, :]]      # (B, t, h, w, nc)
+    slc = slc.permute(0, 4, 1, 2, 3).contiguous().long()
+    # ---- context window
+    Tc, Hc, Wc = (t - 1) * st + kt, (h - 1) * sh + kh, (w - 1) * sw + kw
+    tau = a[:, None] - kt // 2 + ar(Tc)[None]                 # (B, Tc) source indices, may be out of range
+    eta = b[:, None] - kh // 2 + ar(Hc)[None]
+    omg = c[:, None] - kw // 2 + ar(Wc)[None]
+    inside = ((tau >= 0) & (tau < T))[:, :, None, None] & ((eta >= 0) & (eta < H))[:, None, :, None] & \
+             ((omg >= 0) & (omg < W))[:, None, None, :]
+    src_idx = ((tau % st)[:, :, None, None] * sh + (eta % sh)[:, None, :, None]) * sw + (omg % sw)[:, None, None, :]
+    slice_idx = (a * sh + b) * sw + c
+    visible = inside & (src_idx < slice_idx[:, None, None, None])
+    g = v[bi, tau.clamp(0, T - 1)[:, :, None, None], :, eta.clamp(0, H - 1)[:, None, :, None],
+          omg.clamp(0, W - 1)[:, None, None, :]]                                           # (B, Tc, Hc, Wc, nc)
+    ctx = torch.where(visible[..., None], g.long(), torch.full((), pad_value, dtype=torch.long, device=dev))
+    ctx = ctx.permute(0, 4, 1, 2, 3).contiguous()
+    # ---- ignore mask: primed frames of the slice
+    ig = (ti < n_prime)[:, None, :, None, None].expand(B, 1, t, h, w).contiguous() if n_prime > 0 else \
+        torch.zeros((B, 1, t, h, w), dtype=torch.bool, device=dev)
+    return {"context": ctx, "slice": slc, "slice_idx": slice_idx, "ignore_mask": ig}

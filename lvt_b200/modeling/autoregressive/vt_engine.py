@@ -545,6 +545,15 @@ class VTEngine:
         else:
             ws.ignore.zero_()
 
+    def set_inputs_from_videos(self, ws: VTWorkspace, videos, abc, n_prime=1):
+        """Device-side input construction: latent videos (B, T, nc, H, W) already in HBM + slice offsets (B, 3) ->
+        the workspace's context / slice / slice_idx / ignore buffers (lvt_b200.data.prepare_slices_batched: the
+        reference builds them per sample in DataLoader workers, dataset_mapper.py:113-149)."""
+        from ...data.slices import prepare_slices_batched
+        s = self.spec
+        d = prepare_slices_batched(videos, abc, s.kernel, s.stride, n_prime, s.pad_value)
+        self.set_inputs(ws, d["context"], d["slice"], d["slice_idx"], d["ignore_mask"])
+
     def _layer_ws(self, ws, i, train):
         return ws.layers[i] if train else ws.layers[0]
 

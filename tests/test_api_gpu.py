@@ -202,3 +202,30 @@ def test_incremental_sampler_runs_and_respects_priming(cuda_lib, tmp_path):
     assert torch.equal(out[:, :, :14], video[:, :, :14].cpu())
     assert int(out.min()) >= 0 and int(out.max()) < 512
     assert len(torch.unique(out[:, :, 14:])) > 100
+
+
+def test_device_side_slice_construction_feeds_the_engine(cuda_lib):
+    """VTEngine.set_inputs_from_videos (latent videos resident in HBM + slice offsets -> context / slice / ignore on the
+    device, lvt_b200.data.prepare_slices_batched) gives the same loss as staging the host-side mapper output."""
+    import random
+    from oracle import lvt_oracle as O
+    from lvt_b200.data import prepare_slices, sample_abc, synthetic_latent_video
+    from lvt_b200.modeling.autoregressive import VTEngine, VTSpec
+    layers, batch = 2, 3
+    blocks = ((1, 16, 16),) * layers
+    spec = VTSpec(blocks_e=blocks, heads_e=(8,) * layers, blocks_d=blocks, heads_d=(8,) * layers)
+    cfg = O.VTConfig(blocks_e=blocks, heads_e=(8,) * layers, blocks_d=blocks, heads_d=(8,) * layers)
+    eng = VTEngine(spec)
+    eng.load_state_dict(O.synth_weights(O.dsfvt_param_shapes(cfg), seed=5))
+    rng = random.Random(2)
+    vids = torch.stack([synthetic_latent_video(300 + i) for i in range(batch)])
+    abcs = [sample_abc(spec.stride, 16, 1, rng) for _ in range(batch)]
+    host = [prepare_slices(vids[i], abcs[i], spec.kernel, spec.stride, 1, -1) for i in range(batch)]
+    ws = eng.workspace(batch, (1, 16, 16), (7, 16, 16), train=True)
+    eng.set_inputs(ws, *[torch.stack([h[k] for h in host]) for k in ("context", "slice", "slice_idx", "ignore_mask")])
+    want = eng.forward(ws, train=True).item()
+    ctx_host = ws.context.clone()
+    eng.set_inputs_from_videos(ws, vids.cuda(), torch.tensor(abcs).cuda(), n_prime=1)
+    assert torch.equal(ws.context, ctx_host)
+    got = eng.forward(ws, train=True).item()
+    assert got == want

@@ -55,3 +55,21 @@ def test_product_fails_loudly_without_gpu():
     except _lib.LvtError:
         return
     raise AssertionError("expected LvtError on a machine without a B200")
+
+
+def test_batched_slice_preparation_equals_per_sample_mapper():
+    """prepare_slices_batched (one gather per tensor, any device) == stacking prepare_slices, the restatement of the
+    reference mapper (dataset_mapper.py:113-149), for the three shipped VT configs incl. n_prime = 0 and 5."""
+    import random
+    from lvt_b200.data import prepare_slices, prepare_slices_batched, sample_abc, synthetic_latent_video
+    specs = {"DSFVT": ((7, 1, 1), (16, 1, 1), 16), "DSSVT": ((1, 3, 3), (1, 2, 2), 4), "DSTSVT": ((5, 3, 3), (4, 2, 2), 16)}
+    for name, (kernel, stride, T) in specs.items():
+        for n_prime in (0, 1, 5):
+            rng = random.Random(11)
+            vids = torch.stack([synthetic_latent_video(70 + i, (T, 4, 16, 16)) for i in range(5)])
+            abcs = [sample_abc(stride, T, min(n_prime, stride[0] - 1) if stride[0] > 1 else 0, rng) for _ in range(5)]
+            want = [prepare_slices(vids[i], abcs[i], kernel, stride, n_prime, -1) for i in range(5)]
+            got = prepare_slices_batched(vids, torch.tensor(abcs), kernel, stride, n_prime, -1)
+            for key in ("context", "slice", "slice_idx", "ignore_mask"):
+                w = torch.stack([x[key] for x in want])
+                assert got[key].dtype == w.dtype and torch.equal(got[key], w), (name, n_prime, key)
