@@ -28,6 +28,7 @@ from ...ops import Operand, gemm
 
 LN_EPS = 1e-5
 _SPLIT_ATTN = os.environ.get("LVT_SPLIT_ATTN", "0") == "1"
+_SPLIT_BANK = os.environ.get("LVT_SPLIT_BANK", "0") == "1"  # A/B aid: bank gradient as its own kernel on the side stream
 _ALIGN = 64  # elements; keeps every parameter 256 B (fp32) / 128 B (bf16) aligned for TMA
 
 
@@ -508,7 +509,7 @@ class VTEngine:
         # dS = P * (dO V^T - delta) and dQ = scale * dS K in ONE kernel (dS reaches the second MMA through shared
         # memory; it is still written out for the dK GEMM and the bank gradient)
         # (for block (1,16,16) the same epilogue also accumulates the dt/dh/dw_bank gradients from dS)
-        fused_bank = tuple(s.block) == (1, 16, 16)
+        fused_bank = tuple(s.block) == (1, 16, 16) and not _SPLIT_BANK
         gbanks = (st.gf(prefix + "dt_bank"), st.gf(prefix + "dh_bank"), st.gf(prefix + "dw_bank"))
         gemm(L, L, da, do_k, self._qkv_op(qkv, 2, False, L), dS_k, out_bf16=ws.dS, batch=nz, mode=ops.EPI_DS,
              aux=ly.P, delta=ws.delta, alpha=scale, v=self._qkv_op(qkv, 1, True, L), o2=out_blk(0), o2_n=da,
