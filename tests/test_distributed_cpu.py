@@ -39,6 +39,24 @@ def _worker(rank, world, port, out):
     sigs = [None, None]
     dist.all_gather_object(sigs, sig)
     assert sigs[0] != sigs[1]
+    # latent tree loader: rank r takes indices[r::world] of a shared-seed permutation (distributed_sampler.py:45-56),
+    # so in one pass over 8 videos the two ranks see disjoint halves (every video is filled with its own index)
+    import tempfile
+    from lvt_b200.data import latent_slice_loader, save_latent_video
+    root = os.path.join(tempfile.gettempdir(), f"lvt_gloo_latents_{port}")
+    if rank == 0:
+        for v in range(8):
+            save_latent_video(torch.full((16, 4, 16, 16), v, dtype=torch.int64), root, "train", v)
+    comm.synchronize()
+    it = latent_slice_loader(cfg, os.path.join(root, "train"))
+    seen = set()
+    for _ in range(1):                       # IMS_PER_BATCH 8 / world 2 = 4 samples = this rank's half of the 8 videos
+        b = next(it)
+        assert len(b) == 4
+        seen |= {int(x["slice"].flatten()[0]) for x in b}
+    both = [None, None]
+    dist.all_gather_object(both, sorted(seen))
+    assert len(both[0]) == 4 and len(both[1]) == 4 and not (set(both[0]) & set(both[1])), both
     comm.synchronize()
     out.put((rank, "ok"))
     dist.destroy_process_group()
