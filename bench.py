@@ -12,7 +12,13 @@ predicted code index = B * nc * t*h*w per step (1024 per sample).
   roofline  : whole-step useful FLOPs (81.7 GFLOP/sample) / step time vs the measured
               bf16 peak, plus per-kernel figures (QKV GEMM alone; VQ argmin vs HBM)
   cpu_baseline / --impl reference : the oracle port of the reference's CPU path
-              (oracle/lvt_oracle.py) on the host cores, bounded sample
+              (oracle/lvt_oracle.py) on the host cores, bounded sample (batch 8 slices / 32 frames per step);
+              the line declares the steps / warm-up / batch it actually ran
+  incumbent : the same oracle port run as PyTorch eager ON THE B200 (fp32, TF32, autocast-bf16) -- what a
+              user of the reference would otherwise run on this box (SURVEY 8d last row); measurement only
+  --workload vqvae : PR-DVQVAE2 train step, frames/s (second half of BASELINE.json's metric), also at N > 1
+  N > 1     : adds "strong" (global batch 64 split over the ranks, the reference's semantics,
+              data/build.py:62-74) and "dp_parity" (loss trajectory of N ranks vs 1 GPU on a fixed global batch)
 """
 import argparse
 import json
@@ -104,6 +110,129 @@ def cpu_reference_arm(steps, warmup, batch=8):
                       f"{torch.get_num_threads()} threads", "ms_per_step": dt * 1e3}
 
 
+def cpu_vqvae_arm(steps, warmup, frames=32):
+    """The reference's CPU path for the VQ-VAE half (oracle port): PR-DVQVAE2 fwd + bwd + Adam(0.9, 0.9) + EMA."""
+    import torch
+    from oracle import lvt_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    step = _oracle_vqvae_stepper(O, torch, frames, "cpu")
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    return {"value": frames / dt, "unit": "frames/s", "cores": cores, "kind": "port",
+            "sample": f"{steps} PR-DVQVAE2 train steps (fwd+bwd+Adam+EMA), {frames} frames 64x64, fp32, torch CPU "
+                      f"{torch.get_num_threads()} threads", "ms_per_step": dt * 1e3}
+
+
+def _oracle_vqvae_stepper(O, torch, frames, device):
+    cfg = O.VQVAEConfig()
+    shE, shG = O.vqvae_param_shapes(cfg)
+    sdE = {k: v.to(device).requires_grad_(True) for k, v in O.synth_weights(shE, seed=77).items()}
+    sdG = {k: v.to(device).requires_grad_(True) for k, v in O.synth_weights(shG, seed=78).items()}
+    g = torch.Generator().manual_seed(3)
+    cb = (torch.randn(cfg.codebook_num, cfg.codebook_size, cfg.codebook_dim // cfg.codebook_num, generator=g) * 0.3).to(device)
+    state = {"cb": cb, "rs": torch.full(cb.shape[:2], 5.0, device=device), "rsum": cb.clone(), "t": 0}
+    params = list(sdE.values()) + list(sdG.values())
+    opt = torch.optim.Adam(params, lr=3e-4, betas=(0.9, 0.9))
+    x = torch.rand((frames, 3, 64, 64), generator=g).to(device)
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        losses, aux = O.vqvae_supervised_loss(x, sdE, sdG, state["cb"], state["rs"], state["rsum"], cfg)
+        (losses["loss_reconstruction"] + losses["loss_commitment"]).backward()
+        opt.step()
+        state["cb"], state["rs"], state["rsum"] = aux["codebooks"], aux["running_size"], aux["running_sum"]
+    return step
+
+
+def incumbent_arms(batch, frames, steps=5, warmup=2):
+    """PyTorch eager on this B200 (the oracle port of the reference's modules on `cuda`, torch.optim like the
+    reference's solver/build.py:62-72) in fp32, TF32 and autocast-bf16: the incumbent a user of the reference
+    would run on the same box.  Measurement only -- nothing of it is on the product path."""
+    import torch
+    from oracle import lvt_oracle as O
+    out = {}
+    modes = (("fp32", False, None), ("tf32", True, None), ("bf16_autocast", True, torch.bfloat16))
+    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+
+    def timed(step):
+        for _ in range(warmup):
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps
+
+    try:
+        with torch.device("cuda"):
+            # ---- DSFVT train step, same batch as the headline line
+            cfg = O.VTConfig()
+            sd = {k: v.cuda().requires_grad_(True) for k, v in O.synth_weights(O.dsfvt_param_shapes(cfg), seed=1234).items()}
+            ctx, slc, sidx, ign = (t.cuda() for t in O.synth_vt_batch(batch, seed=5, cfg=cfg))
+            opt = torch.optim.RMSprop(list(sd.values()), lr=2e-5, alpha=0.95, momentum=0.9, eps=1e-8)
+            res = {}
+            for name, tf32, ac in modes:
+                torch.backends.cuda.matmul.allow_tf32 = tf32
+                torch.backends.cudnn.allow_tf32 = tf32
+
+                def step():
+                    opt.zero_grad(set_to_none=True)
+                    with torch.autocast("cuda", dtype=ac, enabled=ac is not None):
+                        loss = O.vt_supervised_loss(ctx, slc, sidx, ign, sd, cfg)
+                    loss.backward()
+                    opt.step()
+                try:
+                    ms = timed(step)
+                    res[name] = {"ms_per_step": ms, "value": batch * TOKENS_PER_SAMPLE / (ms * 1e-3), "unit": "latent tokens/s"}
+                except Exception as ex:
+                    res[name] = {"error": repr(ex)[:200]}
+            out["dsfvt"] = dict(res, batch=batch, note="oracle port of the reference modules (oracle/lvt_oracle.py) as "
+                                "PyTorch eager on cuda:0 + torch.optim.RMSprop; incl. the reference's dense one-hot convs")
+            del sd, opt, ctx, slc, sidx, ign
+            torch.cuda.empty_cache()
+            # ---- PR-DVQVAE2 train step
+            res = {}
+            for name, tf32, ac in modes:
+                torch.backends.cuda.matmul.allow_tf32 = tf32
+                torch.backends.cudnn.allow_tf32 = tf32
+                try:
+                    inner = _oracle_vqvae_stepper(O, torch, frames, "cuda")
+
+                    def step():
+                        with torch.autocast("cuda", dtype=ac, enabled=ac is not None):
+                            inner()
+                    ms = timed(step)
+                    res[name] = {"ms_per_step": ms, "value": frames / (ms * 1e-3), "unit": "frames/s"}
+                except Exception as ex:
+                    res[name] = {"error": repr(ex)[:200]}
+            out["vqvae"] = dict(res, frames=frames, note="oracle port of PR-DVQVAE2 (cuDNN convs, ATen codebook search) "
+                                "as PyTorch eager on cuda:0 + torch.optim.Adam(0.9, 0.9) + EMA")
+            torch.cuda.empty_cache()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+    return out
+
+
+def step_traffic():
+    """DRAM bytes of one whole DSFVT step from the tracked ncu launch list (profiles/*_step_traffic.json, written by
+    tools/launch_table.py --json from `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum` over the step)."""
+    import glob
+    cands = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_step_traffic.json")))
+    if not cands:
+        return None, "no tracked step launch list"
+    d = json.load(open(cands[-1]))
+    return d.get("dram_bytes"), (f"DRAM bytes of one whole step ({d.get('launches')} launches), ncu dram__bytes_read+write, "
+                                f"profiles/{os.path.basename(cands[-1])} <- {d.get('source')}")
+
+
 def vqvae_main(args, rank, world, local_rank):
     """BASELINE.json config 3: PR-DVQVAE2 training on synthetic 16-frame 64x64 clips, data-parallel: 32 clips = 512
     frames per GPU and step (weak scaling), EMA counts / sums and the flat gradient summed over ranks with NCCL
@@ -119,6 +248,8 @@ def vqvae_main(args, rank, world, local_rank):
     _lib.require_device()
     _, _, tf_sust, peak_src = measured_peaks()
     nfr = 512
+    if args.strong:  # the reference's semantics: IMS_PER_BATCH (32 clips = 512 frames) is the GLOBAL batch (data/build.py:62-74)
+        nfr = 512 // max(1, world)
     spec = VQVAESpec(n_layers=2)
     ve = VQVAEEngine(spec)
     gq = torch.Generator().manual_seed(7)
@@ -136,7 +267,11 @@ def vqvae_main(args, rank, world, local_rank):
     vw.x.copy_(host)
     allreduce = (lambda t: dist.all_reduce(t)) if world > 1 else None
     step = GraphedVQVAEStep(ve, vw, world_size=world, allreduce=allreduce)
+    n_before = _lib.launch_count()
     step.capture(warmup=2)
+    # kernels inside the captured graphs, per replayed step (capture = 2 eager warm-up steps + 1 captured step,
+    # each eager step also launching Adam once outside the graphs)
+    step.graph_launches = (_lib.launch_count() - n_before - 2) // 3
 
     def barrier():
         if dist is not None:
@@ -146,6 +281,10 @@ def vqvae_main(args, rank, world, local_rank):
     for _ in range(max(3, args.warmup)):
         step.step()
     barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    n0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
@@ -153,6 +292,8 @@ def vqvae_main(args, rank, world, local_rank):
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1) / args.steps
+    clocks = sampler.stop() if sampler else None
+    launches = (_lib.launch_count() - n0) + step.graph_launches * args.steps
     t0 = time.perf_counter()
     e0.record()
     for _ in range(args.steps):   # end to end: frames from pinned host memory in, the two losses out, every step
@@ -169,19 +310,24 @@ def vqvae_main(args, rank, world, local_rank):
     if rank == 0:
         n_gpus = max(1, world)
         tf = 5.57e9 * nfr / (ms * 1e-3) / 1e12
+        cpu = cpu_vqvae_arm(3, 1, frames=32) if (n_gpus == 1 and not args.quick) else None
         print(json.dumps({
             "metric": "VQ-VAE frames/sec (PR-DVQVAE2 train step)", "value": nfr * n_gpus / (ms * 1e-3), "unit": "frames/s",
             "n_gpus": n_gpus, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "PR-DVQVAE2 training on synthetic 16-frame 64x64 clips, 32 clips (512 frames) per GPU "
-                                   "and step, Adam + EMA codebook, data-parallel", "parallelism": f"dp{n_gpus}",
-                       "l2": "512 frames of activations (> 1 GB) exceed the 126 MB L2; no explicit flush"},
+            "scaling": "strong" if args.strong else "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"PR-DVQVAE2 training on synthetic 16-frame 64x64 clips, {nfr // 16} clips ({nfr} frames) per GPU "
+                                   "and step, Adam + EMA codebook, data-parallel (EMA statistics + flat gradient all-reduced)",
+                       "frames_per_gpu": nfr, "global_frames": nfr * n_gpus, "parallelism": f"dp{n_gpus}",
+                       "l2": f"{nfr} frames of activations ({nfr * 2.3e-3:.2f} GB) exceed the 126 MB L2; no explicit flush"},
             "losses": vw.loss.tolist(),
             "e2e": {"value": nfr * n_gpus / (ms_e2e * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": int(host.numel() * 4),
                     "d2h_bytes_per_step": 8, "ms_per_step": ms_e2e},
+            "gpu_launches": int(launches), "gpu_launches_per_step": int(launches // max(1, args.steps)),
+            "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": tf, "peak": tf_sust, "unit": "TFLOP/s", "frac": tf / tf_sust,
                          "traffic": None, "peak_source": peak_src,
-                         "kernel": "gemm_bf16_kernel implicit-GEMM convolutions: 5.57 GFLOP per frame fwd+bwd / step time, per GPU"}}))
+                         "kernel": "gemm_bf16_kernel implicit-GEMM convolutions: 5.57 GFLOP per frame fwd+bwd / step time, per GPU"},
+            "cpu_baseline": ({k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")} if cpu else None)}))
     if dist is not None:
         dist.destroy_process_group()
 
@@ -199,6 +345,8 @@ def main():
                     help="dsfvt (default, the headline line) | vqvae: PR-DVQVAE2 data-parallel training, frames/s "
                          "(BASELINE.json config 3)")
     ap.add_argument("--quick", action="store_true", help="DSFVT step only: skip the per-kernel figures and the CPU baseline")
+    ap.add_argument("--strong", action="store_true", help="strong scaling: the per-GPU batch is the config's global batch "
+                    "(64 slices / 512 frames) divided by the number of ranks, as the reference does (data/build.py:62-74)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -210,19 +358,37 @@ def main():
               "l2": "working set per step (>5 GB activations + 0.6 GB weights/optimizer state) exceeds the "
                     "126 MB L2; no explicit flush"}
 
+    if args.strong:
+        assert PER_GPU_BATCH % max(1, world) == 0
+        args.batch = PER_GPU_BATCH // max(1, world)
+        config.update(per_gpu_batch=args.batch, global_batch=PER_GPU_BATCH)
     if args.workload == "vqvae" and args.impl == "ours":
         return vqvae_main(args, rank, world, local_rank)
     if args.impl == "reference":
+        # The reference's own CPU implementation of the path on the box's host cores (oracle port, all threads).
+        # A step is a BOUNDED sample of the workload (8 slices / 32 frames instead of 64 / 512: a CPU step of the
+        # full batch takes ~8 s); the line declares exactly what ran.  tokens/s and frames/s are batch-normalised.
         if rank != 0:
             return
-        r = cpu_reference_arm(max(1, min(args.steps, 3)), 1)
-        line = {"impl": "reference", "metric": "latent tokens/sec DSFVT train step", "value": r["value"],
-                "unit": "latent tokens/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        steps_run, warm_run = max(1, min(args.steps, 20)), max(1, min(args.warmup, 5))
+        if args.workload == "vqvae":
+            r = cpu_vqvae_arm(steps_run, warm_run, frames=32)
+            metric, unit, sample_cfg = "VQ-VAE frames/sec (PR-DVQVAE2 train step)", "frames/s", {"frames_per_step": 32}
+            wl = "PR-DVQVAE2 training on synthetic 64x64 frames, Adam + EMA codebook"
+        else:
+            r = cpu_reference_arm(steps_run, warm_run, batch=8)
+            metric, unit, sample_cfg = "latent tokens/sec DSFVT train step", "latent tokens/s", {"per_gpu_batch": 8, "global_batch": 8}
+            wl = config["workload"]
+        ref_config = dict(config, workload=wl, parallelism="cpu", **sample_cfg)
+        ref_config["sample_of"] = ("bounded sample of the GPU arm's workload: same network, same synthetic data generator, "
+                                   "smaller batch per step (the metric is per token / per frame)")
+        line = {"impl": "reference", "metric": metric, "value": r["value"], "unit": unit, "n_gpus": args.gpus,
+                "steps": steps_run, "warmup": warm_run, "steps_requested": args.steps, "warmup_requested": args.warmup,
                 "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f32", "data": "synthetic", "config": config,
+                "dtype": "f32", "data": "synthetic", "config": ref_config,
                 "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
-                "e2e": {"value": r["value"], "unit": "latent tokens/s", "h2d_bytes_per_step": 0,
-                        "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+                "e2e": {"value": r["value"], "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
         print(json.dumps(line))
         return
 
@@ -340,9 +506,44 @@ def main():
 
     # ---------------- per-kernel roofline figures (rank 0, timed alone)
     extra = {}
+    incumbent = None
     if rank == 0 and not args.quick:
         from lvt_b200 import ops
         from lvt_b200.ops import Operand
+        # BlockLocalAttention layer alone: forward + backward of ONE layer (LN, QKV, attention, proj, FFN and
+        # all their gradients) as a CUDA-graph replay on the step's own buffers; 4.832 GFLOP per 256-token sequence.
+        try:
+            ly, prefix = ws.layers[0], "encoder.block_local_attention.0."
+            gb = torch.cuda.CUDAGraph()
+            sidestream = torch.cuda.Stream()
+            sidestream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(sidestream):
+                def bla():
+                    eng._layer_fwd(prefix, ws, ly, ws.x0, ly.y, causal=False)
+                    eng._layer_bwd(prefix, ws, ly, ws.x0, ws.dy, ws.dy_bf16, ws.dy, ws.dy_bf16)
+                    eng._side_join()
+                bla()
+                torch.cuda.synchronize()
+                with torch.cuda.graph(gb):
+                    bla()
+            torch.cuda.current_stream().wait_stream(sidestream)
+            torch.cuda.synchronize()
+            for _ in range(3):
+                gb.replay()
+            e0.record()
+            for _ in range(20):
+                gb.replay()
+            e1.record(); torch.cuda.synchronize()
+            t_bla = e0.elapsed_time(e1) / 20 * 1e-3
+            fl_bla = ws.nseq * 4.832e9
+            extra["bla_block"] = {"bound": "tensor", "achieved": fl_bla / t_bla / 1e12, "peak": tf_sust, "unit": "TFLOP/s",
+                                  "frac": fl_bla / t_bla / 1e12 / tf_sust, "frac_of_burst": fl_bla / t_bla / 1e12 / tf_burst,
+                                  "us": t_bla * 1e6, "sequences": ws.nseq,
+                                  "note": "one BlockLocalAttention layer, forward + backward incl. weight gradients, "
+                                          "4.832 GFLOP per 256-token sequence (SURVEY 8d), CUDA-graph replay; target 0.60"}
+            eng.zero_grad()
+        except Exception as ex:
+            extra["bla_block"] = {"error": repr(ex)[:300]}
         M, d, N = B * 256, 512, 3072
         a = torch.randn(M, d, device="cuda").to(torch.bfloat16)
         w = torch.randn(24, d, 128, device="cuda").to(torch.bfloat16)
@@ -449,9 +650,47 @@ def main():
         except Exception as ex:
             extra["sampler"] = {"error": repr(ex)[:300]}
 
+    # ---------------- N > 1: strong-scaling line (reference semantics) and data-parallel loss parity
+    strong, dp_par = None, None
+    if world > 1 and not args.quick and not args.strong:
+        Bs = PER_GPU_BATCH // world
+        if Bs >= 1 and PER_GPU_BATCH % world == 0:
+            host_s = [t[:Bs].contiguous() for t in host]
+            ws_s = eng.workspace(Bs, (1, 16, 16), ctx_shape, train=True)
+            eng.set_inputs(ws_s, *host_s)
+            st_s = GraphedTrainStep(eng, ws_s, world_size=world, allreduce=allreduce, overlap=not args.no_overlap)
+            st_s.capture(warmup=2)
+            for _ in range(3):
+                st_s.step()
+            barrier()
+            e0.record()
+            for _ in range(args.steps):
+                st_s.step()
+            e1.record()
+            barrier()
+            ts = torch.tensor([e0.elapsed_time(e1) / args.steps], device="cuda")
+            dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+            ms_s = ts.item()
+            strong = {"scaling": "strong", "global_batch": PER_GPU_BATCH, "per_gpu_batch": Bs, "ms_per_step": ms_s,
+                      "value": PER_GPU_BATCH * TOKENS_PER_SAMPLE / (ms_s * 1e-3), "unit": "latent tokens/s",
+                      "note": "the reference divides SOLVER.IMS_PER_BATCH (64) by the world size (data/build.py:62-74)"}
+        try:
+            from lvt_b200.utils.dp_check import run_dp_parity
+            dp_par = run_dp_parity(rank, world, dist)
+        except Exception as ex:
+            dp_par = {"error": repr(ex)[:300]}
+
     if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
         return
+    if not args.quick and n_gpus == 1:
+        try:
+            incumbent = incumbent_arms(B, 512)
+        except Exception as ex:
+            incumbent = {"error": repr(ex)[:300]}
     cpu = cpu_reference_arm(2, 1, batch=8) if not args.quick else {k: None for k in ("value", "unit", "cores", "kind", "sample")}
+    traffic, traffic_note = step_traffic()
     step_flops = USEFUL_FLOP_PER_SAMPLE * B  # per GPU
     achieved = step_flops / (ms * 1e-3) / 1e12
     line = {
@@ -465,13 +704,20 @@ def main():
         "gpu_launches_per_step": int(launches_per_step),
         "clocks": clocks,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": tf_sust, "unit": "TFLOP/s",
-                     "frac": achieved / tf_sust, "traffic": 27.49e9, "peak_source": peak_src,
-                     "traffic_note": "DRAM bytes of one whole step (all launches), ncu dram__bytes_read+write, "
-                                     "profiles/r01f_step_launches.csv (first 433 launches); achieved / peak are per step too",
+                     "frac": achieved / tf_sust, "traffic": traffic, "peak_source": peak_src,
+                     "traffic_note": traffic_note + "; achieved / peak are per step too",
                      "kernel": "gemm_bf16_kernel (tcgen05) — whole-step useful FLOPs / step time, per GPU",
                      "kernels": extra},
         "cpu_baseline": {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")},
     }
+    if args.strong:
+        line["scaling"] = "strong"
+    if incumbent is not None:
+        line["incumbent"] = incumbent
+    if strong is not None:
+        line["strong"] = strong
+    if dp_par is not None:
+        line["dp_parity"] = dp_par
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

@@ -106,7 +106,7 @@ enum {
 
 typedef struct LvtGemm {
   int M, N, K, batch;
-  int splits; /* split-K factor (>1 requires LVT_GEMM_ATOMIC and out_bf16 == NULL) */
+  int splits; /* split-K factor (>1 requires LVT_GEMM_ATOMIC and out_bf16 == NULL); < 0: chosen by the library */
   /* A */
   const void* a; int a_mn_major; int a_cin; int a_zdiv;
   long long a_ld, a_s_blk, a_s_zlo, a_s_zhi;

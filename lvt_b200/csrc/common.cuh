@@ -75,20 +75,36 @@ __device__ __forceinline__ void pdl_prologue() {
 }
 bool lvt_pdl_enabled();
 template <typename... P, typename... A>
-static inline cudaError_t lvt_launch(void (*kern)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
-                                     A&&... args) {
+static inline cudaError_t lvt_launch_cluster(int cluster, void (*kern)(P...), dim3 grid, dim3 block, size_t smem,
+                                             cudaStream_t stream, A&&... args) {
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = grid;
   cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (lvt_pdl_enabled()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  if (cluster > 1) {  // thread-block cluster along x (CTA pairs of the cta_group::2 kernels)
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = cluster;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = lvt_pdl_enabled() ? 1 : 0;
+  cfg.numAttrs = n;
   return cudaLaunchKernelEx(&cfg, kern, static_cast<P>(args)...);
+}
+template <typename... P, typename... A>
+static inline cudaError_t lvt_launch(void (*kern)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                     A&&... args) {
+  return lvt_launch_cluster(1, kern, grid, block, smem, stream, static_cast<A&&>(args)...);
 }
 #endif
 
@@ -299,6 +315,76 @@ LVT_DEVICE_INLINE void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
 }
 LVT_DEVICE_INLINE void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ----------------------------------------------------------------------------------------
+// CTA pairs (thread-block cluster of 2, tcgen05 cta_group::2): one 256-row MMA tile spans the two SMs of a
+// TPC; each CTA stages its own 128 rows of A and HALF of the B tile, so the shared-memory fill traffic per
+// SM drops by a third against two independent 128 x 256 tiles.  The leader (cluster rank 0) owns the
+// "operands landed" barriers and issues the MMAs; completion is multicast to both CTAs' barriers.
+// (PTX forms as in the ISA's tcgen05 / cp.async.bulk.tensor .cta_group::2 sections.)
+// ----------------------------------------------------------------------------------------
+LVT_DEVICE_INLINE uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+LVT_DEVICE_INLINE void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `p` (an address in this CTA's shared memory) inside CTA `rank` of the cluster
+LVT_DEVICE_INLINE uint32_t mapa_u32(const void* p, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
+  return r;
+}
+LVT_DEVICE_INLINE void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load whose completion bytes are credited to the LEADER CTA's mbarrier (same offset, cluster rank 0:
+// bit 24 of a shared::cluster address selects the CTA of a pair); issued by both CTAs of the pair.
+LVT_DEVICE_INLINE void tma_load_5d_2sm(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2,
+                                       int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      :
+      : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0),
+        "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+LVT_DEVICE_INLINE void tmem_alloc_2sm(uint32_t* smem_result, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)),
+               "r"(ncols)
+               : "memory");
+}
+LVT_DEVICE_INLINE void tmem_relinquish_2sm() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+LVT_DEVICE_INLINE void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem of both CTAs] (+)= A[256 x 16: 128 rows per CTA] * B[N x 16: N/2 rows per CTA]; issued by ONE thread of the leader
+LVT_DEVICE_INLINE void umma_bf16_ss_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                        uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n"
+      :
+      : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on the barrier at this offset in BOTH CTAs once all previously issued MMAs of this thread have completed
+LVT_DEVICE_INLINE void umma_commit_2sm(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"((uint16_t)3)
+      : "memory");
 }
 
 // ----------------------------------------------------------------------------------------

@@ -16,6 +16,7 @@
 #include <mutex>
 #include <string>
 #include <string.h>
+#include <stdlib.h>
 
 #include "../../include/lvt_b200.h"
 #include "common.cuh"
@@ -76,14 +77,20 @@ constexpr int ST_REDUCE = 4;  // cp.reduce.async.bulk (+=) instead of a plain st
 constexpr int ST_CLOAD = 8;   // a second tensor with the output's addressing is TMA-loaded per slab:
                               // fp32 residual (added), bf16 ReLU-mask source, or bf16 P of the DS epilogue
 
-template <int BN, int ST, int EK = EK_LINEAR>
+template <int BN, int ST, int EK = EK_LINEAR, int CG = 1>
 struct SmemLayout {
   static constexpr bool SOFTMAX = EK == EK_SOFTMAX_1x16x16 || EK == EK_SOFTMAX_4x8x8;
-  static constexpr int B_TILE_BYTES = BN * BK * 2;
+  static constexpr int B_TILE_BYTES = (BN / CG) * BK * 2;  // a CTA pair (CG == 2) splits the B tile
   static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
   // (the attention-probability kernel has K = da = 128: two k-blocks per tile; three stages keep 1.5 tiles in flight)
-  static constexpr int STAGES = SOFTMAX ? 3 : (BN == 256 ? 4 : 6) - ((ST & ST_CLOAD) ? 1 : 0);
-  static constexpr int STG_PER_WARP = (ST & ST_CLOAD) ? 2 * STG_BYTES_PER_WARP : STG_BYTES_PER_WARP;
+  // CTA pairs double-buffer the TMA-store slab of every epilogue warp (a warp fills slab i+1 while the store of
+  // slab i is still reading shared memory): measured, the single-slab epilogue -- not the main loop, which runs
+  // at ~94 % of the cuBLAS rate with the epilogue switched off -- bounded the large GEMMs.
+  static constexpr int NSLAB = (CG == 2 && (ST & ST_TMA)) ? 2 : 1;
+  static constexpr int STAGES = SOFTMAX ? 3
+                                : CG == 2 ? 6 - ((ST & ST_TMA) ? 1 : 0) - ((ST & ST_CLOAD) ? 1 : 0)
+                                          : (BN == 256 ? 4 : 6) - ((ST & ST_CLOAD) ? 1 : 0);
+  static constexpr int STG_PER_WARP = NSLAB * STG_BYTES_PER_WARP + ((ST & ST_CLOAD) ? STG_BYTES_PER_WARP : 0);
   static constexpr int STG_OFFSET = STAGES * STAGE_BYTES;
   static constexpr int XCHG_OFFSET = STG_OFFSET + NUM_EPI_WARPS * STG_PER_WARP;  // [2][2][128] fp32 row max / row sum
   static constexpr int BAR_OFFSET = XCHG_OFFSET + (SOFTMAX ? 2048 : 0);
@@ -106,7 +113,8 @@ struct TileCoord {
   int m0, n0, z, kb_begin, num_kb;
 };
 
-LVT_DEVICE_INLINE TileCoord decode_tile(const GemmParams& p, int tile, int bn) {
+// (CTA pairs: a tile has cg * BM rows, this CTA owns the BM rows starting at rank * BM)
+LVT_DEVICE_INLINE TileCoord decode_tile(const GemmParams& p, int tile, int bn, int cg = 1, int rank = 0) {
   TileCoord t;
   const int tn = tile % p.tiles_n;
   int r = tile / p.tiles_n;
@@ -114,7 +122,7 @@ LVT_DEVICE_INLINE TileCoord decode_tile(const GemmParams& p, int tile, int bn) {
   r /= p.tiles_m;
   const int split = r % p.splits;
   t.z = r / p.splits;
-  t.m0 = tm * BM;
+  t.m0 = (tm * cg + rank) * BM;
   t.n0 = tn * bn;
   const int kb_total = (p.K + BK - 1) / BK;
   t.kb_begin = split * p.kb_per;
@@ -124,14 +132,20 @@ LVT_DEVICE_INLINE TileCoord decode_tile(const GemmParams& p, int tile, int bn) {
 
 // ST: 0 = staged generic epilogue (residual / mask / atomic / dual output / ragged N),
 //     1 = TMA-store epilogue, bf16 output,  2 = TMA-store epilogue, fp32 output
-template <int BN, bool A_MN, bool B_MN, int EK, int ST>
+// CG == 2: the kernel runs as CTA pairs (cluster of 2, tcgen05 cta_group::2) on 256 x BN tiles; see common.cuh.
+template <int BN, bool A_MN, bool B_MN, int EK, int ST, int CG = 1>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                  const __grid_constant__ CUtensorMap tm_o, const __grid_constant__ CUtensorMap tm_c,
                  const GemmParams p) {
-  using L = SmemLayout<BN, ST, EK>;
+  using L = SmemLayout<BN, ST, EK, CG>;
   constexpr int STAGES = L::STAGES;
   constexpr bool SOFTMAX = L::SOFTMAX;
+  constexpr bool PAIR = CG == 2;
+  static_assert(!PAIR || (EK == EK_LINEAR && BN == 256), "CTA pairs: linear epilogue, 256-wide tiles");
+  const int rank = PAIR ? (int)cluster_ctarank() : 0;        // leader = 0
+  const int cta0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;   // first tile of this CTA (pair)
+  const int cta_stride = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte alignment
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -156,18 +170,24 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     }
     mbar_init(&tmem_full_bar[0], 1);
     mbar_init(&tmem_full_bar[1], 1);
-    mbar_init(&tmem_empty_bar[0], SOFTMAX ? 8 : 4);  // one arrive per epilogue warp working on the buffer
-    mbar_init(&tmem_empty_bar[1], SOFTMAX ? 8 : 4);
+    mbar_init(&tmem_empty_bar[0], SOFTMAX ? 8 : 4 * CG);  // one arrive per epilogue warp working on the buffer
+    mbar_init(&tmem_empty_bar[1], SOFTMAX ? 8 : 4 * CG);  // (pair: the leader's barrier also counts the peer's warps)
 #pragma unroll
     for (int w = 0; w < NUM_EPI_WARPS; ++w) mbar_init(&c_bar[w], 1);
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_ptr_smem, 2 * BN);
-    tmem_relinquish();
+    if constexpr (PAIR) {
+      tmem_alloc_2sm(tmem_ptr_smem, 2 * BN);
+      tmem_relinquish_2sm();
+    } else {
+      tmem_alloc(tmem_ptr_smem, 2 * BN);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync();  // the peer's barriers are initialised before any remote arrive / TMA credit
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   pdl_wait();  // everything above overlapped the previous kernel's tail; its results are visible from here on
@@ -176,8 +196,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     // ------------------------------------------------------------------ TMA producer
     if (elect_one()) {
       uint32_t kiter = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const TileCoord t = decode_tile(p, tile, BN);
+      // pair: both CTAs load (own A rows, own half of the B tile); every byte is credited to the leader's barrier
+      auto load5 = [&](void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3, int c4) {
+        if constexpr (PAIR) tma_load_5d_2sm(dst, m, bar, c0, c1, c2, c3, c4);
+        else tma_load_5d(dst, m, bar, c0, c1, c2, c3, c4);
+      };
+      constexpr int BNL = BN / CG;  // B rows / columns staged by this CTA
+      for (int tile = cta0; tile < p.total_tiles; tile += cta_stride) {
+        TileCoord t = decode_tile(p, tile, BN, CG, rank);
+        t.n0 += rank * BNL;
         const int a_zlo = t.z % p.a_zdiv, a_zhi = t.z / p.a_zdiv;
         const int b_zlo = t.z % p.b_zdiv, b_zhi = t.z / p.b_zdiv;
         if (!(p.a_conv | p.b_conv)) {  // plain operands: keep this loop free of the conv address math
@@ -186,27 +213,27 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             const uint32_t ph = (kiter / STAGES) & 1;
             const int k0 = (t.kb_begin + it) * BK;
             mbar_wait(&empty_bar[s], ph ^ 1);
-            mbar_arrive_expect_tx(&full_bar[s], L::STAGE_BYTES);
+            if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], CG * L::STAGE_BYTES);
             uint8_t* a_dst = smem + s * L::STAGE_BYTES;
             uint8_t* b_dst = a_dst + A_TILE_BYTES;
             if (!A_MN) {
-              tma_load_5d(a_dst, &tm_a, &full_bar[s], k0 % p.a_cin, t.m0, k0 / p.a_cin, a_zlo, a_zhi);
+              load5(a_dst, &tm_a, &full_bar[s], k0 % p.a_cin, t.m0, k0 / p.a_cin, a_zlo, a_zhi);
             } else {
   #pragma unroll
               for (int j = 0; j < BM / 64; ++j) {
                 const int c = t.m0 + 64 * j;
-                tma_load_5d(a_dst + j * (64 * BK * 2), &tm_a, &full_bar[s], c % p.a_cin, k0, c / p.a_cin,
-                            a_zlo, a_zhi);
+                load5(a_dst + j * (64 * BK * 2), &tm_a, &full_bar[s], c % p.a_cin, k0, c / p.a_cin,
+                      a_zlo, a_zhi);
               }
             }
             if (!B_MN) {
-              tma_load_5d(b_dst, &tm_b, &full_bar[s], k0 % p.b_cin, t.n0, k0 / p.b_cin, b_zlo, b_zhi);
+              load5(b_dst, &tm_b, &full_bar[s], k0 % p.b_cin, t.n0, k0 / p.b_cin, b_zlo, b_zhi);
             } else {
   #pragma unroll
-              for (int j = 0; j < BN / 64; ++j) {
+              for (int j = 0; j < BNL / 64; ++j) {
                 const int c = t.n0 + 64 * j;
-                tma_load_5d(b_dst + j * (64 * BK * 2), &tm_b, &full_bar[s], c % p.b_cin, k0, c / p.b_cin,
-                            b_zlo, b_zhi);
+                load5(b_dst + j * (64 * BK * 2), &tm_b, &full_bar[s], c % p.b_cin, k0, c / p.b_cin,
+                      b_zlo, b_zhi);
               }
             }
           }
@@ -217,7 +244,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           const uint32_t ph = (kiter / STAGES) & 1;
           const int k0 = (t.kb_begin + it) * BK;
           mbar_wait(&empty_bar[s], ph ^ 1);
-          mbar_arrive_expect_tx(&full_bar[s], L::STAGE_BYTES);
+          if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], CG * L::STAGE_BYTES);
           uint8_t* a_dst = smem + s * L::STAGE_BYTES;
           uint8_t* b_dst = a_dst + A_TILE_BYTES;
           if (!A_MN) {
@@ -226,34 +253,34 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
               const int tap = k0 / p.cv_C, c0 = k0 - tap * p.cv_C;
               const int hw = p.cv_H * p.cv_W;
               const int img = t.m0 / hw, h0 = (t.m0 - img * hw) / p.cv_W;
-              tma_load_5d(a_dst, &tm_a, &full_bar[s], c0, cv_tap(p.cv_dw_pk, tap), h0 + cv_tap(p.cv_dh_pk, tap), img, cv_tap(p.cv_ph_pk, tap));
+              load5(a_dst, &tm_a, &full_bar[s], c0, cv_tap(p.cv_dw_pk, tap), h0 + cv_tap(p.cv_dh_pk, tap), img, cv_tap(p.cv_ph_pk, tap));
             } else {
-              tma_load_5d(a_dst, &tm_a, &full_bar[s], k0 % p.a_cin, t.m0, k0 / p.a_cin, a_zlo, a_zhi);
+              load5(a_dst, &tm_a, &full_bar[s], k0 % p.a_cin, t.m0, k0 / p.a_cin, a_zlo, a_zhi);
             }
           } else {
 #pragma unroll
             for (int j = 0; j < BM / 64; ++j) {
               const int c = t.m0 + 64 * j;
-              tma_load_5d(a_dst + j * (64 * BK * 2), &tm_a, &full_bar[s], c % p.a_cin, k0, c / p.a_cin,
-                          a_zlo, a_zhi);
+              load5(a_dst + j * (64 * BK * 2), &tm_a, &full_bar[s], c % p.a_cin, k0, c / p.a_cin,
+                    a_zlo, a_zhi);
             }
           }
           if (!B_MN) {
-            tma_load_5d(b_dst, &tm_b, &full_bar[s], k0 % p.b_cin, t.n0, k0 / p.b_cin, b_zlo, b_zhi);
+            load5(b_dst, &tm_b, &full_bar[s], k0 % p.b_cin, t.n0, k0 / p.b_cin, b_zlo, b_zhi);
           } else {
 #pragma unroll
-            for (int j = 0; j < BN / 64; ++j) {
+            for (int j = 0; j < BNL / 64; ++j) {
               const int c = t.n0 + 64 * j;
               if (p.b_conv) {
                 // weight gradient: columns = (tap, channel), k-block = 64 consecutive pixels of one image
                 const int tap = c / p.cv_C, c0 = c - tap * p.cv_C;
                 const int hw = p.cv_H * p.cv_W;
                 const int img = k0 / hw, h0 = (k0 - img * hw) / p.cv_W;
-                tma_load_5d(b_dst + j * (64 * BK * 2), &tm_b, &full_bar[s], c0, cv_tap(p.cv_dw_pk, tap),
-                            h0 + cv_tap(p.cv_dh_pk, tap), img, cv_tap(p.cv_ph_pk, tap));
+                load5(b_dst + j * (64 * BK * 2), &tm_b, &full_bar[s], c0, cv_tap(p.cv_dw_pk, tap),
+                      h0 + cv_tap(p.cv_dh_pk, tap), img, cv_tap(p.cv_ph_pk, tap));
               } else {
-                tma_load_5d(b_dst + j * (64 * BK * 2), &tm_b, &full_bar[s], c % p.b_cin, k0, c / p.b_cin,
-                            b_zlo, b_zhi);
+                load5(b_dst + j * (64 * BK * 2), &tm_b, &full_bar[s], c % p.b_cin, k0, c / p.b_cin,
+                      b_zlo, b_zhi);
               }
             }
           }
@@ -262,13 +289,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (elect_one()) {
-      constexpr uint32_t idesc = umma_idesc(BM, BN, /*bf16*/ 1, A_MN, B_MN);
+    if (rank == 0 && elect_one()) {  // (pair: the leader issues for both CTAs)
+      constexpr uint32_t idesc = umma_idesc(BM * CG, BN, /*bf16*/ 1, A_MN, B_MN);
       uint32_t kiter = 0, titer = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++titer) {
-        const TileCoord t = decode_tile(p, tile, BN);
+      for (int tile = cta0; tile < p.total_tiles; tile += cta_stride, ++titer) {
+        const TileCoord t = decode_tile(p, tile, BN, CG, rank);
         const uint32_t buf = titer & 1;
-        if (tile + (int)gridDim.x >= p.total_tiles) pdl_launch_dependents();  // last tile of this CTA (PDL, see common.cuh)
+        if (tile + cta_stride >= p.total_tiles) pdl_launch_dependents();  // last tile of this CTA (PDL, see common.cuh)
         mbar_wait(&tmem_empty_bar[buf], ((titer >> 1) & 1) ^ 1);  // epilogue drained this buffer
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + buf * BN;
@@ -287,11 +314,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                                         : umma_smem_desc(a_base + k4 * 32, 16, 1024);
             const uint64_t bdesc = B_MN ? umma_smem_desc(b_base + k4 * 2048, 64 * BK * 2, 1024)
                                         : umma_smem_desc(b_base + k4 * 32, 16, 1024);
-            umma_bf16_ss(tmem_d, adesc, bdesc, idesc, (it > 0 || k4 > 0) ? 1u : 0u);
+            if constexpr (PAIR) umma_bf16_ss_2sm(tmem_d, adesc, bdesc, idesc, (it > 0 || k4 > 0) ? 1u : 0u);
+            else umma_bf16_ss(tmem_d, adesc, bdesc, idesc, (it > 0 || k4 > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[s]);  // frees the smem slot when these MMAs retire
+          // frees the smem slot (of both CTAs) when these MMAs retire
+          if constexpr (PAIR) umma_commit_2sm(&empty_bar[s]);
+          else umma_commit(&empty_bar[s]);
         }
-        umma_commit(&tmem_full_bar[buf]);  // accumulator of this tile complete
+        // accumulator of this tile complete (in both CTAs' tensor memory)
+        if constexpr (PAIR) umma_commit_2sm(&tmem_full_bar[buf]);
+        else umma_commit(&tmem_full_bar[buf]);
       }
     }
   } else {
@@ -417,8 +449,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     uint32_t titer = grp;
     uint32_t c_phase = 0;  // parity of this warp's C-slab barrier
     (void)c_phase;
-    for (int tile = blockIdx.x + grp * gridDim.x; tile < p.total_tiles; tile += 2 * gridDim.x, titer += 2) {
-      const TileCoord t = decode_tile(p, tile, BN);
+    uint32_t slab_it = 0;  // running slab count of this warp (selects the slab buffer)
+    (void)slab_it;
+    // (pair: the accumulator-drained arrive goes to the leader's barrier, which the MMA issuer waits on)
+    const uint32_t te_remote[2] = {PAIR ? mapa_u32(&tmem_empty_bar[0], 0) : 0u, PAIR ? mapa_u32(&tmem_empty_bar[1], 0) : 0u};
+    for (int tile = cta0 + grp * cta_stride; tile < p.total_tiles; tile += 2 * cta_stride, titer += 2) {
+      const TileCoord t = decode_tile(p, tile, BN, CG, rank);
       const uint32_t buf = grp;
       const uint32_t taddr = tmem_base + buf * BN + (static_cast<uint32_t>(q * 32) << 16);
       const long long o_zbase = (long long)(t.z / p.o_zdiv) * p.o_s_zhi + (long long)(t.z % p.o_zdiv) * p.o_s_zlo;
@@ -435,8 +471,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         constexpr bool F32 = (ST & ST_F32) != 0;
         constexpr bool CLOAD = (ST & ST_CLOAD) != 0;
         constexpr int SLAB_COLS = F32 ? 32 : 64;  // 128 B per row
-        uint4* const slab = reinterpret_cast<uint4*>(stg);
-        const uint4* const cbuf = reinterpret_cast<const uint4*>(reinterpret_cast<uint8_t*>(stg) + STG_BYTES_PER_WARP);
+        constexpr int NSLAB = L::NSLAB;
+        const uint4* const cbuf = reinterpret_cast<const uint4*>(reinterpret_cast<uint8_t*>(stg) + NSLAB * STG_BYTES_PER_WARP);
         const int o_zlo = t.z % p.o_zdiv, o_zhi = t.z / p.o_zdiv;
         const float alpha = p.alpha;
         const bool relu = (p.flags & LVT_GEMM_RELU) != 0;
@@ -469,7 +505,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             __syncwarp();
             if (lane == 0 && c0 + SLAB_COLS < ncols) issue_c(c0 + SLAB_COLS);
           }
-          if (lane == 0) bulk_wait_group_read<0>();  // previous store of this warp has drained the slab
+          // the store that last used this slab buffer has finished reading it
+          uint4* const slab = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(stg) + (slab_it % NSLAB) * STG_BYTES_PER_WARP);
+          ++slab_it;
+          if (lane == 0) bulk_wait_group_read<NSLAB - 1>();
           __syncwarp();
 #pragma unroll
           for (int h = 0; h < SLAB_COLS / 32; ++h) {
@@ -716,17 +755,22 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       // this warp no longer reads the accumulator buffer
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+      if (lane == 0) {
+        if (PAIR && rank != 0) mbar_arrive_cluster(te_remote[buf]);
+        else mbar_arrive(&tmem_empty_bar[buf]);
+      }
     }
     if ((ST & ST_TMA) != 0 && lane == 0) bulk_wait_group<0>();  // all TMA stores of this warp are complete
     }  // !SOFTMAX
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync();  // no CTA leaves (or frees tensor memory) while its peer may still use its smem / barriers
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 2 * BN);
+    if constexpr (PAIR) tmem_dealloc_2sm(tmem_base, 2 * BN);
+    else tmem_dealloc(tmem_base, 2 * BN);
   }
 }
 
@@ -1273,41 +1317,52 @@ struct Maps {
   CUtensorMap a, b, o, c;
 };
 
-template <int BN, bool A_MN, bool B_MN, int EK, int ST = 0>
+template <int BN, bool A_MN, bool B_MN, int EK, int ST = 0, int CG = 1>
 int launch_gemm(const Maps& m, const GemmParams& p, int grid, cudaStream_t stream) {
-  using L = SmemLayout<BN, ST, EK>;
-  auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, EK, ST>;
+  using L = SmemLayout<BN, ST, EK, CG>;
+  auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, EK, ST, CG>;
   static bool configured = false;
   if (!configured) {
     LVT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     configured = true;
   }
-  LVT_CHECK_CUDA(lvt_launch(kern, dim3(grid), dim3(NUM_THREADS), L::TOTAL, stream, m.a, m.b, m.o, m.c, p));
+  LVT_CHECK_CUDA(lvt_launch_cluster(CG, kern, dim3(grid), dim3(NUM_THREADS), L::TOTAL, stream, m.a, m.b, m.o, m.c, p));
   lvt_count_launch(1);
   return LVT_OK;
 }
 
-template <int BN, int EK, int ST>
+template <int BN, int EK, int ST, int CG = 1>
 int dispatch_major(const Maps& m, const GemmParams& p, int grid, bool a_mn, bool b_mn, cudaStream_t stream) {
-  if (!a_mn && !b_mn) return launch_gemm<BN, false, false, EK, ST>(m, p, grid, stream);
-  if (!a_mn && b_mn) return launch_gemm<BN, false, true, EK, ST>(m, p, grid, stream);
-  if (a_mn && !b_mn) return launch_gemm<BN, true, false, EK, ST>(m, p, grid, stream);
-  return launch_gemm<BN, true, true, EK, ST>(m, p, grid, stream);
+  if (!a_mn && !b_mn) return launch_gemm<BN, false, false, EK, ST, CG>(m, p, grid, stream);
+  if (!a_mn && b_mn) return launch_gemm<BN, false, true, EK, ST, CG>(m, p, grid, stream);
+  if (a_mn && !b_mn) return launch_gemm<BN, true, false, EK, ST, CG>(m, p, grid, stream);
+  return launch_gemm<BN, true, true, EK, ST, CG>(m, p, grid, stream);
 }
 
-template <int BN>
+template <int BN, int CG = 1>
 int dispatch_store(const Maps& m, const GemmParams& p, int grid, bool a_mn, bool b_mn, int st,
                    cudaStream_t stream) {
   switch (st) {
-    case ST_TMA: return dispatch_major<BN, EK_LINEAR, ST_TMA>(m, p, grid, a_mn, b_mn, stream);
-    case ST_TMA | ST_F32: return dispatch_major<BN, EK_LINEAR, ST_TMA | ST_F32>(m, p, grid, a_mn, b_mn, stream);
+    case ST_TMA: return dispatch_major<BN, EK_LINEAR, ST_TMA, CG>(m, p, grid, a_mn, b_mn, stream);
+    case ST_TMA | ST_F32: return dispatch_major<BN, EK_LINEAR, ST_TMA | ST_F32, CG>(m, p, grid, a_mn, b_mn, stream);
     case ST_TMA | ST_F32 | ST_REDUCE:
-      return dispatch_major<BN, EK_LINEAR, ST_TMA | ST_F32 | ST_REDUCE>(m, p, grid, a_mn, b_mn, stream);
+      return dispatch_major<BN, EK_LINEAR, ST_TMA | ST_F32 | ST_REDUCE, CG>(m, p, grid, a_mn, b_mn, stream);
     case ST_TMA | ST_F32 | ST_CLOAD:
-      return dispatch_major<BN, EK_LINEAR, ST_TMA | ST_F32 | ST_CLOAD>(m, p, grid, a_mn, b_mn, stream);
-    case ST_TMA | ST_CLOAD: return dispatch_major<BN, EK_LINEAR, ST_TMA | ST_CLOAD>(m, p, grid, a_mn, b_mn, stream);
-    default: return dispatch_major<BN, EK_LINEAR, 0>(m, p, grid, a_mn, b_mn, stream);
+      return dispatch_major<BN, EK_LINEAR, ST_TMA | ST_F32 | ST_CLOAD, CG>(m, p, grid, a_mn, b_mn, stream);
+    case ST_TMA | ST_CLOAD: return dispatch_major<BN, EK_LINEAR, ST_TMA | ST_CLOAD, CG>(m, p, grid, a_mn, b_mn, stream);
+    default: return dispatch_major<BN, EK_LINEAR, 0, CG>(m, p, grid, a_mn, b_mn, stream);
   }
+}
+
+// CTA pairs (cta_group::2, 256 x 256 tiles) for the linear GEMMs: LVT_GEMM_CG=1 in the environment keeps every
+// GEMM on single-CTA 128 x 256 tiles (A/B timing aid).
+bool pairs_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("LVT_GEMM_CG");
+    v = (e && e[0] == '1') ? 0 : 1;
+  }
+  return v == 1;
 }
 
 int num_sms() {
@@ -1330,8 +1385,10 @@ extern "C" int lvt_gemm_bf16(const LvtGemm* g, void* stream_) {
                 g->M, g->N, g->K, g->batch);
   LVT_CHECK_ARG(g->a && g->b, "lvt_gemm_bf16: null operand");
   LVT_CHECK_ARG(g->out_f32 || g->out_bf16 || (g->mode == LVT_EPI_SOFTMAX && g->v), "lvt_gemm_bf16: no output");
+  // splits < 0: split-K factor chosen here (fills the SMs / SM pairs once, >= 4 k-blocks per split)
+  const bool auto_split = g->splits < 0;
   int splits = g->splits > 0 ? g->splits : 1;
-  LVT_CHECK_ARG(splits == 1 || ((g->flags & LVT_GEMM_ATOMIC) && !g->out_bf16 && g->mode == LVT_EPI_LINEAR),
+  LVT_CHECK_ARG((splits == 1 && !auto_split) || ((g->flags & LVT_GEMM_ATOMIC) && !g->out_bf16 && g->mode == LVT_EPI_LINEAR),
                 "lvt_gemm_bf16: split-K needs LVT_GEMM_ATOMIC fp32 output only");
   LVT_CHECK_ARG(!(g->flags & LVT_GEMM_ATOMIC) || (g->out_f32 && !g->res),
                 "lvt_gemm_bf16: atomic output needs out_f32 and no residual");
@@ -1380,20 +1437,33 @@ extern "C" int lvt_gemm_bf16(const LvtGemm* g, void* stream_) {
     bn = (g->N % 256 == 0) ? 256 : 128;
     // latency-bound small problems (a few output tiles, e.g. the M = 256 GEMMs of the sampler): 128-wide tiles
     // give twice the CTAs and six instead of four k-blocks in flight per CTA
-    if (bn == 256 && g->N % 128 == 0 &&
+    if (bn == 256 && g->N % 128 == 0 && !auto_split &&
         (long long)((g->M + BM - 1) / BM) * (g->N / 256) * g->batch * (g->splits > 0 ? g->splits : 1) <= 37)
       bn = 128;
   }
+
+  // CTA pairs on 256 x 256 tiles when the problem has at least one full pair tile per pair of SMs' worth of
+  // rows (M >= 256) -- every linear-epilogue shape of the train step; the small M = 256 sampler GEMMs went to
+  // 128-wide single-CTA tiles above
+  const int cg = (ek == EK_LINEAR && bn == 256 && g->M >= 2 * BM && pairs_enabled()) ? 2 : 1;
 
   GemmParams p;
   memset(&p, 0, sizeof(p));
   p.M = g->M; p.N = g->N; p.K = g->K; p.batch = g->batch;
   const int kb_total = (g->K + BK - 1) / BK;
+  if (auto_split) {
+    // never more tiles than CTAs (pairs): the kernel is persistent, one tile too many doubles the time of one SM
+    const long long tiles = (long long)((g->M + BM * cg - 1) / (BM * cg)) * ((g->N + bn - 1) / bn) * g->batch;
+    const long long slots = num_sms() / cg;
+    long long sp = slots / (tiles > 0 ? tiles : 1);
+    if (sp > g->K / 256) sp = g->K / 256;
+    splits = (int)(sp < 1 ? 1 : sp);
+  }
   if (splits > kb_total) splits = kb_total;
   p.kb_per = (kb_total + splits - 1) / splits;
   splits = (kb_total + p.kb_per - 1) / p.kb_per;  // no empty split
   p.splits = splits;
-  p.tiles_m = (g->M + BM - 1) / BM;
+  p.tiles_m = (g->M + BM * cg - 1) / (BM * cg);
   p.tiles_n = (g->N + bn - 1) / bn;
   const long long total = (long long)p.tiles_m * p.tiles_n * splits * g->batch;
   LVT_CHECK_ARG(total < (1ll << 30), "lvt_gemm_bf16: too many tiles");
@@ -1456,7 +1526,7 @@ extern "C" int lvt_gemm_bf16(const LvtGemm* g, void* stream_) {
   if (!g->b_conv) {
     rc = g->b_mn_major
              ? make_operand_map(&m.b, g->b, g->N, g->K, g->b_cin, g->b_ld, g->b_s_blk, g->batch, g->b_zdiv, g->b_s_zlo, g->b_s_zhi, BK)
-             : make_operand_map(&m.b, g->b, g->K, g->N, g->b_cin, g->b_ld, g->b_s_blk, g->batch, g->b_zdiv, g->b_s_zlo, g->b_s_zhi, bn);
+             : make_operand_map(&m.b, g->b, g->K, g->N, g->b_cin, g->b_ld, g->b_s_blk, g->batch, g->b_zdiv, g->b_s_zlo, g->b_s_zhi, bn / cg);
     if (rc) return rc;
   }
 
@@ -1498,7 +1568,8 @@ extern "C" int lvt_gemm_bf16(const LvtGemm* g, void* stream_) {
 
   LVT_CHECK_ARG(!(g->flags & LVT_GEMM_ROWDOT) || st == (ST_TMA | ST_CLOAD),
                 "lvt_gemm_bf16: ROWDOT needs 128-byte aligned bf16 output / aux rows (TMA epilogue)");
-  const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+  const int grid = cg == 2 ? 2 * (p.total_tiles < num_sms() / 2 ? p.total_tiles : num_sms() / 2)
+                           : (p.total_tiles < num_sms() ? p.total_tiles : num_sms());
   const bool amn = g->a_mn_major != 0, bmn = g->b_mn_major != 0;
   if ((ek == EK_SOFTMAX_1x16x16 || ek == EK_SOFTMAX_4x8x8) && g->out_bf16) {
     rc = make_operand_map(&m.o, g->out_bf16, g->N, g->M, g->o_cin, g->o_ld, g->o_s_blk, g->batch, g->o_zdiv,
@@ -1551,6 +1622,7 @@ extern "C" int lvt_gemm_bf16(const LvtGemm* g, void* stream_) {
     if (bn == 256) return launch_gemm<256, false, false, EK_DS>(m, p, grid, stream);
     return launch_gemm<128, false, false, EK_DS>(m, p, grid, stream);
   }
+  if (cg == 2) return dispatch_store<256, 2>(m, p, grid, amn, bmn, st, stream);
   if (bn == 256) return dispatch_store<256>(m, p, grid, amn, bmn, st, stream);
   return dispatch_store<128>(m, p, grid, amn, bmn, st, stream);
 }

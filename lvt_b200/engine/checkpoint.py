@@ -32,7 +32,23 @@ class Checkpointer:
             return {}
         data = torch.load(path, map_location="cpu")
         state = data.pop("model") if "model" in data else data
-        self.model.load_state_dict(state, strict=False)
+        res = self.model.load_state_dict(state, strict=False)
+        missing = list(getattr(res, "missing_keys", []) or [])
+        unexpected = list(getattr(res, "unexpected_keys", []) or [])
+        if missing or unexpected:  # fvcore logs both lists; a silent no-op load is the failure to avoid
+            import logging
+            log = logging.getLogger("lvt_b200.checkpoint")
+            if missing:
+                log.warning("checkpoint %s: keys missing in the file: %s", path, missing)
+            if unexpected:
+                log.warning("checkpoint %s: keys not used by the model: %s", path, unexpected)
+            if state and len(unexpected) == len(state):
+                raise KeyError(f"checkpoint {path}: none of its {len(state)} keys matches the model")
+        # the bf16 / packed weight shadows of the owning engine are stale now (sub-module checkpointers wrap
+        # ResEncoder / ResDecoder / DVQEmbedding, which share their parent model's engine)
+        eng = getattr(self.model, "engine", None)
+        if eng is not None and hasattr(eng, "shadows_fresh"):
+            eng.shadows_fresh = False
         return data
 
     def resume_or_load(self, path, resume=True):

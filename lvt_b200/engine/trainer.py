@@ -82,7 +82,7 @@ class Trainer:
     @classmethod
     def build_model(cls, cfg):
         model = build_model(cfg)
-        logging.getLogger(__name__).info("Model:\\n{}".format(type(model).__name__))
+        logging.getLogger(__name__).info("Model:\n{}".format(type(model).__name__))
         return model
 
     def resume_or_load(self, resume=True):
@@ -107,7 +107,7 @@ class Trainer:
         if (self.iter + 1) % 20 == 0 or self.iter == self.start_iter:   # PeriodicWriter period (host sync)
             vals = {k: float(v.detach()) for k, v in loss_dict.items()}
             if not all(map(lambda x: x == x and abs(x) != float("inf"), vals.values())):
-                raise FloatingPointError(f"Loss became infinite or NaN at iteration={self.iter}!\\nloss_dict = {vals}")
+                raise FloatingPointError(f"Loss became infinite or NaN at iteration={self.iter}!\nloss_dict = {vals}")
             self.storage.put_scalars(data_time=data_time, total_loss=sum(vals.values()), **vals)
             if comm.is_main_process():
                 logging.getLogger(__name__).info("iter %d  %s", self.iter,

@@ -390,12 +390,9 @@ class VTEngine:
 
     @staticmethod
     def _splits(m, n, k):
-        """split-K factor of a weight-gradient GEMM: fill the 148 SMs once with 128 x (256|128) tiles,
-        keeping at least 4 k-blocks of 64 per tile."""
-        bn = 256 if n % 256 == 0 else 128
-        tiles = ((m + 127) // 128) * ((n + bn - 1) // bn)
-        # never more than 148 CTAs: the kernel is persistent, a 149th tile would double the time of one SM
-        return int(max(1, min(k // 256, 148 // tiles)))
+        """split-K factor of a weight-gradient GEMM: chosen by the library (fills the SMs / SM pairs once with
+        its tile shape, at least 4 k-blocks of 64 per split; lvt_gemm_bf16, splits < 0)."""
+        return -1
 
     def _wgrad(self, dy_ptr, ld_dy, x_ptr, ld_x, out: Operand, n_out, n_in, tokens):
         """dW[n_out, n_in] += dY[tokens, n_out]^T X[tokens, n_in] (split-K, fp32 red.add)."""
@@ -486,6 +483,10 @@ class VTEngine:
             self._wgrad(ws.dz1.data_ptr(), d, ly.ln2.data_ptr(), d, Operand(st.gf(prefix + "ffn.1.weight"), d), d, d, M)
         gemm(M, d, d, Operand(ws.dz1.data_ptr(), d), Operand(st.pb(prefix + "ffn.1.weight"), d, mn_major=True),
              Operand(ws.dln_bf16.data_ptr(), d), out_bf16=ws.dln_bf16)
+        if dyb == ws.dh_bf16.data_ptr():
+            # last encoder layer: the incoming gradient lives in ws.dh / ws.dh_bf16, which the LayerNorm backward
+            # below overwrites -- the side-stream ffn.3 bias / weight gradients must have read it first
+            torch.cuda.current_stream().wait_event(ev_dy_read)
         self._ln_bwd(ws.dln_bf16, ly.h, ly.mean2, ly.rstd2, st.pf(prefix + "ffn.0.weight"), dy, ws.dh, ws.dh_bf16,
                      st.gf(prefix + "ffn.0.weight"), st.gf(prefix + "ffn.0.bias"), M)
         # ---- attention output projection
@@ -728,6 +729,13 @@ class VTEngine:
         self.opt_s2 = torch.zeros_like(self.store.master)
 
     def optimizer_step(self, grad_scale=1.0):
+        self.optimizer_kernel(grad_scale)
+        self._refresh_special()
+        self.shadows_fresh = True
+
+    def optimizer_kernel(self, grad_scale=1.0):
+        """The fused multi-tensor update alone.  lr and Adam's bias corrections are passed BY VALUE, so this launch
+        must stay outside CUDA graphs (a captured launch would freeze the schedule and the step count)."""
         o, st = self.opt, self.store
         o["step"] += 1
         if o["name"] == "rmsprop":
@@ -738,8 +746,6 @@ class VTEngine:
             check(self.lib.lvt_adam_step(ptr(st.master), ptr(st.grad), ptr(self.opt_s1), ptr(self.opt_s2),
                                          ptr(st.shadow), st.numel, o["lr"], o["betas"][0], o["betas"][1], o["eps"],
                                          o["step"], grad_scale, stream_ptr()), "lvt_adam_step")
-        self._refresh_special()
-        self.shadows_fresh = True
 
     def train_step(self, ws: VTWorkspace, grad_hook=None, grad_scale=1.0):
         """forward + backward + optimizer on the batch staged in `ws` (trainer.py:79-87)."""
@@ -782,7 +788,22 @@ class GraphedTrainStep:
         self.engine.backward_decoder(self.ws)
 
     def _opt(self):
-        self.engine.optimizer_step(grad_scale=1.0 / self.world_size)
+        """eager: lr / bias corrections are by-value kernel arguments (LR schedules, Adam step count)"""
+        self.engine.optimizer_kernel(grad_scale=1.0 / self.world_size)
+
+    def _refresh(self):
+        self.engine._refresh_special()
+        self.engine.shadows_fresh = True
+
+    def _snapshot(self):
+        eng = self.engine
+        return (eng.store.master.clone(), eng.opt_s1.clone(), eng.opt_s2.clone(), eng.opt["step"])
+
+    def _restore(self, snap):
+        eng = self.engine
+        eng.store.master.copy_(snap[0]); eng.opt_s1.copy_(snap[1]); eng.opt_s2.copy_(snap[2])
+        eng.opt["step"] = snap[3]
+        eng.refresh_shadows()
 
     def _reduce_overlapped(self, run_encoder_backward):
         """bucket 0 (decoder + predictor gradients) on the communication stream during the encoder backward"""
@@ -802,7 +823,11 @@ class GraphedTrainStep:
         main.wait_stream(self.comm)
 
     def capture(self, warmup=2):
+        """Warm-up (kernel attributes, TMA maps, NCCL channels) runs real steps on whatever is staged in the
+        workspace; parameters and optimizer state are snapshotted before and restored after, so capturing
+        does not train."""
         eng = self.engine
+        snap = self._snapshot()
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -813,7 +838,10 @@ class GraphedTrainStep:
                 else:
                     self._fwd_bwd()
                 self._opt()
+                self._refresh()
         torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self._restore(snap)
         torch.cuda.synchronize()
         n0 = _lib.launch_count()
         self.g_fb = torch.cuda.CUDAGraph()
@@ -826,15 +854,16 @@ class GraphedTrainStep:
             self.g_enc = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.g_enc):
                 eng.backward_encoder(self.ws)
-        self.g_opt = torch.cuda.CUDAGraph()
+        self.g_opt = torch.cuda.CUDAGraph()  # weight re-layouts after the (eager) optimizer kernel
         with torch.cuda.graph(self.g_opt):
-            self._opt()
-        self.launches_per_step = _lib.launch_count() - n0
+            self._refresh()
+        self.launches_per_step = _lib.launch_count() - n0 + 1  # + the eager optimizer kernel
         torch.cuda.synchronize()
 
     def step(self):
         self.g_fb.replay()
         if self.allreduce is not None:
             self._reduce_overlapped(self.g_enc.replay)
+        self._opt()
         self.g_opt.replay()
         return self.ws.loss

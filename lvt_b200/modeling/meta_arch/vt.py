@@ -53,8 +53,10 @@ class VideoTransformerModel(nn.Module):
     @torch.no_grad()
     def init_weights(module, init_type="normal", slope=0.2):
         """vt.py:34-57: the reference re-initialises modules whose class name contains Conv / Linear
-        (weights `normal` or `xavier_uniform`, biases 0) and then calls init_weights of children that
-        define it (MultiHeadAttention: xavier_normal_ on w_q/w_k/w_v/proj).  Same rule, by parameter name."""
+        (weights `normal` or `xavier_uniform`, biases 0).  Its second loop only visits the DIRECT children of
+        VideoTransformer (encoder, decoder, ch_predictor), none of which defines init_weights, so
+        MultiHeadAttention.init_weights is never re-run: w_q/w_k/w_v keep the xavier_normal_ draw of their
+        constructor (vt_attention.py:106-112) and mha.proj.weight (an nn.Linear) keeps the INIT_TYPE init."""
         conv_or_linear = ("encoder.conv.", "encoder.linear_projector.", "decoder.conv.conv.", "decoder.linear_projector.",
                           ".mha.proj.", ".ffn.1.", ".ffn.3.", "ch_predictor.U.", "ch_predictor.P.")
         for name, p in module.named_parameters():
@@ -70,9 +72,6 @@ class VideoTransformerModel(nn.Module):
                     raise ValueError
             elif name.endswith("bias"):
                 p.zero_()
-        for name, p in module.named_parameters():
-            if ".mha.w_" in name or name.endswith("mha.proj.weight"):
-                nn.init.xavier_normal_(p)
         eng = module.engine
         eng.store.p["decoder.conv.conv.weight"][:, :, -1, -1, 1:] = 0
         eng.shadows_fresh = False

@@ -255,9 +255,9 @@ class VQVAEEngine:
 
     @staticmethod
     def _splits(m, n, k):
-        bn = 256 if n % 256 == 0 else 128
-        tiles = ((m + 127) // 128) * ((n + bn - 1) // bn)
-        return int(max(1, min(k // 256, (148 + tiles // 2) // tiles)))
+        """split-K factor of a weight-gradient GEMM: chosen by the library (fills the SMs / SM pairs once with
+        its tile shape, at least 4 k-blocks of 64 per split; lvt_gemm_bf16, splits < 0)."""
+        return -1
 
     def _wgrad_conv(self, dy, co, x, C, n, taps, grad, P=1, s_phase=0):
         """grad[co][tap*C + c] += sum_m dy[m, co] * x[m + tap, c]."""
@@ -539,12 +539,24 @@ class GraphedVQVAEStep:
         self._refresh()
 
     def capture(self, warmup=2):
+        """The eager warm-up runs real steps; parameters, Adam state and the EMA codebook state are restored
+        afterwards so that capturing does not train."""
+        eng = self.engine
+        snap = [t.clone() for t in (eng.store.master, eng.opt_m, eng.opt_v, eng.codebook, eng.running_size,
+                                    eng.running_sum)]
+        step0 = eng.opt["step"]
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(warmup):  # eager warm-up: kernel attributes, TMA maps
                 self._eager()
         torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        for dst, src in zip((eng.store.master, eng.opt_m, eng.opt_v, eng.codebook, eng.running_size,
+                             eng.running_sum), snap):
+            dst.copy_(src)
+        eng.opt["step"] = step0
+        eng.refresh_shadows()
         torch.cuda.synchronize()
         segs = [self._seg_a, self._seg_b] if self.allreduce is not None else [lambda: (self._seg_a(), self._seg_b())]
         self.graphs = []

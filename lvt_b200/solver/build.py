@@ -80,10 +80,13 @@ class _Scheduler:
     def get_last_lr(self):
         return [g["lr"] for g in self.optimizer.param_groups]
 
+    def _apply(self, it):
+        for g, base in zip(self.optimizer.param_groups, self.base_lrs):
+            g["lr"] = base * self.factor(it)
+
     def step(self):
         self.last_epoch += 1
-        for g, base in zip(self.optimizer.param_groups, self.base_lrs):
-            g["lr"] = base * self.factor(self.last_epoch)
+        self._apply(self.last_epoch)
 
 
 def _warmup(method, it, warmup_iters, warmup_factor):
@@ -99,6 +102,7 @@ class WarmupMultiStepLR(_Scheduler):
     def __init__(self, optimizer, milestones, gamma, warmup_factor, warmup_iters, warmup_method):
         super().__init__(optimizer)
         self.m, self.gamma, self.wf, self.wi, self.wm = list(milestones), gamma, warmup_factor, warmup_iters, warmup_method
+        self._apply(0)  # torch's _LRScheduler does an initial step: iteration 0 runs at base_lr * factor(0)
 
     def factor(self, it):
         return _warmup(self.wm, it, self.wi, self.wf) * self.gamma ** bisect_right(self.m, it)
@@ -108,6 +112,7 @@ class WarmupCosineLR(_Scheduler):
     def __init__(self, optimizer, max_iters, warmup_factor, warmup_iters, warmup_method):
         super().__init__(optimizer)
         self.max_iters, self.wf, self.wi, self.wm = max_iters, warmup_factor, warmup_iters, warmup_method
+        self._apply(0)
 
     def factor(self, it):
         return _warmup(self.wm, it, self.wi, self.wf) * 0.5 * (1.0 + math.cos(math.pi * it / self.max_iters))

@@ -1,8 +1,9 @@
 """Summarise an `ncu --metrics gpu__time_duration.sum[,dram__bytes_read.sum,dram__bytes_write.sum] --csv` launch
 list per kernel: time share, launches, average duration and (when captured) DRAM traffic."""
-import collections, csv, re, sys
+import collections, csv, json, os, re, sys
 path = sys.argv[1]
-top = int(sys.argv[2]) if len(sys.argv) > 2 else 25
+top = int(sys.argv[2]) if len(sys.argv) > 2 and not sys.argv[2].startswith('--') else 25
+json_out = sys.argv[sys.argv.index('--json') + 1] if '--json' in sys.argv else None  # totals for bench.py's roofline.traffic
 with open(path) as f:
     lines = [l for l in f if not l.startswith('==')]
 SCALE = {'ns': 1e-3, 'us': 1.0, 'usecond': 1.0, 'ms': 1e3, 'msecond': 1e3, 'nsecond': 1e-3, 'second': 1e6,
@@ -27,3 +28,7 @@ for k, (n, t, b) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:top]:
     print(f"{t/1000:8.3f} ms {100*t/tot_t:5.1f}%  n={len(n):4d} avg {t/len(n):8.1f} us  {k}{extra}")
 print(f"total {tot_t/1000:.3f} ms over {len(ids)} launches" + (f"; DRAM traffic {tot_b/1e9:.2f} GB = {tot_b/1e3/tot_t:.0f} GB/s "
       f"averaged over the summed kernel time" if tot_b else ""))
+if json_out:
+    json.dump({"source": os.path.basename(path), "launches": len(ids), "dram_bytes": tot_b, "kernel_time_us": tot_t,
+               "note": "sum over all launches of one DSFVT train step (ncu, cold-cache, serialised): "
+                       "dram__bytes_read.sum + dram__bytes_write.sum"}, open(json_out, "w"), indent=1)
