@@ -172,11 +172,14 @@ def incumbent_arms(batch, frames, steps=5, warmup=2):
         return e0.elapsed_time(e1) / steps
 
     try:
+        # synthetic weights / inputs are built on the host (the oracle's generators mix numpy and torch), then moved
+        cfg = O.VTConfig()
+        sd_host = O.synth_weights(O.dsfvt_param_shapes(cfg), seed=1234)
+        batch_host = O.synth_vt_batch(batch, seed=5, cfg=cfg)
         with torch.device("cuda"):
             # ---- DSFVT train step, same batch as the headline line
-            cfg = O.VTConfig()
-            sd = {k: v.cuda().requires_grad_(True) for k, v in O.synth_weights(O.dsfvt_param_shapes(cfg), seed=1234).items()}
-            ctx, slc, sidx, ign = (t.cuda() for t in O.synth_vt_batch(batch, seed=5, cfg=cfg))
+            sd = {k: v.cuda().requires_grad_(True) for k, v in sd_host.items()}
+            ctx, slc, sidx, ign = (t.cuda() for t in batch_host)
             opt = torch.optim.RMSprop(list(sd.values()), lr=2e-5, alpha=0.95, momentum=0.9, eps=1e-8)
             res = {}
             for name, tf32, ac in modes:
@@ -204,7 +207,8 @@ def incumbent_arms(batch, frames, steps=5, warmup=2):
                 torch.backends.cuda.matmul.allow_tf32 = tf32
                 torch.backends.cudnn.allow_tf32 = tf32
                 try:
-                    inner = _oracle_vqvae_stepper(O, torch, frames, "cuda")
+                    with torch.device("cpu"):
+                        inner = _oracle_vqvae_stepper(O, torch, frames, "cuda")
 
                     def step():
                         with torch.autocast("cuda", dtype=ac, enabled=ac is not None):

@@ -190,8 +190,99 @@ def golden_vq_only():
     print("vq ok")
 
 
+SUBSCALE = {"DSSVT": ((1, 3, 3), (1, 2, 2), (4, 16, 16)), "DSTSVT": ((5, 3, 3), (4, 2, 2), (16, 16, 16))}
+
+
+def golden_subscale():
+    """configs/vt/DSSVT.yaml and DSTSVT.yaml with 2+2 layers (spatially strided one-hot conv, t > 1 masked
+    conv, (4,8,8) blocks with a three-axis bias, partially true ignore mask): loss, sub-sampled logits and
+    gradient checksums -- pins the oracle paths the DSFVT fixtures do not reach."""
+    ref_shim.install()
+    from vidgen.modeling.meta_arch import build_model
+    from vidgen.utils.events import EventStorage
+    layers, batch = 2, 2
+    blocks = str(tuple([(4, 8, 8)] * layers))
+    heads = str(tuple([8] * layers))
+    for name, (kernel, stride, vshape) in SUBSCALE.items():
+        cfg = ref_shim.reference_cfg(f"configs/vt/{name}.yaml", [
+            "MODEL.AUTOREGRESSIVE.VT.BLOCKS_E", blocks, "MODEL.AUTOREGRESSIVE.VT.N_HEAD_E", heads,
+            "MODEL.AUTOREGRESSIVE.VT.BLOCKS_D", blocks, "MODEL.AUTOREGRESSIVE.VT.N_HEAD_D", heads])
+        torch.manual_seed(0)
+        model = build_model(cfg)
+        ocfg = O.VTConfig(kernel=kernel, stride=stride, video_shape=vshape, blocks_e=tuple([(4, 8, 8)] * layers),
+                          heads_e=tuple([8] * layers), blocks_d=tuple([(4, 8, 8)] * layers), heads_d=tuple([8] * layers))
+        weights = O.synth_weights(O.dsfvt_param_shapes(ocfg), seed=4321)
+        load_into(model.model, weights)
+        model.train()
+        context, slc, slice_idx, ignore = O.synth_vt_batch(batch, seed=5, cfg=ocfg)
+        data = [{"context": context[i], "slice": slc[i], "slice_idx": slice_idx[i], "ignore_mask": ignore[i]}
+                for i in range(batch)]
+        with EventStorage(0):
+            loss = model(data, mode="supervised")["loss_cross_entropy"]
+        loss.backward()
+        with torch.no_grad():
+            logits = torch.stack(model.model(context, slc, slice_idx))  # nc, b, nv, t, h, w
+        grads = {k: p.grad for k, p in model.model.named_parameters()}
+        fix = {"loss": loss.detach().numpy(), "logits_sub": logits[:, :, ::7, :, ::3, ::5].numpy(),
+               "logits_sum": logits.double().sum().numpy(), "slice_idx": slice_idx.numpy(),
+               "context_sum": context.sum().numpy(), "ignore_sum": ignore.sum().numpy()}
+        for k in ("encoder.conv.weight", "encoder.slice_embedding.weight", "decoder.conv.conv.weight",
+                  "decoder.ch_embedder.2.weight", "ch_predictor.U.3.weight",
+                  "decoder.block_local_attention.1.dt_bank", "decoder.block_local_attention.0.dh_bank",
+                  "encoder.block_local_attention.1.dw_bank", "encoder.block_local_attention.0.mha.w_q",
+                  "decoder.block_local_attention.1.ffn.3.weight", "decoder.linear_projector.weight"):
+            g = grads[k]
+            fix["gnorm:" + k] = g.double().norm().numpy()
+            fix["gsub:" + k] = g.reshape(-1)[::max(1, g.numel() // 64)][:64].numpy()
+        np.savez_compressed(os.path.join(OUT, name.lower() + "_l2.npz"), **fix)
+        print(name, "loss", float(loss))
+
+
+def golden_kdvqvae():
+    """K-DVQVAE (configs/vqvae/K-DVQVAE.yaml, N_LAYERS 4): inference latents / reconstruction and one
+    supervised step's losses (spread codebook)."""
+    ref_shim.install()
+    from vidgen.modeling.meta_arch import build_model
+    cfg = ref_shim.reference_cfg("configs/vqvae/K-DVQVAE.yaml")
+    torch.manual_seed(0)
+    model = build_model(cfg)
+    ocfg = O.VQVAEConfig(n_layers=4)
+    eshape, gshape = O.vqvae_param_shapes(ocfg)
+    we, wg = O.synth_weights(eshape, seed=21), O.synth_weights(gshape, seed=22)
+    load_into(model.encoder, we)
+    load_into(model.generator, wg)
+    x = torch.rand((4, 3, 64, 64), generator=torch.Generator().manual_seed(4321))
+    with torch.no_grad():
+        z_std = model.encoder((x - 0.5) / 0.5).std()
+    cb = torch.randn((4, 512, 64), generator=torch.Generator().manual_seed(6)) * z_std
+    fix = {"spread_std": z_std.numpy()}
+    for g in range(4):
+        ve = model.codebook.ve[g]
+        ve.embedding.weight.data.copy_(cb[g])
+        ve.running_sum = cb[g].clone()
+        ve.running_size.zero_()
+    model.eval()
+    with torch.no_grad():
+        out = model([{"image": x[i]} for i in range(x.shape[0])])
+    fix["latent"] = torch.stack([o["latent"] for o in out]).numpy()
+    fix["recon_sub"] = torch.stack([o["reconstruction"] for o in out])[:, :, ::5, ::7].numpy()
+    model.train()
+    model.zero_grad()
+    losses = model([{"image": x[i]} for i in range(x.shape[0])], mode="supervised")
+    sum(losses.values()).backward()
+    fix["loss_reconstruction"] = losses["loss_reconstruction"].detach().numpy()
+    fix["loss_commitment"] = losses["loss_commitment"].detach().numpy()
+    for k in ("layers.0.weight", "layers.8.block.1.weight"):
+        fix[f"gE:{k}"] = dict(model.encoder.named_parameters())[k].grad.double().norm().numpy()
+    for k in ("layers.0.weight", "layers.4.block.3.weight", "layers.8.weight"):
+        fix[f"gG:{k}"] = dict(model.generator.named_parameters())[k].grad.double().norm().numpy()
+    np.savez_compressed(os.path.join(OUT, "kdvqvae.npz"), **fix)
+    print("kdvqvae ok")
+
+
 if __name__ == "__main__":
     assert ref_shim.available(), "run in the authoring container (needs /root/reference)"
-    which = sys.argv[1:] or ["vq", "vqvae", "mapper", "dsfvt"]
+    which = sys.argv[1:] or ["vq", "vqvae", "kdvqvae", "mapper", "dsfvt", "subscale"]
     for w in which:
-        {"vq": golden_vq_only, "vqvae": golden_vqvae, "mapper": golden_mapper, "dsfvt": golden_dsfvt}[w]()
+        {"vq": golden_vq_only, "vqvae": golden_vqvae, "kdvqvae": golden_kdvqvae, "mapper": golden_mapper,
+         "dsfvt": golden_dsfvt, "subscale": golden_subscale}[w]()

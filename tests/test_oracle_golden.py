@@ -126,3 +126,59 @@ def test_dsfvt_oracle_matches_reference(tag, layers, batch):
             assert np.allclose(g.double().norm().item(), fix[key], rtol=1e-4), k
             sub = g.reshape(-1)[::max(1, g.numel() // 64)][:64].numpy()
             assert np.allclose(sub, fix["gsub:" + k], rtol=1e-3, atol=1e-7), k
+
+
+@pytest.mark.parametrize("name,kernel,stride,vshape", [("DSSVT", (1, 3, 3), (1, 2, 2), (4, 16, 16)),
+                                                        ("DSTSVT", (5, 3, 3), (4, 2, 2), (16, 16, 16))])
+def test_subscale_oracle_matches_reference(name, kernel, stride, vshape):
+    """configs/vt/DSSVT.yaml / DSTSVT.yaml (2+2 layers): strided one-hot conv, t > 1 masked conv, (4,8,8)
+    blocks with a three-axis bias, partially true ignore mask -- the oracle paths the DSFVT fixtures do not
+    reach, pinned to the unmodified reference (tests/golden/make_golden.py subscale)."""
+    fix = _load(name.lower() + "_l2.npz")
+    layers, batch = 2, 2
+    blocks = tuple([(4, 8, 8)] * layers)
+    cfg = O.VTConfig(kernel=kernel, stride=stride, video_shape=vshape, blocks_e=blocks, heads_e=(8,) * layers,
+                     blocks_d=blocks, heads_d=(8,) * layers)
+    sd = {k: v.requires_grad_(True) for k, v in O.synth_weights(O.dsfvt_param_shapes(cfg), seed=4321).items()}
+    context, slc, slice_idx, ignore = O.synth_vt_batch(batch, seed=5, cfg=cfg)
+    assert np.array_equal(slice_idx.numpy(), fix["slice_idx"]) and context.sum().item() == fix["context_sum"]
+    assert ignore.sum().item() == fix["ignore_sum"]
+    loss = O.vt_supervised_loss(context, slc, slice_idx, ignore, sd, cfg)
+    loss.backward()
+    assert np.allclose(loss.item(), fix["loss"], rtol=1e-6)
+    with torch.no_grad():
+        logits = torch.stack(O.vt_logits(context, slc, slice_idx, sd, cfg))
+    assert np.allclose(logits[:, :, ::7, :, ::3, ::5].numpy(), fix["logits_sub"], rtol=1e-4, atol=1e-5)
+    assert np.allclose(logits.double().sum().item(), fix["logits_sum"], rtol=1e-5)
+    for key in fix.files:
+        if key.startswith("gnorm:"):
+            k = key[6:]
+            g = sd[k].grad
+            assert np.allclose(g.double().norm().item(), fix[key], rtol=1e-4), k
+            sub = g.reshape(-1)[::max(1, g.numel() // 64)][:64].numpy()
+            # (sparse gradients: entries that are sums of a few large terms of both signs differ by summation order)
+            assert np.allclose(sub, fix["gsub:" + k], rtol=1e-3, atol=1e-3 * float(g.abs().max()) + 1e-7), k
+
+
+def test_kdvqvae_oracle_matches_reference():
+    """configs/vqvae/K-DVQVAE.yaml (N_LAYERS 4): latents bit-exact, reconstruction, one supervised step."""
+    fix = _load("kdvqvae.npz")
+    cfg = O.VQVAEConfig(n_layers=4)
+    eshape, gshape = O.vqvae_param_shapes(cfg)
+    we, wg = O.synth_weights(eshape, seed=21), O.synth_weights(gshape, seed=22)
+    x = torch.rand((4, 3, 64, 64), generator=torch.Generator().manual_seed(4321))
+    cb = torch.randn((4, 512, 64), generator=torch.Generator().manual_seed(6)) * torch.tensor(fix["spread_std"])
+    with torch.no_grad():
+        recon, latent = O.vqvae_inference(x, we, wg, cb, cfg)
+    assert np.array_equal(latent.numpy(), fix["latent"])
+    assert np.allclose(recon[:, :, ::5, ::7].numpy(), fix["recon_sub"], rtol=1e-5, atol=1e-6)
+    we_g = {k: v.clone().requires_grad_(True) for k, v in we.items()}
+    wg_g = {k: v.clone().requires_grad_(True) for k, v in wg.items()}
+    losses, aux = O.vqvae_supervised_loss(x, we_g, wg_g, cb, torch.zeros(4, 512), cb.clone(), cfg)
+    sum(losses.values()).backward()
+    for k in ("loss_reconstruction", "loss_commitment"):
+        assert np.allclose(losses[k].item(), fix[k], rtol=1e-5), k
+    for k in ("layers.0.weight", "layers.8.block.1.weight"):
+        assert np.allclose(we_g[k].grad.double().norm().item(), fix[f"gE:{k}"], rtol=1e-4), k
+    for k in ("layers.0.weight", "layers.4.block.3.weight", "layers.8.weight"):
+        assert np.allclose(wg_g[k].grad.double().norm().item(), fix[f"gG:{k}"], rtol=1e-4), k
