@@ -159,6 +159,34 @@ typedef struct LvtGemm {
 int lvt_gemm_bf16(const LvtGemm* g, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Fused attention backward (autograd of ScaledDotProductAttention.forward, vt_attention.py:61-81, with the
+ * relative-position bias of BlockLocalAttention.get_B, vt_attention.py:169-174), one 256-position block per
+ * (sequence, head), da = 128.  Neither P nor dS touches HBM: the kernel recomputes P = exp(scale*QK^T + B - lse)
+ * from the row log-sum-exp the fused forward saved (LvtGemm.lse) and produces
+ *   dV = P^T dO,  dS = P * (dO V^T - delta),  dK = scale * dS^T Q,  dQ = scale * dS K,  dbank_x += sums of dS.
+ *   qkv / dqkv  bf16 [nseq*256, ld]: q | k | v at columns 0, heads*128, 2*heads*128, head h at + h*128
+ *   dO          bf16 [nseq*256, do_ld], head h at column h*128
+ *   lse, delta  fp32 [nseq*heads, 256]  (natural-log lse; delta = rowsum(dO * O), LVT_GEMM_ROWDOT)
+ *   bank_x      fp32 [heads, 2*bx-1] values;  dbank_x: their gradients, ACCUMULATED (+=)
+ *   scratch     lvt_attn_bwd_scratch_bytes() bytes of device memory (dQ partial sums; contents irrelevant)
+ * ---------------------------------------------------------------------------------------- */
+typedef struct LvtAttnBwd {
+  int nseq, heads;
+  int bt, bh, bw;          /* attention block: (1,16,16) or (4,8,8) */
+  int causal;              /* keys after the query were filled with -1e4 in the forward */
+  float scale;             /* 1/sqrt(da) */
+  const void* qkv; long long qkv_ld;
+  const void* dO; long long do_ld;
+  void* dqkv; long long dqkv_ld;
+  const float* lse; const float* delta;
+  const float* bank_t; const float* bank_h; const float* bank_w;
+  float* dbank_t; float* dbank_h; float* dbank_w;
+  float* scratch; long long scratch_bytes;
+} LvtAttnBwd;
+long long lvt_attn_bwd_scratch_bytes(void);
+int lvt_attn_bwd(const LvtAttnBwd* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * DSFVT bandwidth-bound operators
  * ---------------------------------------------------------------------------------------- */
 /* nn.LayerNorm(d) forward (vt_attention.py:121,138; videotransformer.py:143): x fp32 [M,d] ->

@@ -53,6 +53,22 @@ class LvtGemm(ctypes.Structure):
     ]
 
 
+class LvtAttnBwd(ctypes.Structure):
+    """Mirror of `struct LvtAttnBwd` (include/lvt_b200.h)."""
+    _fields_ = [
+        ("nseq", ctypes.c_int), ("heads", ctypes.c_int),
+        ("bt", ctypes.c_int), ("bh", ctypes.c_int), ("bw", ctypes.c_int),
+        ("causal", ctypes.c_int), ("scale", ctypes.c_float),
+        ("qkv", ctypes.c_void_p), ("qkv_ld", ctypes.c_longlong),
+        ("dO", ctypes.c_void_p), ("do_ld", ctypes.c_longlong),
+        ("dqkv", ctypes.c_void_p), ("dqkv_ld", ctypes.c_longlong),
+        ("lse", ctypes.c_void_p), ("delta", ctypes.c_void_p),
+        ("bank_t", ctypes.c_void_p), ("bank_h", ctypes.c_void_p), ("bank_w", ctypes.c_void_p),
+        ("dbank_t", ctypes.c_void_p), ("dbank_h", ctypes.c_void_p), ("dbank_w", ctypes.c_void_p),
+        ("scratch", ctypes.c_void_p), ("scratch_bytes", ctypes.c_longlong),
+    ]
+
+
 class LvtRowsLinear(ctypes.Structure):
     """Mirror of `struct LvtRowsLinear` (include/lvt_b200.h)."""
     _fields_ = [
@@ -88,6 +104,8 @@ SYMBOLS = {
     "lvt_vq_ema_update": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _d, _d, _vp]),
     "lvt_vq_gather": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "lvt_gemm_bf16": (_i, [ctypes.POINTER(LvtGemm), _vp]),
+    "lvt_attn_bwd_scratch_bytes": (_ll, []),
+    "lvt_attn_bwd": (_i, [ctypes.POINTER(LvtAttnBwd), _vp]),
     "lvt_layernorm_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp]),
     "lvt_layernorm_bwd": (_i, [_vp] * 10 + [_i, _i, _vp]),
     "lvt_layernorm_bwd_bf16dy": (_i, [_vp] * 10 + [_i, _i, _vp]),

@@ -1378,6 +1378,13 @@ int num_sms() {
 
 }  // namespace
 
+// (shared with the other tcgen05 kernels of the library: attn_bwd.cu)
+int lvt_make_operand_map(CUtensorMap* out, const void* base, long long c_extent, long long r_extent, int cin,
+                         long long ld, long long s_blk, int batch, int zdiv, long long s_zlo, long long s_zhi,
+                         int box_rows, int esize) {
+  return make_operand_map(out, base, c_extent, r_extent, cin, ld, s_blk, batch, zdiv, s_zlo, s_zhi, box_rows, esize);
+}
+
 extern "C" int lvt_gemm_bf16(const LvtGemm* g, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   LVT_CHECK_ARG(g != nullptr, "lvt_gemm_bf16: null descriptor");

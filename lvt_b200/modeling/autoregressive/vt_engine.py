@@ -29,6 +29,9 @@ from ...ops import Operand, gemm
 LN_EPS = 1e-5
 _SPLIT_ATTN = os.environ.get("LVT_SPLIT_ATTN", "0") == "1"
 _SPLIT_BANK = os.environ.get("LVT_SPLIT_BANK", "0") == "1"  # A/B aid: bank gradient as its own kernel on the side stream
+# A/B aid: LVT_ATTN_BWD=split keeps the round-1 attention backward (P stored by the forward, dV GEMM, fused dS + dQ
+# kernel with dS stored, dK GEMM) instead of the single fused kernel that recomputes P from the saved log-sum-exp
+_OLD_ATTN_BWD = os.environ.get("LVT_ATTN_BWD", "fused") == "split" or _SPLIT_ATTN
 _ALIGN = 64  # elements; keeps every parameter 256 B (fp32) / 128 B (bf16) aligned for TMA
 
 
@@ -157,7 +160,7 @@ def _i3(v):
 
 class _Layer:
     """Saved activations of one BlockLocalAttention layer (all needed by its backward)."""
-    __slots__ = ("x", "mean1", "rstd1", "ln1", "qkv", "P", "o", "h", "mean2", "rstd2", "ln2", "a1", "y",
+    __slots__ = ("x", "mean1", "rstd1", "ln1", "qkv", "P", "lse", "o", "h", "mean2", "rstd2", "ln2", "a1", "y",
                  "y_bf16")
 
 
@@ -194,7 +197,10 @@ class VTWorkspace:
             ly.mean1, ly.rstd1, ly.mean2, ly.rstd2 = (e((M,), f32) for _ in range(4))
             ly.ln1, ly.ln2, ly.a1 = e((M, d), bf16), e((M, d), bf16), e((M, d), bf16)
             ly.qkv = e((M, 3 * H * da), bf16)
-            ly.P = e((self.nseq, H, L, L), bf16)
+            # the attention probabilities never reach HBM: the forward keeps the row log-sum-exp, the backward
+            # recomputes P from it (csrc/attn_bwd.cu)
+            ly.lse = e((self.nseq * H, L), f32)
+            ly.P = e((self.nseq, H, L, L), bf16) if (_OLD_ATTN_BWD and train) else None
             ly.o = e((M, H * da), bf16)
             ly.h = e((M, d), f32)
             ly.y = e((M, d), f32)
@@ -219,7 +225,7 @@ class VTWorkspace:
             self.dz1 = e((M, d), bf16)
             self.do = e((M, H * da), bf16)
             self.delta = e((self.nseq, H, L), f32)
-            self.dS = e((self.nseq, H, L, L), bf16)
+            self.dS = e((self.nseq, H, L, L), bf16) if _OLD_ATTN_BWD else None
             self.dqkv = e((M, 3 * H * da), bf16)
             self.dA0 = e((M, ntaps * de), f32)
             self.de0, self.de0_bf16 = e((M, de), f32), e((M, de), bf16)
@@ -429,8 +435,10 @@ class VTEngine:
                  batch=nz)
         else:
             gemm(L, L, da, self._qkv_op(ly.qkv.data_ptr(), 0, False, L), self._qkv_op(ly.qkv.data_ptr(), 1, False, L),
-                 Operand(ly.P.data_ptr(), L, zdiv=1, s_zhi=L * L), out_bf16=ly.P if keep_p else None, batch=nz,
+                 Operand(ly.P.data_ptr() if ly.P is not None else ly.o.data_ptr(), L, zdiv=1, s_zhi=L * L),
+                 out_bf16=ly.P if (keep_p and ly.P is not None) else None, batch=nz,
                  alpha=1.0 / math.sqrt(da), mode=ops.EPI_SOFTMAX, flags=ops.GEMM_CAUSAL if causal else 0,
+                 lse=ly.lse if keep_p else None,
                  banks=banks, block=s.block, heads=H, v=self._qkv_op(ly.qkv.data_ptr(), 2, True, L),
                  o2=Operand(ly.o.data_ptr(), H * da, cin=da, zdiv=H, s_zlo=da, s_zhi=L * H * da), o2_n=da)
         # output projection + residual (:127-128)
@@ -459,7 +467,7 @@ class VTEngine:
             torch.cuda.current_stream().wait_stream(self._side)
             self._side_pending = False
 
-    def _layer_bwd(self, prefix, ws: VTWorkspace, ly: _Layer, x, dy, dy_bf16, dx, dx_bf16):
+    def _layer_bwd(self, prefix, ws: VTWorkspace, ly: _Layer, x, dy, dy_bf16, dx, dx_bf16, causal=False):
         """dy (fp32 + bf16 copy) = gradient wrt the layer output; writes dx (fp32 + bf16).
         Main stream: the data-gradient chain.  Side stream: parameter gradients (they only meet again in the
         optimizer); the scratch buffers they read (dy_bf16, dz1, dh_bf16, dS, dqkv) are protected by a join at
@@ -497,32 +505,16 @@ class VTEngine:
         gemm(M, H * da, d, Operand(dhb, d), Operand(st.pb(prefix + "mha.proj.weight"), H * da, mn_major=True),
              Operand(ws.do.data_ptr(), H * da), out_bf16=ws.do, aux=ly.o, rowdot=ws.delta, rd_block=da, rd_L=L)
         # ---- softmax attention backward
-        P_k = Operand(ly.P.data_ptr(), L, zdiv=1, s_zhi=L * L)
-        P_mn = Operand(ly.P.data_ptr(), L, mn_major=True, zdiv=1, s_zhi=L * L)
-        do_k = Operand(ws.do.data_ptr(), H * da, cin=da, zdiv=H, s_zlo=da, s_zhi=L * H * da)
-        do_mn = Operand(ws.do.data_ptr(), H * da, mn_major=True, cin=da, zdiv=H, s_zlo=da, s_zhi=L * H * da)
-        dS_k = Operand(ws.dS.data_ptr(), L, zdiv=1, s_zhi=L * L)
-        dS_mn = Operand(ws.dS.data_ptr(), L, mn_major=True, zdiv=1, s_zhi=L * L)
         qkv, dqkv = ly.qkv.data_ptr(), ws.dqkv.data_ptr()
-        out_blk = lambda which: self._qkv_op(dqkv, which, False, L)  # noqa: E731
-        # dV = P^T dO
-        gemm(L, da, L, P_mn, do_mn, out_blk(2), out_bf16=out_blk(2).data, batch=nz)
-        # dS = P * (dO V^T - delta) and dQ = scale * dS K in ONE kernel (dS reaches the second MMA through shared
-        # memory; it is still written out for the dK GEMM and the bank gradient)
-        # (for block (1,16,16) the same epilogue also accumulates the dt/dh/dw_bank gradients from dS)
-        fused_bank = tuple(s.block) == (1, 16, 16) and not _SPLIT_BANK
         gbanks = (st.gf(prefix + "dt_bank"), st.gf(prefix + "dh_bank"), st.gf(prefix + "dw_bank"))
-        gemm(L, L, da, do_k, self._qkv_op(qkv, 2, False, L), dS_k, out_bf16=ws.dS, batch=nz, mode=ops.EPI_DS,
-             aux=ly.P, delta=ws.delta, alpha=scale, v=self._qkv_op(qkv, 1, True, L), o2=out_blk(0), o2_n=da,
-             banks=gbanks if fused_bank else None, block=s.block, heads=H)
-        if not fused_bank:
-            with self._side_begin():
-                check(self.lib.lvt_relpos_bank_grad(ptr(ws.dS), _vp(gbanks[0]), _vp(gbanks[1]), _vp(gbanks[2]),
-                                                    ws.nseq, H, s.block[0], s.block[1], s.block[2], stream_ptr()),
-                      "lvt_relpos_bank_grad")
-        # dK = scale * dS^T Q
-        gemm(L, da, L, dS_mn, self._qkv_op(qkv, 0, True, L), out_blk(1), out_bf16=out_blk(1).data, batch=nz,
-             alpha=scale)
+        if not _OLD_ATTN_BWD:
+            # ONE kernel: P recomputed from the saved log-sum-exp, dV = P^T dO, dS = P * (dO V^T - delta),
+            # dK = scale * dS^T Q, dQ = scale * dS K and the dt/dh/dw_bank gradients; neither P nor dS reaches HBM
+            banks = (st.pf(prefix + "dt_bank"), st.pf(prefix + "dh_bank"), st.pf(prefix + "dw_bank"))
+            ops.attn_bwd(qkv, ws.do.data_ptr(), dqkv, ly.lse, ws.delta, banks, gbanks, ws.nseq, H, s.block, causal,
+                         scale, qkv_ld=3 * H * da, do_ld=H * da)
+        else:
+            self._attn_bwd_split(prefix, ws, ly, qkv, dqkv, gbanks, scale)
         # ---- QKV projection
         with self._side_begin():
             gemm(d, 3 * H * da, M, Operand(ly.ln1.data_ptr(), d, mn_major=True),
@@ -535,6 +527,36 @@ class VTEngine:
         torch.cuda.current_stream().wait_event(ev_dy_read)  # dx_bf16 may alias dy_bf16
         self._ln_bwd(ws.dln_bf16, x, ly.mean1, ly.rstd1, st.pf(prefix + "mha.layer_norm.weight"), ws.dh, dx, dx_bf16,
                      st.gf(prefix + "mha.layer_norm.weight"), st.gf(prefix + "mha.layer_norm.bias"), M)
+
+    def _attn_bwd_split(self, prefix, ws, ly, qkv, dqkv, gbanks, scale):
+        """Round-1 attention backward (A/B aid, LVT_ATTN_BWD=split): P read from HBM, dS written to HBM."""
+        s, st = self.spec, self.store
+        M, d, H, da, L = ws.M, s.d, s.H, s.da, 256
+        nz = ws.nseq * H
+        P_k = Operand(ly.P.data_ptr(), L, zdiv=1, s_zhi=L * L)
+        P_mn = Operand(ly.P.data_ptr(), L, mn_major=True, zdiv=1, s_zhi=L * L)
+        do_k = Operand(ws.do.data_ptr(), H * da, cin=da, zdiv=H, s_zlo=da, s_zhi=L * H * da)
+        do_mn = Operand(ws.do.data_ptr(), H * da, mn_major=True, cin=da, zdiv=H, s_zlo=da, s_zhi=L * H * da)
+        dS_k = Operand(ws.dS.data_ptr(), L, zdiv=1, s_zhi=L * L)
+        dS_mn = Operand(ws.dS.data_ptr(), L, mn_major=True, zdiv=1, s_zhi=L * L)
+        out_blk = lambda which: self._qkv_op(dqkv, which, False, L)  # noqa: E731
+        # dV = P^T dO
+        gemm(L, da, L, P_mn, do_mn, out_blk(2), out_bf16=out_blk(2).data, batch=nz)
+        # dS = P * (dO V^T - delta) and dQ = scale * dS K in ONE kernel (dS reaches the second MMA through shared
+        # memory; it is still written out for the dK GEMM and the bank gradient)
+        # (for block (1,16,16) the same epilogue also accumulates the dt/dh/dw_bank gradients from dS)
+        fused_bank = tuple(s.block) == (1, 16, 16) and not _SPLIT_BANK
+        gemm(L, L, da, do_k, self._qkv_op(qkv, 2, False, L), dS_k, out_bf16=ws.dS, batch=nz, mode=ops.EPI_DS,
+             aux=ly.P, delta=ws.delta, alpha=scale, v=self._qkv_op(qkv, 1, True, L), o2=out_blk(0), o2_n=da,
+             banks=gbanks if fused_bank else None, block=s.block, heads=H)
+        if not fused_bank:
+            with self._side_begin():
+                check(self.lib.lvt_relpos_bank_grad(ptr(ws.dS), _vp(gbanks[0]), _vp(gbanks[1]), _vp(gbanks[2]),
+                                                    ws.nseq, H, s.block[0], s.block[1], s.block[2], stream_ptr()),
+                      "lvt_relpos_bank_grad")
+        # dK = scale * dS^T Q
+        gemm(L, da, L, dS_mn, self._qkv_op(qkv, 0, True, L), out_blk(1), out_bf16=out_blk(1).data, batch=nz,
+             alpha=scale)
 
     # ------------------------------------------------------------------ whole network
     def set_inputs(self, ws: VTWorkspace, context, slc, slice_idx, ignore_mask=None):
@@ -678,7 +700,8 @@ class VTEngine:
         for i in reversed(range(nD)):
             ly = ws.layers[nE + i]
             x = ws.layers[nE + i - 1].y if i > 0 else ws.y0
-            self._layer_bwd(f"decoder.block_local_attention.{i}.", ws, ly, x, ws.dy, ws.dy_bf16, ws.dy, ws.dy_bf16)
+            self._layer_bwd(f"decoder.block_local_attention.{i}.", ws, ly, x, ws.dy, ws.dy_bf16, ws.dy, ws.dy_bf16,
+                            causal=True)
         self._side_join()
         # ---- decoder front: y0 = conv(emb) + posenc + bias + zl Wlp^T
         dyb = ws.dy_bf16.data_ptr()

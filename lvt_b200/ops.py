@@ -9,7 +9,7 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import LvtGemm, check, ptr, stream_ptr
+from ._lib import LvtAttnBwd, LvtGemm, check, ptr, stream_ptr
 
 EPI_LINEAR, EPI_SOFTMAX, EPI_DS = 0, 1, 2
 GEMM_RELU, GEMM_MASK, GEMM_ATOMIC, GEMM_CAUSAL, GEMM_AUX_ADD, GEMM_ROWDOT = 1, 2, 4, 8, 16, 32
@@ -176,6 +176,43 @@ def gemm(M, N, K, a: Operand, b: Operand, out: Operand, out_f32=None, out_bf16=N
         g.rowdot, g.rd_block, g.rd_L = p(rowdot), rd_block, rd_L
         g.flags |= GEMM_ROWDOT
     check(lib.lvt_gemm_bf16(ctypes.byref(g), stream_ptr()), "lvt_gemm_bf16")
+
+
+_attn_scratch = {}
+
+
+def attn_bwd_scratch(device=None):
+    """Per-device scratch of the fused attention backward (dQ partial sums; lvt_attn_bwd_scratch_bytes())."""
+    dev = torch.device(device if device is not None else torch.cuda.current_device())
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    if key not in _attn_scratch:
+        n = int(_lib.require_device().lvt_attn_bwd_scratch_bytes())
+        _attn_scratch[key] = torch.empty(n // 4, dtype=torch.float32, device=f"cuda:{key}")
+    return _attn_scratch[key]
+
+
+def attn_bwd(qkv, dO, dqkv, lse, delta, banks, dbanks, nseq, heads, block, causal, scale, qkv_ld=None, do_ld=None,
+             scratch=None):
+    """Fused attention backward (lvt_attn_bwd): dqkv <- (dQ | dK | dV), dbanks += bank gradients; P and dS never
+    reach HBM.  Tensors or raw device pointers (ints)."""
+    lib = _lib.require_device()
+
+    def p(x):
+        return ctypes.c_void_p(x) if isinstance(x, int) else ctypes.c_void_p(x.data_ptr())
+
+    a = LvtAttnBwd()
+    a.nseq, a.heads = nseq, heads
+    a.bt, a.bh, a.bw = block
+    a.causal, a.scale = int(bool(causal)), scale
+    a.qkv, a.qkv_ld = p(qkv), qkv_ld or 3 * heads * 128
+    a.dO, a.do_ld = p(dO), do_ld or heads * 128
+    a.dqkv, a.dqkv_ld = p(dqkv), qkv_ld or 3 * heads * 128
+    a.lse, a.delta = p(lse), p(delta)
+    a.bank_t, a.bank_h, a.bank_w = (p(b) for b in banks)
+    a.dbank_t, a.dbank_h, a.dbank_w = (p(b) for b in dbanks)
+    scratch = scratch if scratch is not None else attn_bwd_scratch()
+    a.scratch, a.scratch_bytes = p(scratch), scratch.numel() * 4
+    check(lib.lvt_attn_bwd(ctypes.byref(a), stream_ptr()), "lvt_attn_bwd")
 
 
 def linear_bf16(x, w, bias=None, relu=False, out_dtype=torch.bfloat16, res=None):
