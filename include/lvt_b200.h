@@ -182,6 +182,7 @@ typedef struct LvtAttnBwd {
   const float* bank_t; const float* bank_h; const float* bank_w;
   float* dbank_t; float* dbank_h; float* dbank_w;
   float* scratch; long long scratch_bytes;
+  void* prof;              /* NULL, or 64*16 int64: clock64 timeline of CTA 0 (tools/attn_bwd_prof.py) */
 } LvtAttnBwd;
 long long lvt_attn_bwd_scratch_bytes(void);
 int lvt_attn_bwd(const LvtAttnBwd* a, void* stream);

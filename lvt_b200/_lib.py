@@ -66,6 +66,7 @@ class LvtAttnBwd(ctypes.Structure):
         ("bank_t", ctypes.c_void_p), ("bank_h", ctypes.c_void_p), ("bank_w", ctypes.c_void_p),
         ("dbank_t", ctypes.c_void_p), ("dbank_h", ctypes.c_void_p), ("dbank_w", ctypes.c_void_p),
         ("scratch", ctypes.c_void_p), ("scratch_bytes", ctypes.c_longlong),
+        ("prof", ctypes.c_void_p),
     ]
 
 

@@ -203,6 +203,14 @@ LVT_DEVICE_INLINE void tma_load_5d(void* smem_dst, const CUtensorMap* m, uint64_
       : "memory");
 }
 
+// pulls one box into L2 ahead of the TMA load that will want it
+LVT_DEVICE_INLINE void tma_prefetch_5d(const CUtensorMap* m, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.prefetch.tensor.5d.L2.global.tile [%0, {%1, %2, %3, %4, %5}];"
+               :
+               : "l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+               : "memory");
+}
+
 // TMA store, shared -> global (bulk async group completion)
 LVT_DEVICE_INLINE void tma_store_5d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2,
                                     int c3, int c4) {

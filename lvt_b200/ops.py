@@ -192,7 +192,7 @@ def attn_bwd_scratch(device=None):
 
 
 def attn_bwd(qkv, dO, dqkv, lse, delta, banks, dbanks, nseq, heads, block, causal, scale, qkv_ld=None, do_ld=None,
-             scratch=None):
+             scratch=None, prof=None):
     """Fused attention backward (lvt_attn_bwd): dqkv <- (dQ | dK | dV), dbanks += bank gradients; P and dS never
     reach HBM.  Tensors or raw device pointers (ints)."""
     lib = _lib.require_device()
@@ -212,6 +212,7 @@ def attn_bwd(qkv, dO, dqkv, lse, delta, banks, dbanks, nseq, heads, block, causa
     a.dbank_t, a.dbank_h, a.dbank_w = (p(b) for b in dbanks)
     scratch = scratch if scratch is not None else attn_bwd_scratch()
     a.scratch, a.scratch_bytes = p(scratch), scratch.numel() * 4
+    a.prof = p(prof) if prof is not None else None
     check(lib.lvt_attn_bwd(ctypes.byref(a), stream_ptr()), "lvt_attn_bwd")
 
 

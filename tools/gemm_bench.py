@@ -63,6 +63,10 @@ dS = torch.empty_like(P)
 dqkv = torch.empty_like(o3)
 gbanks = [torch.zeros(H, 1, device="cuda"), torch.zeros(H, 31, device="cuda"), torch.zeros(H, 31, device="cuda")]
 tests["attn_bwd_fused"] = (lambda: ops.gemm(L, L, da, Operand(dOb.data_ptr(), H * da, cin=da, zdiv=H, s_zlo=da, s_zhi=L * H * da), qkv_op(o3, 2, False), Operand(dS.data_ptr(), L, zdiv=1, s_zhi=L * L), out_bf16=dS, batch=nb * H, mode=ops.EPI_DS, aux=P, delta=delta, alpha=0.088, v=qkv_op(o3, 1, True), o2=qkv_op(dqkv, 0, False), o2_n=da, banks=gbanks, block=(1, 16, 16), heads=H), 4.0 * nb * H * L * L * da)
+lse = torch.randn(nb * H, L, device="cuda") + 8.0
+for cz, nm in ((False, "attn_bwd_all"), (True, "attn_bwd_all_causal")):
+    tests[nm] = ((lambda cz=cz: ops.attn_bwd(o3, dOb, dqkv, lse, delta, banks, gbanks, nb, H, (1, 16, 16), cz, 0.088)),
+                 (8.0 if cz else 10.0) * nb * H * L * L * da)
 DBG = int(os.environ.get("GEMM_DBG", "0"))
 if DBG:
     tests["qkv"] = (lambda: ops.gemm(M, 3072, d, Operand(x.data_ptr(), d), Operand(wq.data_ptr(), da, mn_major=True, cin=da, s_blk=d * da), Operand(o3.data_ptr(), 3072), out_bf16=o3, flags=DBG), 2.0 * M * 3072 * d)
