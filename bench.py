@@ -654,6 +654,72 @@ def main():
         except Exception as ex:
             extra["sampler"] = {"error": repr(ex)[:300]}
 
+        # BASELINE.json config 5 at script level: scripts/generate_videos.py sample_videos(args) -- 5 priming PNGs ->
+        # VQ-VAE codes -> 11 sampled latent frames (DSFVT, 8+8 layers) -> VQ-VAE decode -> 16 PNGs; frames/s of the
+        # whole call (model construction included, as in the reference's 338 s figure), second call = warm.
+        try:
+            import argparse as _ap
+            import tempfile
+            import numpy as np
+            from PIL import Image
+            sys.path.insert(0, os.path.join(ROOT, "scripts"))
+            import generate_videos as gv
+            tmp = tempfile.mkdtemp(prefix="lvt_gen_")
+            rs = np.random.RandomState(0)
+            for i in range(5):
+                Image.fromarray(rs.randint(0, 255, (64, 64, 3), dtype=np.uint8)).save(os.path.join(tmp, f"{i}.png"))
+            ga = _ap.Namespace(video_dir=tmp, config_file="DSFVT", vqvae_config="PR-DVQVAE2",
+                               out_dir=os.path.join(tmp, "out"), n_frames=16)
+            times = []
+            for _ in range(2):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                vid = gv.sample_videos(ga)
+                torch.cuda.synchronize()
+                times.append(time.perf_counter() - t0)
+            extra["generate_videos"] = {
+                "frames": 16, "sampled_frames": 11, "seconds_first_call": times[0], "seconds": times[1],
+                "frames_per_s": 16 / times[1], "sampled_frames_per_s": 11 / times[1], "output_shape": list(vid.shape),
+                "note": "scripts/generate_videos.py sample_videos(): PNG priming frames in, PNG video out, random-init "
+                        "weights (no checkpoints offline); the reference's CPU run of the same script: 338 s (BASELINE.md)"}
+        except Exception as ex:
+            extra["generate_videos"] = {"error": repr(ex)[:300]}
+        # The reference-facing training surface: Trainer.run_step -> model(list[dict], 'supervised') -> loss.backward()
+        # -> optimizer.step() (engine/trainer.py), batches in the DatasetMapper's per-sample dict format on the host.
+        try:
+            import itertools
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import train_net
+            from lvt_b200.config.presets import preset
+            from lvt_b200.engine import Trainer
+            from lvt_b200.utils.events import EventStorage
+            cfgt = preset("DSFVT", ["OUTPUT_DIR", "/tmp/lvt_bench_trainer", "SOLVER.IMS_PER_BATCH", B,
+                                    "SOLVER.CHECKPOINT_PERIOD", 0, "SEED", 1])
+            cfgt.freeze()
+            gen = train_net.synthetic_loader(cfgt)
+            batches = [next(gen) for _ in range(3)]   # per-sample dicts of host tensors, as the mapper yields them
+            tr = Trainer(cfgt, data_loader=itertools.cycle(batches))
+            tr.model.train()
+            with EventStorage(0) as tr.storage:
+                tr.iter = 0
+                for _ in range(3):
+                    tr.run_step(); tr.iter += 1
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                nit = 10
+                for _ in range(nit):
+                    tr.run_step(); tr.iter += 1
+                torch.cuda.synchronize()
+                dt = (time.perf_counter() - t0) / nit
+            extra["trainer_path"] = {"ms_per_step": dt * 1e3, "value": B * TOKENS_PER_SAMPLE / dt, "unit": "latent tokens/s",
+                                     "graph_replay": bool(getattr(tr.model, "_graphed", False)),
+                                     "note": "tools/train_net.py's Trainer.run_step on the DSFVT preset, batch 64: per-sample "
+                                             "dicts stacked on the host, H2D, forward + backward as one CUDA-graph replay, "
+                                             "RMSprop, LR scheduler; wall clock"}
+            del tr
+        except Exception as ex:
+            extra["trainer_path"] = {"error": repr(ex)[:300]}
+
     # ---------------- N > 1: strong-scaling line (reference semantics) and data-parallel loss parity
     strong, dp_par = None, None
     if world > 1 and not args.quick and not args.strong:

@@ -72,6 +72,10 @@ class Trainer:
         self.cfg = cfg
         self.model = self.build_model(cfg)
         self.optimizers, self.checkpointers = self.model.configure_optimizers_and_checkpointers()
+        # run_step always follows model(data, 'supervised') with loss.backward(): the models may therefore replay
+        # forward + backward as one CUDA graph (LVT_TRAINER_GRAPH=0 keeps the eager launch sequence)
+        if hasattr(self.model, "enable_graphed_step") and os.environ.get("LVT_TRAINER_GRAPH", "1") != "0":
+            self.model.enable_graphed_step(True)
         self.data_loader = data_loader
         self._iter = iter(data_loader) if data_loader is not None else None
         if comm.get_world_size() > 1:

@@ -33,6 +33,30 @@ class _SupervisedLoss(torch.autograd.Function):
         return None, None, None
 
 
+class _GraphedSupervisedLoss(torch.autograd.Function):
+    """Trainer fast path: [encoder, codebook search] and [EMA update, decoder, losses, backward] replayed as two
+    CUDA graphs at forward time (Trainer.run_step calls loss.backward() right after, trainer.py:79-82); the
+    cross-rank sums (EMA statistics between the graphs, the flat gradient in backward()) stay eager."""
+
+    @staticmethod
+    def forward(ctx, anchor, model, ws, graphs):
+        ctx.model = model
+        graphs[0].replay()
+        if comm.get_world_size() > 1:
+            comm.all_reduce_sum_(ws.counts)
+            comm.all_reduce_sum_(ws.sums)
+        graphs[1].replay()
+        return ws.loss.clone()
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        eng = ctx.model.engine
+        if comm.get_world_size() > 1:
+            comm.all_reduce_sum_(eng.store.grad)
+            eng.store.grad.div_(comm.get_world_size())
+        return None, None, None, None
+
+
 @META_ARCH_REGISTRY.register()
 class VQVAEModel(nn.Module):
     def __init__(self, cfg):
@@ -60,6 +84,7 @@ class VQVAEModel(nn.Module):
         self.beta = cfg.MODEL.CODEBOOK.BETA
         self.vis_period = cfg.VIS_PERIOD
         self._anchor = torch.zeros(1, device=self.device, requires_grad=True)
+        self._graphed, self._graphs = False, {}
         self.back_normalizer = lambda y: y * spec.std + spec.mean
         self.normalizer = lambda x: (x - spec.mean) / spec.std
 
@@ -82,6 +107,41 @@ class VQVAEModel(nn.Module):
     def train(self, mode=True):
         self.training = mode
         return self
+
+    def enable_graphed_step(self, on=True):
+        """Trainer fast path (see _GraphedSupervisedLoss): valid when every supervised forward is followed by
+        loss.backward(), which is what Trainer.run_step does."""
+        self._graphed = bool(on)
+
+    def _graphs_for(self, w):
+        eng = self.engine
+        if not eng.shadows_fresh:            # (inside a graph this host-side check would be frozen)
+            eng.refresh_shadows()
+        g = self._graphs.get(id(w))
+        if g is None:
+            # the eager warm-up runs real forward / backward passes: the gradient buffer and the EMA codebook
+            # state they touch are restored afterwards
+            keep = (eng.store.grad, eng.codebook, eng.running_size, eng.running_sum)
+            snap = [t.clone() for t in keep]
+            allreduce = comm.all_reduce_sum_ if comm.get_world_size() > 1 else None
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    eng.forward_train(w, allreduce=allreduce)
+                    eng.backward(w)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            for dst, src in zip(keep, snap):
+                dst.copy_(src)
+            ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(ga):
+                eng._forward_train_a(w)
+            with torch.cuda.graph(gb):
+                eng._forward_train_b(w)
+                eng.backward(w)
+            g = self._graphs[id(w)] = (ga, gb)
+        return g
 
     def load_state_dict(self, *a, **k):
         out = super().load_state_dict(*a, **k)
@@ -118,7 +178,10 @@ class VQVAEModel(nn.Module):
         x, seq = self.preprocess_data(data)
         if mode in ("supervised", "generator"):
             w = self._stage(x, train=True)
-            losses = _SupervisedLoss.apply(self._anchor, self, w)
+            if self._graphed:
+                losses = _GraphedSupervisedLoss.apply(self._anchor, self, w, self._graphs_for(w))
+            else:
+                losses = _SupervisedLoss.apply(self._anchor, self, w)
             return {"loss_reconstruction": losses[0], "loss_commitment": losses[1]}
         if mode == "inference":
             w = self._stage(x, train=False)

@@ -34,6 +34,25 @@ class _SupervisedLoss(torch.autograd.Function):
         return None, None, None
 
 
+class _GraphedSupervisedLoss(torch.autograd.Function):
+    """The same bridge with the ~400 launches of forward + backward replayed as ONE CUDA graph at forward time
+    (Trainer.run_step always calls loss.backward() right after model(data, 'supervised'), trainer.py:79-82, and the
+    gradients are accumulated into the flat buffer exactly as engine.backward does); backward() is left with the
+    data-parallel gradient hook."""
+
+    @staticmethod
+    def forward(ctx, anchor, engine, ws, graph):
+        ctx.engine = engine
+        graph.replay()
+        return ws.loss[0].clone()
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        if ctx.engine.grad_hook is not None:
+            ctx.engine.grad_hook(ctx.engine.store.grad)
+        return None, None, None, None
+
+
 @META_ARCH_REGISTRY.register()
 class VideoTransformerModel(nn.Module):
     def __init__(self, cfg):
@@ -48,6 +67,36 @@ class VideoTransformerModel(nn.Module):
         self.sampler_graph = os.environ.get("LVT_SAMPLER_GRAPH", "1") != "0"
         self.model.engine.grad_hook = None
         self._anchor = torch.zeros(1, device=self.device, requires_grad=True)
+        self._graphed, self._graphs = False, {}
+
+    def enable_graphed_step(self, on=True):
+        """Trainer fast path: model(data, 'supervised') stages the batch into the engine's static buffers and
+        replays forward + backward as one CUDA graph (captured on first use per batch shape) instead of launching
+        ~400 kernels from the host.  Only valid when every supervised forward is followed by loss.backward(), which
+        is what Trainer.run_step does."""
+        self._graphed = bool(on)
+
+    def _graph_for(self, eng, ws):
+        if not eng.shadows_fresh:            # (inside a graph this host-side check would be frozen)
+            eng.refresh_shadows()
+        g = self._graphs.get(id(ws))
+        if g is None:
+            grad0 = eng.store.grad.clone()   # a capture must not leave warm-up gradients behind
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):           # eager warm-up: kernel attributes, TMA maps, scratch allocations
+                    eng.forward(ws, train=True)
+                    eng.backward(ws)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            eng.store.grad.copy_(grad0)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                eng.forward(ws, train=True)
+                eng.backward(ws)
+            self._graphs[id(ws)] = g
+        return g
 
     @staticmethod
     @torch.no_grad()
@@ -126,6 +175,8 @@ class VideoTransformerModel(nn.Module):
         eng = self.model.engine
         ws = eng.workspace(context.shape[0], tuple(slc.shape[2:]), tuple(context.shape[2:]), train=True)
         eng.set_inputs(ws, context, slc, slice_idx, ignore_mask)
+        if self._graphed:
+            return {"loss_cross_entropy": _GraphedSupervisedLoss.apply(self._anchor, eng, ws, self._graph_for(eng, ws))}
         return {"loss_cross_entropy": _SupervisedLoss.apply(self._anchor, eng, ws)}
 
     # ------------------------------------------------------------------ evaluation / sampling

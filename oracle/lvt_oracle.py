@@ -144,7 +144,7 @@ def dvq_straight_through(z_e: Tensor, codebooks: Tensor, running_size: Tensor, r
         ind = idx[:, g].reshape(-1)
         x = z_e[:, g * D:(g + 1) * D].permute(0, 2, 3, 1).reshape(-1, D)
         size = torch.zeros(K).index_add_(0, ind, torch.ones(ind.numel()))
-        s = torch.zeros(K, D).index_add_(0, ind, x)
+        s = torch.zeros(K, D).index_add_(0, ind, x.float())
         if world_counts is not None:
             size, s = world_counts[g], world_sums[g]
         rs = running_size[g] * cfg.ema_decay + (1 - cfg.ema_decay) * size

@@ -58,6 +58,50 @@ def test_trainer_runs_supervised_steps(cuda_lib, tmp_path):
         assert os.path.exists(tmp_path / name / ("netG" if name == "DSFVT" else "netE") / "model_final.pth")
 
 
+@pytest.mark.parametrize("name", ["DSFVT", "PR-DVQVAE2"])
+def test_trainer_graph_replay_matches_eager_launches(cuda_lib, tmp_path, monkeypatch, name):
+    """Trainer fast path: model(data, 'supervised') replaying forward + backward as CUDA graphs gives the loss
+    trajectory and the parameters of the eager launch sequence (same seeds, same batches; fp32 sums accumulated with
+    atomics in both, hence 1e-5 rather than bit equality)."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import train_net
+    from lvt_b200.config.presets import preset
+    from lvt_b200.engine import Trainer
+    over = (SMALL + ["SOLVER.IMS_PER_BATCH", 4]) if name == "DSFVT" else ["SOLVER.IMS_PER_BATCH", 8]
+    runs = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("LVT_TRAINER_GRAPH", mode)
+        cfg = preset(name, over + ["SOLVER.MAX_ITER", 4, "SOLVER.CHECKPOINT_PERIOD", 0,
+                                   "OUTPUT_DIR", str(tmp_path / (name + mode)), "SEED", 3])
+        cfg.freeze()
+        torch.manual_seed(11)
+        tr = Trainer(cfg, data_loader=train_net.synthetic_loader(cfg))
+        assert getattr(tr.model, "_graphed") == (mode == "1")
+        losses = []
+        tr.model.train()
+        from lvt_b200.utils.events import EventStorage
+        with EventStorage(0) as tr.storage:
+            for tr.iter in range(4):
+                data = next(tr._iter)
+                ld = tr.model(data, mode="supervised")
+                sum(ld.values()).backward()
+                losses.append(float(sum(v.detach() for v in ld.values())))
+                for o in tr.optimizers:
+                    o["optimizer"].step()
+                for o in tr.optimizers:
+                    o["optimizer"].zero_grad()
+        eng = tr.model.model.engine if name == "DSFVT" else tr.model.engine
+        runs[mode] = (losses, eng.store.master.clone())
+    la, lb = runs["0"][0], runs["1"][0]
+    assert all(abs(a - b) <= 1e-5 * abs(a) for a, b in zip(la, lb)), (la, lb)
+    # parameters: identical up to the atomics' summation order, except the handful of entries whose gradient is pure
+    # cancellation noise (dt_bank of block (1,16,16)): RMSprop / Adam normalise those to a full-size, sign-random step
+    pa, pb = runs["0"][1], runs["1"][1]
+    off = ((pa - pb).abs() > 1e-5 * pa.abs().max()).float().mean().item()
+    assert off <= 1e-4, off
+
+
 def test_vqvae_model_inference_and_sampling_roundtrip(cuda_lib, tmp_path):
     from lvt_b200.config.presets import preset
     from lvt_b200.modeling import build_model
