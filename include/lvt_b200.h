@@ -203,6 +203,12 @@ int lvt_layernorm_bwd(const float* dy, const float* x, const float* mean, const 
 int lvt_layernorm_bwd_bf16dy(const void* dy_bf16, const float* x, const float* mean, const float* rstd,
                              const float* gamma, const float* dres, float* dx_f32, void* dx_bf16,
                              float* dgamma, float* dbeta, int M, int d, void* stream);
+/* general form: dy fp32 or bf16; dx_colsum [d] (optional) is ACCUMULATED with the column sums of dx -- the bias
+ * gradient of the nn.Linear whose output x is (ffn.3 of the previous BlockLocalAttention layer,
+ * vt_attention.py:138), which saves a separate pass over dx.                                 */
+int lvt_layernorm_bwd_ex(const void* dy, int dy_is_bf16, const float* x, const float* mean, const float* rstd,
+                         const float* gamma, const float* dres, float* dx_f32, void* dx_bf16, float* dgamma,
+                         float* dbeta, float* dx_colsum, int M, int d, void* stream);
 /* out[n] += sum_m x[m*ld + n], x bf16 (bias gradients of nn.Linear / Conv3d).                */
 int lvt_colsum_bf16(const void* x, float* out, int M, int N, long long ld, void* stream);
 /* delta[b,h,i] = sum_d dO[b*L+i, h*da+d] * O[b*L+i, h*da+d] (softmax backward row term of

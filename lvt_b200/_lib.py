@@ -110,6 +110,7 @@ SYMBOLS = {
     "lvt_layernorm_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp]),
     "lvt_layernorm_bwd": (_i, [_vp] * 10 + [_i, _i, _vp]),
     "lvt_layernorm_bwd_bf16dy": (_i, [_vp] * 10 + [_i, _i, _vp]),
+    "lvt_layernorm_bwd_ex": (_i, [_vp, _i] + [_vp] * 10 + [_i, _i, _vp]),
     "lvt_colsum_bf16": (_i, [_vp, _vp, _i, _i, _ll, _vp]),
     "lvt_attn_delta": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "lvt_relpos_bank_grad": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),

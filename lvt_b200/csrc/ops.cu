@@ -77,17 +77,18 @@ ln_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x,
               const float* __restrict__ mean, const float* __restrict__ rstd,
               const float* __restrict__ gamma, const float* __restrict__ dres,
               float* __restrict__ dx, __nv_bfloat16* __restrict__ dx_bf16,
-              float* __restrict__ dgamma, float* __restrict__ dbeta, int M) {
+              float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dxsum, int M) {
   pdl_prologue();
   constexpr int d = V4 * 128;
   __shared__ float s_red[8][d + 4];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float4 gm[V4], ag[V4], ab[V4];
+  float4 gm[V4], ag[V4], ab[V4], ac[V4];  // ac: column sums of dx (the bias gradient of the Linear that produced x)
 #pragma unroll
   for (int i = 0; i < V4; ++i) {
     gm[i] = ld4(gamma + (i * 32 + lane) * 4);
     ag[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    ac[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   for (int row = blockIdx.x * 8 + warp; row < M; row += gridDim.x * 8) {
     const float mu = mean[row], rs = rstd[row];
@@ -126,18 +127,19 @@ ln_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x,
       }
       if (dx) st4(dx + (size_t)row * d + c, o);
       if (dx_bf16) st_bf16x4(dx_bf16 + (size_t)row * d + c, o.x, o.y, o.z, o.w);
+      ac[i].x += o.x; ac[i].y += o.y; ac[i].z += o.z; ac[i].w += o.w;
     }
   }
   // block reduction of the parameter gradients
-  for (int pass = 0; pass < 2; ++pass) {
+  for (int pass = 0; pass < (dxsum ? 3 : 2); ++pass) {
 #pragma unroll
-    for (int i = 0; i < V4; ++i) st4(&s_red[warp][(i * 32 + lane) * 4], pass == 0 ? ag[i] : ab[i]);
+    for (int i = 0; i < V4; ++i) st4(&s_red[warp][(i * 32 + lane) * 4], pass == 0 ? ag[i] : (pass == 1 ? ab[i] : ac[i]));
     __syncthreads();
     for (int c = threadIdx.x; c < d; c += 256) {
       float s = 0.f;
 #pragma unroll
       for (int w = 0; w < 8; ++w) s += s_red[w][c];
-      atomicAdd((pass == 0 ? dgamma : dbeta) + c, s);
+      atomicAdd((pass == 0 ? dgamma : (pass == 1 ? dbeta : dxsum)) + c, s);
     }
     __syncthreads();
   }
@@ -741,7 +743,7 @@ extern "C" int lvt_layernorm_fwd(const float* x, const float* gamma, const float
 
 static int layernorm_bwd_impl(const void* dy, bool dy_bf16, const float* x, const float* mean, const float* rstd,
                               const float* gamma, const float* dres, float* dx_f32, void* dx_bf16, float* dgamma,
-                              float* dbeta, int M, int d, void* stream) {
+                              float* dbeta, float* dxsum, int M, int d, void* stream) {
   LVT_CHECK_ARG(dy && x && mean && rstd && gamma && dgamma && dbeta && M > 0, "lvt_layernorm_bwd: bad argument");
   LVT_CHECK_ARG(d % 128 == 0 && d <= 512, "lvt_layernorm_bwd: d must be 128, 256 or 512");
   const int blocks = min(lvt_ceil_div(M, 8), kSMs * 4);
@@ -750,10 +752,10 @@ static int layernorm_bwd_impl(const void* dy, bool dy_bf16, const float* x, cons
     if constexpr (V4 <= 4) {
       if (dy_bf16)
         LVT_CHECK_CUDA(lvt_launch(ln_bwd_kernel<V4, true>, dim3(blocks), dim3(256), 0, STREAM(stream), dy, x, mean, rstd,
-                                  gamma, dres, dx_f32, reinterpret_cast<__nv_bfloat16*>(dx_bf16), dgamma, dbeta, M));
+                                  gamma, dres, dx_f32, reinterpret_cast<__nv_bfloat16*>(dx_bf16), dgamma, dbeta, dxsum, M));
       else
         LVT_CHECK_CUDA(lvt_launch(ln_bwd_kernel<V4, false>, dim3(blocks), dim3(256), 0, STREAM(stream), dy, x, mean, rstd,
-                                  gamma, dres, dx_f32, reinterpret_cast<__nv_bfloat16*>(dx_bf16), dgamma, dbeta, M));
+                                  gamma, dres, dx_f32, reinterpret_cast<__nv_bfloat16*>(dx_bf16), dgamma, dbeta, dxsum, M));
     }
     return LVT_OK;
   });
@@ -765,13 +767,20 @@ static int layernorm_bwd_impl(const void* dy, bool dy_bf16, const float* x, cons
 extern "C" int lvt_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd,
                                  const float* gamma, const float* dres, float* dx_f32, void* dx_bf16,
                                  float* dgamma, float* dbeta, int M, int d, void* stream) {
-  return layernorm_bwd_impl(dy, false, x, mean, rstd, gamma, dres, dx_f32, dx_bf16, dgamma, dbeta, M, d, stream);
+  return layernorm_bwd_impl(dy, false, x, mean, rstd, gamma, dres, dx_f32, dx_bf16, dgamma, dbeta, nullptr, M, d, stream);
 }
 
 extern "C" int lvt_layernorm_bwd_bf16dy(const void* dy_bf16, const float* x, const float* mean, const float* rstd,
                                         const float* gamma, const float* dres, float* dx_f32, void* dx_bf16,
                                         float* dgamma, float* dbeta, int M, int d, void* stream) {
-  return layernorm_bwd_impl(dy_bf16, true, x, mean, rstd, gamma, dres, dx_f32, dx_bf16, dgamma, dbeta, M, d, stream);
+  return layernorm_bwd_impl(dy_bf16, true, x, mean, rstd, gamma, dres, dx_f32, dx_bf16, dgamma, dbeta, nullptr, M, d, stream);
+}
+
+extern "C" int lvt_layernorm_bwd_ex(const void* dy, int dy_is_bf16, const float* x, const float* mean, const float* rstd,
+                                    const float* gamma, const float* dres, float* dx_f32, void* dx_bf16, float* dgamma,
+                                    float* dbeta, float* dx_colsum, int M, int d, void* stream) {
+  return layernorm_bwd_impl(dy, dy_is_bf16 != 0, x, mean, rstd, gamma, dres, dx_f32, dx_bf16, dgamma, dbeta, dx_colsum, M, d,
+                            stream);
 }
 
 extern "C" int lvt_colsum_bf16(const void* x, float* out, int M, int N, long long ld, void* stream) {

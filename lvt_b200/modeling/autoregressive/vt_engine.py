@@ -385,11 +385,12 @@ class VTEngine:
         check(self.lib.lvt_layernorm_fwd(_vp(x), _vp(g), _vp(b), _vp(y), _vp(mean), _vp(rstd), M, self.spec.d,
                                          LN_EPS, stream_ptr()), "lvt_layernorm_fwd")
 
-    def _ln_bwd(self, dy, x, mean, rstd, g, dres, dx, dxb, dg, db, M):
-        fn = self.lib.lvt_layernorm_bwd_bf16dy if getattr(dy, "dtype", None) == torch.bfloat16 else self.lib.lvt_layernorm_bwd
-        check(fn(_vp(dy), _vp(x), _vp(mean), _vp(rstd), _vp(g), _vp(dres), _vp(dx),
-                                         _vp(dxb), _vp(dg), _vp(db), M, self.spec.d, stream_ptr()),
-              "lvt_layernorm_bwd")
+    def _ln_bwd(self, dy, x, mean, rstd, g, dres, dx, dxb, dg, db, M, dx_colsum=None):
+        """dx_colsum: gradient buffer of the bias of the Linear that produced x (+= column sums of dx)"""
+        is_bf16 = int(getattr(dy, "dtype", None) == torch.bfloat16)
+        check(self.lib.lvt_layernorm_bwd_ex(_vp(dy), is_bf16, _vp(x), _vp(mean), _vp(rstd), _vp(g), _vp(dres), _vp(dx),
+                                            _vp(dxb), _vp(dg), _vp(db), _vp(dx_colsum) if dx_colsum is not None else None,
+                                            M, self.spec.d, stream_ptr()), "lvt_layernorm_bwd_ex")
 
     def _colsum(self, x, out, M, N, ld=None):
         check(self.lib.lvt_colsum_bf16(_vp(x), _vp(out), M, N, ld or N, stream_ptr()), "lvt_colsum_bf16")
@@ -467,7 +468,8 @@ class VTEngine:
             torch.cuda.current_stream().wait_stream(self._side)
             self._side_pending = False
 
-    def _layer_bwd(self, prefix, ws: VTWorkspace, ly: _Layer, x, dy, dy_bf16, dx, dx_bf16, causal=False):
+    def _layer_bwd(self, prefix, ws: VTWorkspace, ly: _Layer, x, dy, dy_bf16, dx, dx_bf16, causal=False,
+                   bias3_done=False, dx_colsum=None):
         """dy (fp32 + bf16 copy) = gradient wrt the layer output; writes dx (fp32 + bf16).
         Main stream: the data-gradient chain.  Side stream: parameter gradients (they only meet again in the
         optimizer); the scratch buffers they read (dy_bf16, dz1, dh_bf16, dS, dqkv) are protected by a join at
@@ -479,8 +481,12 @@ class VTEngine:
         dyb = _vp(dy_bf16).value
         self._side_join()  # previous layer's parameter gradients no longer read the scratch buffers
         # ---- FFN
+        # (bias3_done: the LayerNorm backward that produced dy already accumulated its column sums = the ffn.3 bias
+        # gradient; dx_colsum: where this layer's last LayerNorm backward puts the column sums of dx, the bias
+        # gradient of the Linear that produced x)
         with self._side_begin():
-            self._colsum(dyb, st.gf(prefix + "ffn.3.bias"), M, d)
+            if not bias3_done:
+                self._colsum(dyb, st.gf(prefix + "ffn.3.bias"), M, d)
             self._wgrad(dyb, d, ly.a1.data_ptr(), d, Operand(st.gf(prefix + "ffn.3.weight"), d), d, d, M)
             ev_dy_read = torch.cuda.Event()
             ev_dy_read.record()
@@ -526,7 +532,8 @@ class VTEngine:
              Operand(ws.dln_bf16.data_ptr(), d), out_bf16=ws.dln_bf16)
         torch.cuda.current_stream().wait_event(ev_dy_read)  # dx_bf16 may alias dy_bf16
         self._ln_bwd(ws.dln_bf16, x, ly.mean1, ly.rstd1, st.pf(prefix + "mha.layer_norm.weight"), ws.dh, dx, dx_bf16,
-                     st.gf(prefix + "mha.layer_norm.weight"), st.gf(prefix + "mha.layer_norm.bias"), M)
+                     st.gf(prefix + "mha.layer_norm.weight"), st.gf(prefix + "mha.layer_norm.bias"), M,
+                     dx_colsum=dx_colsum)
 
     def _attn_bwd_split(self, prefix, ws, ly, qkv, dqkv, gbanks, scale):
         """Round-1 attention backward (A/B aid, LVT_ATTN_BWD=split): P read from HBM, dS written to HBM."""
@@ -695,17 +702,20 @@ class VTEngine:
                  Operand(ws.dln.data_ptr(), d), out_f32=ws.dln, res=ws.dln if k else None)
         self._ln_bwd(ws.dln, ws.y_final, ws.mean_p, ws.rstd_p, st.pf("ch_predictor.layer_norm.weight"), None,
                      ws.dy, ws.dy_bf16, st.gf("ch_predictor.layer_norm.weight"),
-                     st.gf("ch_predictor.layer_norm.bias"), M)
+                     st.gf("ch_predictor.layer_norm.bias"), M,
+                     dx_colsum=st.gf(f"decoder.block_local_attention.{nD - 1}.ffn.3.bias"))
         # ---- decoder stack
         for i in reversed(range(nD)):
             ly = ws.layers[nE + i]
             x = ws.layers[nE + i - 1].y if i > 0 else ws.y0
+            # every LayerNorm backward also emits the column sums of its dx: the bias gradient of whatever Linear
+            # produced its input (ffn.3 of the layer below, or the masked conv for layer 0)
+            below = st.gf(f"decoder.block_local_attention.{i - 1}.ffn.3.bias") if i > 0 else st.gf("decoder.conv.conv.bias")
             self._layer_bwd(f"decoder.block_local_attention.{i}.", ws, ly, x, ws.dy, ws.dy_bf16, ws.dy, ws.dy_bf16,
-                            causal=True)
+                            causal=True, bias3_done=True, dx_colsum=below)
         self._side_join()
         # ---- decoder front: y0 = conv(emb) + posenc + bias + zl Wlp^T
         dyb = ws.dy_bf16.data_ptr()
-        self._colsum(dyb, st.gf("decoder.conv.conv.bias"), M, d)
         self._wgrad(dyb, d, ws.zl_bf16.data_ptr(), d, Operand(st.gf("decoder.linear_projector.weight"), d), d, d, M)
         self._wgrad(dyb, d, ws.A0.data_ptr(), ntaps * de, Operand(dwp.data_ptr(), ntaps * de), d, ntaps * de, M)
         gemm(M, ntaps * de, d, Operand(dyb, d), Operand(wp.data_ptr(), ntaps * de, mn_major=True),
@@ -729,8 +739,10 @@ class VTEngine:
             ly = ws.layers[i]
             x = ws.layers[i - 1].y if i > 0 else ws.x0
             first = i == nE - 1
+            below = st.gf(f"encoder.block_local_attention.{i - 1}.ffn.3.bias") if i > 0 else None
             self._layer_bwd(f"encoder.block_local_attention.{i}.", ws, ly, x, ws.dh if first else ws.dy,
-                            ws.dh_bf16 if first else ws.dy_bf16, ws.dy, ws.dy_bf16)
+                            ws.dh_bf16 if first else ws.dy_bf16, ws.dy, ws.dy_bf16, bias3_done=not first,
+                            dx_colsum=below)
         self._side_join()
         # ---- encoder front: x0 = e0 Wlp_e^T ; e0 = gather-sum + bias + slice_emb
         dxb = ws.dy_bf16.data_ptr()

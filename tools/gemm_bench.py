@@ -10,14 +10,33 @@ reps = int(os.environ.get("GEMM_REPS", 20))
 which = sys.argv[1:] or ["qkv", "ffn", "proj", "ffn_dgrad", "ffn_wgrad", "qkv_wgrad", "pv", "softmax"]
 
 
+GRAPH = os.environ.get("GEMM_GRAPH", "1") == "1"  # time `reps` launches inside one CUDA graph (no host launch cost)
+
+
 def timeit(fn, flops, name):
     for _ in range(3):
         fn()
+    torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(reps):
-        fn()
-    e1.record()
+    if GRAPH:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(side):
+            with torch.cuda.graph(g):
+                for _ in range(reps):
+                    fn()
+        torch.cuda.current_stream().wait_stream(side)
+        g.replay()
+        torch.cuda.synchronize()
+        e0.record()
+        g.replay()
+        e1.record()
+    else:
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
     torch.cuda.synchronize()
     t = e0.elapsed_time(e1) / reps * 1e-3
     print(f"{name:12s} {t*1e6:9.1f} us  {flops/t/1e12:8.1f} TFLOP/s")
@@ -50,6 +69,11 @@ tests = {
     "ffn": (lambda: ops.gemm(M, d, d, Operand(x.data_ptr(), d), Operand(w.data_ptr(), d), Operand(o1.data_ptr(), d), out_bf16=o1), 2.0 * M * d * d),
     "proj": (lambda: ops.gemm(M, d, 2 * d, Operand(x2.data_ptr(), 2 * d), Operand(wp.data_ptr(), 2 * d), Operand(of.data_ptr(), d), out_f32=of, res=of), 2.0 * M * d * 2 * d),
     "ffn_dgrad": (lambda: ops.gemm(M, d, d, Operand(x.data_ptr(), d), Operand(w.data_ptr(), d, mn_major=True), Operand(of.data_ptr(), d), out_f32=of), 2.0 * M * d * d),
+    "ffn_res": (lambda: ops.gemm(M, d, d, Operand(x.data_ptr(), d), Operand(w.data_ptr(), d), Operand(of.data_ptr(), d), out_f32=of, res=of), 2.0 * M * d * d),
+    "ffn_mask": (lambda: ops.gemm(M, d, d, Operand(x.data_ptr(), d), Operand(w.data_ptr(), d, mn_major=True), Operand(o1.data_ptr(), d), out_bf16=o1, aux=x, flags=ops.GEMM_MASK), 2.0 * M * d * d),
+    "qkv_dgrad": (lambda: ops.gemm(M, d, 3072, Operand(o3.data_ptr(), 3072), Operand(wq.data_ptr(), da, mn_major=False, cin=da, s_blk=d * da), Operand(o1.data_ptr(), d), out_bf16=o1), 2.0 * M * 3072 * d),
+    "ffn_wgrad_auto": (lambda: ops.gemm(d, d, M, Operand(x.data_ptr(), d, mn_major=True), Operand(o1.data_ptr(), d, mn_major=True), Operand(gw.data_ptr(), d), out_f32=gw, splits=-1, flags=ops.GEMM_ATOMIC), 2.0 * M * d * d),
+    "qkv_wgrad_auto": (lambda: ops.gemm(d, 3072, M, Operand(x.data_ptr(), d, mn_major=True), Operand(o3.data_ptr(), 3072, mn_major=True), Operand(gq.data_ptr(), da, cin=da, s_blk=d * da), out_f32=gq, splits=-1, flags=ops.GEMM_ATOMIC), 2.0 * M * 3072 * d),
     "ffn_wgrad": (lambda: ops.gemm(d, d, M, Operand(x.data_ptr(), d, mn_major=True), Operand(o1.data_ptr(), d, mn_major=True), Operand(gw.data_ptr(), d), out_f32=gw, splits=int(os.environ.get('WGRAD_SPLITS', 18)), flags=ops.GEMM_ATOMIC), 2.0 * M * d * d),
     "qkv_wgrad": (lambda: ops.gemm(d, 3072, M, Operand(x.data_ptr(), d, mn_major=True), Operand(o3.data_ptr(), 3072, mn_major=True), Operand(gq.data_ptr(), da, cin=da, s_blk=d * da), out_f32=gq, splits=6, flags=ops.GEMM_ATOMIC), 2.0 * M * 3072 * d),
     "pv": (lambda: ops.gemm(L, da, L, Operand(P.data_ptr(), L, zdiv=1, s_zhi=L * L), qkv_op(o3, 2, True), Operand(x2.data_ptr(), H * da, cin=da, zdiv=H, s_zlo=da, s_zhi=L * H * da), out_bf16=x2, batch=nb * H), 2.0 * nb * H * L * L * da),
