@@ -405,6 +405,9 @@ def main():
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:
+        # the gradient all-reduce runs NEXT TO the backward: it gets LVT_COMM_SMS SMs (NCCL_MAX_CTAS), the
+        # overlapped backward segments are captured with that many SMs fewer (GraphedTrainStep)
+        os.environ.setdefault("NCCL_MAX_CTAS", os.environ.get("LVT_COMM_SMS", "8") if int(os.environ.get("LVT_COMM_SMS", "8")) > 0 else "32")
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     _lib.require_device()
@@ -511,7 +514,9 @@ def main():
     # ---------------- per-kernel roofline figures (rank 0, timed alone)
     extra = {}
     incumbent = None
-    if rank == 0 and not args.quick:
+    # (single-GPU runs only: at N > 1 the other ranks would sit in a collective while rank 0 measures, and the
+    # Trainer figure would issue rank-0-only collectives)
+    if rank == 0 and world == 1 and not args.quick:
         from lvt_b200 import ops
         from lvt_b200.ops import Operand
         # BlockLocalAttention layer alone: forward + backward of ONE layer (LN, QKV, attention, proj, FFN and
@@ -780,6 +785,10 @@ def main():
                      "kernels": extra},
         "cpu_baseline": {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")},
     }
+    if world > 1 and not args.no_graph:
+        line["comm"] = {"collective": "NCCL all-reduce of the flat fp32 gradient", "buckets": len(stepper.graphs),
+                        "overlap": bool(stepper.overlap), "comm_sms": stepper.comm_sms,
+                        "nccl_max_ctas": os.environ.get("NCCL_MAX_CTAS"), "grad_bytes": int(eng.store.numel * 4)}
     if args.strong:
         line["scaling"] = "strong"
     if incumbent is not None:

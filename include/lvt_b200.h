@@ -35,6 +35,10 @@ const char* lvt_last_error(void);
 /* 0 if the current CUDA device is sm_100 (B200); negative otherwise. No CPU fallback exists. */
 int lvt_device_check(void);
 /* number of kernels this library has launched since load / last reset (bench `gpu_launches`) */
+/* SM budget of the persistent tensor-core kernels (GEMM, attention): n > 0 sizes their grids for n SMs, 0 = all.
+   Used while an NCCL gradient all-reduce holds a few SMs next to the backward (the launches captured into a CUDA
+   graph keep the budget they were captured with). */
+void lvt_set_sm_limit(int n);
 long long lvt_launch_count(void);
 void lvt_launch_count_reset(void);
 

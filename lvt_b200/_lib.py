@@ -95,6 +95,7 @@ SYMBOLS = {
     "lvt_abi_version": (_i, []),
     "lvt_last_error": (ctypes.c_char_p, []),
     "lvt_device_check": (_i, []),
+    "lvt_set_sm_limit": (None, [_i]),
     "lvt_launch_count": (_ll, []),
     "lvt_launch_count_reset": (None, []),
     "lvt_vt_sample_pixel": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _vp]),

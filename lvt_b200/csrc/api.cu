@@ -30,6 +30,14 @@ bool lvt_pdl_enabled() {
 
 void lvt_count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+// SM budget of the persistent tensor-core kernels (0 = every SM).  While a gradient bucket is being all-reduced the
+// collective's CTAs hold a few SMs for its whole duration; a persistent grid sized for ALL SMs would then run its
+// last CTAs as a second wave (twice the kernel time), so the overlapped part of the backward is launched -- and
+// captured into its CUDA graphs -- with that many SMs fewer.
+static std::atomic<int> g_sm_limit{0};
+int lvt_sm_limit() { return g_sm_limit.load(std::memory_order_relaxed); }
+extern "C" void lvt_set_sm_limit(int n) { g_sm_limit.store(n > 0 ? n : 0, std::memory_order_relaxed); }
+
 extern "C" int lvt_abi_version(void) { return LVT_B200_ABI_VERSION; }
 
 extern "C" const char* lvt_last_error(void) { return g_last_error; }

@@ -28,6 +28,7 @@
 #include "common.cuh"
 
 extern void lvt_count_launch(int n);
+extern int lvt_sm_limit();
 int lvt_make_operand_map(CUtensorMap* out, const void* base, long long c_extent, long long r_extent, int cin,
                          long long ld, long long s_blk, int batch, int zdiv, long long s_zlo, long long s_zhi,
                          int box_rows, int esize);
@@ -622,7 +623,9 @@ extern "C" int lvt_attn_bwd(const LvtAttnBwd* a, void* stream_) {
   p.dbank_t = a->dbank_t; p.dbank_h = a->dbank_h; p.dbank_w = a->dbank_w;
   p.scratch = a->scratch;
   p.prof = reinterpret_cast<long long*>(a->prof);
-  const int grid = (int)(nz < sm_count() ? nz : sm_count());
+  const int lim = lvt_sm_limit();
+  const int sms = (lim > 0 && lim < sm_count()) ? lim : sm_count();
+  const int grid = (int)(nz < sms ? nz : sms);
   auto launch = [&](auto kern, int which) -> int {
     static bool configured[2] = {false, false};
     if (!configured[which]) {

@@ -22,6 +22,7 @@
 #include "common.cuh"
 
 extern void lvt_count_launch(int n);
+extern int lvt_sm_limit();
 
 namespace {
 
@@ -1373,7 +1374,8 @@ int num_sms() {
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     if (n <= 0) n = 148;
   }
-  return n;
+  const int lim = lvt_sm_limit();  // (lvt_set_sm_limit: SMs left to a concurrent collective)
+  return (lim > 0 && lim < n) ? lim : n;
 }
 
 }  // namespace

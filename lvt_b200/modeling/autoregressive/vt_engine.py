@@ -231,6 +231,33 @@ class VTWorkspace:
             self.de0, self.de0_bf16 = e((M, de), f32), e((M, de), bf16)
 
 
+def layer_cuts(n, parts):
+    """layer boundaries of a stack of n layers split into `parts` backward segments, top down: (8, 2) -> [8, 4, 0]"""
+    p = max(1, min(parts, n))
+    return [n - (n * j) // p for j in range(p + 1)]
+
+
+def bucket_ranges(offsets, numel, n_enc, n_dec, parts):
+    """Flat-gradient ranges [lo, hi) of the backward segments of VTEngine.backward_plan, in execution order: the
+    parameters are laid out in forward order (encoder front, encoder layers, decoder front, decoder layers,
+    predictor), the backward completes them back to front, so every bucket is contiguous and the buckets tile
+    [0, numel) from the top down."""
+    def layer_off(stack, i):
+        return offsets[f"{stack}.block_local_attention.{i}.dt_bank"]
+
+    out, hi = [], numel
+    cd, ce = layer_cuts(n_dec, parts), layer_cuts(n_enc, parts)
+    for j in range(len(cd) - 1):
+        lo = offsets["decoder.ch_embedder.0.weight"] if j == len(cd) - 2 else layer_off("decoder", cd[j + 1])
+        out.append((lo, hi))
+        hi = lo
+    for j in range(len(ce) - 1):
+        lo = 0 if j == len(ce) - 2 else layer_off("encoder", ce[j + 1])
+        out.append((lo, hi))
+        hi = lo
+    return out
+
+
 class VTEngine:
     def __init__(self, spec: VTSpec, device="cuda"):
         _lib.require_device()
@@ -336,13 +363,17 @@ class VTEngine:
                        (s.nc, ktaps, s.nv, s.de), (ktaps * s.nv * s.de, s.nv * s.de, s.de, 1),
                        (s.nv * ktaps, 1, ktaps, s.nc * s.nv * ktaps))
 
-    def _fold_special_grads_dec(self, slice_shape):
-        """... one-hot half of the predictor's U[k], live taps of the masked conv."""
+    def _fold_special_grads_pred(self):
+        """... one-hot half of the predictor's U[k] (complete after the predictor backward)"""
         s, st = self.spec, self.store
         for k in range(1, s.nc):
             ld = s.d + k * s.nv
             self._permute4(self.dut[k], st.gf(f"ch_predictor.U.{k}.weight") + 4 * s.d, False, True,
                            (1, 1, k * s.nv, s.d), (0, 0, s.d, 1), (0, 0, 1, ld))
+
+    def _fold_special_grads_conv(self, slice_shape):
+        """... live taps of the masked conv (complete after the decoder front)"""
+        s, st = self.spec, self.store
         taps, offs, wp, dwp = self._live_taps(slice_shape)
         ntaps = len(taps)
         for q, (it, ih, iw) in enumerate(taps):
@@ -675,16 +706,47 @@ class VTEngine:
         off = self.store.offsets["decoder.ch_embedder.0.weight"]
         return self.store.grad[off:], self.store.grad[:off]
 
+    def backward_plan(self, ws: VTWorkspace, parts=2):
+        """The backward as 2 * parts segments in execution order, [(callable, lo, hi)]: after segment i has run, the
+        slice [lo, hi) of the flat gradient is final (the parameters are laid out in forward order, so the buckets
+        are contiguous and complete back to front) and may be all-reduced while the next segments run."""
+        s = self.spec
+        nE, nD = len(s.blocks_e), len(s.blocks_d)
+        ranges = bucket_ranges(self.store.offsets, self.store.numel, nE, nD, parts)
+        cd, ce = layer_cuts(nD, parts), layer_cuts(nE, parts)
+        segs = []
+        for j in range(len(cd) - 1):
+            def seg(top=cd[j], bot=cd[j + 1], first=j == 0, last=j == len(cd) - 2):
+                if first:
+                    self._bwd_predictor(ws)
+                self._bwd_dec_layers(ws, top, bot)
+                if last:
+                    self._bwd_dec_front(ws)
+            segs.append(seg)
+        for j in range(len(ce) - 1):
+            def seg(top=ce[j], bot=ce[j + 1], last=j == len(ce) - 2):
+                self._bwd_enc_layers(ws, top, bot)
+                if last:
+                    self._bwd_enc_front(ws)
+            segs.append(seg)
+        return [(fn, lo, hi) for fn, (lo, hi) in zip(segs, ranges)]
+
     def backward_decoder(self, ws: VTWorkspace):
         """Channel predictor, decoder stack, decoder front; leaves d(loss)/d(zl) in ws.dh / ws.dh_bf16."""
+        self._bwd_predictor(ws)
+        self._bwd_dec_layers(ws, len(self.spec.blocks_d), 0)
+        self._bwd_dec_front(ws)
+
+    def backward_encoder(self, ws: VTWorkspace):
+        """Encoder stack and encoder front (gradient entering through ws.dh / ws.dh_bf16)."""
+        self._bwd_enc_layers(ws, len(self.spec.blocks_e), 0)
+        self._bwd_enc_front(ws)
+
+    def _bwd_predictor(self, ws: VTWorkspace):
         s, st = self.spec, self.store
-        M, d, de, nv, nc = ws.M, s.d, s.de, s.nv, s.nc
-        t, h, w = ws.slice_shape
-        taps, offs, wp, dwp = self._live_taps(ws.slice_shape)
-        ntaps = len(taps)
-        nE, nD = len(s.blocks_e), len(s.blocks_d)
+        M, d, nv, nc = ws.M, s.d, s.nv, s.nc
+        nD = len(s.blocks_d)
         self._zero_special_grads()
-        # ---- channel predictor
         for k in range(nc):
             ld = d + k * nv
             dl = ws.dlogits[k].data_ptr()
@@ -700,12 +762,17 @@ class VTEngine:
             gemm(M, d, d, Operand(ws.du.data_ptr(), d),
                  Operand(st.pb(f"ch_predictor.U.{k}.weight"), ld, mn_major=True),
                  Operand(ws.dln.data_ptr(), d), out_f32=ws.dln, res=ws.dln if k else None)
+        self._fold_special_grads_pred()
         self._ln_bwd(ws.dln, ws.y_final, ws.mean_p, ws.rstd_p, st.pf("ch_predictor.layer_norm.weight"), None,
                      ws.dy, ws.dy_bf16, st.gf("ch_predictor.layer_norm.weight"),
                      st.gf("ch_predictor.layer_norm.bias"), M,
                      dx_colsum=st.gf(f"decoder.block_local_attention.{nD - 1}.ffn.3.bias"))
-        # ---- decoder stack
-        for i in reversed(range(nD)):
+
+    def _bwd_dec_layers(self, ws: VTWorkspace, top, bot):
+        """decoder layers top-1 .. bot"""
+        st = self.store
+        nE = len(self.spec.blocks_e)
+        for i in reversed(range(bot, top)):
             ly = ws.layers[nE + i]
             x = ws.layers[nE + i - 1].y if i > 0 else ws.y0
             # every LayerNorm backward also emits the column sums of its dx: the bias gradient of whatever Linear
@@ -714,7 +781,14 @@ class VTEngine:
             self._layer_bwd(f"decoder.block_local_attention.{i}.", ws, ly, x, ws.dy, ws.dy_bf16, ws.dy, ws.dy_bf16,
                             causal=True, bias3_done=True, dx_colsum=below)
         self._side_join()
-        # ---- decoder front: y0 = conv(emb) + posenc + bias + zl Wlp^T
+
+    def _bwd_dec_front(self, ws: VTWorkspace):
+        """decoder front: y0 = conv(emb) + posenc + bias + zl Wlp^T"""
+        s, st = self.spec, self.store
+        M, d, de, nv, nc = ws.M, s.d, s.de, s.nv, s.nc
+        t, h, w = ws.slice_shape
+        taps, offs, wp, dwp = self._live_taps(ws.slice_shape)
+        ntaps = len(taps)
         dyb = ws.dy_bf16.data_ptr()
         self._wgrad(dyb, d, ws.zl_bf16.data_ptr(), d, Operand(st.gf("decoder.linear_projector.weight"), d), d, d, M)
         self._wgrad(dyb, d, ws.A0.data_ptr(), ntaps * de, Operand(dwp.data_ptr(), ntaps * de), d, ntaps * de, M)
@@ -727,15 +801,13 @@ class VTEngine:
         # (written to the dh buffers: the GEMM may not overwrite its own A operand)
         gemm(M, d, d, Operand(dyb, d), Operand(st.pb("decoder.linear_projector.weight"), d, mn_major=True),
              Operand(ws.dh.data_ptr(), d), out_f32=ws.dh, out_bf16=ws.dh_bf16)
-        self._fold_special_grads_dec(ws.slice_shape)
+        self._fold_special_grads_conv(ws.slice_shape)
 
-    def backward_encoder(self, ws: VTWorkspace):
-        """Encoder stack and encoder front (gradient entering through ws.dh / ws.dh_bf16)."""
-        s, st = self.spec, self.store
-        M, d, de, nv, nc = ws.M, s.d, s.de, s.nv, s.nc
-        nE = len(s.blocks_e)
-        # ---- encoder stack
-        for i in reversed(range(nE)):
+    def _bwd_enc_layers(self, ws: VTWorkspace, top, bot):
+        """encoder layers top-1 .. bot"""
+        st = self.store
+        nE = len(self.spec.blocks_e)
+        for i in reversed(range(bot, top)):
             ly = ws.layers[i]
             x = ws.layers[i - 1].y if i > 0 else ws.x0
             first = i == nE - 1
@@ -744,7 +816,11 @@ class VTEngine:
                             ws.dh_bf16 if first else ws.dy_bf16, ws.dy, ws.dy_bf16, bias3_done=not first,
                             dx_colsum=below)
         self._side_join()
-        # ---- encoder front: x0 = e0 Wlp_e^T ; e0 = gather-sum + bias + slice_emb
+
+    def _bwd_enc_front(self, ws: VTWorkspace):
+        """encoder front: x0 = e0 Wlp_e^T ; e0 = gather-sum + bias + slice_emb"""
+        s, st = self.spec, self.store
+        M, d, de, nv, nc = ws.M, s.d, s.de, s.nv, s.nc
         dxb = ws.dy_bf16.data_ptr()
         self._wgrad(dxb, d, ws.e0.data_ptr(), de, Operand(st.gf("encoder.linear_projector.weight"), de), d, de, M)
         gemm(M, de, d, Operand(dxb, d), Operand(st.pb("encoder.linear_projector.weight"), de, mn_major=True),
@@ -796,18 +872,24 @@ class VTEngine:
 class GraphedTrainStep:
     """The DSFVT train step (zero_grad + forward + backward [+ gradient all-reduce] + optimizer)
     captured once into CUDA graphs and replayed: one host launch per step instead of ~700.
-    With world_size > 1 the flat fp32 gradient is summed across ranks in two buckets (reference: DDP over
-    self.model, meta_arch/vt.py:61-63): the decoder + predictor bucket is reduced on a communication stream
-    WHILE the encoder half of the backward runs, the encoder bucket after it; the optimizer kernel's
-    grad_scale averages."""
+    With world_size > 1 the flat fp32 gradient is summed across ranks (reference: DDP over self.model,
+    meta_arch/vt.py:61-63) in 2 * parts buckets, back to front as the backward completes them
+    (VTEngine.backward_plan): bucket i is all-reduced on a communication stream WHILE the segments after it
+    run; only the last bucket (the bottom encoder layers) is exposed.  The overlapped segments are captured with
+    an SM budget of (all - comm_sms) for the persistent GEMM / attention kernels (lvt_set_sm_limit): NCCL's CTAs
+    hold their SMs for the whole collective, and a persistent grid sized for every SM would run its last CTAs as
+    a second wave.  The optimizer kernel's grad_scale averages."""
 
-    def __init__(self, engine: VTEngine, ws: VTWorkspace, world_size=1, allreduce=None, overlap=True):
+    def __init__(self, engine: VTEngine, ws: VTWorkspace, world_size=1, allreduce=None, overlap=True, parts=None,
+                 comm_sms=None):
         self.engine, self.ws = engine, ws
         self.world_size = world_size
         self.allreduce = allreduce
         self.overlap = overlap  # False: one all-reduce of the whole flat gradient after the backward
-        self.g_fb = None     # zero-grad + forward + backward (decoder half only when world_size > 1)
-        self.g_enc = None    # encoder half of the backward (world_size > 1)
+        self.parts = int(os.environ.get("LVT_GRAD_PARTS", "8")) if parts is None else parts
+        self.comm_sms = int(os.environ.get("LVT_COMM_SMS", "8")) if comm_sms is None else comm_sms
+        self.graphs = []     # [zero-grad + forward + segment 0, segment 1, ...]
+        self.plan = None
         self.g_opt = None
         self.comm = torch.cuda.Stream() if allreduce is not None else None
         self.launches_per_step = 0
@@ -816,11 +898,6 @@ class GraphedTrainStep:
         self.engine.zero_grad()
         self.engine.forward(self.ws, train=True)
         self.engine.backward(self.ws)
-
-    def _fwd_bwd_dec(self):
-        self.engine.zero_grad()
-        self.engine.forward(self.ws, train=True)
-        self.engine.backward_decoder(self.ws)
 
     def _opt(self):
         """eager: lr / bias corrections are by-value kernel arguments (LR schedules, Adam step count)"""
@@ -840,36 +917,44 @@ class GraphedTrainStep:
         eng.opt["step"] = snap[3]
         eng.refresh_shadows()
 
-    def _reduce_overlapped(self, run_encoder_backward):
-        """bucket 0 (decoder + predictor gradients) on the communication stream during the encoder backward"""
+    def _run(self, segments):
+        """segments[i](): [zero-grad + forward +] backward segment i; the all-reduce of bucket i goes to the
+        communication stream as soon as the segment has been issued"""
+        grad = self.engine.store.grad
         if not self.overlap:
-            run_encoder_backward()
-            self.allreduce(self.engine.store.grad)
+            for seg in segments:
+                seg()
+            self.allreduce(grad)
             return
         main = torch.cuda.current_stream()
-        b_dec, b_enc = self.engine.grad_buckets()
-        self.comm.wait_stream(main)
-        with torch.cuda.stream(self.comm):
-            self.allreduce(b_dec)
-        run_encoder_backward()
-        self.comm.wait_stream(main)
-        with torch.cuda.stream(self.comm):
-            self.allreduce(b_enc)
+        for seg, (_, lo, hi) in zip(segments, self.plan):
+            seg()
+            self.comm.wait_stream(main)
+            with torch.cuda.stream(self.comm):
+                self.allreduce(grad[lo:hi])
         main.wait_stream(self.comm)
 
     def capture(self, warmup=2):
         """Warm-up (kernel attributes, TMA maps, NCCL channels) runs real steps on whatever is staged in the
         workspace; parameters and optimizer state are snapshotted before and restored after, so capturing
         does not train."""
-        eng = self.engine
+        eng, lib = self.engine, self.engine.lib
+        dist = self.allreduce is not None
+        if dist:
+            self.plan = eng.backward_plan(self.ws, self.parts)
+
+            def first():
+                eng.zero_grad()
+                eng.forward(self.ws, train=True)
+                self.plan[0][0]()
+            eager = [first] + [p[0] for p in self.plan[1:]]
         snap = self._snapshot()
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(warmup):  # eager warm-up: sets kernel attributes, builds TMA maps
-                if self.allreduce is not None:
-                    self._fwd_bwd_dec()
-                    self._reduce_overlapped(lambda: eng.backward_encoder(self.ws))
+                if dist:
+                    self._run(eager)
                 else:
                     self._fwd_bwd()
                 self._opt()
@@ -879,16 +964,22 @@ class GraphedTrainStep:
         self._restore(snap)
         torch.cuda.synchronize()
         n0 = _lib.launch_count()
-        self.g_fb = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.g_fb):
-            if self.allreduce is not None:
-                self._fwd_bwd_dec()
-            else:
+        self.graphs = []
+        if dist:
+            sms = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+            for i, fn in enumerate(eager):
+                # segments after the first run next to the all-reduce of the bucket before them
+                lib.lvt_set_sm_limit(sms - self.comm_sms if (i > 0 and self.overlap and self.comm_sms > 0) else 0)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    fn()
+                self.graphs.append(g)
+            lib.lvt_set_sm_limit(0)
+        else:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
                 self._fwd_bwd()
-        if self.allreduce is not None:
-            self.g_enc = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.g_enc):
-                eng.backward_encoder(self.ws)
+            self.graphs.append(g)
         self.g_opt = torch.cuda.CUDAGraph()  # weight re-layouts after the (eager) optimizer kernel
         with torch.cuda.graph(self.g_opt):
             self._refresh()
@@ -896,9 +987,10 @@ class GraphedTrainStep:
         torch.cuda.synchronize()
 
     def step(self):
-        self.g_fb.replay()
         if self.allreduce is not None:
-            self._reduce_overlapped(self.g_enc.replay)
+            self._run([g.replay for g in self.graphs])
+        else:
+            self.graphs[0].replay()
         self._opt()
         self.g_opt.replay()
         return self.ws.loss

@@ -39,9 +39,15 @@ def run_dp_parity(rank, world, dist=None, layers=2, global_b=16, steps=4, tol=1e
     ws = eng.workspace(per, (1, 16, 16), tuple(mine[0].shape[2:]), train=True)
     eng.set_inputs(ws, *mine)
     hook = (lambda flat: dist.all_reduce(flat)) if world > 1 else None
+    stepper = None
+    if world > 1:
+        # the production multi-GPU path: CUDA-graph segments with the bucketed all-reduce overlapped (GraphedTrainStep)
+        from ..modeling.autoregressive.vt_engine import GraphedTrainStep
+        stepper = GraphedTrainStep(eng, ws, world_size=world, allreduce=hook, overlap=True)
+        stepper.capture(warmup=1)
     dp = []
     for _ in range(steps):
-        loss = eng.train_step(ws, grad_hook=hook, grad_scale=1.0 / world).clone()
+        loss = (stepper.step() if stepper is not None else eng.train_step(ws, grad_hook=hook, grad_scale=1.0 / world)).clone()
         if world > 1:
             dist.all_reduce(loss)
             loss /= world
@@ -53,7 +59,7 @@ def run_dp_parity(rank, world, dist=None, layers=2, global_b=16, steps=4, tol=1e
         ref_eng.set_inputs(ws1, *batch)
         ref = [ref_eng.train_step(ws1).item() for _ in range(steps)]
         err = max(abs(a - b) / abs(b) for a, b in zip(dp, ref))
-        out = {"world": world, "global_batch": global_b, "layers": f"{layers}+{layers}", "steps": steps,
+        out = {"world": world, "global_batch": global_b, "path": "GraphedTrainStep, bucketed all-reduce overlapped", "layers": f"{layers}+{layers}", "steps": steps,
                "losses": dp, "losses_1gpu": ref, "max_rel_diff": err, "tol": tol, "ok": bool(err <= tol)}
     if world > 1:
         dist.barrier()

@@ -73,3 +73,28 @@ def test_batched_slice_preparation_equals_per_sample_mapper():
             for key in ("context", "slice", "slice_idx", "ignore_mask"):
                 w = torch.stack([x[key] for x in want])
                 assert got[key].dtype == w.dtype and torch.equal(got[key], w), (name, n_prime, key)
+
+
+def test_gradient_buckets_tile_the_flat_buffer_in_backward_order():
+    """VTEngine.backward_plan's buckets (bucket_ranges): contiguous, cover the whole flat gradient from the top down,
+    and every parameter lies in the bucket of the backward segment that completes it."""
+    from lvt_b200.modeling.autoregressive.vt_engine import ParamStore, VTSpec, bucket_ranges, layer_cuts
+    spec = VTSpec()
+    store = ParamStore(spec.param_shapes(), "cpu")
+    for parts in (1, 2, 4, 8):
+        r = bucket_ranges(store.offsets, store.numel, 8, 8, parts)
+        assert len(r) == 2 * parts and r[0][1] == store.numel and r[-1][0] == 0
+        assert all(r[i][0] == r[i + 1][1] for i in range(len(r) - 1)) and all(lo < hi for lo, hi in r)
+        cd = layer_cuts(8, parts)
+
+        def bucket_of(name):
+            o = store.offsets[name]
+            return next(i for i, (lo, hi) in enumerate(r) if lo <= o < hi)
+        assert bucket_of("ch_predictor.P.3.bias") == 0 and bucket_of("decoder.block_local_attention.7.ffn.3.bias") == 0
+        assert bucket_of("decoder.ch_embedder.0.weight") == parts - 1 and bucket_of("decoder.conv.conv.weight") == parts - 1
+        assert bucket_of("encoder.block_local_attention.7.mha.w_q") == parts
+        assert bucket_of("encoder.conv.weight") == 2 * parts - 1 and bucket_of("encoder.block_local_attention.0.dt_bank") == 2 * parts - 1
+        for j in range(parts):   # decoder layers cd[j]-1 .. cd[j+1] are completed by segment j
+            for i in range(cd[j + 1], cd[j]):
+                assert bucket_of(f"decoder.block_local_attention.{i}.ffn.1.weight") == j
+                assert bucket_of(f"encoder.block_local_attention.{i}.ffn.1.weight") == parts + j
