@@ -330,6 +330,15 @@ int lvt_vq_gather_nhwc(const int64_t* idx, const float* codebook, float* out, vo
  * x fp32 NCHW [n,3,64,64] -> A bf16 [4*n*256, 64] (48 columns k=(kh*4+kw)*3+c, 16 zeros), rows in
  * phase-major order of the 32x32 output.                                                      */
 int lvt_vqvae_in_im2col(const float* x, void* a_bf16, int n, float mean, float std, void* stream);
+/* High-precision encoder (inference / CodesExtractor: the latents are the wire format between the two models, and a
+ * bf16 encoder flips ~1-2 % of the codes of near-tied positions).  Every fp32 value v is carried as the bf16 pair
+ * hi = bf16(v), lo = bf16(v - hi); activations are stored [hi | lo | hi], weights [hi | hi | lo] (three C-wide segments),
+ * so ONE lvt_gemm_bf16 over K = 3C contracts a_hi w_hi + a_lo w_hi + a_hi w_lo with fp32 accumulation: a w up to
+ * ~2^-17 relative.  lvt_split3_bf16: v = [relu](in [+ add]) (fp32 [rows, C]) -> out_bf16 [rows, 3C] (+ out_f32 = v);
+ * lvt_vqvae_in_im2col_split: as lvt_vqvae_in_im2col with A [4*n*256, 192] in the [hi | lo | hi] form.            */
+int lvt_split3_bf16(const float* in, const float* add, void* out_bf16, float* out_f32, long long rows, int C, int relu,
+                    int weight_pattern, void* stream);
+int lvt_vqvae_in_im2col_split(const float* x, void* a_bf16, int n, float mean, float std, void* stream);
 /* ConvTranspose2d(C->3, k4, s2, p1) + tanh (resdecoder.py:56,68-69), second half: the contraction over the C
  * input channels is one lvt_gemm_bf16 call Y[row, (kh*4+kw)*3+co] = sum_c act[row,c] * w[c][co][kh][kw] over the
  * phase-major 32x32 input pixels; this entry gathers the 2x2 (input pixel, tap) pairs of every output pixel, adds

@@ -129,6 +129,8 @@ SYMBOLS = {
     "lvt_vq_argmin_nhwc": (_i, [_vp] * 7 + [_i] * 5 + [_vp]),
     "lvt_vq_gather_nhwc": (_i, [_vp] * 4 + [_i] * 5 + [_vp]),
     "lvt_vqvae_in_im2col": (_i, [_vp, _vp, _i, _f, _f, _vp]),
+    "lvt_split3_bf16": (_i, [_vp, _vp, _vp, _vp, _ll, _i, _i, _i, _vp]),
+    "lvt_vqvae_in_im2col_split": (_i, [_vp, _vp, _i, _f, _f, _vp]),
     "lvt_vqvae_out_col2im_tanh": (_i, [_vp, _vp, _vp, _i, _vp]),
     "lvt_vqvae_recon_loss": (_i, [_vp] * 5 + [_i, _f, _f, _f, _vp]),
     "lvt_vqvae_out_convt_g": (_i, [_vp, _vp, _i, _vp]),

@@ -17,6 +17,9 @@ LVT_DEVICE_INLINE float4 ld4(const float* p) { return *reinterpret_cast<const fl
 // Conv2d(3 -> nf/2, k4, s2, p1) input side: normalise (x-mean)/std and write the im2col matrix
 // A1 [4*n*256, 64] bf16 (48 real columns k = (kh*4+kw)*3 + c, 16 zero columns), rows in phase-major
 // order of the 32x32 output grid.  One thread per (row, tap).
+// SPLIT: every value v is written as the bf16 pair hi = bf16(v), lo = bf16(v - hi) in three 64-column segments
+// [hi | lo | hi] (row stride 192): the A operand of the 3-term split product of the high-precision encoder.
+template <bool SPLIT>
 __global__ void __launch_bounds__(256)
 in_im2col_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ A, int n, float mean, float inv_std) {
   const long long gid = (long long)blockIdx.x * 256 + threadIdx.x;
@@ -36,12 +39,64 @@ in_im2col_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ A, int
 #pragma unroll
     for (int c = 0; c < 3; ++c) v[c] = (x[(((long long)img * 3 + c) * 64 + ih) * 64 + iw] - mean) * inv_std;
   }
-  __nv_bfloat16* a = A + row * 64 + tap * 3;
+  if constexpr (SPLIT) {
+    __nv_bfloat16* a = A + row * 192 + tap * 3;
 #pragma unroll
-  for (int c = 0; c < 3; ++c) a[c] = __float2bfloat16(v[c]);
-  if (tap == 15) {
+    for (int c = 0; c < 3; ++c) {
+      const __nv_bfloat16 hi = __float2bfloat16(v[c]);
+      a[c] = hi;
+      a[64 + c] = __float2bfloat16(v[c] - __bfloat162float(hi));
+      a[128 + c] = hi;
+    }
+    if (tap == 15) {
 #pragma unroll
-    for (int c = 48; c < 64; ++c) A[row * 64 + c] = __float2bfloat16(0.f);
+      for (int seg = 0; seg < 3; ++seg)
+#pragma unroll
+        for (int c = 48; c < 64; ++c) A[row * 192 + seg * 64 + c] = __float2bfloat16(0.f);
+    }
+  } else {
+    __nv_bfloat16* a = A + row * 64 + tap * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) a[c] = __float2bfloat16(v[c]);
+    if (tap == 15) {
+#pragma unroll
+      for (int c = 48; c < 64; ++c) A[row * 64 + c] = __float2bfloat16(0.f);
+    }
+  }
+}
+
+// v = [relu](in [+ add]) -> out_f32 (optional) and the bf16 split of v in three C-wide segments of a 3C-wide row:
+// activations [hi | lo | hi], weights [hi | hi | lo], so that one GEMM over K = 3C contracts
+// a_hi w_hi + a_lo w_hi + a_hi w_lo = a w up to the dropped a_lo w_lo term (~2^-17 relative instead of bf16's 2^-9).
+__global__ void __launch_bounds__(256)
+split3_kernel(const float* __restrict__ in, const float* __restrict__ add, __nv_bfloat16* __restrict__ out,
+              float* __restrict__ out_f32, long long rows, int C, int relu, int weight_pattern) {
+  const int c4 = C >> 2;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < rows * c4; i += (long long)gridDim.x * 256) {
+    const long long r = i / c4;
+    const int c = (int)(i - r * c4) * 4;
+    float4 v = *reinterpret_cast<const float4*>(in + r * C + c);
+    if (add) {
+      const float4 a = *reinterpret_cast<const float4*>(add + r * C + c);
+      v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+    }
+    if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+    if (out_f32) *reinterpret_cast<float4*>(out_f32 + r * C + c) = v;
+    const float e[4] = {v.x, v.y, v.z, v.w};
+    __nv_bfloat16 hi[4], lo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      hi[j] = __float2bfloat16(e[j]);
+      lo[j] = __float2bfloat16(e[j] - __bfloat162float(hi[j]));
+    }
+    __nv_bfloat16* o = out + r * 3 * C + c;
+    const uint2 uh = make_uint2(((uint32_t)__bfloat16_as_ushort(hi[1]) << 16) | __bfloat16_as_ushort(hi[0]),
+                                ((uint32_t)__bfloat16_as_ushort(hi[3]) << 16) | __bfloat16_as_ushort(hi[2]));
+    const uint2 ul = make_uint2(((uint32_t)__bfloat16_as_ushort(lo[1]) << 16) | __bfloat16_as_ushort(lo[0]),
+                                ((uint32_t)__bfloat16_as_ushort(lo[3]) << 16) | __bfloat16_as_ushort(lo[2]));
+    *reinterpret_cast<uint2*>(o) = uh;
+    *reinterpret_cast<uint2*>(o + C) = weight_pattern ? uh : ul;
+    *reinterpret_cast<uint2*>(o + 2 * C) = weight_pattern ? ul : uh;
   }
 }
 
@@ -216,8 +271,28 @@ int grid_for(long long n) { return (int)((n + 255) / 256 < 148 * 8 ? (n + 255) /
 extern "C" int lvt_vqvae_in_im2col(const float* x, void* a_bf16, int n, float mean, float std, void* stream) {
   LVT_CHECK_ARG(x && a_bf16 && n > 0 && std != 0.f, "lvt_vqvae_in_im2col: bad argument");
   const long long threads = (long long)4 * n * 256 * 16;
-  in_im2col_kernel<<<lvt_ceil_div(threads, 256), 256, 0, STREAM(stream)>>>(
+  in_im2col_kernel<false><<<lvt_ceil_div(threads, 256), 256, 0, STREAM(stream)>>>(
       x, reinterpret_cast<__nv_bfloat16*>(a_bf16), n, mean, 1.f / std);
+  LVT_CHECK_LAUNCH();
+  lvt_count_launch(1);
+  return LVT_OK;
+}
+
+extern "C" int lvt_vqvae_in_im2col_split(const float* x, void* a_bf16, int n, float mean, float std, void* stream) {
+  LVT_CHECK_ARG(x && a_bf16 && n > 0 && std != 0.f, "lvt_vqvae_in_im2col_split: bad argument");
+  const long long threads = (long long)4 * n * 256 * 16;
+  in_im2col_kernel<true><<<lvt_ceil_div(threads, 256), 256, 0, STREAM(stream)>>>(
+      x, reinterpret_cast<__nv_bfloat16*>(a_bf16), n, mean, 1.f / std);
+  LVT_CHECK_LAUNCH();
+  lvt_count_launch(1);
+  return LVT_OK;
+}
+
+extern "C" int lvt_split3_bf16(const float* in, const float* add, void* out_bf16, float* out_f32, long long rows, int C,
+                               int relu, int weight_pattern, void* stream) {
+  LVT_CHECK_ARG(in && out_bf16 && rows > 0 && C > 0 && C % 4 == 0, "lvt_split3_bf16: bad argument");
+  split3_kernel<<<grid_for(rows * (C / 4)), 256, 0, STREAM(stream)>>>(in, add, reinterpret_cast<__nv_bfloat16*>(out_bf16),
+                                                                      out_f32, rows, C, relu, weight_pattern);
   LVT_CHECK_LAUNCH();
   lvt_count_launch(1);
   return LVT_OK;

@@ -85,6 +85,9 @@ class VQVAEModel(nn.Module):
         self.vis_period = cfg.VIS_PERIOD
         self._anchor = torch.zeros(1, device=self.device, requires_grad=True)
         self._graphed, self._graphs = False, {}
+        # encode / inference run the encoder in the high-precision split form (VQVAEEngine.encode_precise): the code
+        # indices are the wire format between the two models; LVT_VQVAE_PRECISE=0 selects the plain bf16 encoder
+        self.precise_latents = os.environ.get("LVT_VQVAE_PRECISE", "1") != "0"
         self.back_normalizer = lambda y: y * spec.std + spec.mean
         self.normalizer = lambda x: (x - spec.mean) / spec.std
 
@@ -185,7 +188,7 @@ class VQVAEModel(nn.Module):
             return {"loss_reconstruction": losses[0], "loss_commitment": losses[1]}
         if mode == "inference":
             w = self._stage(x, train=False)
-            recon, idx = self.engine.inference(w)
+            recon, idx = self.engine.inference(w, precise=self.precise_latents)
             recon, idx = recon.clone(), idx.clone()
             if seq is not None:
                 recon = recon.view(*seq, *recon.shape[1:])
@@ -199,7 +202,10 @@ class VQVAEModel(nn.Module):
         seq = x01.shape[:2] if x01.dim() == 5 else None
         x = x01.reshape(-1, *x01.shape[-3:])
         w = self._stage(x, train=False)
-        self.engine.encode(w)
+        if self.precise_latents:
+            self.engine.encode_precise(w)
+        else:
+            self.engine.encode(w)
         self.engine.quantize(w, train=False)
         idx = w.idx.clone()
         return idx.view(*seq, *idx.shape[1:]) if seq is not None else idx

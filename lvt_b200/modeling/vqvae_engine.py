@@ -114,6 +114,8 @@ class VQVAEEngine:
         self._ws = {}
         self.shadows_fresh = False
         self.opt = None
+        self._pp = None             # [hi | hi | lo] split packs of the encoder weights (high-precision encode)
+        self._pp_fresh = False
 
     # ------------------------------------------------------------------ parameters
     def load_state_dict(self, netE=None, netG=None, codebook=None, running_size=None, running_sum=None):
@@ -135,6 +137,7 @@ class VQVAEEngine:
                                     stream_ptr()), "lvt_permute4")
 
     def refresh_shadows(self, cast=True):
+        self._pp_fresh = False
         s, st = self.spec, self.store
         if cast:
             check(self.lib.lvt_cast_bf16(ptr(st.master), ptr(st.shadow), st.numel, stream_ptr()), "lvt_cast_bf16")
@@ -321,6 +324,94 @@ class VQVAEEngine:
                 self._block_fwd(f"E.layers.{5 + i}", i, w.er[i], w.eh[i], w.z_e if last else w.er[i + 1], n,
                                 last_f32=last, relu_out=not last)
 
+    # ------------------------------------------------------------------ high-precision encoder (inference)
+    def _split3(self, src, add, out, out_f32, rows, C, relu, weight):
+        check(self.lib.lvt_split3_bf16(_vp(src), _vp(add) if add is not None else None, _vp(out),
+                                       _vp(out_f32) if out_f32 is not None else None, rows, C, int(relu), int(weight),
+                                       stream_ptr()), "lvt_split3_bf16")
+
+    def _refresh_precise(self):
+        """Encoder weights as [hi | hi | lo] bf16 triples per (output channel, tap), built from the fp32 master."""
+        s, st = self.spec, self.store
+        nf, rc, L = s.nf, s.rc, s.n_layers
+        f32, bf16 = torch.float32, torch.bfloat16
+        z = lambda shape, dt: torch.zeros(shape, dtype=dt, device=self.device)  # noqa: E731
+        if self._pp is None:
+            pp = {"w1": z((nf // 2, 192), bf16), "scratch": z((nf * 16 * nf,), f32)}
+            for name in ["E.layers.2.weight", "E.layers.4.weight"] + [f"E.layers.{5 + i}.block.1.weight" for i in range(L)]:
+                e = self.pk[name]
+                pp[name] = z((e["co"], e["T"] * 3 * e["ci"]), bf16)
+            for i in range(L):
+                pp[f"E.layers.{5 + i}.block.3.weight"] = z((nf, 3 * rc), bf16)
+            self._pp = pp
+        pp, sc = self._pp, self._pp["scratch"]
+        # conv1: [128][3][16] -> [128][(tap, c)] padded to 64 columns, then split
+        sc[:(nf // 2) * 64].zero_()
+        self._permute4(st.pf("E.layers.0.weight"), sc, False, False, (nf // 2, 16, 3, 1), (48, 1, 16, 0), (64, 3, 1, 0))
+        self._split3(sc, None, pp["w1"], None, nf // 2, 64, False, True)
+        for name, dst in pp.items():
+            if name in ("w1", "scratch"):
+                continue
+            if name.endswith("block.3.weight"):      # 1x1 conv: the master layout [nf][rc] is already K-major
+                self._split3(st.pf(name), None, dst, None, nf, rc, False, True)
+                continue
+            e = self.pk[name]
+            co, ci, T = e["co"], e["ci"], e["T"]
+            self._permute4(st.pf(name), sc, False, False, (co, T, ci, 1), (ci * T, 1, T, 0), (T * ci, ci, 1, 0))
+            self._split3(sc, None, dst, None, co * T, ci, False, True)
+        self._pp_fresh = True
+
+    def _precise_ws(self, w):
+        if getattr(w, "pz", None) is None:
+            s = self.spec
+            M, nf, rc = w.M, s.nf, s.rc
+            f32, bf16 = torch.float32, torch.bfloat16
+            e = lambda shape, dt: torch.empty(shape, dtype=dt, device=self.device)  # noqa: E731
+            w.pz = dict(A1=e((4 * M, 192), bf16), t1=e((4 * M, nf // 2), f32), act1=e((4 * M, 3 * (nf // 2)), bf16),
+                        t2=e((M, nf), f32), act2=e((M, 3 * nf), bf16), r32=e((M, nf), f32), r=e((M, 3 * nf), bf16),
+                        th=e((M, rc), f32), h=e((M, 3 * rc), bf16))
+        return w.pz
+
+    def encode_precise(self, w):
+        """ResEncoder.forward with every product carried as a 3-term bf16 split (lvt_split3_bf16): fp32 accumulation
+        of a_hi w_hi + a_lo w_hi + a_hi w_lo, i.e. ~2^-17 relative per product instead of bf16's 2^-9.  Used for
+        encode / inference, where the code indices are the product (CodesExtractor -> VT training data); the
+        training step keeps the plain bf16 convolutions.  w.x -> w.z_e."""
+        s, st = self.spec, self.store
+        if not self.shadows_fresh:
+            self.refresh_shadows()
+        if not self._pp_fresh:
+            self._refresh_precise()
+        n, M, nf, rc, L = w.n, w.M, s.nf, s.rc, s.n_layers
+        pz, pp = self._precise_ws(w), self._pp
+        c1 = nf // 2
+        check(self.lib.lvt_vqvae_in_im2col_split(ptr(w.x), ptr(pz["A1"]), n, s.mean, s.std, stream_ptr()),
+              "lvt_vqvae_in_im2col_split")
+        gemm(4 * M, c1, 192, Operand(pz["A1"].data_ptr(), 192), Operand(pp["w1"].data_ptr(), 192),
+             Operand(pz["t1"].data_ptr(), c1), out_f32=pz["t1"], bias=st.pf("E.layers.0.bias"))
+        self._split3(pz["t1"], None, pz["act1"], None, 4 * M, c1, True, False)
+        self._conv(pz["act1"], 3 * c1, n, pp["E.layers.2.weight"], 16 * 3 * c1, nf, pz["t2"], st.pf("E.layers.2.bias"),
+                   TAPS_K4S2, relu=False, P=4, s_phase=M * 3 * c1, f32=True)
+        self._split3(pz["t2"], None, pz["act2"], None, M, nf, True, False)
+        out0 = w.z_e if L == 0 else pz["t2"]
+        self._conv(pz["act2"], 3 * nf, n, pp["E.layers.4.weight"], 9 * 3 * nf, nf, out0, st.pf("E.layers.4.bias"),
+                   TAPS3, relu=False, f32=True)
+        if L == 0:
+            return
+        self._split3(pz["t2"], None, pz["r"], pz["r32"], M, nf, True, False)        # r_0 = relu(conv3(...))
+        for i in range(L):
+            pre = f"E.layers.{5 + i}"
+            last = i == L - 1
+            self._conv(pz["r"], 3 * nf, n, pp[f"{pre}.block.1.weight"], 9 * 3 * nf, rc, pz["th"],
+                       st.pf(f"{pre}.block.1.bias"), TAPS3, relu=False, f32=True)
+            self._split3(pz["th"], None, pz["h"], None, M, rc, True, False)
+            out = w.z_e if last else pz["t2"]
+            # out = r + conv1x1(h) + bias (the skip adds the ReLU'd block input, resencoder.py:10-21)
+            gemm(M, nf, 3 * rc, Operand(pz["h"].data_ptr(), 3 * rc), Operand(pp[f"{pre}.block.3.weight"].data_ptr(), 3 * rc),
+                 Operand(out.data_ptr(), nf), out_f32=out, bias=st.pf(f"{pre}.block.3.bias"), res=pz["r32"])
+            if not last:
+                self._split3(pz["t2"], None, pz["r"], pz["r32"], M, nf, True, False)
+
     def quantize(self, w, train):
         s = self.spec
         n = w.n
@@ -364,10 +455,14 @@ class VQVAEEngine:
         check(self.lib.lvt_vqvae_out_col2im_tanh(ptr(w.Y), _vp(st.pf(f"G.layers.{k + 3}.bias")), ptr(w.x_tilde), n,
                                                  stream_ptr()), "lvt_vqvae_out_col2im_tanh")
 
-    def inference(self, w):
-        """AutoEncoderModel.forward(mode='inference') (ae.py:120-147): x in [0,1] -> recon in [0,1], latent."""
+    def inference(self, w, precise=False):
+        """AutoEncoderModel.forward(mode='inference') (ae.py:120-147): x in [0,1] -> recon in [0,1], latent.
+        precise: the encoder runs its convolutions as 3-term bf16 splits (encode_precise)."""
         s = self.spec
-        self.encode(w)
+        if precise:
+            self.encode_precise(w)
+        else:
+            self.encode(w)
         self.quantize(w, train=False)
         self.decode(w)
         check(self.lib.lvt_denorm_clamp(ptr(w.x_tilde), ptr(w.recon), w.x_tilde.numel(), s.mean, s.std, 0.0, 1.0,

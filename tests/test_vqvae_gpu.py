@@ -56,6 +56,35 @@ def test_vqvae_inference_vs_oracle(cuda_lib, n, L):
     assert recon.min().item() >= 0.0 and recon.max().item() <= 1.0
 
 
+@pytest.mark.parametrize("n,L", [(32, 2), (8, 4)])
+def test_precise_encoder_latents_vs_oracle(cuda_lib, n, L):
+    """BASELINE.json config 1 (PR-DVQVAE2 forward + VQ on one synthetic 64x64x3 batch of 32 frames; also the K-DVQVAE
+    depth): the high-precision encoder (3-term bf16 split products, VQVAEEngine.encode_precise) gives z_e within 5e-5
+    relative L2 of the fp32 oracle and code indices that agree on >= 99.9 % of the 32768 (position, codebook) pairs
+    -- against ~98-99 % for the plain bf16 encoder; the rate is printed."""
+    from oracle import lvt_oracle as O
+    from lvt_b200.modeling.vqvae_engine import VQVAEEngine, VQVAESpec
+    torch.set_num_threads(min(8, os.cpu_count() or 1))
+    cfg, we, wg, x, cb, z_ref = _setup(n, L)
+    eng = VQVAEEngine(VQVAESpec(n_layers=L))
+    eng.load_state_dict(we, wg, cb)
+    w = eng.workspace(n, train=False)
+    w.x.copy_(x)
+    with torch.no_grad():
+        _, idx_ref = O.vqvae_inference(x, we, wg, cb, cfg)
+    rates = {}
+    for precise in (False, True):
+        recon, idx = eng.inference(w, precise=precise)
+        torch.cuda.synchronize()
+        z_got = w.z_e.cpu().view(n, 16, 16, 256).permute(0, 3, 1, 2)
+        rates[precise] = ((idx.cpu() == idx_ref).float().mean().item(), _rel(z_got, z_ref))
+    print(f"latent agreement with the oracle, {n} frames, N_LAYERS {L}: bf16 encoder {rates[False][0]:.5f} "
+          f"(z_e rel-L2 {rates[False][1]:.2e}), split encoder {rates[True][0]:.5f} (z_e rel-L2 {rates[True][1]:.2e})")
+    assert rates[True][1] <= 5e-5, rates
+    assert rates[True][0] >= 0.999, rates
+    assert rates[False][0] >= 0.98, rates
+
+
 def test_vqvae_train_step_vs_oracle(cuda_lib):
     from oracle import lvt_oracle as O
     from lvt_b200.modeling.vqvae_engine import VQVAEEngine, VQVAESpec
