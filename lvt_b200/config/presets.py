@@ -1,4 +1,4 @@
-"""The six shipped experiment configurations of the reference (configs/vqvae/*.yaml, configs/vt/*.yaml) as
+"""The seven shipped experiment configurations of the reference (configs/vqvae/*.yaml, configs/vt/*.yaml) as
 override lists for `get_cfg()`, so that everything runs without the reference checkout.  A YAML path from the
 reference can be used instead via cfg.merge_from_file — both routes give the same tree."""
 from .config import get_cfg
@@ -38,6 +38,8 @@ def _vt(kernel, stride, block, n_train):
 
 
 PRESETS = {
+    "Base-VQVAE": _VQVAE_COMMON + ["MODEL.CODEBOOK.NUM", 1, "MODEL.ENCODER.N_LAYERS", 2, "MODEL.GENERATOR.N_LAYERS", 2,
+                                   "SOLVER.MAX_ITER", 500000, "SOLVER.CHECKPOINT_PERIOD", 50000],
     "PR-DVQVAE2": _VQVAE_COMMON + ["MODEL.ENCODER.N_LAYERS", 2, "MODEL.GENERATOR.N_LAYERS", 2, "SOLVER.MAX_ITER", 500000,
                                    "SOLVER.CHECKPOINT_PERIOD", 50000],
     "K-DVQVAE": _VQVAE_COMMON + ["MODEL.ENCODER.N_LAYERS", 4, "MODEL.GENERATOR.N_LAYERS", 4, "SOLVER.MAX_ITER", 1000000,

@@ -167,41 +167,50 @@ vq_argmin_smem_kernel(const float* __restrict__ z_e, const float* __restrict__ c
 }
 
 // Generic path (any D % 8 == 0, any K): codebook streamed from L2. Correctness path for the
-// non-DVQ configurations (CODEBOOK.NUM == 1, D == 256); not tuned.
+// non-DVQ configurations (CODEBOOK.NUM == 1, D == 256: configs/vqvae/Base-VQVAE.yaml); not tuned.
+// |c_k|^2 of the group is computed by the block into shared memory (K floats); z_e / zq are addressed with a
+// position stride and a channel stride, so NCHW (1, hw) and channels-last (num*D, 1) share the kernel.
 __global__ void vq_argmin_generic_kernel(const float* __restrict__ z_e,
                                          const float* __restrict__ codebook,
-                                         const float* __restrict__ csq_all,
                                          int64_t* __restrict__ idx_out, float* __restrict__ zq_out,
+                                         __nv_bfloat16* __restrict__ zq_bf16,
                                          float* __restrict__ counts, float* __restrict__ sums,
-                                         long long total_pos, int num, int K, int D, int hw) {
+                                         long long total_pos, int num, int K, int D, int hw,
+                                         long long pos_stride, long long ch_stride) {
+  extern __shared__ float csq_s[];
   const int g = blockIdx.y;
+  const float* cbg = codebook + (size_t)g * K * D;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) csq_s[k] = sqnorm_aten_order_rt(cbg + (size_t)k * D, 1, D);
+  __syncthreads();
   const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= total_pos) return;
   const long long frame = p / hw;
   const int s = (int)(p - frame * hw);
-  const long long C = (long long)num * D;
-  const float* xp = z_e + (frame * C + (long long)g * D) * hw + s;
-  const float* cbg = codebook + (size_t)g * K * D;
-  const float xsq = sqnorm_aten_order_rt(xp, hw, D);
+  const long long base = frame * (long long)num * D * hw + (long long)s * pos_stride + (long long)g * D * ch_stride;
+  const float* xp = z_e + base;
+  const float xsq = sqnorm_aten_order_rt(xp, ch_stride, D);
   float best = INFINITY;
   int besti = 0;
   for (int k = 0; k < K; ++k) {
     const float* cr = cbg + (size_t)k * D;
     float acc = 0.f;
-    for (int j = 0; j < D; ++j) acc = __fmaf_rn(xp[(long long)j * hw], __ldg(cr + j), acc);
-    const float d = __fmaf_rn(-2.f, acc, __fadd_rn(csq_all[(size_t)g * K + k], xsq));
+    for (int j = 0; j < D; ++j) acc = __fmaf_rn(xp[(long long)j * ch_stride], __ldg(cr + j), acc);
+    const float d = __fmaf_rn(-2.f, acc, __fadd_rn(csq_s[k], xsq));
     if (d < best) { best = d; besti = k; }
   }
   idx_out[(frame * num + g) * hw + s] = (int64_t)besti;
   const float* cr = cbg + (size_t)besti * D;
-  if (zq_out) {
-    float* zp = zq_out + (frame * C + (long long)g * D) * hw + s;
-    for (int j = 0; j < D; ++j) zp[(long long)j * hw] = cr[j];
+  if (zq_out || zq_bf16) {
+    for (int j = 0; j < D; ++j) {
+      const float v = cr[j];
+      if (zq_out) zq_out[base + (long long)j * ch_stride] = v;
+      if (zq_bf16) zq_bf16[base + (long long)j * ch_stride] = __float2bfloat16(v);
+    }
   }
   if (counts) atomicAdd(counts + (size_t)g * K + besti, 1.f);
   if (sums) {
     float* sp = sums + ((size_t)g * K + besti) * D;
-    for (int j = 0; j < D; ++j) atomicAdd(sp + j, xp[(long long)j * hw]);
+    for (int j = 0; j < D; ++j) atomicAdd(sp + j, xp[(long long)j * ch_stride]);
   }
 }
 
@@ -415,18 +424,13 @@ static int vq_argmin_impl(const float* z_e, const float* codebook, int64_t* idx_
     lvt_count_launch(1);
     return LVT_OK;
   }
-  LVT_CHECK_ARG(!nhwc && !zq_bf16, "lvt_vq_argmin: the generic (D != 64) path supports NCHW fp32 only");
-  // generic path needs |c|^2 scratch: keep caller-owned buffers untouched and use a small
-  // stream-ordered allocation.
-  float* csq = nullptr;
-  LVT_CHECK_CUDA(cudaMallocAsync(&csq, (size_t)num * K * sizeof(float), stream));
-  vq_csq_kernel<<<lvt_ceil_div((long long)num * K, 128), 128, 0, stream>>>(codebook, csq, num * K, D);
+  LVT_CHECK_ARG((size_t)K * 4 <= 48 * 1024, "lvt_vq_argmin: the generic (D != 64) path keeps |c|^2 of %d codes in shared memory", K);
   dim3 grid(lvt_ceil_div(total, 128), num);
-  vq_argmin_generic_kernel<<<grid, 128, 0, stream>>>(z_e, codebook, csq, idx_out, zq_out, counts,
-                                                     sums, total, num, K, D, hw);
+  vq_argmin_generic_kernel<<<grid, 128, (size_t)K * 4, stream>>>(z_e, codebook, idx_out, zq_out,
+                                                                 reinterpret_cast<__nv_bfloat16*>(zq_bf16), counts, sums, total,
+                                                                 num, K, D, hw, pos_stride, ch_stride);
   LVT_CHECK_LAUNCH();
-  LVT_CHECK_CUDA(cudaFreeAsync(csq, stream));
-  lvt_count_launch(2);
+  lvt_count_launch(1);
   return LVT_OK;
 }
 

@@ -8,7 +8,7 @@ from torch import nn
 from ...solver import build_lr_scheduler, build_optimizer
 from ...utils import comm
 from ..vqvae_engine import VQVAEEngine, VQVAESpec
-from ..vqvae_modules import DVQEmbedding, build_encoder, build_generator
+from ..vqvae_modules import DVQEmbedding, VQEmbedding, build_encoder, build_generator
 from .build import META_ARCH_REGISTRY
 
 
@@ -64,8 +64,6 @@ class VQVAEModel(nn.Module):
         self.cfg = cfg
         self.device = torch.device(cfg.MODEL.DEVICE)
         m = cfg.MODEL
-        if m.CODEBOOK.NUM < 2:
-            raise NotImplementedError("the engine implements the DVQ configs (CODEBOOK.NUM 4: PR-DVQVAE2, K-DVQVAE)")
         assert len(m.PIXEL_MEAN) == len(m.PIXEL_STD)
         assert len(set(m.PIXEL_MEAN)) == 1 and len(set(m.PIXEL_STD)) == 1, "per-channel identical mean/std"
         spec = VQVAESpec(in_channels=m.ENCODER.IN_CHANNELS, nf=m.ENCODER.NF, res_channels=m.ENCODER.RES_CHANNELS,
@@ -80,7 +78,12 @@ class VQVAEModel(nn.Module):
         self.init_weights(self.encoder, cfg.MODEL.INIT_TYPE)
         self.init_weights(self.generator, cfg.MODEL.INIT_TYPE)
         self.use_codebook_ema = cfg.MODEL.CODEBOOK.EMA
-        self.codebook = DVQEmbedding(self.engine, self.use_codebook_ema)
+        # vqvae.py:26-31: one VQEmbedding (Base-VQVAE.yaml, CODEBOOK.NUM 1: latents (n, h, w)) or the DVQ stack
+        if m.CODEBOOK.NUM == 1:
+            self.codebook = VQEmbedding(self.engine, 0, self.use_codebook_ema, standalone=True)
+        else:
+            self.codebook = DVQEmbedding(self.engine, self.use_codebook_ema)
+        self._single = m.CODEBOOK.NUM == 1
         self.beta = cfg.MODEL.CODEBOOK.BETA
         self.vis_period = cfg.VIS_PERIOD
         self._anchor = torch.zeros(1, device=self.device, requires_grad=True)
@@ -190,6 +193,8 @@ class VQVAEModel(nn.Module):
             w = self._stage(x, train=False)
             recon, idx = self.engine.inference(w, precise=self.precise_latents)
             recon, idx = recon.clone(), idx.clone()
+            if self._single:
+                idx = idx[:, 0]
             if seq is not None:
                 recon = recon.view(*seq, *recon.shape[1:])
                 idx = idx.view(*seq, *idx.shape[1:])
@@ -208,13 +213,18 @@ class VQVAEModel(nn.Module):
             self.engine.encode(w)
         self.engine.quantize(w, train=False)
         idx = w.idx.clone()
+        if self._single:
+            idx = idx[:, 0]
         return idx.view(*seq, *idx.shape[1:]) if seq is not None else idx
 
     @torch.no_grad()
     def decode(self, latents):
         """vqvae.py:103-106: codes (n, num, 16, 16) -> x_tilde in [-1, 1] (n, 3, 64, 64)."""
+        latents = latents.to(self.device)
+        if self._single:
+            latents = latents.unsqueeze(1)
         w = self.engine.workspace(latents.shape[0], train=False)
-        return self.engine.decode_indices(w, latents.to(self.device).contiguous()).clone()
+        return self.engine.decode_indices(w, latents.contiguous()).clone()
 
     def configure_optimizers_and_checkpointers(self):
         """ae.py:224-244 + vqvae.py:108-124: optimizers for netE / netG, checkpointers netE / netG / netC."""

@@ -71,13 +71,28 @@ class VQEmbedding(nn.Module):
     """vq_embedding.py:9-66: `embedding.weight` (K, D), buffers running_size (K), running_sum (K, D) — views of
     the engine's stacked codebook state."""
 
-    def __init__(self, engine, index, ema=True):
+    def __init__(self, engine, index, ema=True, standalone=False):
         super().__init__()
         self.K, self.ema = engine.spec.K, ema
         self.embedding = nn.Embedding(engine.spec.K, engine.spec.D, _weight=engine.codebook[index])
         self.embedding.weight.requires_grad_(False)
         self.register_buffer("running_size", engine.running_size[index])
         self.register_buffer("running_sum", engine.running_sum[index])
+        if standalone:  # CODEBOOK.NUM == 1 (vqvae.py:26-27): this module IS the model's codebook
+            object.__setattr__(self, "engine", engine)
+            with torch.no_grad():  # vq_embedding.py:12-21
+                engine.codebook.uniform_(-1.0 / engine.spec.K, 1.0 / engine.spec.K)
+                engine.running_sum.copy_(engine.codebook)
+                engine.running_size.zero_()
+
+    def forward(self, z_e_x, mode=""):
+        """vq_embedding.py:23-34, modes "" (indices (n, h, w)) and "emb" (codes -> NHWC vectors)."""
+        eng = self.engine
+        if mode == "":
+            return ops.vq_argmin(z_e_x.contiguous().float(), eng.codebook)[:, 0]
+        if mode == "emb":
+            return ops.vq_gather(z_e_x.unsqueeze(1).contiguous(), eng.codebook).permute(0, 2, 3, 1)
+        raise ValueError("mode 'st' runs inside VQVAEEngine.forward_train (EMA + straight-through)")
 
 
 class DVQEmbedding(nn.Module):

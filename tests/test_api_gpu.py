@@ -132,6 +132,41 @@ def test_vqvae_model_inference_and_sampling_roundtrip(cuda_lib, tmp_path):
     assert int(sample.min()) >= 0 and int(sample.max()) < 512
 
 
+def test_base_vqvae_single_codebook(cuda_lib, tmp_path):
+    """configs/vqvae/Base-VQVAE.yaml (CODEBOOK.NUM 1: one 512 x 256 VQEmbedding, vqvae.py:26-27): latents are (n, h, w),
+    bit-exact against the C oracle on the engine's own z_e (generic D = 256 search path); encode -> decode round trip;
+    a supervised step runs through the Trainer surface; netC checkpoint keys are the reference's."""
+    from oracle import vq as ovq
+    from lvt_b200.config.presets import preset
+    from lvt_b200.modeling import build_model
+    cfg = preset("Base-VQVAE", ["OUTPUT_DIR", str(tmp_path)])
+    cfg.freeze()
+    torch.manual_seed(3)
+    model = build_model(cfg)
+    assert set(model.codebook.state_dict()) == {"embedding.weight", "running_size", "running_sum"}
+    assert tuple(model.codebook.embedding.weight.shape) == (512, 256)
+    with torch.no_grad():
+        model.engine.codebook.normal_(0.0, 0.05)
+    model.train(False)
+    x = torch.rand((6, 3, 64, 64), generator=torch.Generator().manual_seed(1))
+    out = model([{"image": x[i]} for i in range(6)])
+    lat = torch.stack([o["latent"] for o in out])
+    assert lat.shape == (6, 16, 16) and out[0]["reconstruction"].shape == (3, 64, 64)
+    w = model.engine.workspace(6, train=False)
+    z_e = w.z_e.cpu().view(6, 16, 16, 256).permute(0, 3, 1, 2).contiguous()   # the z_e the latents were taken from
+    want = ovq.vq_argmin_c(z_e, model.engine.codebook.cpu())[:, 0]
+    assert torch.equal(lat.cpu(), want)
+    assert torch.equal(model.encode(x.cuda()).cpu(), lat.cpu())
+    assert model.decode(lat).shape == (6, 3, 64, 64)
+    model.train(True)
+    from lvt_b200.utils.events import EventStorage
+    with EventStorage(0):
+        losses = model([{"image": x[i]} for i in range(6)], mode="supervised")
+        sum(losses.values()).backward()
+    assert all(torch.isfinite(v) for v in losses.values())
+    assert model.engine.store.grad.abs().sum().item() > 0
+
+
 def test_graph_sampler_matches_per_pixel_loop(cuda_lib, tmp_path):
     """VideoTransformer.sample_slice (one CUDA-graph replay per position) against the reference-shaped per-pixel
     loop (vt.py:107-134): at temperature -> 0 the multinomial draw is the argmax of identical logits, so the sampled
