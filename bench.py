@@ -238,18 +238,28 @@ def step_traffic():
 
 
 def vqvae_main(args, rank, world, local_rank):
-    """BASELINE.json config 3: PR-DVQVAE2 training on synthetic 16-frame 64x64 clips, data-parallel: 32 clips = 512
-    frames per GPU and step (weak scaling), EMA counts / sums and the flat gradient summed over ranks with NCCL
-    (vq_embedding.py:44-59, ae.py:69-73); CUDA-graph replay, max over ranks."""
     import torch
     from lvt_b200 import _lib
-    from lvt_b200.modeling.vqvae_engine import GraphedVQVAEStep, VQVAEEngine, VQVAESpec
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     _lib.require_device()
+    line = vqvae_measure(args, rank, world, local_rank, dist)
+    if rank == 0:
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def vqvae_measure(args, rank, world, local_rank, dist, with_cpu=True):
+    """BASELINE.json config 3: PR-DVQVAE2 training on synthetic 16-frame 64x64 clips, data-parallel: 32 clips = 512
+    frames per GPU and step (weak scaling), EMA counts / sums and the flat gradient summed over ranks with NCCL
+    (vq_embedding.py:44-59, ae.py:69-73); CUDA-graph replay, max over ranks.  Returns the JSON line (rank 0)."""
+    import torch
+    from lvt_b200 import _lib
+    from lvt_b200.modeling.vqvae_engine import GraphedVQVAEStep, VQVAEEngine, VQVAESpec
     _, _, tf_sust, peak_src = measured_peaks()
     nfr = 512
     if args.strong:  # the reference's semantics: IMS_PER_BATCH (32 clips = 512 frames) is the GLOBAL batch (data/build.py:62-74)
@@ -311,11 +321,12 @@ def vqvae_main(args, rank, world, local_rank):
         t = torch.tensor([ms, ms_e2e], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, ms_e2e = t.tolist()
+    line = None
     if rank == 0:
         n_gpus = max(1, world)
         tf = 5.57e9 * nfr / (ms * 1e-3) / 1e12
-        cpu = cpu_vqvae_arm(3, 1, frames=32) if (n_gpus == 1 and not args.quick) else None
-        print(json.dumps({
+        cpu = cpu_vqvae_arm(3, 1, frames=32) if (with_cpu and n_gpus == 1 and not args.quick) else None
+        line = ({
             "metric": "VQ-VAE frames/sec (PR-DVQVAE2 train step)", "value": nfr * n_gpus / (ms * 1e-3), "unit": "frames/s",
             "n_gpus": n_gpus, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": True,
             "scaling": "strong" if args.strong else "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
@@ -331,9 +342,10 @@ def vqvae_main(args, rank, world, local_rank):
             "roofline": {"bound": "tensor", "achieved": tf, "peak": tf_sust, "unit": "TFLOP/s", "frac": tf / tf_sust,
                          "traffic": None, "peak_source": peak_src,
                          "kernel": "gemm_bf16_kernel implicit-GEMM convolutions: 5.57 GFLOP per frame fwd+bwd / step time, per GPU"},
-            "cpu_baseline": ({k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")} if cpu else None)}))
-    if dist is not None:
-        dist.destroy_process_group()
+            "cpu_baseline": ({k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")} if cpu else None)})
+    del step, ve, vw
+    torch.cuda.empty_cache()
+    return line
 
 
 def main():
@@ -763,6 +775,14 @@ def main():
         except Exception as ex:
             dp_par = {"error": repr(ex)[:300]}
 
+    # second half of BASELINE.json's metric at N > 1: PR-DVQVAE2 data-parallel frames/s (every rank takes part; at
+    # N = 1 the same step is timed under roofline.kernels.vqvae)
+    vq_dp = None
+    if world > 1 and not args.quick and not args.strong:
+        try:
+            vq_dp = vqvae_measure(args, rank, world, local_rank, dist, with_cpu=False)
+        except Exception as ex:
+            vq_dp = {"error": repr(ex)[:300]}
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -805,6 +825,9 @@ def main():
         line["strong"] = strong
     if dp_par is not None:
         line["dp_parity"] = dp_par
+    if vq_dp is not None:
+        line["vqvae_dp"] = {k: vq_dp.get(k) for k in ("metric", "value", "unit", "n_gpus", "ms_per_step", "scaling", "e2e",
+                                                      "config", "losses", "error") if k in vq_dp}
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
