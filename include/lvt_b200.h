@@ -299,6 +299,45 @@ int lvt_rows_qkv(const float* x, const float* ln_gamma, const float* ln_beta, fl
 int lvt_attn_row(const float* q, const void* k_cache_bf16, const void* v_cache_bf16, const float* bank_t,
                  const float* bank_h, const float* bank_w, int bt, int bh, int bw, const int64_t* pos, float scale,
                  float* o, int B, int H, int L, int da, void* stream);
+/* The whole per-position step of the incremental sampler as ONE persistent kernel (32 CTAs, grid barriers between
+ * dependent stages): row *pos through the masked decoder against the K/V caches (the stages of lvt_vt_dec_front_fwd,
+ * lvt_rows_linear, lvt_rows_qkv, lvt_attn_row above, same arithmetic), then -- if do_sample -- per channel the
+ * predictor (U[k] with the one-hot row gather, P[k]) and the categorical draw of lvt_vt_sample_pixel into
+ * slice[b, k, *pos].  q_exp [nc, B, nv]: Exp(1) noise drawn by the caller, channel by channel, BEFORE the call (torch's
+ * generator: the random stream of torch.multinomial in meta_arch/vt.py:107-134, videotransformer.py:161-185).
+ * Activation scratch xa, xb, hbuf, a1, abuf [B, d], q, o [B, H*da], logits [B, nv] fp32; barrier: 2 zero-initialised
+ * unsigned ints owned by this entry point.  B <= 16, da == 128, L = t*h*w = bt*bh*bw <= 256, <= 8 layers, <= 4 channels. */
+typedef struct LvtDecodeLayer {
+  const float* ln1_g; const float* ln1_b;        /* mha.layer_norm                                   */
+  const void* w_qkv;                              /* w_q | w_k | w_v [3H, d, da] bf16                 */
+  void* k_cache; void* v_cache;                   /* bf16 [B, H, L, da]                               */
+  const float* bank_t; const float* bank_h; const float* bank_w;
+  const void* w_proj;                             /* mha.proj.weight [d, H*da] bf16                   */
+  const float* ln2_g; const float* ln2_b;        /* ffn.0                                            */
+  const void* w_ffn1; const float* b_ffn1;       /* ffn.1 [d, d] bf16, bias fp32                     */
+  const void* w_ffn3; const float* b_ffn3;       /* ffn.3                                            */
+} LvtDecodeLayer;
+typedef struct LvtDecodeStep {
+  int B, d, H, da, L, nc, nv, de, ntaps, n_layers;
+  int bt, bh, bw, t, h, w;
+  float scale, ln_eps, temp;
+  int do_sample;                                  /* 0: decoder row only (primed position: fills the K/V caches) */
+  const int64_t* pos;                             /* ONE int64 in device memory                       */
+  int64_t* slice;                                 /* [B, nc, L]                                       */
+  const float* emb;                               /* decoder.ch_embedder [nc, nv, de] fp32            */
+  const int* taps;                                /* live taps of the masked conv, int[ntaps*3]       */
+  const void* conv_w;                             /* packed live-tap conv weight [d, ntaps*de] bf16   */
+  const float* y0s;                               /* [B*L, d]: zl Wlp^T + positional encoding + conv bias */
+  LvtDecodeLayer layer[8];
+  const float* lnp_g; const float* lnp_b;        /* ch_predictor.layer_norm                          */
+  const void* U[4]; long long U_ld[4]; const float* U_bias[4]; const float* gtab[4];
+  const void* P[4]; const float* P_bias[4];
+  const float* q_exp;
+  float* xa; float* xb; float* hbuf; float* a1; float* q; float* o; float* abuf; float* logits;
+  unsigned* barrier;
+  long long* prof;                                /* NULL, or 128 int64: %globaltimer stamps of CTA 0 per stage (tools/) */
+} LvtDecodeStep;
+int lvt_vt_decode_step(const LvtDecodeStep* p, void* stream);
 /* torch.optim.RMSprop / Adam steps (solver/build.py:62-72) over flat fp32 buffers of n elements
  * (n % 4 == 0), gradients pre-multiplied by grad_scale; p_bf16 (optional) receives the bf16
  * shadow copy the GEMMs read.                                                               */

@@ -88,6 +88,26 @@ class LvtRowsLinear(ctypes.Structure):
     ]
 
 
+class LvtDecodeLayer(ctypes.Structure):
+    """Mirror of `struct LvtDecodeLayer` (include/lvt_b200.h)."""
+    _fields_ = [(n, ctypes.c_void_p) for n in ("ln1_g", "ln1_b", "w_qkv", "k_cache", "v_cache", "bank_t", "bank_h", "bank_w",
+                                               "w_proj", "ln2_g", "ln2_b", "w_ffn1", "b_ffn1", "w_ffn3", "b_ffn3")]
+
+
+class LvtDecodeStep(ctypes.Structure):
+    """Mirror of `struct LvtDecodeStep` (include/lvt_b200.h)."""
+    _fields_ = ([(n, ctypes.c_int) for n in ("B", "d", "H", "da", "L", "nc", "nv", "de", "ntaps", "n_layers",
+                                              "bt", "bh", "bw", "t", "h", "w")]
+                + [(n, ctypes.c_float) for n in ("scale", "ln_eps", "temp")]
+                + [("do_sample", ctypes.c_int)]
+                + [(n, ctypes.c_void_p) for n in ("pos", "slice", "emb", "taps", "conv_w", "y0s")]
+                + [("layer", LvtDecodeLayer * 8)]
+                + [("lnp_g", ctypes.c_void_p), ("lnp_b", ctypes.c_void_p)]
+                + [("U", ctypes.c_void_p * 4), ("U_ld", ctypes.c_longlong * 4), ("U_bias", ctypes.c_void_p * 4),
+                   ("gtab", ctypes.c_void_p * 4), ("P", ctypes.c_void_p * 4), ("P_bias", ctypes.c_void_p * 4)]
+                + [(n, ctypes.c_void_p) for n in ("q_exp", "xa", "xb", "hbuf", "a1", "q", "o", "abuf", "logits", "barrier", "prof")])
+
+
 _vp, _i, _ll, _d, _f = (ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_double,
                         ctypes.c_float)
 # symbol -> (restype, argtypes); one entry per function include/lvt_b200.h declares
@@ -100,6 +120,7 @@ SYMBOLS = {
     "lvt_launch_count_reset": (None, []),
     "lvt_vt_sample_pixel": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _vp]),
     "lvt_rows_linear": (_i, [_vp, _vp]),
+    "lvt_vt_decode_step": (_i, [ctypes.POINTER(LvtDecodeStep), _vp]),
     "lvt_rows_qkv": (_i, [_vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "lvt_attn_row": (_i, [_vp] * 6 + [_i, _i, _i, _vp, _f, _vp, _i, _i, _i, _i, _vp]),
     "lvt_vq_argmin": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),

@@ -8,10 +8,11 @@ tiles.  Activations that are bf16 in the full pass are rounded at the same place
 by summation order only (checked in tests/test_api_gpu.py)."""
 import ctypes
 import math
+import os
 
 import torch
 
-from ..._lib import LvtRowsLinear, check, ptr, stream_ptr
+from ..._lib import LvtDecodeStep, LvtRowsLinear, check, ptr, stream_ptr
 from ...ops import Operand, gemm
 from .vt_engine import LN_EPS, _vp
 
@@ -39,6 +40,15 @@ class IncrementalDecoder:
         self.q_exp = e((B, nv))
         self.y0s = e((ws.M, d))  # positional encoding + conv bias + zl Wlp^T: the part of y0 that does not depend on the slice
         self.pos = torch.zeros(1, dtype=torch.int64, device=dev)
+        # the whole per-position step as ONE persistent kernel (csrc/decode_step.cu) instead of ~58 launches: measured
+        # 0.44 against 0.50 ms per position for one sequence, slower from two sequences on (32 CTAs, 2.5 us per grid
+        # barrier), so it is the default for B == 1 only; LVT_SAMPLER_FUSED=1 / 0 forces it on / off (same arithmetic,
+        # same sampled codes either way)
+        env = os.environ.get("LVT_SAMPLER_FUSED", "")
+        self.fused = (env == "1" or (env != "0" and B == 1)) and nD <= 8 and s.nc <= 4
+        self.q_exp4 = e((s.nc, B, nv))
+        self._barrier = torch.zeros(2, dtype=torch.int32, device=dev)
+        self._desc = {}
 
     # ------------------------------------------------------------------ helpers
     def _rows(self, x, K, w, w_ld, N, out, *, x_ldb=None, x_pos_mul=0, x_bf16=False, ln=None, round_in=False, bias=None,
@@ -105,6 +115,57 @@ class IncrementalDecoder:
             x, y = y, x
         self.y_final = x
         del nE
+
+    # ------------------------------------------------------------------ fused per-position step
+    def _fused_desc(self, do_sample, temp):
+        key = (bool(do_sample), float(temp))
+        if key in self._desc:
+            return self._desc[key]
+        eng, ws, st, s = self.eng, self.ws, self.eng.store, self.eng.spec
+        taps, offs, wp, _ = eng._live_taps(ws.slice_shape)
+        t, h, w = ws.slice_shape
+        p = LvtDecodeStep()
+        p.B, p.d, p.H, p.da, p.L, p.nc, p.nv, p.de = ws.B, s.d, s.H, s.da, ws.thw, s.nc, s.nv, s.de
+        p.ntaps, p.n_layers = len(taps), len(s.blocks_d)
+        p.bt, p.bh, p.bw = s.block
+        p.t, p.h, p.w = t, h, w
+        p.scale, p.ln_eps, p.temp, p.do_sample = 1.0 / math.sqrt(s.da), LN_EPS, float(temp), int(do_sample)
+        p.pos, p.slice = self.pos.data_ptr(), ws.slice.data_ptr()
+        p.emb, p.taps = st.pf("decoder.ch_embedder.0.weight"), offs.data_ptr()
+        p.conv_w, p.y0s = wp.data_ptr(), self.y0s.data_ptr()
+        for i in range(p.n_layers):
+            pre, ly = f"decoder.block_local_attention.{i}.", p.layer[i]
+            ly.ln1_g, ly.ln1_b = st.pf(pre + "mha.layer_norm.weight"), st.pf(pre + "mha.layer_norm.bias")
+            ly.w_qkv = st.pb(pre + "mha.w_q")
+            ly.k_cache, ly.v_cache = self.kc[i].data_ptr(), self.vc[i].data_ptr()
+            ly.bank_t, ly.bank_h, ly.bank_w = st.pf(pre + "dt_bank"), st.pf(pre + "dh_bank"), st.pf(pre + "dw_bank")
+            ly.w_proj = st.pb(pre + "mha.proj.weight")
+            ly.ln2_g, ly.ln2_b = st.pf(pre + "ffn.0.weight"), st.pf(pre + "ffn.0.bias")
+            ly.w_ffn1, ly.b_ffn1 = st.pb(pre + "ffn.1.weight"), st.pf(pre + "ffn.1.bias")
+            ly.w_ffn3, ly.b_ffn3 = st.pb(pre + "ffn.3.weight"), st.pf(pre + "ffn.3.bias")
+        p.lnp_g, p.lnp_b = st.pf("ch_predictor.layer_norm.weight"), st.pf("ch_predictor.layer_norm.bias")
+        for k in range(s.nc):
+            p.U[k], p.U_ld[k] = st.pb(f"ch_predictor.U.{k}.weight"), s.d + k * s.nv
+            p.U_bias[k] = st.pf(f"ch_predictor.U.{k}.bias")
+            p.gtab[k] = eng.ut[k].data_ptr() if k else None
+            p.P[k], p.P_bias[k] = st.pb(f"ch_predictor.P.{k}.weight"), st.pf(f"ch_predictor.P.{k}.bias")
+        p.q_exp = self.q_exp4.data_ptr()
+        p.xa, p.xb, p.hbuf, p.a1 = self.xa.data_ptr(), self.xb.data_ptr(), self.h.data_ptr(), self.a1.data_ptr()
+        p.q, p.o, p.abuf, p.logits = self.q.data_ptr(), self.o.data_ptr(), self.a.data_ptr(), self.logits.data_ptr()
+        p.barrier = self._barrier.data_ptr()
+        self._desc[key] = p
+        return p
+
+    def decode_row_fused(self):
+        """decode_row as one kernel (primed positions: only the K/V caches of the row are needed)."""
+        check(self.eng.lib.lvt_vt_decode_step(ctypes.byref(self._fused_desc(False, 1.0)), stream_ptr()), "lvt_vt_decode_step")
+
+    def sample_row_fused(self, temp=1.0):
+        """sample_row as one kernel; the Exp(1) noise of the four draws comes from torch's generator in the order of
+        the reference's torch.multinomial calls, before the launch."""
+        for k in range(self.eng.spec.nc):
+            self.q_exp4[k].exponential_(1)
+        check(self.eng.lib.lvt_vt_decode_step(ctypes.byref(self._fused_desc(True, temp)), stream_ptr()), "lvt_vt_decode_step")
 
     def channel_logits(self, k):
         """ChannelPredictor for channel k at *pos (videotransformer.py:144-160): self.logits [B, nv]."""

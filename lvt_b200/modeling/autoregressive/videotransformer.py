@@ -172,7 +172,10 @@ class VideoTransformer(Autoregressive):
             if incremental:
                 dec = IncrementalDecoder(eng, ws)
                 pos_t = dec.pos
-                steps = {"sample": lambda: dec.sample_row(temp), "fill": dec.decode_row}
+                if dec.fused:   # one persistent kernel per position (csrc/decode_step.cu)
+                    steps = {"sample": lambda: dec.sample_row_fused(temp), "fill": dec.decode_row_fused}
+                else:
+                    steps = {"sample": lambda: dec.sample_row(temp), "fill": dec.decode_row}
             else:
                 dec = None
                 pos_t = torch.zeros(1, dtype=torch.int64, device=ws.slice.device)
