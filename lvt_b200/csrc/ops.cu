@@ -359,7 +359,7 @@ enc_front_bwd_kernel(const int64_t* __restrict__ ctx, const int64_t* __restrict_
   float* se = dslice_emb + (size_t)slice_idx[b] * D.de;
   for (int c0 = lane * 4; c0 < D.de; c0 += 128) {
     const float4 g = ld4(dout + (size_t)pos * D.de + c0);
-    atomicAdd(se + c0, g.x); atomicAdd(se + c0 + 1, g.y); atomicAdd(se + c0 + 2, g.z); atomicAdd(se + c0 + 3, g.w);
+    red_add_f32x4(se + c0, g.x, g.y, g.z, g.w);
     for (int c = 0; c < D.nc; ++c)
       for (int i = 0; i < D.kt; ++i)
         for (int j = 0; j < D.kh; ++j)
@@ -368,8 +368,7 @@ enc_front_bwd_kernel(const int64_t* __restrict__ ctx, const int64_t* __restrict_
             const long long code = ctx[((((size_t)b * D.nc + c) * D.Tc + tt) * D.Hc + hh) * D.Wc + ww];
             if (code == D.pad_value) continue;
             const size_t rowi = ((((size_t)c * D.kt + i) * D.kh + j) * D.kw + l) * D.nv + (size_t)code;
-            float* w = dwt + rowi * D.de + c0;
-            atomicAdd(w, g.x); atomicAdd(w + 1, g.y); atomicAdd(w + 2, g.z); atomicAdd(w + 3, g.w);
+            red_add_f32x4(dwt + rowi * D.de + c0, g.x, g.y, g.z, g.w);
           }
   }
 }
@@ -439,8 +438,7 @@ dec_front_bwd_kernel(const int64_t* __restrict__ slc, const float* __restrict__ 
     }
     for (int k = 0; k < D.nc; ++k) {
       const long long code = slc[((size_t)b * D.nc + k) * thw + p];
-      float* e = demb_tab + ((size_t)k * D.nv + code) * D.de + c0;
-      atomicAdd(e, acc.x); atomicAdd(e + 1, acc.y); atomicAdd(e + 2, acc.z); atomicAdd(e + 3, acc.w);
+      red_add_f32x4(demb_tab + ((size_t)k * D.nv + code) * D.de + c0, acc.x, acc.y, acc.z, acc.w);
     }
   }
 }
@@ -483,8 +481,7 @@ chpred_combine_bwd_kernel(const __nv_bfloat16* __restrict__ du, const int64_t* _
     const float4 g = ld_bf16x4(du + (size_t)m * d + c0);
     for (int j = 0; j < k; ++j) {
       const long long code = slc[((size_t)b * nc + j) * thw + p];
-      float* w = dut + ((size_t)j * nv + code) * d + c0;
-      atomicAdd(w, g.x); atomicAdd(w + 1, g.y); atomicAdd(w + 2, g.z); atomicAdd(w + 3, g.w);
+      red_add_f32x4(dut + ((size_t)j * nv + code) * d + c0, g.x, g.y, g.z, g.w);
     }
   }
 }
