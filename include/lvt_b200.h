@@ -158,6 +158,7 @@ typedef struct LvtGemm {
      in the epilogue (BlockLocalAttention.get_B, vt_attention.py:169-174).                                     */
   const void* v; int v_cin, v_zdiv; long long v_ld, v_s_zlo, v_s_zhi;
   void* o2_bf16; int o2_n, o2_cin, o2_zdiv; long long o2_ld, o2_s_zlo, o2_s_zhi;
+  void* prof;  /* NULL, or 32*8 int64: clock64 timeline of CTA 0 of the fused attention forward (tools/attn_fwd_prof.py) */
 } LvtGemm;
 
 int lvt_gemm_bf16(const LvtGemm* g, void* stream);

@@ -50,6 +50,7 @@ class LvtGemm(ctypes.Structure):
         ("v_ld", ctypes.c_longlong), ("v_s_zlo", ctypes.c_longlong), ("v_s_zhi", ctypes.c_longlong),
         ("o2_bf16", ctypes.c_void_p), ("o2_n", ctypes.c_int), ("o2_cin", ctypes.c_int), ("o2_zdiv", ctypes.c_int),
         ("o2_ld", ctypes.c_longlong), ("o2_s_zlo", ctypes.c_longlong), ("o2_s_zhi", ctypes.c_longlong),
+        ("prof", ctypes.c_void_p),
     ]
 
 

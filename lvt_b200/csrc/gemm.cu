@@ -68,6 +68,7 @@ struct GemmParams {
   int a_conv, b_conv, cv_C, cv_W, cv_H;
   // per-tap offsets packed 4 bits each (value + 8): no dynamically indexed parameter arrays -> no stack copy
   unsigned long long cv_dh_pk, cv_dw_pk, cv_ph_pk;
+  long long* prof;  // fused attention kernels: optional clock64 timeline of CTA 0 (tools/attn_fwd_prof.py)
 };
 LVT_DEVICE_INLINE int cv_tap(unsigned long long pk, int tap) { return (int)((pk >> (4 * tap)) & 15ull) - 8; }
 
@@ -946,11 +947,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     uint4* const slab0 = reinterpret_cast<uint4*>(smem + A::P_OFF + (2 * half) * 16384 + q * 4096);
     uint4* const slab1 = reinterpret_cast<uint4*>(smem + A::P_OFF + (2 * half + 1) * 16384 + q * 4096);
     uint32_t it = 0;
+#define APROF(slot)                                                                                       \
+  do {                                                                                                    \
+    if (p.prof && blockIdx.x == 0 && ew == 0 && lane == 0 && it < 32) p.prof[it * 8 + (slot)] = clock64(); \
+  } while (0)
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const TileCoord t = decode_tile(p, tile, 256);
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + half * 128;
       const int row_base = t.m0 + q * 32;
       const int row = row_base + lane;
+      APROF(0);
       float rs_h[8], cs_w[16];  // bank-gradient partial sums of this row (EK_DS)
       (void)rs_h;
       (void)cs_w;
@@ -1021,6 +1027,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       for (int x = 0; x < BW; ++x) bw[x] = kLog2e * __ldg(p.bank_w + head * (2 * BW - 1) + (wi - x + BW - 1));
       mbar_wait(s_full, it & 1);
       tc_fence_after();
+      APROF(1);
       uint32_t racc[128];
 #pragma unroll
       for (int c = 0; c < 4; ++c) tmem_ld_32x32(taddr + 32 * c, *reinterpret_cast<uint32_t(*)[32]>(&racc[32 * c]));
@@ -1028,6 +1035,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(s_empty);  // S may be overwritten by the next tile's QK^T
+      APROF(2);
       float* const l = reinterpret_cast<float*>(racc);
       float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
@@ -1042,6 +1050,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       *x_own_max = mx;
       asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
       mx = fmaxf(mx, *x_oth_max);
+      APROF(3);
       float s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int i = 0; i < 128; ++i) {
@@ -1052,6 +1061,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       *x_own_sum = sum;
       asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
       sum += *x_oth_sum;
+      APROF(4);
       const float inv = 1.f / sum;
       if (p.lse && half == 0) p.lse[(long long)t.z * p.M + row] = (mx + log2f(sum)) * 0.6931471805599453f;
       // P slabs (the previous tile's P V has completed: this warp waited for pv_done in its O epilogue; its own
@@ -1123,8 +1133,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         }
       }
       // O = P V: 64 of the 128 output columns per warp
+      APROF(5);
       mbar_wait(pv_done, it & 1);
       tc_fence_after();
+      APROF(6);
       {
         uint32_t r0[32], r1[32];
         const uint32_t taddr_o = tmem_base + 256 + (static_cast<uint32_t>(q * 32) << 16) + half * 64;
@@ -1163,6 +1175,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           bulk_commit_group();
         }
       }
+      APROF(7);
     }
     if (lane == 0) bulk_wait_group<0>();
   }
@@ -1496,6 +1509,7 @@ extern "C" int lvt_gemm_bf16(const LvtGemm* g, void* stream_) {
   p.bank_t = g->bank_t; p.bank_h = g->bank_h; p.bank_w = g->bank_w;
   p.heads = g->heads > 0 ? g->heads : 1;
   p.rowdot = g->rowdot; p.rd_block = g->rd_block; p.rd_L = g->rd_L;
+  p.prof = reinterpret_cast<long long*>(g->prof);
 
   Maps m;
   memset(&m, 0, sizeof(m));

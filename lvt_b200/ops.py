@@ -131,7 +131,7 @@ class ConvSpec:
 def gemm(M, N, K, a: Operand, b: Operand, out: Operand, out_f32=None, out_bf16=None, batch=1,
          splits=1, alpha=1.0, mode=EPI_LINEAR, flags=0, bias=None, bias_mod=0, res=None, aux=None,
          lse=None, delta=None, banks=None, block=None, heads=1, conv: Optional[ConvSpec] = None,
-         rowdot=None, rd_block=0, rd_L=0, v: Optional[Operand] = None, o2: Optional[Operand] = None, o2_n=0):
+         rowdot=None, rd_block=0, rd_L=0, v: Optional[Operand] = None, o2: Optional[Operand] = None, o2_n=0, prof=None):
     """D[z] = epilogue(alpha * A[z] @ B[z]^T); pointers may be torch tensors or ints."""
     lib = _lib.require_device()
 
@@ -175,6 +175,8 @@ def gemm(M, N, K, a: Operand, b: Operand, out: Operand, out_f32=None, out_bf16=N
     if rowdot is not None:
         g.rowdot, g.rd_block, g.rd_L = p(rowdot), rd_block, rd_L
         g.flags |= GEMM_ROWDOT
+    if prof is not None:
+        g.prof = p(prof)
     check(lib.lvt_gemm_bf16(ctypes.byref(g), stream_ptr()), "lvt_gemm_bf16")
 
 
