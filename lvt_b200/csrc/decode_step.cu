@@ -396,7 +396,7 @@ LVT_DEVICE_INLINE void stage_sample(const LvtDecodeStep& p, int k, int pos) {
     const float* qr = p.q_exp + ((long long)k * p.B + b) * nv;
     float mx = -INFINITY;
     if (act)
-      for (int i = threadIdx.x; i < nv; i += 256) mx = fmaxf(mx, __ldcg(row + i) * inv_temp);
+      for (int i = threadIdx.x; i < nv; i += 256) mx = fmaxf(mx, __fmul_rn(__ldcg(row + i), inv_temp));
     mx = warp_max(mx);
     if (act && lane == 0) s_f[warp] = mx;
     __syncthreads();
@@ -406,7 +406,7 @@ LVT_DEVICE_INLINE void stage_sample(const LvtDecodeStep& p, int k, int pos) {
     __syncthreads();
     float sum = 0.f;
     if (act)
-      for (int i = threadIdx.x; i < nv; i += 256) sum += expf(__ldcg(row + i) * inv_temp - mx);
+      for (int i = threadIdx.x; i < nv; i += 256) sum += expf(__fmul_rn(__ldcg(row + i), inv_temp) - mx);
     sum = warp_sum(sum);
     if (act && lane == 0) s_f[warp] = sum;
     __syncthreads();
@@ -418,7 +418,7 @@ LVT_DEVICE_INLINE void stage_sample(const LvtDecodeStep& p, int k, int pos) {
     int besti = 0x7fffffff;
     if (act)
       for (int i = threadIdx.x; i < nv; i += 256) {
-        const float v = (expf(__ldcg(row + i) * inv_temp - mx) / sum) / qr[i];
+        const float v = (expf(__fmul_rn(__ldcg(row + i), inv_temp) - mx) / sum) / qr[i];
         if (v > best) { best = v; besti = i; }
       }
 #pragma unroll

@@ -667,6 +667,9 @@ int dispatch_v4(int n128, F f) {
 // Same arithmetic as torch.multinomial(softmax(.), 1) on CUDA: argmax_i p_i / q_i with q ~ Exp(1) drawn by
 // the caller (torch's generator, so both paths consume the same random stream); first index wins ties.
 // One block per sequence; pos is read from device memory (CUDA-graph replay with a moving position).
+// logit * (1 / temp) is rounded BEFORE the maximum is subtracted (__fmul_rn: no contraction into an FMA, whose exact
+// product would leave exp() of the maximum entry at exp(rounding residual) -- harmless at temp 1, overflow / all-zero at
+// temp -> 0), as ATen's elementwise division and softmax do.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 sample_pixel_kernel(const float* __restrict__ logits, const float* __restrict__ q, const int64_t* __restrict__ pos_ptr,
@@ -681,7 +684,7 @@ sample_pixel_kernel(const float* __restrict__ logits, const float* __restrict__ 
   const float* qr = q + (long long)b * nv;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float mx = -INFINITY;
-  for (int i = threadIdx.x; i < nv; i += 256) mx = fmaxf(mx, row[i] * inv_temp);
+  for (int i = threadIdx.x; i < nv; i += 256) mx = fmaxf(mx, __fmul_rn(row[i], inv_temp));
   mx = warp_max(mx);
   if (lane == 0) s_f[warp] = mx;
   __syncthreads();
@@ -690,7 +693,7 @@ sample_pixel_kernel(const float* __restrict__ logits, const float* __restrict__ 
   for (int w = 1; w < 8; ++w) mx = fmaxf(mx, s_f[w]);
   __syncthreads();
   float sum = 0.f;
-  for (int i = threadIdx.x; i < nv; i += 256) sum += expf(row[i] * inv_temp - mx);
+  for (int i = threadIdx.x; i < nv; i += 256) sum += expf(__fmul_rn(row[i], inv_temp) - mx);
   sum = warp_sum(sum);
   if (lane == 0) s_f[warp] = sum;
   __syncthreads();
@@ -701,7 +704,7 @@ sample_pixel_kernel(const float* __restrict__ logits, const float* __restrict__ 
   float best = -INFINITY;
   int besti = 0x7fffffff;
   for (int i = threadIdx.x; i < nv; i += 256) {
-    const float v = (expf(row[i] * inv_temp - mx) / sum) / qr[i];
+    const float v = (expf(__fmul_rn(row[i], inv_temp) - mx) / sum) / qr[i];
     if (v > best) { best = v; besti = i; }  // ascending i per thread: the first maximum is kept
   }
 #pragma unroll

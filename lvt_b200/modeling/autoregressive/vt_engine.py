@@ -607,6 +607,33 @@ class VTEngine:
         else:
             ws.ignore.zero_()
 
+    def prefetch_inputs(self, ws: VTWorkspace, context, slc, slice_idx, ignore_mask=None):
+        """Start the H2D copy of the NEXT batch (pinned host tensors) into a staging copy of the input buffers on a
+        copy stream, while the current step still runs on the buffers the captured graphs read; commit_inputs() then
+        moves it into place (device-to-device, a few microseconds).  What a DataLoader with pin_memory does for the
+        reference (data/build.py)."""
+        if getattr(ws, "_stage_in", None) is None:
+            ws._stage_in = [torch.empty_like(t) for t in (ws.context, ws.slice, ws.slice_idx, ws.ignore)]
+            ws._copy_stream = torch.cuda.Stream()
+            ws._copy_done = torch.cuda.Event()
+        st = ws._stage_in
+        ws._copy_stream.wait_stream(torch.cuda.current_stream())  # the previous commit has read the staging buffers
+        with torch.cuda.stream(ws._copy_stream):
+            st[0].copy_(context.reshape(st[0].shape), non_blocking=True)
+            st[1].copy_(slc.reshape(st[1].shape), non_blocking=True)
+            st[2].copy_(slice_idx.reshape(-1), non_blocking=True)
+            if ignore_mask is not None:
+                st[3].copy_(ignore_mask.reshape(st[3].shape).to(torch.uint8), non_blocking=True)
+            else:
+                st[3].zero_()
+            ws._copy_done.record()
+
+    def commit_inputs(self, ws: VTWorkspace):
+        """Prefetched batch -> the static input buffers (ordered after the H2D copy and after the previous step)."""
+        torch.cuda.current_stream().wait_event(ws._copy_done)
+        for dst, src in zip((ws.context, ws.slice, ws.slice_idx, ws.ignore), ws._stage_in):
+            dst.copy_(src, non_blocking=True)
+
     def set_inputs_from_videos(self, ws: VTWorkspace, videos, abc, n_prime=1):
         """Device-side input construction: latent videos (B, T, nc, H, W) already in HBM + slice offsets (B, 3) ->
         the workspace's context / slice / slice_idx / ignore buffers (lvt_b200.data.prepare_slices_batched: the

@@ -168,17 +168,16 @@ def test_base_vqvae_single_codebook(cuda_lib, tmp_path):
 
 
 def test_graph_sampler_matches_per_pixel_loop(cuda_lib, tmp_path):
-    """VideoTransformer.sample_slice (one CUDA-graph replay per position) against (a) the same fused per-position step
-    launched eagerly: identical code for code, and (b) the reference-shaped per-pixel loop (vt.py:107-134) at
-    temperature -> 0, where the multinomial draw is the argmax of identical logits.  (b) is checked on the first
-    sampled rows only: a randomly initialised network collapses to two alternating codes with logits ~1e-7 apart
-    further down the frame, and there the draw at temperature 1e-4 is a coin flip that one ulp of logit / temp decides;
-    one different code changes everything after it.)"""
+    """VideoTransformer.sample_slice (one CUDA-graph replay per position) against the same fused per-position step
+    launched eagerly and against the reference-shaped per-pixel loop (vt.py:107-134).  At temperature 1e-10 the
+    multinomial draw IS the argmax of identical logits (every other probability underflows to exactly 0), so the three
+    sampled frames must be identical code for code whatever random stream each path consumes.  (At 1e-4, as in round 1,
+    a randomly initialised network that has collapsed to two alternating codes with logits ~1e-7 apart still leaves
+    the draw to the noise, and torch's graph-captured generator does not replay the eager offsets: flaky.)"""
     from lvt_b200.config.presets import preset
     from lvt_b200.modeling import build_model
     cfgv = preset("DSFVT", SMALL + ["TEST.EVALUATORS", "VTSampler", "OUTPUT_DIR", str(tmp_path)])
     cfgv.freeze()
-    torch.manual_seed(1234)
     vt = build_model(cfgv)
     vt.train(False)
     video = torch.randint(0, 512, (1, 4, 16, 16, 16)).cuda()
@@ -188,10 +187,10 @@ def test_graph_sampler_matches_per_pixel_loop(cuda_lib, tmp_path):
     for graph in (True, "eager", False):
         vt.sampler_graph = graph
         torch.manual_seed(0)
-        outs[graph] = vt.sample_video(video.clone(), temp=1e-4, n_prime=15).cpu()
+        outs[graph] = vt.sample_video(video.clone(), temp=1e-10, n_prime=15).cpu()
     assert torch.equal(outs[True], outs["eager"])
+    assert torch.equal(outs[True], outs[False])
     assert torch.equal(outs[True][:, :, :15], video[:, :, :15].cpu())
-    assert torch.equal(outs[True][:, :, 15, :4], outs[False][:, :, 15, :4])
 
 
 def test_codes_extractor_round_trip(cuda_lib, tmp_path):
