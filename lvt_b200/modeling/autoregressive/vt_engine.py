@@ -874,15 +874,21 @@ class VTEngine:
     def optimizer_kernel(self, grad_scale=1.0):
         """The fused multi-tensor update alone.  lr and Adam's bias corrections are passed BY VALUE, so this launch
         must stay outside CUDA graphs (a captured launch would freeze the schedule and the step count)."""
+        self.opt["step"] += 1
+        self.optimizer_slice(0, self.store.numel, grad_scale)
+
+    def optimizer_slice(self, lo, hi, grad_scale=1.0):
+        """The update of the parameters [lo, hi) of the flat buffers (the update is elementwise, so a gradient bucket
+        can be applied as soon as it has been reduced); the caller advances opt["step"] once per step."""
         o, st = self.opt, self.store
-        o["step"] += 1
+        at = lambda t, esize: ctypes.c_void_p(t.data_ptr() + esize * lo)  # noqa: E731
         if o["name"] == "rmsprop":
-            check(self.lib.lvt_rmsprop_step(ptr(st.master), ptr(st.grad), ptr(self.opt_s1), ptr(self.opt_s2),
-                                            ptr(st.shadow), st.numel, o["lr"], o["alpha"], o["momentum"], o["eps"],
+            check(self.lib.lvt_rmsprop_step(at(st.master, 4), at(st.grad, 4), at(self.opt_s1, 4), at(self.opt_s2, 4),
+                                            at(st.shadow, 2), hi - lo, o["lr"], o["alpha"], o["momentum"], o["eps"],
                                             grad_scale, stream_ptr()), "lvt_rmsprop_step")
         else:
-            check(self.lib.lvt_adam_step(ptr(st.master), ptr(st.grad), ptr(self.opt_s1), ptr(self.opt_s2),
-                                         ptr(st.shadow), st.numel, o["lr"], o["betas"][0], o["betas"][1], o["eps"],
+            check(self.lib.lvt_adam_step(at(st.master, 4), at(st.grad, 4), at(self.opt_s1, 4), at(self.opt_s2, 4),
+                                         at(st.shadow, 2), hi - lo, o["lr"], o["betas"][0], o["betas"][1], o["eps"],
                                          o["step"], grad_scale, stream_ptr()), "lvt_adam_step")
 
     def train_step(self, ws: VTWorkspace, grad_hook=None, grad_scale=1.0):
@@ -918,7 +924,13 @@ class GraphedTrainStep:
         self.graphs = []     # [zero-grad + forward + segment 0, segment 1, ...]
         self.plan = None
         self.g_opt = None
-        self.comm = torch.cuda.Stream() if allreduce is not None else None
+        # one GPU: LVT_OPT_OVERLAP=1 uses the same segmentation to run the optimizer update of a bucket on the side
+        # stream while the backward segments below it are still going; measured neutral (9.58-9.72 against 9.61 ms:
+        # the update is an HBM pass that competes with the backward), so one graph + one optimizer launch stays
+        self.segmented = allreduce is not None or (overlap and os.environ.get("LVT_OPT_OVERLAP", "0") == "1")
+        if allreduce is None and parts is None:
+            self.parts = int(os.environ.get("LVT_GRAD_PARTS", "2"))
+        self.comm = torch.cuda.Stream() if self.segmented else None
         self.launches_per_step = 0
 
     def _fwd_bwd(self):
@@ -946,19 +958,27 @@ class GraphedTrainStep:
 
     def _run(self, segments):
         """segments[i](): [zero-grad + forward +] backward segment i; the all-reduce of bucket i goes to the
-        communication stream as soon as the segment has been issued"""
-        grad = self.engine.store.grad
+        communication stream as soon as the segment has been issued, and the optimizer update of that bucket's
+        parameters (elementwise, eager launch) follows it there: when the backward ends only the last bucket's
+        reduction and update are still outstanding"""
+        eng = self.engine
+        grad = eng.store.grad
+        eng.opt["step"] += 1
         if not self.overlap:
             for seg in segments:
                 seg()
-            self.allreduce(grad)
+            if self.allreduce is not None:
+                self.allreduce(grad)
+            eng.optimizer_slice(0, eng.store.numel, 1.0 / self.world_size)
             return
         main = torch.cuda.current_stream()
         for seg, (_, lo, hi) in zip(segments, self.plan):
             seg()
             self.comm.wait_stream(main)
             with torch.cuda.stream(self.comm):
-                self.allreduce(grad[lo:hi])
+                if self.allreduce is not None:
+                    self.allreduce(grad[lo:hi])
+                eng.optimizer_slice(lo, hi, 1.0 / self.world_size)
         main.wait_stream(self.comm)
 
     def capture(self, warmup=2):
@@ -966,7 +986,7 @@ class GraphedTrainStep:
         workspace; parameters and optimizer state are snapshotted before and restored after, so capturing
         does not train."""
         eng, lib = self.engine, self.engine.lib
-        dist = self.allreduce is not None
+        dist = self.segmented
         if dist:
             self.plan = eng.backward_plan(self.ws, self.parts)
 
@@ -984,7 +1004,7 @@ class GraphedTrainStep:
                     self._run(eager)
                 else:
                     self._fwd_bwd()
-                self._opt()
+                    self._opt()
                 self._refresh()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
@@ -996,7 +1016,8 @@ class GraphedTrainStep:
             sms = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
             for i, fn in enumerate(eager):
                 # segments after the first run next to the all-reduce of the bucket before them
-                lib.lvt_set_sm_limit(sms - self.comm_sms if (i > 0 and self.overlap and self.comm_sms > 0) else 0)
+                lib.lvt_set_sm_limit(sms - self.comm_sms if (i > 0 and self.overlap and self.comm_sms > 0 and
+                                                             self.allreduce is not None) else 0)
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
                     fn()
@@ -1010,14 +1031,15 @@ class GraphedTrainStep:
         self.g_opt = torch.cuda.CUDAGraph()  # weight re-layouts after the (eager) optimizer kernel
         with torch.cuda.graph(self.g_opt):
             self._refresh()
-        self.launches_per_step = _lib.launch_count() - n0 + 1  # + the eager optimizer kernel
+        # + the eager optimizer launches (one per gradient bucket when the update follows each all-reduce)
+        self.launches_per_step = _lib.launch_count() - n0 + (len(self.plan) if (dist and self.overlap) else 1)
         torch.cuda.synchronize()
 
     def step(self):
-        if self.allreduce is not None:
+        if self.segmented:
             self._run([g.replay for g in self.graphs])
         else:
             self.graphs[0].replay()
-        self._opt()
+            self._opt()
         self.g_opt.replay()
         return self.ws.loss
