@@ -353,6 +353,18 @@ int lvt_cast_bf16(const float* in, void* out_bf16, long long n, void* stream);
 int lvt_permute4(const float* in, void* out, int out_is_bf16, int accumulate, const int* dims,
                  const long long* in_strides, const long long* out_strides, void* stream);
 
+/* The same for a table of jobs in ONE launch (per-step weight packs / gradient folds).  jobs: DEVICE array; job j covers
+ * blocks [first_block, first_block + ceil(numel / 1024)), ascending; total_blocks = their sum.  The jobs of one call must
+ * not depend on each other.                                                                  */
+typedef struct LvtPermuteJob {
+  const float* in; void* out;
+  int out_is_bf16, accumulate;
+  int dims[4];
+  long long in_strides[4], out_strides[4];
+  long long first_block;
+} LvtPermuteJob;
+int lvt_permute4_batch(const LvtPermuteJob* jobs, int n_jobs, int total_blocks, void* stream);
+
 /* Channels-last variants used inside the VQ-VAE engine (z_e [n*hw, num*D] fp32 as written by the
  * last encoder GEMM): same arithmetic and index layout ([n, num, hw] int64) as lvt_vq_argmin;
  * zq may additionally be produced as bf16 (decoder GEMM operand).                             */

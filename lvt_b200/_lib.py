@@ -89,6 +89,45 @@ class LvtRowsLinear(ctypes.Structure):
     ]
 
 
+class LvtPermuteJob(ctypes.Structure):
+    """Mirror of `struct LvtPermuteJob` (include/lvt_b200.h)."""
+    _fields_ = [("in_", ctypes.c_void_p), ("out", ctypes.c_void_p), ("out_is_bf16", ctypes.c_int), ("accumulate", ctypes.c_int),
+                ("dims", ctypes.c_int * 4), ("in_strides", ctypes.c_longlong * 4), ("out_strides", ctypes.c_longlong * 4),
+                ("first_block", ctypes.c_longlong)]
+
+
+class PermuteBatch:
+    """A fixed list of lvt_permute4 jobs (same arguments) replayed as ONE launch: the table is uploaded once."""
+
+    def __init__(self):
+        self.jobs, self.table, self.blocks = [], None, 0
+
+    def add(self, src, dst, bf16, acc, dims, istr, ostr):
+        ptr_of = lambda x: x if isinstance(x, int) else x.data_ptr()  # noqa: E731
+        n = 1
+        for d in dims:
+            n *= int(d)
+        if n > 0:
+            self.jobs.append((ptr_of(src), ptr_of(dst), int(bf16), int(acc), tuple(int(d) for d in dims),
+                              tuple(int(v) for v in istr), tuple(int(v) for v in ostr), n))
+
+    def run(self, device):
+        if not self.jobs:
+            return
+        if self.table is None:
+            arr = (LvtPermuteJob * len(self.jobs))()
+            blk = 0
+            for a, (src, dst, bf16, acc, dims, istr, ostr, n) in zip(arr, self.jobs):
+                a.in_, a.out, a.out_is_bf16, a.accumulate = src, dst, bf16, acc
+                a.dims[:], a.in_strides[:], a.out_strides[:] = dims, istr, ostr
+                a.first_block = blk
+                blk += (n + 1023) // 1024
+            self.blocks = blk
+            self.table = torch.frombuffer(bytearray(arr), dtype=torch.uint8).to(device)
+        check(load().lvt_permute4_batch(ctypes.c_void_p(self.table.data_ptr()), len(self.jobs), self.blocks, stream_ptr()),
+              "lvt_permute4_batch")
+
+
 class LvtDecodeLayer(ctypes.Structure):
     """Mirror of `struct LvtDecodeLayer` (include/lvt_b200.h)."""
     _fields_ = [(n, ctypes.c_void_p) for n in ("ln1_g", "ln1_b", "w_qkv", "k_cache", "v_cache", "bank_t", "bank_h", "bank_w",
@@ -148,6 +187,7 @@ SYMBOLS = {
     "lvt_adam_step": (_i, [_vp] * 5 + [_ll] + [_f] * 4 + [_i, _f, _vp]),
     "lvt_cast_bf16": (_i, [_vp, _vp, _ll, _vp]),
     "lvt_permute4": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),
+    "lvt_permute4_batch": (_i, [_vp, _i, _i, _vp]),
     "lvt_vq_argmin_nhwc": (_i, [_vp] * 7 + [_i] * 5 + [_vp]),
     "lvt_vq_gather_nhwc": (_i, [_vp] * 4 + [_i] * 5 + [_vp]),
     "lvt_vqvae_in_im2col": (_i, [_vp, _vp, _i, _f, _f, _vp]),

@@ -649,6 +649,38 @@ permute4_kernel(const float* __restrict__ in, void* __restrict__ out, Permute4 P
   }
 }
 
+// Many small re-layout jobs in ONE launch (the per-step weight packs / gradient folds of the engines are 20-70
+// launches of a few microseconds each): block b works on 1024 elements of the job whose block range contains b.
+__global__ void __launch_bounds__(256)
+permute4_batch_kernel(const LvtPermuteJob* __restrict__ jobs, int n_jobs) {
+  pdl_prologue();
+  int lo = 0, hi = n_jobs - 1;
+  while (lo < hi) {  // last job with first_block <= blockIdx.x
+    const int mid = (lo + hi + 1) >> 1;
+    if (jobs[mid].first_block <= (long long)blockIdx.x) lo = mid;
+    else hi = mid - 1;
+  }
+  const LvtPermuteJob J = jobs[lo];
+  const long long total = (long long)J.dims[0] * J.dims[1] * J.dims[2] * J.dims[3];
+  const long long base = ((long long)blockIdx.x - J.first_block) * 1024;
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const long long i = base + u * 256 + threadIdx.x;
+    if (i >= total) break;
+    long long r = i;
+    const int i3 = (int)(r % J.dims[3]); r /= J.dims[3];
+    const int i2 = (int)(r % J.dims[2]); r /= J.dims[2];
+    const int i1 = (int)(r % J.dims[1]); r /= J.dims[1];
+    const int i0 = (int)r;
+    const long long so = i0 * J.in_strides[0] + i1 * J.in_strides[1] + i2 * J.in_strides[2] + i3 * J.in_strides[3];
+    const long long oo = i0 * J.out_strides[0] + i1 * J.out_strides[1] + i2 * J.out_strides[2] + i3 * J.out_strides[3];
+    const float v = J.in[so];
+    if (J.out_is_bf16) reinterpret_cast<__nv_bfloat16*>(J.out)[oo] = __float2bfloat16(v);
+    else if (J.accumulate) reinterpret_cast<float*>(J.out)[oo] += v;
+    else reinterpret_cast<float*>(J.out)[oo] = v;
+  }
+}
+
 template <typename F>
 int dispatch_v4(int n128, F f) {
   switch (n128) {
@@ -977,6 +1009,14 @@ extern "C" int lvt_permute4(const float* in, void* out, int out_is_bf16, int acc
   if (out_is_bf16) LVT_CHECK_CUDA(lvt_launch(permute4_kernel<true, false>, dim3(grid), dim3(256), 0, STREAM(stream), in, out, P, total));
   else if (accumulate) LVT_CHECK_CUDA(lvt_launch(permute4_kernel<false, true>, dim3(grid), dim3(256), 0, STREAM(stream), in, out, P, total));
   else LVT_CHECK_CUDA(lvt_launch(permute4_kernel<false, false>, dim3(grid), dim3(256), 0, STREAM(stream), in, out, P, total));
+  LVT_CHECK_LAUNCH();
+  lvt_count_launch(1);
+  return LVT_OK;
+}
+
+extern "C" int lvt_permute4_batch(const LvtPermuteJob* jobs_dev, int n_jobs, int total_blocks, void* stream) {
+  LVT_CHECK_ARG(jobs_dev && n_jobs > 0 && total_blocks > 0, "lvt_permute4_batch: bad argument");
+  LVT_CHECK_CUDA(lvt_launch(permute4_batch_kernel, dim3(total_blocks), dim3(256), 0, STREAM(stream), jobs_dev, n_jobs));
   LVT_CHECK_LAUNCH();
   lvt_count_launch(1);
   return LVT_OK;

@@ -277,6 +277,7 @@ class VTEngine:
         self.dut = [None] + [torch.zeros_like(self.ut[k]) for k in range(1, s.nc)]
         self._taps_cache = {}
         self.conv_wp = None  # packed masked-conv weight, depends on the slice shape (live taps)
+        self._rec, self._pbatch = None, {}
         self._side = torch.cuda.Stream()  # parameter-gradient stream of the backward pass
         self._side_pending = False
         self.shadows_fresh = False
@@ -314,9 +315,25 @@ class VTEngine:
         return self._taps_cache[key]
 
     def _permute4(self, src, dst, bf16, acc, dims, istr, ostr):
+        if self._rec is not None:  # inside _batched(): recorded, launched together
+            self._rec.add(src, dst, bf16, acc, dims, istr, ostr)
+            return
         check(self.lib.lvt_permute4(_vp(src), _vp(dst), int(bf16), int(acc), (ctypes.c_int * 4)(*dims),
                                     (ctypes.c_longlong * 4)(*istr), (ctypes.c_longlong * 4)(*ostr),
                                     stream_ptr()), "lvt_permute4")
+
+    def _batched(self, key, fn):
+        """The lvt_permute4 calls of fn() as ONE launch (lvt_permute4_batch): recorded on first use -- pointers, shapes
+        and strides are fixed per key --, replayed afterwards."""
+        b = self._pbatch.get(key)
+        if b is None:
+            b = self._pbatch[key] = _lib.PermuteBatch()
+            self._rec = b
+            try:
+                fn()
+            finally:
+                self._rec = None
+        b.run(self.device)
 
     def refresh_shadows(self):
         """master fp32 -> bf16 shadow + the re-laid-out small weights (after load / optimizer)."""
@@ -326,6 +343,9 @@ class VTEngine:
         self.shadows_fresh = True
 
     def _refresh_special(self):
+        self._batched(("refresh", len(self._taps_cache)), self._refresh_special_jobs)
+
+    def _refresh_special_jobs(self):
         s, st = self.spec, self.store
         ktaps = s.kernel[0] * s.kernel[1] * s.kernel[2]
         # encoder.conv.weight [de, nc*nv, ktaps] -> enc_wt [nc, ktaps, nv, de]
@@ -357,6 +377,9 @@ class VTEngine:
 
     def _fold_special_grads_enc(self):
         """re-laid-out gradients -> master gradient layout (+=): encoder one-hot conv."""
+        self._batched(("fold_enc",), self._fold_enc_jobs)
+
+    def _fold_enc_jobs(self):
         s, st = self.spec, self.store
         ktaps = s.kernel[0] * s.kernel[1] * s.kernel[2]
         self._permute4(self.enc_dwt, st.gf("encoder.conv.weight"), False, True,
@@ -365,6 +388,9 @@ class VTEngine:
 
     def _fold_special_grads_pred(self):
         """... one-hot half of the predictor's U[k] (complete after the predictor backward)"""
+        self._batched(("fold_pred",), self._fold_pred_jobs)
+
+    def _fold_pred_jobs(self):
         s, st = self.spec, self.store
         for k in range(1, s.nc):
             ld = s.d + k * s.nv
@@ -373,6 +399,9 @@ class VTEngine:
 
     def _fold_special_grads_conv(self, slice_shape):
         """... live taps of the masked conv (complete after the decoder front)"""
+        self._batched(("fold_conv", tuple(slice_shape)), lambda: self._fold_conv_jobs(slice_shape))
+
+    def _fold_conv_jobs(self, slice_shape):
         s, st = self.spec, self.store
         taps, offs, wp, dwp = self._live_taps(slice_shape)
         ntaps = len(taps)

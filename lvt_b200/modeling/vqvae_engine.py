@@ -114,6 +114,7 @@ class VQVAEEngine:
         self._ws = {}
         self.shadows_fresh = False
         self.opt = None
+        self._rec, self._pbatch = None, {}
         self._pp = None             # [hi | hi | lo] split packs of the encoder weights (high-precision encode)
         self._pp_fresh = False
 
@@ -132,15 +133,36 @@ class VQVAEEngine:
         self.shadows_fresh = False
 
     def _permute4(self, src, dst, bf16, acc, dims, istr, ostr):
+        if self._rec is not None:  # inside _batched(): recorded, launched together
+            self._rec.add(src, dst, bf16, acc, dims, istr, ostr)
+            return
         check(self.lib.lvt_permute4(_vp(src), _vp(dst), int(bf16), int(acc), (ctypes.c_int * 4)(*dims),
                                     (ctypes.c_longlong * 4)(*istr), (ctypes.c_longlong * 4)(*ostr),
                                     stream_ptr()), "lvt_permute4")
 
+    def _batched(self, key, fn):
+        """The lvt_permute4 calls of fn() as ONE launch (lvt_permute4_batch): recorded on first use (pointers, shapes
+        and strides are fixed), replayed afterwards -- the per-step weight packs and gradient folds were 74 launches."""
+        b = self._pbatch.get(key)
+        if b is None:
+            b = self._pbatch[key] = _lib.PermuteBatch()
+            self._rec = b
+            try:
+                fn()
+            finally:
+                self._rec = None
+        b.run(self.device)
+
     def refresh_shadows(self, cast=True):
         self._pp_fresh = False
-        s, st = self.spec, self.store
+        st = self.store
         if cast:
             check(self.lib.lvt_cast_bf16(ptr(st.master), ptr(st.shadow), st.numel, stream_ptr()), "lvt_cast_bf16")
+        self._batched(("refresh",), self._refresh_jobs)
+        self.shadows_fresh = True
+
+    def _refresh_jobs(self):
+        s, st = self.spec, self.store
         nf = s.nf
         # conv1 [128][3][16] -> [128][(tap, c)] padded to 64 columns
         self._permute4(st.pf("E.layers.0.weight"), self.w1p, True, False, (nf // 2, 16, 3, 1), (48, 1, 16, 0),
@@ -172,10 +194,12 @@ class VQVAEEngine:
         c2 = nf // 2
         self._permute4(wo, self.w_out_fwd, True, False, (16, 3, c2, 1), (1, 16, 48, 0), (3 * c2, c2, 1, 0))
         self._permute4(wo, self.w_out_dg, True, False, (c2, 48, 1, 1), (48, 1, 0, 0), (64, 1, 0, 0))
-        self.shadows_fresh = True
 
     def _fold_packed_grads(self):
         """packed-layout weight gradients -> reference layout in the flat gradient (+=)."""
+        self._batched(("fold",), self._fold_jobs)
+
+    def _fold_jobs(self):
         s, st = self.spec, self.store
         nf = s.nf
         self._permute4(self.dw1p, st.gf("E.layers.0.weight"), False, True, (nf // 2, 16, 3, 1), (64, 3, 1, 0),
