@@ -11,11 +11,13 @@ predicted code index = B * nc * t*h*w per step (1024 per sample).
               every step) with the loss read back to the host every step
   roofline  : whole-step useful FLOPs (81.7 GFLOP/sample) / step time vs the measured
               bf16 peak, plus per-kernel figures (QKV GEMM alone; VQ argmin vs HBM)
-  cpu_baseline / --impl reference : the oracle port of the reference's CPU path
-              (oracle/lvt_oracle.py) on the host cores, bounded sample (batch 8 slices / 32 frames per step);
-              the line declares the steps / warm-up / batch it actually ran
-  incumbent : the same oracle port run as PyTorch eager ON THE B200 (fp32, TF32, autocast-bf16) -- what a
-              user of the reference would otherwise run on this box (SURVEY 8d last row); measurement only
+  cpu_baseline / --impl reference : the UNMODIFIED reference (pip-installed under baseline/_ref by build(),
+              kind "reference": its own build_model / forward(data, 'supervised') / optimizer) on the host cores,
+              else the oracle port (oracle/lvt_oracle.py, kind "port"); bounded sample (batch 8 slices / 32 frames
+              per step); the line declares the steps / warm-up / batch it actually ran
+  incumbent : the oracle port and (when baseline/_ref is there) the unmodified reference modules run as PyTorch
+              eager ON THE B200 (fp32, TF32, autocast-bf16) -- what a user of the reference would otherwise run
+              on this box (SURVEY 8d last row); measurement only
   --workload vqvae : PR-DVQVAE2 train step, frames/s (second half of BASELINE.json's metric), also at N > 1
   N > 1     : adds "strong" (global batch 64 split over the ranks, the reference's semantics,
               data/build.py:62-74) and "dp_parity" (loss trajectory of N ranks vs 1 GPU on a fixed global batch)
@@ -80,6 +82,8 @@ class ClockSampler(threading.Thread):
 
 def cpu_reference_arm(steps, warmup, batch=8):
     """The reference's CPU path (oracle port, all host threads): DSFVT fwd + bwd + RMSprop."""
+    if live_reference_root():
+        return live_reference_arm(steps, warmup, batch=batch)
     import torch
     from oracle import lvt_oracle as O
     cores = os.cpu_count() or 1
@@ -110,8 +114,79 @@ def cpu_reference_arm(steps, warmup, batch=8):
                       f"{torch.get_num_threads()} threads", "ms_per_step": dt * 1e3}
 
 
+def live_reference_root():
+    """baseline/_ref holds the UNMODIFIED reference, pip-installed by __graft_entry__.build() in the authoring
+    container (`pip install --no-index --no-deps --target baseline/_ref <copy of /root/reference>`); git-ignored,
+    not gpurun-ignored, so it is on the GPU box.  None when it is absent (then the arms fall back to the oracle port)."""
+    p = os.path.join(ROOT, "baseline", "_ref")
+    return p if os.path.isdir(os.path.join(p, "vidgen")) and os.environ.get("LVT_REF_PORT", "0") != "1" else None
+
+
+def _live_reference_model(preset_name, device="cpu"):
+    """build_model(cfg) of the unmodified reference for one of its shipped configurations, with the optimizer its
+    own Trainer would build (engine/trainer.py:39-40)."""
+    import tempfile
+    from oracle import ref_shim
+    ref_shim.use_root(live_reference_root())
+    ref_shim.install()
+    from vidgen.config import get_cfg
+    from vidgen.modeling.meta_arch import build_model
+    from lvt_b200.config.presets import PRESETS     # the YAML's values as an override list (pure Python, no kernels)
+    cfg = get_cfg()
+    cfg.merge_from_list(list(PRESETS[preset_name]) + ["MODEL.DEVICE", device, "OUTPUT_DIR", tempfile.mkdtemp(prefix="lvt_ref_")])
+    cfg.freeze()
+    model = build_model(cfg)
+    optimizers, _ = model.configure_optimizers_and_checkpointers()
+    model.train()
+    return model, [o["optimizer"] for o in optimizers]
+
+
+def live_reference_arm(steps, warmup, batch=8, workload="dsfvt"):
+    """The UNMODIFIED reference through its own public API on the host cores: build_model(cfg), model(data,
+    mode='supervised'), backward, optimizer.step(), zero_grad() = the body of Trainer.run_step
+    (engine/trainer.py:78-87) on the mapper's per-sample dicts (data/dataset_mapper.py:144-149)."""
+    import torch
+    from oracle import lvt_oracle as O       # synthetic batch generator only
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    if workload == "vqvae":
+        model, opts = _live_reference_model("PR-DVQVAE2")
+        x = torch.rand((batch, 3, 64, 64), generator=torch.Generator().manual_seed(3))
+        data = [{"image": x[i]} for i in range(batch)]
+        units, unit, what = batch, "frames/s", f"PR-DVQVAE2 train steps (fwd+bwd+Adam+EMA), {batch} frames 64x64"
+    else:
+        model, opts = _live_reference_model("DSFVT")
+        ctx, slc, sidx, ign = O.synth_vt_batch(batch, seed=5, cfg=O.VTConfig())
+        data = [{"context": ctx[i], "slice": slc[i], "slice_idx": sidx[i], "ignore_mask": ign[i]} for i in range(batch)]
+        units, unit, what = batch * TOKENS_PER_SAMPLE, "latent tokens/s", f"DSFVT train steps (fwd+bwd+RMSprop), batch {batch} slices"
+    from vidgen.utils.events import EventStorage
+
+    def step():
+        losses = sum(model(data, mode="supervised").values())
+        losses.backward()
+        for o in opts:
+            o.step()
+        for o in opts:
+            o.zero_grad()
+        return losses.item()
+
+    with EventStorage(0):
+        for _ in range(warmup):
+            step()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            step()
+        dt = (time.perf_counter() - t0) / steps
+    return {"value": units / dt, "unit": unit, "cores": cores, "kind": "reference",
+            "sample": f"{steps} {what}, fp32, the unmodified reference modules (baseline/_ref) on torch CPU "
+                      f"{torch.get_num_threads()} threads", "ms_per_step": dt * 1e3}
+
+
 def cpu_vqvae_arm(steps, warmup, frames=32):
     """The reference's CPU path for the VQ-VAE half (oracle port): PR-DVQVAE2 fwd + bwd + Adam(0.9, 0.9) + EMA."""
+    if live_reference_root():
+        return live_reference_arm(steps, warmup, batch=frames, workload="vqvae")
     import torch
     from oracle import lvt_oracle as O
     cores = os.cpu_count() or 1
@@ -220,9 +295,54 @@ def incumbent_arms(batch, frames, steps=5, warmup=2):
             out["vqvae"] = dict(res, frames=frames, note="oracle port of PR-DVQVAE2 (cuDNN convs, ATen codebook search) "
                                 "as PyTorch eager on cuda:0 + torch.optim.Adam(0.9, 0.9) + EMA")
             torch.cuda.empty_cache()
+        if live_reference_root():
+            out["reference_modules"] = _incumbent_live_reference(batch, frames, timed, modes[:2])
     finally:
         torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
     return out
+
+
+def _incumbent_live_reference(batch, frames, timed, modes):
+    """The UNMODIFIED reference (baseline/_ref) on cuda:0 through its own API: build_model(cfg) with MODEL.DEVICE
+    cuda, model(data, mode='supervised'), backward, its own optimizer -- Trainer.run_step's body (engine/trainer.py:78-87)."""
+    import torch
+    from oracle import lvt_oracle as O
+    res = {}
+    for wl, preset_name in (("dsfvt", "DSFVT"), ("vqvae", "PR-DVQVAE2")):
+        try:
+            torch.manual_seed(0)
+            model, opts = _live_reference_model(preset_name, device="cuda")
+            from vidgen.utils.events import EventStorage
+            if wl == "dsfvt":
+                ctx, slc, sidx, ign = (t.cuda() for t in O.synth_vt_batch(batch, seed=5, cfg=O.VTConfig()))
+                data = [{"context": ctx[i], "slice": slc[i], "slice_idx": sidx[i], "ignore_mask": ign[i]} for i in range(batch)]
+                units, unit = batch * TOKENS_PER_SAMPLE, "latent tokens/s"
+            else:
+                x = torch.rand((frames, 3, 64, 64), generator=torch.Generator().manual_seed(3)).cuda()
+                data = [{"image": x[i]} for i in range(frames)]
+                units, unit = frames, "frames/s"
+
+            def step():
+                sum(model(data, mode="supervised").values()).backward()
+                for o in opts:
+                    o.step()
+                for o in opts:
+                    o.zero_grad()
+            r = {}
+            with EventStorage(0):
+                for name, tf32, _ in modes:
+                    torch.backends.cuda.matmul.allow_tf32 = tf32
+                    torch.backends.cudnn.allow_tf32 = tf32
+                    ms = timed(step)
+                    r[name] = {"ms_per_step": ms, "value": units / (ms * 1e-3), "unit": unit}
+            res[wl] = dict(r, units_per_step=units)
+            del model, opts, data
+            torch.cuda.empty_cache()
+        except Exception as ex:
+            res[wl] = {"error": repr(ex)[:300]}
+    res["note"] = ("the unmodified reference package (pip-installed under baseline/_ref) as PyTorch eager on cuda:0, "
+                   "its own build_model / forward(data, 'supervised') / optimizer")
+    return res
 
 
 def step_traffic():
@@ -395,7 +515,8 @@ def main():
             r = cpu_reference_arm(steps_run, warm_run, batch=8)
             metric, unit, sample_cfg = "latent tokens/sec DSFVT train step", "latent tokens/s", {"per_gpu_batch": 8, "global_batch": 8}
             wl = config["workload"]
-        ref_config = dict(config, workload=wl, parallelism="cpu", **sample_cfg)
+        base_cfg = config if args.workload != "vqvae" else {"l2": "n/a (CPU)"}
+        ref_config = dict(base_cfg, workload=wl, parallelism="cpu", **sample_cfg)
         ref_config["sample_of"] = ("bounded sample of the GPU arm's workload: same network, same synthetic data generator, "
                                    "smaller batch per step (the metric is per token / per frame)")
         line = {"impl": "reference", "metric": metric, "value": r["value"], "unit": unit, "n_gpus": args.gpus,

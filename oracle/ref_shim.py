@@ -5,7 +5,9 @@ not installed here and cannot be fetched (no network): fvcore, yacs (via fvcore)
 None of them does arithmetic.  `install()` registers small in-memory stand-ins for exactly the
 names the reference imports and puts the reference on sys.path; nothing is written to disk and
 nothing of the reference is copied.  Used by tests/golden/make_golden.py and
-tests/test_oracle_vs_reference.py; never on the GPU box (the reference does not exist there).
+tests/test_oracle_vs_reference.py (from /root/reference, authoring container only) and by
+`bench.py --impl reference` / `cpu_baseline` (from the pip-installed copy under baseline/_ref,
+git-ignored, which travels to the GPU box; `use_root`).
 """
 import copy
 import os
@@ -22,6 +24,14 @@ REFERENCE_ROOT = os.environ.get("LVT_REFERENCE_ROOT", "/root/reference")
 
 def available():
     return os.path.isdir(os.path.join(REFERENCE_ROOT, "vidgen"))
+
+
+def use_root(path):
+    """Point the shim at another copy of the unmodified reference (bench.py --impl reference uses the
+    pip-installed one under baseline/_ref, which travels to the GPU box).  Call before install()."""
+    global REFERENCE_ROOT
+    assert not _installed or path == REFERENCE_ROOT, "reference already imported from another root"
+    REFERENCE_ROOT = path
 
 
 # --------------------------------------------------------------------------------------------
