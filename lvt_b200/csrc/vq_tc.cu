@@ -57,6 +57,10 @@ LVT_DEVICE_INLINE void tma_load_2d(void* smem_dst, const CUtensorMap* m, uint64_
       : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+LVT_DEVICE_INLINE void tma_prefetch_2d(const CUtensorMap* m, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1)
+               : "memory");
+}
 LVT_DEVICE_INLINE void epi_bar(int id) { asm volatile("bar.sync %0, 512;" ::"r"(id) : "memory"); }
 LVT_DEVICE_INLINE float fmin3(float a, float b, float c) {
   float r;
@@ -487,6 +491,473 @@ vq_argmin_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __res
   }
 }
 
+// ------------------------------------------------------------------------------------------------------
+// v2: the same algorithm as a free-running pipeline (no CTA-wide barrier inside the tile loop).
+//   * the 16 scan warps form two SETS that take alternate tiles (set = tile parity = A slot); a set is four
+//     PAIRS of warps, one pair per TMEM lane quarter: the pair owns rows q*32.. of the set's tiles, warp pw of
+//     the pair scans codes h*256 + pw*128 .. +127 of both accumulator halves.  All exchanges (|x|^2 partial
+//     sums, minima, candidate list, winners) stay inside the pair: three 64-thread named barriers per tile.
+//   * ONE pass over TMEM: each 32-column chunk is tested against the RUNNING minimum + 2E while it is in
+//     registers (a superset of the final window: the running minimum only decreases), the buffer is released
+//     to the MMA warp right after, and chunks whose own minimum is above the final threshold are dropped later.
+//   * the threshold tests are split over the two fp32 pipes: NF of 32 scores as
+//     flag = sat((thr - s) * 2^64) (FFMA.SAT, exactly 0 or 1 by construction of thr) accumulated into a float
+//     bit mask by a second FFMA, the rest as SETP + predicated LOP3 on the ALU pipe, next to the FMNMX3 tree.
+constexpr int WL2_CAP = 96;                         // list entries per warp and tile (two per lane; the rest go lane by lane)
+constexpr int S2_XP = SM_AX + TM * 32;              // [2 sets][5][128] f32: S0 of warp 0, L4..L7 of warp 1
+constexpr int S2_X2 = S2_XP + 2 * 5 * TM * 4;       // [2][128] |x|^2
+constexpr int S2_PMIN = S2_X2 + 2 * TM * 4;         // [2][2][128] minimum of each warp's 256 codes
+constexpr int S2_RB = S2_PMIN + 2 * 2 * TM * 4;     // [2][128] u64 winners (ordered d << 32 | code)
+constexpr int S2_WL = S2_RB + 2 * TM * 8;           // [16 warps][WL2_CAP] u16 (lane << 9 | code)
+constexpr int S2_WN = S2_WL + 16 * WL2_CAP * 2;      // [16] entries in each warp's list
+constexpr int S2_BAR = S2_WN + 64;
+constexpr int S2_TOTAL = S2_BAR + 256 + 1024;
+static_assert(S2_TOTAL <= 232448, "shared memory budget (v2)");
+static_assert(S2_RB % 8 == 0 && S2_BAR % 8 == 0, "alignment");
+
+// sat(thrH - s * 2^64): the multiplier is an immediate (FFMA imm-form issues at twice the rate of the 3-register form)
+LVT_DEVICE_INLINE float flag_below(float s, float thrH) {
+  float r;
+  asm("fma.rn.sat.f32 %0, %1, 0fDF800000, %2;" : "=f"(r) : "f"(s), "f"(thrH));
+  return r;
+}
+LVT_DEVICE_INLINE void pair_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+#define VQ_TEST_LT(w, v, thr, bit) \
+  asm("{\n\t.reg .pred p;\n\tsetp.lt.f32 p, %1, %2;\n\t@p or.b32 %0, %0, %3;\n\t}" : "+r"(w) : "f"(v), "f"(thr), "r"(bit))
+
+// One 32-column chunk in registers: its minimum, the running minimum, and the mask of scores below
+// thr' = (running minimum + 2E) nudged up by >= 1 ulp and kept out of (-2^-40, 2^-40), so that for every fp32
+// score s the product (thr' - s) * 2^64 is either <= 0 or >= 1: the saturated FFMA is an exact 0 / 1 flag.
+template <int NF>
+LVT_DEVICE_INLINE uint32_t scan_chunk(const uint32_t (&r)[32], float& rmin, const float twoE, float& submin) {
+#define F(i) __uint_as_float(r[i])
+  const float t0 = fmin3(F(0), F(1), F(2)), t1 = fmin3(F(3), F(4), F(5)), t2 = fmin3(F(6), F(7), F(8));
+  const float t3 = fmin3(F(9), F(10), F(11)), t4 = fmin3(F(12), F(13), F(14)), t5 = fmin3(F(15), F(16), F(17));
+  const float t6 = fmin3(F(18), F(19), F(20)), t7 = fmin3(F(21), F(22), F(23)), t8 = fmin3(F(24), F(25), F(26));
+  const float t9 = fmin3(F(27), F(28), F(29)), t10 = fminf(F(30), F(31));
+  const float u0 = fmin3(t0, t1, t2), u1 = fmin3(t3, t4, t5), u2 = fmin3(t6, t7, t8), u3 = fmin3(t9, t10, u0);
+  submin = fmin3(u1, u2, u3);
+  rmin = fminf(rmin, submin);
+  float thr = rmin + twoE;
+  thr = thr + fmaxf(fabsf(thr) * 2.4e-7f, 1e-18f);
+  thr = fabsf(thr) < 1e-12f ? 1e-12f : thr;
+  constexpr float H = 18446744073709551616.f;  // 2^64
+  const float thrH = thr * H;
+  (void)H;
+  // the two kinds of test are interleaved in program order so that both pipes have work at any time; the float
+  // masks hold 16 flags each (weights 2^0 .. 2^15: exact), two accumulators per mask for shorter chains
+  float a00 = 0.f, a01 = 0.f, a10 = 0.f, a11 = 0.f;
+  uint32_t w = 0;
+#pragma unroll
+  for (int t = 0; t < 32; ++t) {
+    const int nfb = t * NF / 32;
+    if ((t + 1) * NF / 32 > nfb) {  // scores 0 .. NF-1: fma pipe
+      const float fl = flag_below(F(nfb), thrH);
+      const float wt = (float)(1u << (nfb & 15));
+      if (nfb < 16) {
+        if (nfb & 1) a01 = __fmaf_rn(fl, wt, a01);
+        else a00 = __fmaf_rn(fl, wt, a00);
+      } else {
+        if (nfb & 1) a11 = __fmaf_rn(fl, wt, a11);
+        else a10 = __fmaf_rn(fl, wt, a10);
+      }
+    } else {                        // scores NF .. 31: alu pipe
+      const int e = NF + t - nfb;
+      VQ_TEST_LT(w, F(e), thr, 1u << e);
+    }
+  }
+#undef F
+  w |= (uint32_t)(a00 + a01);
+  if (NF > 16) w |= (uint32_t)(a10 + a11) << 16;
+  return w;
+}
+
+// <x, c> as the reference's sequential fp32 FMA chain over the 64 dims (vq.cu): the position from the (swizzled) A
+// tile in shared memory, the code row from global memory (L2; the MMAs take most of the shared-memory bandwidth).
+// Not inlined: its 64 staging registers stay out of the register allocation of the scan loop.
+template <bool NHWC>
+__device__ __noinline__ float exact_dot_smem(const uint8_t* xr, int rsw, const float4* __restrict__ crow) {
+  float4 cv[16];
+#pragma unroll
+  for (int jj = 0; jj < 16; ++jj) cv[jj] = __ldg(crow + jj);
+  float acc = 0.f;
+#pragma unroll
+  for (int jj = 0; jj < 16; ++jj) {
+    float4 xv;
+    if (NHWC) {
+      xv = *reinterpret_cast<const float4*>(xr + (jj >> 3) * 16384 + (((jj & 7) ^ rsw) << 4));
+    } else {
+      xv.x = *reinterpret_cast<const float*>(xr + (4 * jj) * 128 + ((rsw ^ 0) << 5));
+      xv.y = *reinterpret_cast<const float*>(xr + (4 * jj + 1) * 128 + ((rsw ^ 1) << 5));
+      xv.z = *reinterpret_cast<const float*>(xr + (4 * jj + 2) * 128 + ((rsw ^ 2) << 5));
+      xv.w = *reinterpret_cast<const float*>(xr + (4 * jj + 3) * 128 + ((rsw ^ 3) << 5));
+    }
+    acc = __fmaf_rn(xv.x, cv[jj].x, acc);
+    acc = __fmaf_rn(xv.y, cv[jj].y, acc);
+    acc = __fmaf_rn(xv.z, cv[jj].z, acc);
+    acc = __fmaf_rn(xv.w, cv[jj].w, acc);
+  }
+  return acc;
+}
+
+template <bool NHWC, int NF>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+vq_argmin_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __restrict__ z_e,
+                     const float* __restrict__ codebook, int64_t* __restrict__ idx_out, float* __restrict__ zq_out,
+                     __nv_bfloat16* __restrict__ zq_bf16, float* __restrict__ counts,
+                     float* __restrict__ sums, int num, int hw, int num_tiles, int ctas_per_group,
+                     int prefetch, unsigned* __restrict__ clk) {
+  static_assert(NF % 2 == 0 && NF <= 32, "flags accumulated in two 16-bit float masks");
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + S2_BAR);  // [2]  slot == set == tile parity
+  uint64_t* a_empty = a_full + 2;                                  // [2]
+  uint64_t* t_full = a_empty + 2;                                  // [2 halves][2 sets]
+  uint64_t* t_empty = t_full + 4;                                  // [2 halves]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(t_empty + 2);
+  float* cmax2_s = reinterpret_cast<float*>(tmem_ptr_smem + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = blockIdx.x % num;
+  const int sub = blockIdx.x / num;
+  const float* cbg = codebook + (size_t)g * TK * TD;
+  const int tiles_per_frame = hw / TM;
+  const int C = num * TD;
+
+  // ---- one-time setup (as v1): B = -2 * codebook[g] (K-major, 128B swizzle), B_x = [c2_hi, c2_lo, 0...], A_x = [1, 1, 0...]
+  for (int i = threadIdx.x; i < TK * TD / 4; i += TC_THREADS) {
+    const int k = i >> 4, jj = i & 15;
+    float4 v = __ldg(reinterpret_cast<const float4*>(cbg) + i);
+    v.x *= -2.f; v.y *= -2.f; v.z *= -2.f; v.w *= -2.f;
+    const int kb = jj >> 3, chunk = jj & 7;
+    *reinterpret_cast<float4*>(smem + kb * (TK * 128) + k * 128 + ((chunk ^ (k & 7)) << 4)) = v;
+  }
+  float cm = 0.f;
+  for (int k = threadIdx.x; k < TK; k += TC_THREADS) {
+    const float* row = cbg + (size_t)k * TD;
+    const float c2 = sqnorm64([&](int j) { return __ldg(row + j); });
+    cm = fmaxf(cm, c2);
+    const float hi = __uint_as_float(__float_as_uint(c2) & 0xFFFFE000u);  // tf32-exact part; hi + lo == c2 exactly
+    const float lo = c2 - hi;
+    const int sw = (k >> 2) & 1;
+    *reinterpret_cast<float4*>(smem + SM_BX + k * 32 + (sw << 4)) = make_float4(hi, lo, 0.f, 0.f);
+    *reinterpret_cast<float4*>(smem + SM_BX + k * 32 + ((sw ^ 1) << 4)) = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (int r = threadIdx.x; r < TM; r += TC_THREADS) {
+    const int sw = (r >> 2) & 1;
+    *reinterpret_cast<float4*>(smem + SM_AX + r * 32 + (sw << 4)) = make_float4(1.f, 1.f, 0.f, 0.f);
+    *reinterpret_cast<float4*>(smem + SM_AX + r * 32 + ((sw ^ 1) << 4)) = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (int i = threadIdx.x; i < 2 * TM; i += TC_THREADS) reinterpret_cast<unsigned long long*>(smem + S2_RB)[i] = ~0ull;
+  cm = warp_max(cm);
+  if (threadIdx.x == 0) {
+    *cmax2_s = 0.f;
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&a_full[s], 1);
+      mbar_init(&a_empty[s], 8);
+      mbar_init(&t_empty[s], 8);
+    }
+    for (int s = 0; s < 4; ++s) mbar_init(&t_full[s], 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&tm_x);
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr_smem, 512);
+    tmem_relinquish();
+  }
+  __syncthreads();
+  if (lane == 0) atomicMax(reinterpret_cast<int*>(cmax2_s), __float_as_int(cm));
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  const float cmax2 = *cmax2_s;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (elect_one()) {
+      int it = 0;
+      for (int tile = sub; tile < num_tiles; tile += ctas_per_group, ++it) {
+        const int slot = it & 1;
+        mbar_wait(&a_empty[slot], ((it >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(&a_full[slot], A_BYTES);
+        uint8_t* dst = smem + SM_A + slot * A_BYTES;
+        if (NHWC) {
+#pragma unroll
+          for (int kb = 0; kb < 2; ++kb)
+            tma_load_2d(dst + kb * 16384, &tm_x, &a_full[slot], g * TD + kb * 32, tile * TM);
+        } else {
+          const int frame = tile / tiles_per_frame, s0 = (tile - frame * tiles_per_frame) * TM;
+#pragma unroll
+          for (int a = 0; a < 4; ++a)
+            tma_load_2d(dst + a * 8192, &tm_x, &a_full[slot], s0 + 32 * a, frame * C + g * TD);
+        }
+        // the slot's next tile goes to L2 now: its load (issued when this tile's re-rank is over) then costs an
+        // L2 hit instead of an HBM round trip
+        const int nt = tile + 2 * ctas_per_group;
+        if (prefetch && nt < num_tiles) {
+          if (NHWC) {
+#pragma unroll
+            for (int kb = 0; kb < 2; ++kb) tma_prefetch_2d(&tm_x, g * TD + kb * 32, nt * TM);
+          } else {
+            const int frame = nt / tiles_per_frame, s0 = (nt - frame * tiles_per_frame) * TM;
+#pragma unroll
+            for (int a = 0; a < 4; ++a) tma_prefetch_2d(&tm_x, s0 + 32 * a, frame * C + g * TD);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (kind::tf32)
+    if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc(TM, 256, /*tf32*/ 2, !NHWC, false);
+      constexpr uint32_t idesc_x = umma_idesc(TM, 256, /*tf32*/ 2, false, false);
+      const uint32_t b_base = smem_u32(smem);
+      const uint64_t ax_desc = smem_desc_lt(smem_u32(smem + SM_AX), 16, 256, 6);
+      int it = 0;
+      for (int tile = sub; tile < num_tiles; tile += ctas_per_group, ++it) {
+        const int slot = it & 1;
+        mbar_wait(&a_full[slot], (it >> 1) & 1);
+        if (clk && blockIdx.x == 0 && it < 24) clk[(it * 4) * 16 + 0] = (unsigned)clock();
+        const uint32_t a_base = smem_u32(smem + SM_A + slot * A_BYTES);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          mbar_wait(&t_empty[h], (it & 1) ^ 1);  // the other set has finished its pass over buffer h
+          if (clk && blockIdx.x == 0 && it < 24) clk[(it * 4) * 16 + 1 + h] = (unsigned)clock();
+          tc_fence_after();
+          umma_tf32_ss(tmem_base + h * 256, ax_desc, smem_desc_lt(smem_u32(smem + SM_BX + h * 256 * 32), 16, 256, 6),
+                       idesc_x, 0u);
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {
+            const uint64_t adesc = NHWC ? smem_desc_lt(a_base + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024, 2)
+                                        : smem_desc_lt(a_base + ks * 1024, 8192, 512, 1);
+            const uint64_t bdesc = umma_smem_desc(b_base + (ks >> 2) * (TK * 128) + h * (256 * 128) + (ks & 3) * 32, 16, 1024);
+            umma_tf32_ss(tmem_base + h * 256, adesc, bdesc, idesc, 1u);
+          }
+          umma_commit(&t_full[h * 2 + slot]);
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ scan + exact re-rank, pair-local
+    const int sw_ = warp - 2;
+    const int set = sw_ >> 3;
+    const int pw = (sw_ >> 2) & 1;
+    const int q = warp & 3;       // TMEM lane quarter this warp may access
+    const int m = q * 32 + lane;  // row (position) inside the tile
+    const int pair_bar = 1 + set * 4 + q;
+    float* xp = reinterpret_cast<float*>(smem + S2_XP) + set * 5 * TM;
+    float* x2s = reinterpret_cast<float*>(smem + S2_X2) + set * TM;
+    float* pmin = reinterpret_cast<float*>(smem + S2_PMIN) + set * 2 * TM;
+    unsigned long long* rb = reinterpret_cast<unsigned long long*>(smem + S2_RB) + set * TM;
+    uint16_t* wl = reinterpret_cast<uint16_t*>(smem + S2_WL) + sw_ * WL2_CAP;
+    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + pw * 128;
+    const uint8_t* a_tile = smem + SM_A + set * A_BYTES;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const int who = sw_ == 0 ? 1 : (sw_ == 8 ? 2 : (sw_ == 4 ? 3 : -1));
+#define VQ2_CLK(ev) do { if (clk && who > 0 && blockIdx.x == 0 && it < 24 && lane == 0) clk[(it * 4 + who) * 16 + (ev)] = (unsigned)clock(); } while (0)
+    auto xptr = [&](int r) { return NHWC ? a_tile + r * 128 : a_tile + (r >> 5) * 8192 + (r & 7) * 4; };
+    auto xelem = [&](const uint8_t* xr, int rsw, int j) {
+      return NHWC ? *reinterpret_cast<const float*>(xr + (j >> 5) * 16384 + ((((j >> 2) & 7) ^ rsw) << 4) + (j & 3) * 4)
+                  : *reinterpret_cast<const float*>(xr + j * 128 + ((rsw ^ (j & 3)) << 5));
+    };
+    int i = 0;
+    for (int it = set;; it += 2, ++i) {
+      const int tile = sub + it * ctas_per_group;
+      if (tile >= num_tiles) break;
+      const uint32_t pos = (uint32_t)tile * TM + m;
+      const uint32_t frame = pos / (uint32_t)hw, s = pos - frame * (uint32_t)hw;
+      // exact reference distance (vq.cu): sequential fp32 FMA chain over the 64 dims, d = fl(fl(c2 + x2) - 2*dot);
+      // the code row comes from global memory (L2), the position from the A tile
+      auto exact_d = [&](int r, int k) {
+        const float4* crow = reinterpret_cast<const float4*>(cbg + (size_t)k * TD);
+        const float acc = exact_dot_smem<NHWC>(xptr(r), NHWC ? (r & 7) : ((r & 31) >> 3), crow);
+        const float2 c2p = *reinterpret_cast<const float2*>(smem + SM_BX + k * 32 + (((k >> 2) & 1) << 4));
+        return __fadd_rn(-2.f * acc, __fadd_rn(__fadd_rn(c2p.x, c2p.y), x2s[r]));  // hi + lo == c2 and -2 * acc are exact
+      };
+      VQ2_CLK(0);
+      mbar_wait(&a_full[set], i & 1);
+      VQ2_CLK(1);
+      {
+        // |x|^2 in ATen's order (vq.cu): lanes l = 0..7 left to right, L_l = ((a0+a1)+a2)+a3,
+        // a_j = x[8j+l]^2 + x[8(j+4)+l]^2.  Warp 0 of the pair takes l = 0..3 (and sums them: a prefix of the
+        // chain), warp 1 takes l = 4..7.
+        const uint8_t* xr = xptr(m);
+        const int rsw = NHWC ? (m & 7) : ((m & 31) >> 3);
+        float L[4];
+#pragma unroll
+        for (int ll = 0; ll < 4; ++ll) {
+          const int l = 4 * pw + ll;
+          float a[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float x0 = xelem(xr, rsw, 8 * j + l), x1 = xelem(xr, rsw, 8 * (j + 4) + l);
+            a[j] = __fadd_rn(__fmul_rn(x0, x0), __fmul_rn(x1, x1));
+          }
+          L[ll] = __fadd_rn(__fadd_rn(__fadd_rn(a[0], a[1]), a[2]), a[3]);
+        }
+        if (pw == 0) {
+          xp[m] = __fadd_rn(__fadd_rn(__fadd_rn(L[0], L[1]), L[2]), L[3]);
+        } else {
+#pragma unroll
+          for (int ll = 0; ll < 4; ++ll) xp[(1 + ll) * TM + m] = L[ll];
+        }
+      }
+      pair_sync(pair_bar);  // R1; both warps are also past their reads of the previous tile's winners
+      float x2 = xp[m];
+#pragma unroll
+      for (int ll = 1; ll < 5; ++ll) x2 = __fadd_rn(x2, xp[ll * TM + m]);
+      if (pw == 0) {
+        x2s[m] = x2;
+        rb[m] = ~0ull;
+      }
+      const float twoE = 2.f * (1.1f * 0.00390625f * sqrtf(x2 * cmax2) + 3.8146973e-6f * (x2 + cmax2));
+      VQ2_CLK(2);
+      float rmin = INFINITY;
+      uint32_t w[8];
+      float sub_[8];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        mbar_wait(&t_full[h * 2 + set], i & 1);
+        tc_fence_after();
+        VQ2_CLK(3 + 2 * h);
+        uint32_t b0[32], b1[32];
+        tmem_ld_32x32(t_row + h * 256, b0);
+        tmem_ld_wait();
+        tmem_ld_32x32(t_row + h * 256 + 32, b1);
+        w[h * 4 + 0] = scan_chunk<NF>(b0, rmin, twoE, sub_[h * 4 + 0]);
+        tmem_ld_wait();
+        tmem_ld_32x32(t_row + h * 256 + 64, b0);
+        w[h * 4 + 1] = scan_chunk<NF>(b1, rmin, twoE, sub_[h * 4 + 1]);
+        tmem_ld_wait();
+        tmem_ld_32x32(t_row + h * 256 + 96, b1);
+        w[h * 4 + 2] = scan_chunk<NF>(b0, rmin, twoE, sub_[h * 4 + 2]);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&t_empty[h]);  // the last chunk is in registers: buffer h may be overwritten
+        w[h * 4 + 3] = scan_chunk<NF>(b1, rmin, twoE, sub_[h * 4 + 3]);
+        VQ2_CLK(4 + 2 * h);
+      }
+      pmin[pw * TM + m] = rmin;
+      pair_sync(pair_bar);  // R2
+      VQ2_CLK(11);
+      const float omin = pmin[(pw ^ 1) * TM + m];
+      const float gthr = fminf(rmin, omin) + twoE;
+      const bool partner_has = omin <= gthr;
+      // drop the chunks whose minimum is outside the final window; up to three surviving codes go into registers
+      // (any three: the re-rank is order-free), a lane with more goes through all of its codes itself
+      int cnt = 0, k1 = 0, k2 = 0, k3 = 0;
+      bool over = false;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        uint32_t ww = (sub_[c] <= gthr) ? w[c] : 0u;
+        w[c] = ww;
+        cnt += __popc(ww);
+        if (ww) {
+          const int base = (c >> 2) * 256 + pw * 128 + (c & 3) * 32 - 1;
+          k3 = k2; k2 = k1; k1 = base + __ffs(ww);
+          ww &= ww - 1;
+          if (ww) {
+            k3 = k2; k2 = k1; k1 = base + __ffs(ww);
+            ww &= ww - 1;
+            over |= ww != 0;
+          }
+        }
+      }
+      over |= cnt > 3;
+      const bool need_exact = !over && (cnt >= 2 || (cnt >= 1 && partner_has));
+      VQ2_CLK(14);
+      if (cnt == 1 && !partner_has) rb[m] = (unsigned long long)k1;  // the only code inside the window IS the exact argmin
+      {
+        // per-warp list of (lane, code): ballots give every entry its slot, no atomics
+        const uint32_t b1_ = __ballot_sync(0xffffffffu, need_exact);
+        const uint32_t b2_ = __ballot_sync(0xffffffffu, need_exact && cnt >= 2);
+        const uint32_t b3_ = __ballot_sync(0xffffffffu, need_exact && cnt >= 3);
+        const int n1 = __popc(b1_), n2 = n1 + __popc(b2_), n = n2 + __popc(b3_);  // <= 96 = WL2_CAP
+        if (need_exact) wl[__popc(b1_ & lt_mask)] = (uint16_t)((lane << 9) | k1);
+        if (need_exact && cnt >= 2) wl[n1 + __popc(b2_ & lt_mask)] = (uint16_t)((lane << 9) | k2);
+        if (need_exact && cnt >= 3) wl[n2 + __popc(b3_ & lt_mask)] = (uint16_t)((lane << 9) | k3);
+        if (__ballot_sync(0xffffffffu, over)) {  // rows with many near-ties (adversarial codebooks)
+          if (over) {
+#pragma unroll 1
+            for (int c = 0; c < 8; ++c) {
+              uint32_t ww = c == 0 ? w[0] : c == 1 ? w[1] : c == 2 ? w[2] : c == 3 ? w[3] : c == 4 ? w[4] : c == 5 ? w[5] : c == 6 ? w[6] : w[7];
+              const int base = (c >> 2) * 256 + pw * 128 + (c & 3) * 32 - 1;
+              while (ww) {
+                const int k = base + __ffs(ww);
+                ww &= ww - 1;
+                atomicMin(&rb[m], ((unsigned long long)ordered_f32(exact_d(m, k)) << 32) | (unsigned)k);
+              }
+            }
+          }
+        }
+        int* wn = reinterpret_cast<int*>(smem + S2_WN);
+        if (lane == 0) wn[sw_] = n;
+        VQ2_CLK(7);
+        pair_sync(pair_bar);  // R3: both lists of the pair are complete; the two warps share the re-rank evenly
+        const int nA = wn[sw_ & ~4], nT = nA + wn[sw_ | 4];
+        const uint16_t* wlA = reinterpret_cast<const uint16_t*>(smem + S2_WL) + (sw_ & ~4) * WL2_CAP;
+        const uint16_t* wlB = reinterpret_cast<const uint16_t*>(smem + S2_WL) + (sw_ | 4) * WL2_CAP;
+        VQ2_CLK(15);
+        for (int e = pw * 32 + lane; e < nT; e += 64) {
+          const uint32_t ent = e < nA ? wlA[e] : wlB[e - nA];
+          const int r = q * 32 + (int)(ent >> 9), k = (int)(ent & 511u);
+          atomicMin(&rb[r], ((unsigned long long)ordered_f32(exact_d(r, k)) << 32) | (unsigned)k);
+        }
+      }
+      VQ2_CLK(8);
+      if (!sums) {  // the re-rank was the last reader of the A tile (the MMAs completed before the scan)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a_empty[set]);
+      }
+      pair_sync(pair_bar);  // R4: winners final
+      VQ2_CLK(9);
+      const int besti = (int)(rb[m] & 511ull);
+      if (pw == 0) idx_out[((size_t)frame * num + g) * hw + s] = (int64_t)besti;
+      if (pw == 1 && (zq_out || zq_bf16)) {
+        const float* cr = cbg + (size_t)besti * TD;
+        if (NHWC) {
+          const size_t o = (size_t)pos * C + (size_t)g * TD;
+#pragma unroll
+          for (int jj = 0; jj < 16; ++jj) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(cr) + jj);
+            if (zq_out) *reinterpret_cast<float4*>(zq_out + o + 4 * jj) = v;
+            if (zq_bf16) {
+              uint2 u;
+              u.x = pack_bf16x2(v.x, v.y);
+              u.y = pack_bf16x2(v.z, v.w);
+              *reinterpret_cast<uint2*>(zq_bf16 + o + 4 * jj) = u;
+            }
+          }
+        } else {
+          float* zp = zq_out + ((size_t)frame * C + (size_t)g * TD) * hw + s;
+#pragma unroll 8
+          for (int j = 0; j < TD; ++j) zp[(size_t)j * hw] = __ldg(cr + j);
+        }
+      }
+      if (pw == 0 && counts) atomicAdd(counts + (size_t)g * TK + besti, 1.f);
+      if (sums) {  // each warp of the pair adds half of the row
+        float* sp = sums + ((size_t)g * TK + besti) * TD;
+        const uint8_t* xr = xptr(m);
+        const int rsw = NHWC ? (m & 7) : ((m & 31) >> 3);
+#pragma unroll 8
+        for (int j = 0; j < TD / 2; ++j) atomicAdd(sp + pw * 32 + j, xelem(xr, rsw, pw * 32 + j));
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a_empty[set]);
+      }
+      VQ2_CLK(10);
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -544,11 +1015,14 @@ int lvt_vq_argmin_tc_try(const float* z_e, const float* codebook, int64_t* idx_o
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   }
   if (r != CUDA_SUCCESS) return 1;
-  static bool configured = false;
-  if (!configured) {
-    LVT_CHECK_CUDA(cudaFuncSetAttribute(vq_argmin_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
-    LVT_CHECK_CUDA(cudaFuncSetAttribute(vq_argmin_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
-    configured = true;
+  static int version = -1, nf = 16, pf = 1;
+  if (version < 0) {
+    const char* e = getenv("LVT_VQ_TC1");
+    const char* f = getenv("LVT_VQ_NF");
+    if (f) nf = atoi(f);
+    const char* pe = getenv("LVT_VQ_NOPF");
+    if (pe && pe[0] == '1') pf = 0;
+    version = (e && e[0] == '1') ? 1 : 2;
   }
   const int num_tiles = (int)(positions / TM);
   int sms = 148;
@@ -556,13 +1030,42 @@ int lvt_vq_argmin_tc_try(const float* z_e, const float* codebook, int64_t* idx_o
   int per_group = sms / num;
   if (per_group < 1) per_group = 1;
   if (per_group > num_tiles) per_group = num_tiles;
-  if (nhwc)
-    vq_argmin_tc_kernel<true><<<per_group * num, TC_THREADS, SM_TOTAL, stream>>>(
-        tm, codebook, idx_out, zq_out, reinterpret_cast<__nv_bfloat16*>(zq_bf16), counts, sums, num, hw, num_tiles,
-        per_group, g_dbg_scores, g_dbg_clk);
-  else
-    vq_argmin_tc_kernel<false><<<per_group * num, TC_THREADS, SM_TOTAL, stream>>>(
-        tm, codebook, idx_out, zq_out, nullptr, counts, sums, num, hw, num_tiles, per_group, g_dbg_scores, g_dbg_clk);
+  __nv_bfloat16* zb = reinterpret_cast<__nv_bfloat16*>(zq_bf16);
+  if (version == 1) {
+    static bool configured = false;
+    if (!configured) {
+      LVT_CHECK_CUDA(cudaFuncSetAttribute(vq_argmin_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
+      LVT_CHECK_CUDA(cudaFuncSetAttribute(vq_argmin_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
+      configured = true;
+    }
+    if (nhwc)
+      vq_argmin_tc_kernel<true><<<per_group * num, TC_THREADS, SM_TOTAL, stream>>>(
+          tm, codebook, idx_out, zq_out, zb, counts, sums, num, hw, num_tiles, per_group, g_dbg_scores, g_dbg_clk);
+    else
+      vq_argmin_tc_kernel<false><<<per_group * num, TC_THREADS, SM_TOTAL, stream>>>(
+          tm, codebook, idx_out, zq_out, nullptr, counts, sums, num, hw, num_tiles, per_group, g_dbg_scores, g_dbg_clk);
+  } else {
+#define VQ2_LAUNCH(L, F)                                                                                              \
+  do {                                                                                                                \
+    static bool cfg = false;                                                                                          \
+    if (!cfg) {                                                                                                       \
+      LVT_CHECK_CUDA(cudaFuncSetAttribute(vq_argmin_tc2_kernel<L, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, S2_TOTAL)); \
+      cfg = true;                                                                                                     \
+    }                                                                                                                 \
+    vq_argmin_tc2_kernel<L, F><<<per_group * num, TC_THREADS, S2_TOTAL, stream>>>(                                    \
+        tm, z_e, codebook, idx_out, zq_out, L ? zb : nullptr, counts, sums, num, hw, num_tiles, per_group, pf, g_dbg_clk); \
+  } while (0)
+    if (nhwc) {
+      if (nf == 32) VQ2_LAUNCH(true, 32);
+      else if (nf == 24) VQ2_LAUNCH(true, 24);
+      else VQ2_LAUNCH(true, 16);
+    } else {
+      if (nf == 32) VQ2_LAUNCH(false, 32);
+      else if (nf == 24) VQ2_LAUNCH(false, 24);
+      else VQ2_LAUNCH(false, 16);
+    }
+#undef VQ2_LAUNCH
+  }
   LVT_CHECK_LAUNCH();
   lvt_count_launch(1);
   return LVT_OK;

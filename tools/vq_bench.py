@@ -8,12 +8,19 @@ init = os.environ.get("VQ_INIT", "spread")
 g = torch.Generator().manual_seed(0)
 z = (torch.randn(nfr, 256, 16, 16, generator=g) * 0.3).cuda()
 cb = (torch.randn(4, 512, 64, generator=g) * 0.3 if init == "spread" else (torch.rand(4, 512, 64, generator=g) * 2 - 1) / 512).cuda()
+nhwc = os.environ.get("VQ_NHWC", "0") == "1"   # the VQ-VAE engine's channels-last layout
+if nhwc:
+    zl = z.permute(0, 2, 3, 1).reshape(-1, 256).contiguous()
+    run = lambda: ops.vq_argmin_nhwc(zl, cb, 256, want_zq_bf16=True)
+    init += " nhwc+zq_bf16"
+else:
+    run = lambda: ops.vq_argmin(z, cb)
 for _ in range(3):
-    ops.vq_argmin(z, cb)
+    run()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
 for _ in range(10):
-    ops.vq_argmin(z, cb)
+    run()
 e1.record(); torch.cuda.synchronize()
 t = e0.elapsed_time(e1) / 10 * 1e-3
 pos = nfr * 256
