@@ -13,8 +13,11 @@
 //   3. the reference's exact arithmetic on the candidates only (typically 1-2 of 512), lowest index
 //      wins ties  =>  bit-identical indices to the SIMT kernel / the oracle.
 // One CTA = one codebook group (its 128 KiB of -2*c stay resident), persistent over 128-position tiles;
-// warp 0 TMA producer, warp 1 MMA issuer, 16 scan warps in four groups of 128 codes each (two 256-column TMEM
-// buffers); candidates are compacted per warp so the exact re-rank keeps all lanes busy.
+// warp 0 TMA producer, warp 1 MMA issuer, 16 scan warps.  Two kernels share this file:
+//   vq_argmin_tc2_kernel (default): free-running pipeline -- two sets of warps on alternate tiles, one pass over
+//     TMEM with a running threshold, pair-local exchanges only (see the comment above it);
+//   vq_argmin_tc_kernel (round 1, LVT_VQ_TC1=1, kept for A/B runs): all 16 warps in lock step on one tile, two
+//     passes over TMEM (row minimum, then threshold), CTA-wide barriers between the phases.
 #include <mutex>
 #include <stdlib.h>
 #include <string.h>
@@ -495,15 +498,24 @@ vq_argmin_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __res
 // v2: the same algorithm as a free-running pipeline (no CTA-wide barrier inside the tile loop).
 //   * the 16 scan warps form two SETS that take alternate tiles (set = tile parity = A slot); a set is four
 //     PAIRS of warps, one pair per TMEM lane quarter: the pair owns rows q*32.. of the set's tiles, warp pw of
-//     the pair scans codes h*256 + pw*128 .. +127 of both accumulator halves.  All exchanges (|x|^2 partial
-//     sums, minima, candidate list, winners) stay inside the pair: three 64-thread named barriers per tile.
+//     the pair scans its half of the codes of every accumulator buffer.  All exchanges (|x|^2 partial sums,
+//     minima, candidate lists, winners) stay inside the pair: four 64-thread named barriers per tile.
 //   * ONE pass over TMEM: each 32-column chunk is tested against the RUNNING minimum + 2E while it is in
 //     registers (a superset of the final window: the running minimum only decreases), the buffer is released
 //     to the MMA warp right after, and chunks whose own minimum is above the final threshold are dropped later.
 //   * the threshold tests are split over the two fp32 pipes: NF of 32 scores as
-//     flag = sat((thr - s) * 2^64) (FFMA.SAT, exactly 0 or 1 by construction of thr) accumulated into a float
-//     bit mask by a second FFMA, the rest as SETP + predicated LOP3 on the ALU pipe, next to the FMNMX3 tree.
-constexpr int WL2_CAP = 96;                         // list entries per warp and tile (two per lane; the rest go lane by lane)
+//     flag = sat((thr - s) * 2^64) (FFMA.SAT with an immediate multiplier, exactly 0 or 1 by construction of thr)
+//     accumulated into a float bit mask by a second FFMA, the rest as SETP + predicated LOP3 on the ALU pipe,
+//     next to the FMNMX3 tree; the two kinds are interleaved in program order.
+//   * candidates: up to three codes per lane are extracted branch-free into registers and placed into a
+//     per-warp list by ballots (no atomics); the two warps of a pair share both lists evenly for the exact
+//     re-rank, which reads the position from the A tile and the code row from the resident B operand
+//     (-2c, halved exactly); a row whose window holds one code needs no re-rank at all.
+//   * the slot's next tile is prefetched into L2 when a tile is loaded; the A slot is released after the re-rank.
+// Measured on the way and not kept: re-rank operands from global memory with an early A release,
+// one warp per TMEM lane quarter scanning all 512 codes (three tiles in flight, no pair barriers: a single
+// scanning warp per scheduler issues one instruction every ~4 cycles), four 128-column accumulator buffers.
+constexpr int WL2_CAP = 96;                         // list entries per warp and tile: three per lane
 constexpr int S2_XP = SM_AX + TM * 32;              // [2 sets][5][128] f32: S0 of warp 0, L4..L7 of warp 1
 constexpr int S2_X2 = S2_XP + 2 * 5 * TM * 4;       // [2][128] |x|^2
 constexpr int S2_PMIN = S2_X2 + 2 * TM * 4;         // [2][2][128] minimum of each warp's 256 codes
@@ -572,14 +584,16 @@ LVT_DEVICE_INLINE uint32_t scan_chunk(const uint32_t (&r)[32], float& rmin, cons
   return w;
 }
 
-// <x, c> as the reference's sequential fp32 FMA chain over the 64 dims (vq.cu): the position from the (swizzled) A
-// tile in shared memory, the code row from global memory (L2; the MMAs take most of the shared-memory bandwidth).
-// Not inlined: its 64 staging registers stay out of the register allocation of the scan loop.
+// <x, c> as the reference's sequential fp32 FMA chain over the 64 dims (vq.cu), both operands from shared memory:
+// the position from the (swizzled) A tile, the code row from the resident B operand, which holds -2*c -- halving
+// is exact, so c is recovered bit for bit (an L2 round trip per candidate was the long pole of the re-rank).
+// Not inlined: its staging registers stay out of the register allocation of the scan loop.
 template <bool NHWC>
-__device__ __noinline__ float exact_dot_smem(const uint8_t* xr, int rsw, const float4* __restrict__ crow) {
+__device__ __forceinline__ float exact_dot_smem(const uint8_t* xr, int rsw, const uint8_t* bsm, int k) {
   float4 cv[16];
 #pragma unroll
-  for (int jj = 0; jj < 16; ++jj) cv[jj] = __ldg(crow + jj);
+  for (int jj = 0; jj < 16; ++jj)
+    cv[jj] = *reinterpret_cast<const float4*>(bsm + (jj >> 3) * (TK * 128) + k * 128 + (((jj & 7) ^ (k & 7)) << 4));
   float acc = 0.f;
 #pragma unroll
   for (int jj = 0; jj < 16; ++jj) {
@@ -592,15 +606,15 @@ __device__ __noinline__ float exact_dot_smem(const uint8_t* xr, int rsw, const f
       xv.z = *reinterpret_cast<const float*>(xr + (4 * jj + 2) * 128 + ((rsw ^ 2) << 5));
       xv.w = *reinterpret_cast<const float*>(xr + (4 * jj + 3) * 128 + ((rsw ^ 3) << 5));
     }
-    acc = __fmaf_rn(xv.x, cv[jj].x, acc);
-    acc = __fmaf_rn(xv.y, cv[jj].y, acc);
-    acc = __fmaf_rn(xv.z, cv[jj].z, acc);
-    acc = __fmaf_rn(xv.w, cv[jj].w, acc);
+    acc = __fmaf_rn(xv.x, -0.5f * cv[jj].x, acc);
+    acc = __fmaf_rn(xv.y, -0.5f * cv[jj].y, acc);
+    acc = __fmaf_rn(xv.z, -0.5f * cv[jj].z, acc);
+    acc = __fmaf_rn(xv.w, -0.5f * cv[jj].w, acc);
   }
   return acc;
 }
 
-template <bool NHWC, int NF>
+template <bool NHWC, int NF, int NQ>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 vq_argmin_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __restrict__ z_e,
                      const float* __restrict__ codebook, int64_t* __restrict__ idx_out, float* __restrict__ zq_out,
@@ -608,13 +622,16 @@ vq_argmin_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __re
                      float* __restrict__ sums, int num, int hw, int num_tiles, int ctas_per_group,
                      int prefetch, unsigned* __restrict__ clk) {
   static_assert(NF % 2 == 0 && NF <= 32, "flags accumulated in two 16-bit float masks");
+  static_assert(NQ == 2 || NQ == 4, "TMEM accumulator buffers per tile");
+  constexpr int CB = TK / NQ;       // codes (TMEM columns) per accumulator buffer
+  constexpr int CH = 8 / NQ;        // 32-column chunks of a buffer that one warp of a pair scans
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + S2_BAR);  // [2]  slot == set == tile parity
   uint64_t* a_empty = a_full + 2;                                  // [2]
-  uint64_t* t_full = a_empty + 2;                                  // [2 halves][2 sets]
-  uint64_t* t_empty = t_full + 4;                                  // [2 halves]
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(t_empty + 2);
+  uint64_t* t_full = a_empty + 2;                                  // [NQ buffers][2 sets]
+  uint64_t* t_empty = t_full + 8;                                  // [NQ buffers]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(t_empty + 4);
   float* cmax2_s = reinterpret_cast<float*>(tmem_ptr_smem + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -634,8 +651,13 @@ vq_argmin_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __re
   }
   float cm = 0.f;
   for (int k = threadIdx.x; k < TK; k += TC_THREADS) {
-    const float* row = cbg + (size_t)k * TD;
-    const float c2 = sqnorm64([&](int j) { return __ldg(row + j); });
+    float4 rv[16];  // the whole row in 16 vector loads (64 scalar loads per thread throttle the load queue)
+#pragma unroll
+    for (int jj = 0; jj < 16; ++jj) rv[jj] = __ldg(reinterpret_cast<const float4*>(cbg + (size_t)k * TD) + jj);
+    const float c2 = sqnorm64([&](int j) {
+      const float4 v = rv[j >> 2];
+      return (j & 3) == 0 ? v.x : ((j & 3) == 1 ? v.y : ((j & 3) == 2 ? v.z : v.w));
+    });
     cm = fmaxf(cm, c2);
     const float hi = __uint_as_float(__float_as_uint(c2) & 0xFFFFE000u);  // tf32-exact part; hi + lo == c2 exactly
     const float lo = c2 - hi;
@@ -655,9 +677,9 @@ vq_argmin_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __re
     for (int s = 0; s < 2; ++s) {
       mbar_init(&a_full[s], 1);
       mbar_init(&a_empty[s], 8);
-      mbar_init(&t_empty[s], 8);
     }
-    for (int s = 0; s < 4; ++s) mbar_init(&t_full[s], 1);
+    for (int s = 0; s < NQ; ++s) mbar_init(&t_empty[s], 8);
+    for (int s = 0; s < 2 * NQ; ++s) mbar_init(&t_full[s], 1);
     fence_barrier_init();
     tma_prefetch_desc(&tm_x);
   }
@@ -711,8 +733,8 @@ vq_argmin_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __re
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (kind::tf32)
     if (elect_one()) {
-      constexpr uint32_t idesc = umma_idesc(TM, 256, /*tf32*/ 2, !NHWC, false);
-      constexpr uint32_t idesc_x = umma_idesc(TM, 256, /*tf32*/ 2, false, false);
+      constexpr uint32_t idesc = umma_idesc(TM, CB, /*tf32*/ 2, !NHWC, false);
+      constexpr uint32_t idesc_x = umma_idesc(TM, CB, /*tf32*/ 2, false, false);
       const uint32_t b_base = smem_u32(smem);
       const uint64_t ax_desc = smem_desc_lt(smem_u32(smem + SM_AX), 16, 256, 6);
       int it = 0;
@@ -722,18 +744,18 @@ vq_argmin_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __re
         if (clk && blockIdx.x == 0 && it < 24) clk[(it * 4) * 16 + 0] = (unsigned)clock();
         const uint32_t a_base = smem_u32(smem + SM_A + slot * A_BYTES);
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
+        for (int h = 0; h < NQ; ++h) {
           mbar_wait(&t_empty[h], (it & 1) ^ 1);  // the other set has finished its pass over buffer h
-          if (clk && blockIdx.x == 0 && it < 24) clk[(it * 4) * 16 + 1 + h] = (unsigned)clock();
+          if (clk && blockIdx.x == 0 && it < 24 && h < 2) clk[(it * 4) * 16 + 1 + h] = (unsigned)clock();
           tc_fence_after();
-          umma_tf32_ss(tmem_base + h * 256, ax_desc, smem_desc_lt(smem_u32(smem + SM_BX + h * 256 * 32), 16, 256, 6),
+          umma_tf32_ss(tmem_base + h * CB, ax_desc, smem_desc_lt(smem_u32(smem + SM_BX + h * CB * 32), 16, 256, 6),
                        idesc_x, 0u);
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks) {
             const uint64_t adesc = NHWC ? smem_desc_lt(a_base + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024, 2)
                                         : smem_desc_lt(a_base + ks * 1024, 8192, 512, 1);
-            const uint64_t bdesc = umma_smem_desc(b_base + (ks >> 2) * (TK * 128) + h * (256 * 128) + (ks & 3) * 32, 16, 1024);
-            umma_tf32_ss(tmem_base + h * 256, adesc, bdesc, idesc, 1u);
+            const uint64_t bdesc = umma_smem_desc(b_base + (ks >> 2) * (TK * 128) + h * (CB * 128) + (ks & 3) * 32, 16, 1024);
+            umma_tf32_ss(tmem_base + h * CB, adesc, bdesc, idesc, 1u);
           }
           umma_commit(&t_full[h * 2 + slot]);
         }
@@ -752,7 +774,7 @@ vq_argmin_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __re
     float* pmin = reinterpret_cast<float*>(smem + S2_PMIN) + set * 2 * TM;
     unsigned long long* rb = reinterpret_cast<unsigned long long*>(smem + S2_RB) + set * TM;
     uint16_t* wl = reinterpret_cast<uint16_t*>(smem + S2_WL) + sw_ * WL2_CAP;
-    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + pw * 128;
+    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + pw * (CB / 2);
     const uint8_t* a_tile = smem + SM_A + set * A_BYTES;
     const uint32_t lt_mask = (1u << lane) - 1u;
     const int who = sw_ == 0 ? 1 : (sw_ == 8 ? 2 : (sw_ == 4 ? 3 : -1));
@@ -768,11 +790,9 @@ vq_argmin_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __re
       if (tile >= num_tiles) break;
       const uint32_t pos = (uint32_t)tile * TM + m;
       const uint32_t frame = pos / (uint32_t)hw, s = pos - frame * (uint32_t)hw;
-      // exact reference distance (vq.cu): sequential fp32 FMA chain over the 64 dims, d = fl(fl(c2 + x2) - 2*dot);
-      // the code row comes from global memory (L2), the position from the A tile
+      // exact reference distance (vq.cu): sequential fp32 FMA chain over the 64 dims, d = fl(fl(c2 + x2) - 2*dot)
       auto exact_d = [&](int r, int k) {
-        const float4* crow = reinterpret_cast<const float4*>(cbg + (size_t)k * TD);
-        const float acc = exact_dot_smem<NHWC>(xptr(r), NHWC ? (r & 7) : ((r & 31) >> 3), crow);
+        const float acc = exact_dot_smem<NHWC>(xptr(r), NHWC ? (r & 7) : ((r & 31) >> 3), smem, k);
         const float2 c2p = *reinterpret_cast<const float2*>(smem + SM_BX + k * 32 + (((k >> 2) & 1) << 4));
         return __fadd_rn(-2.f * acc, __fadd_rn(__fadd_rn(c2p.x, c2p.y), x2s[r]));  // hi + lo == c2 and -2 * acc are exact
       };
@@ -818,27 +838,30 @@ vq_argmin_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __re
       uint32_t w[8];
       float sub_[8];
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
+      for (int h = 0; h < NQ; ++h) {
         mbar_wait(&t_full[h * 2 + set], i & 1);
         tc_fence_after();
-        VQ2_CLK(3 + 2 * h);
+        if (h == 0) VQ2_CLK(3);
+        if (h == NQ / 2) VQ2_CLK(5);
         uint32_t b0[32], b1[32];
-        tmem_ld_32x32(t_row + h * 256, b0);
-        tmem_ld_wait();
-        tmem_ld_32x32(t_row + h * 256 + 32, b1);
-        w[h * 4 + 0] = scan_chunk<NF>(b0, rmin, twoE, sub_[h * 4 + 0]);
-        tmem_ld_wait();
-        tmem_ld_32x32(t_row + h * 256 + 64, b0);
-        w[h * 4 + 1] = scan_chunk<NF>(b1, rmin, twoE, sub_[h * 4 + 1]);
-        tmem_ld_wait();
-        tmem_ld_32x32(t_row + h * 256 + 96, b1);
-        w[h * 4 + 2] = scan_chunk<NF>(b0, rmin, twoE, sub_[h * 4 + 2]);
-        tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&t_empty[h]);  // the last chunk is in registers: buffer h may be overwritten
-        w[h * 4 + 3] = scan_chunk<NF>(b1, rmin, twoE, sub_[h * 4 + 3]);
-        VQ2_CLK(4 + 2 * h);
+        tmem_ld_32x32(t_row + h * CB, b0);
+#pragma unroll
+        for (int c = 0; c < CH; c += 2) {
+          tmem_ld_wait();
+          tmem_ld_32x32(t_row + h * CB + (c + 1) * 32, b1);
+          w[h * CH + c] = scan_chunk<NF>(b0, rmin, twoE, sub_[h * CH + c]);
+          tmem_ld_wait();
+          if (c + 2 < CH) {
+            tmem_ld_32x32(t_row + h * CB + (c + 2) * 32, b0);
+          } else {  // the last chunk is in registers: buffer h may be overwritten
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&t_empty[h]);
+          }
+          w[h * CH + c + 1] = scan_chunk<NF>(b1, rmin, twoE, sub_[h * CH + c + 1]);
+        }
+        if (h == NQ / 2 - 1) VQ2_CLK(4);
+        if (h == NQ - 1) VQ2_CLK(6);
       }
       pmin[pw * TM + m] = rmin;
       pair_sync(pair_bar);  // R2
@@ -855,16 +878,14 @@ vq_argmin_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __re
         uint32_t ww = (sub_[c] <= gthr) ? w[c] : 0u;
         w[c] = ww;
         cnt += __popc(ww);
-        if (ww) {
-          const int base = (c >> 2) * 256 + pw * 128 + (c & 3) * 32 - 1;
-          k3 = k2; k2 = k1; k1 = base + __ffs(ww);
-          ww &= ww - 1;
-          if (ww) {
-            k3 = k2; k2 = k1; k1 = base + __ffs(ww);
-            ww &= ww - 1;
-            over |= ww != 0;
-          }
-        }
+        // branch-free: most words are empty, but some lane of the warp almost always has one that is not
+        const int base = (c / CH) * CB + pw * (CB / 2) + (c % CH) * 32 - 1;
+        const uint32_t ww2 = ww & (ww - 1);
+        const int t1 = base + __ffs(ww), t2 = base + __ffs(ww2);
+        const bool h1 = ww != 0, h2 = ww2 != 0;
+        k3 = h1 ? k2 : k3; k2 = h1 ? k1 : k2; k1 = h1 ? t1 : k1;
+        k3 = h2 ? k2 : k3; k2 = h2 ? k1 : k2; k1 = h2 ? t2 : k1;
+        over |= (ww2 & (ww2 - 1)) != 0;
       }
       over |= cnt > 3;
       const bool need_exact = !over && (cnt >= 2 || (cnt >= 1 && partner_has));
@@ -884,7 +905,7 @@ vq_argmin_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __re
 #pragma unroll 1
             for (int c = 0; c < 8; ++c) {
               uint32_t ww = c == 0 ? w[0] : c == 1 ? w[1] : c == 2 ? w[2] : c == 3 ? w[3] : c == 4 ? w[4] : c == 5 ? w[5] : c == 6 ? w[6] : w[7];
-              const int base = (c >> 2) * 256 + pw * 128 + (c & 3) * 32 - 1;
+              const int base = (c / CH) * CB + pw * (CB / 2) + (c % CH) * 32 - 1;
               while (ww) {
                 const int k = base + __ffs(ww);
                 ww &= ww - 1;
@@ -1015,11 +1036,13 @@ int lvt_vq_argmin_tc_try(const float* z_e, const float* codebook, int64_t* idx_o
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   }
   if (r != CUDA_SUCCESS) return 1;
-  static int version = -1, nf = 16, pf = 1;
+  static int version = -1, nf = 16, pf = 1, nq = 2;
   if (version < 0) {
     const char* e = getenv("LVT_VQ_TC1");
     const char* f = getenv("LVT_VQ_NF");
     if (f) nf = atoi(f);
+    const char* qe = getenv("LVT_VQ_NQ");
+    if (qe) nq = atoi(qe);
     const char* pe = getenv("LVT_VQ_NOPF");
     if (pe && pe[0] == '1') pf = 0;
     version = (e && e[0] == '1') ? 1 : 2;
@@ -1045,24 +1068,24 @@ int lvt_vq_argmin_tc_try(const float* z_e, const float* codebook, int64_t* idx_o
       vq_argmin_tc_kernel<false><<<per_group * num, TC_THREADS, SM_TOTAL, stream>>>(
           tm, codebook, idx_out, zq_out, nullptr, counts, sums, num, hw, num_tiles, per_group, g_dbg_scores, g_dbg_clk);
   } else {
-#define VQ2_LAUNCH(L, F)                                                                                              \
+#define VQ2_LAUNCH(L, F, Q)                                                                                            \
   do {                                                                                                                \
     static bool cfg = false;                                                                                          \
     if (!cfg) {                                                                                                       \
-      LVT_CHECK_CUDA(cudaFuncSetAttribute(vq_argmin_tc2_kernel<L, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, S2_TOTAL)); \
+      LVT_CHECK_CUDA(cudaFuncSetAttribute(vq_argmin_tc2_kernel<L, F, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, S2_TOTAL)); \
       cfg = true;                                                                                                     \
     }                                                                                                                 \
-    vq_argmin_tc2_kernel<L, F><<<per_group * num, TC_THREADS, S2_TOTAL, stream>>>(                                    \
+    vq_argmin_tc2_kernel<L, F, Q><<<per_group * num, TC_THREADS, S2_TOTAL, stream>>>(                                 \
         tm, z_e, codebook, idx_out, zq_out, L ? zb : nullptr, counts, sums, num, hw, num_tiles, per_group, pf, g_dbg_clk); \
   } while (0)
     if (nhwc) {
-      if (nf == 32) VQ2_LAUNCH(true, 32);
-      else if (nf == 24) VQ2_LAUNCH(true, 24);
-      else VQ2_LAUNCH(true, 16);
+      if (nf == 32) VQ2_LAUNCH(true, 32, 2);
+      else if (nq == 4) VQ2_LAUNCH(true, 16, 4);
+      else VQ2_LAUNCH(true, 16, 2);
     } else {
-      if (nf == 32) VQ2_LAUNCH(false, 32);
-      else if (nf == 24) VQ2_LAUNCH(false, 24);
-      else VQ2_LAUNCH(false, 16);
+      if (nf == 32) VQ2_LAUNCH(false, 32, 2);
+      else if (nq == 4) VQ2_LAUNCH(false, 16, 4);
+      else VQ2_LAUNCH(false, 16, 2);
     }
 #undef VQ2_LAUNCH
   }

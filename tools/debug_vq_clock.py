@@ -1,5 +1,5 @@
 """Timeline of the tensor-core VQ kernel (CTA 0, first tiles): clock() stamps written by lvt_dbg_vq_clock.
-LVT_VQ_TC1=1 / LVT_VQ_TC2=1 select the older kernels (see csrc/vq_tc.cu); default is v3 (warp-owns-rows)."""
+LVT_VQ_TC1=1 selects the round-1 kernel (see csrc/vq_tc.cu)."""
 import os, sys, ctypes
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -19,18 +19,15 @@ torch.cuda.synchronize()
 lib.lvt_dbg_vq_clock(ctypes.c_void_p(0))
 c = clk.cpu().view(24, 4, 16).numpy().astype("int64") & 0xFFFFFFFF
 t0 = c[3, 0, 0]
-ver = 1 if os.environ.get("LVT_VQ_TC1", "0") == "1" else (2 if os.environ.get("LVT_VQ_TC2", "0") == "1" else 3)
+ver = 1 if os.environ.get("LVT_VQ_TC1", "0") == "1" else 2
 mma = ["a_full", "t_empty0", "t_empty1"]
 if ver == 1:
     ev = {0: "start", 1: "a_full", 2: "x2done", 3: "t_full", 4: "p1", 5: "bar1", 6: "p2", 7: "bar2", 8: "exact", 9: "bar3", 10: "out"}
     whos = lambda it: ((1, "ew0/g0"), (2, "ew12/g3"), (3, "ew5/g1"))
-elif ver == 2:
+else:
     ev = {0: "start", 1: "a_full", 2: "x2", 3: "t_full0", 4: "scan0", 5: "t_full1", 6: "scan1", 11: "R2", 14: "filtered",
           7: "listed", 15: "R3", 8: "exact", 9: "R4", 10: "out"}
     whos = lambda it: ((1, "set0 pw0"), (3, "set0 pw1")) if it % 2 == 0 else ((2, "set1 pw0"),)
-else:
-    ev = {0: "start", 1: "a_ready", 2: "x2", 3: "t_full0", 4: "scan0", 5: "t_full1", 6: "scan1", 7: "filtered", 8: "exact", 10: "out"}
-    whos = lambda it: ((1 + it % 3, f"set{it % 3}"),)
 for it in range(3, 15):
     print(f"tile {it}")
     print("  mma        " + " ".join(f"{n}={int(c[it, 0, i] - t0)}" for i, n in enumerate(mma)))
