@@ -148,7 +148,7 @@ class IncrementalDecoder:
             p.U[k], p.U_ld[k] = st.pb(f"ch_predictor.U.{k}.weight"), s.d + k * s.nv
             p.U_bias[k] = st.pf(f"ch_predictor.U.{k}.bias")
             p.gtab[k] = eng.ut[k].data_ptr() if k else None
-            p.P[k], p.P_bias[k] = st.pb(f"ch_predictor.P.{k}.weight"), st.pf(f"ch_predictor.P.{k}.bias")
+            p.P[k], p.P_bias[k] = st.pb(s.p_name(k) + ".weight"), st.pf(s.p_name(k) + ".bias")
         p.q_exp = self.q_exp4.data_ptr()
         p.xa, p.xb, p.hbuf, p.a1 = self.xa.data_ptr(), self.xb.data_ptr(), self.h.data_ptr(), self.a1.data_ptr()
         p.q, p.o, p.abuf, p.logits = self.q.data_ptr(), self.o.data_ptr(), self.a.data_ptr(), self.logits.data_ptr()
@@ -175,7 +175,7 @@ class IncrementalDecoder:
                    ln=(st.pf("ch_predictor.layer_norm.weight"), st.pf("ch_predictor.layer_norm.bias")), round_in=True,
                    bias=st.pf(f"ch_predictor.U.{k}.bias"), gtab=eng.ut[k] if k else None, g_count=k, relu=True,
                    round_out=True)
-        self._rows(self.a, d, st.pb(f"ch_predictor.P.{k}.weight"), d, nv, self.logits, bias=st.pf(f"ch_predictor.P.{k}.bias"))
+        self._rows(self.a, d, st.pb(s.p_name(k) + ".weight"), d, nv, self.logits, bias=st.pf(s.p_name(k) + ".bias"))
 
     def sample_row(self, temp=1.0):
         """decode_row + channel-by-channel categorical draw into ws.slice[:, :, *pos] (videotransformer.py:161-185)."""

@@ -49,9 +49,9 @@ class VTSpec:
         self.blocks_d = tuple(tuple(b) for b in blocks_d)
         self.heads_e, self.heads_d = tuple(heads_e), tuple(heads_d)
         self.pad_value, self.ignore_index = int(pad_value), int(ignore_index)
-        if share_p or share_embeddings or class_num:
-            raise _lib.LvtError("lvt_b200 implements the shipped VT configs: SHARE_P=False, "
-                                "SHARE_EMBEDDINGS=False, CLASS_NUM=0")
+        self.share_p = bool(share_p)  # one P for all channels (videotransformer.py:121-123,150-151)
+        if share_embeddings or class_num:
+            raise _lib.LvtError("lvt_b200 implements SHARE_EMBEDDINGS=False, CLASS_NUM=0 (every shipped VT config)")
         heads = set(self.heads_e) | set(self.heads_d)
         if len(heads) != 1:
             raise _lib.LvtError("all attention layers must use the same number of heads")
@@ -104,10 +104,15 @@ class VTSpec:
         for k in range(self.nc):
             s[f"ch_predictor.U.{k}.weight"] = (self.d, self.d + k * self.nv)
             s[f"ch_predictor.U.{k}.bias"] = (self.d,)
-        for k in range(self.nc):
-            s[f"ch_predictor.P.{k}.weight"] = (self.nv, self.d)
-            s[f"ch_predictor.P.{k}.bias"] = (self.nv,)
+        for k in range(1 if self.share_p else self.nc):
+            s[self.p_name(k) + ".weight"] = (self.nv, self.d)
+            s[self.p_name(k) + ".bias"] = (self.nv,)
         return s
+
+    def p_name(self, k):
+        """state_dict prefix of channel k's output Linear: `ch_predictor.P` when SHARE_P (one nn.Linear,
+        videotransformer.py:121-123), else `ch_predictor.P.<k>` (a ModuleList, :127-130)."""
+        return "ch_predictor.P" if self.share_p else f"ch_predictor.P.{k}"
 
 
 class ParamStore:
@@ -735,8 +740,8 @@ class VTEngine:
             check(self.lib.lvt_chpred_combine_fwd(ptr(ws.u), ptr(self.ut[k]) if k else None, ptr(ws.slice),
                                                   ptr(ws.a[k]), M, nc, nv, d, ws.thw, k, stream_ptr()),
                   "lvt_chpred_combine_fwd")
-            gemm(M, nv, d, Operand(ws.a[k].data_ptr(), d), Operand(st.pb(f"ch_predictor.P.{k}.weight"), d),
-                 Operand(ws.logits[k].data_ptr(), nv), out_f32=ws.logits[k], bias=st.pf(f"ch_predictor.P.{k}.bias"))
+            gemm(M, nv, d, Operand(ws.a[k].data_ptr(), d), Operand(st.pb(s.p_name(k) + ".weight"), d),
+                 Operand(ws.logits[k].data_ptr(), nv), out_f32=ws.logits[k], bias=st.pf(s.p_name(k) + ".bias"))
 
     def forward(self, ws: VTWorkspace, train=True, want_loss=True):
         """VideoTransformer.forward(mode="logits") (videotransformer.py:232-239) [+ the CE loss of
@@ -806,9 +811,10 @@ class VTEngine:
         for k in range(nc):
             ld = d + k * nv
             dl = ws.dlogits[k].data_ptr()
-            self._colsum(dl, st.gf(f"ch_predictor.P.{k}.bias"), M, nv)
-            self._wgrad(dl, nv, ws.a[k].data_ptr(), d, Operand(st.gf(f"ch_predictor.P.{k}.weight"), d), nv, d, M)
-            gemm(M, d, nv, Operand(dl, nv), Operand(st.pb(f"ch_predictor.P.{k}.weight"), d, mn_major=True),
+            # (with SHARE_P the four channels add into the same gradient: both kernels accumulate with red.add)
+            self._colsum(dl, st.gf(s.p_name(k) + ".bias"), M, nv)
+            self._wgrad(dl, nv, ws.a[k].data_ptr(), d, Operand(st.gf(s.p_name(k) + ".weight"), d), nv, d, M)
+            gemm(M, d, nv, Operand(dl, nv), Operand(st.pb(s.p_name(k) + ".weight"), d, mn_major=True),
                  Operand(ws.du.data_ptr(), d), out_bf16=ws.du, aux=ws.a[k], flags=ops.GEMM_MASK)
             self._colsum(ws.du, st.gf(f"ch_predictor.U.{k}.bias"), M, d)
             self._wgrad(ws.du.data_ptr(), d, ws.ln_y.data_ptr(), d,

@@ -41,6 +41,7 @@ class VTConfig:
     pad_value: int = -1
     ignore_index: int = -100
     video_shape: Tuple[int, int, int] = (16, 16, 16)  # (T, H, W) of the latent video
+    share_p: bool = False  # SHARE_P: one output Linear for all channels (videotransformer.py:121-123; every shipped config: False)
 
     @property
     def slice_shape(self):
@@ -386,7 +387,8 @@ def channel_predictor_logits(slc: Tensor, yl: Tensor, sd, cfg: VTConfig) -> List
     for k in range(cfg.nc):
         inp = y if k == 0 else torch.cat((y, oh[:, :, :k * cfg.nv]), dim=2)
         u = torch.relu(F.linear(inp, sd[f"ch_predictor.U.{k}.weight"], sd[f"ch_predictor.U.{k}.bias"]))
-        o = F.linear(u, sd[f"ch_predictor.P.{k}.weight"], sd[f"ch_predictor.P.{k}.bias"])
+        pk = "ch_predictor.P" if cfg.share_p else f"ch_predictor.P.{k}"  # videotransformer.py:150-155
+        o = F.linear(u, sd[pk + ".weight"], sd[pk + ".bias"])
         outs.append(o.transpose(1, 2).reshape(b, cfg.nv, t, h, w))
     return outs
 
@@ -474,9 +476,10 @@ def dsfvt_param_shapes(cfg: VTConfig) -> Dict[str, Tuple[int, ...]]:
     for k in range(cfg.nc):
         s[f"ch_predictor.U.{k}.weight"] = (cfg.d, cfg.d + k * cfg.nv)
         s[f"ch_predictor.U.{k}.bias"] = (cfg.d,)
-    for k in range(cfg.nc):
-        s[f"ch_predictor.P.{k}.weight"] = (cfg.nv, cfg.d)
-        s[f"ch_predictor.P.{k}.bias"] = (cfg.nv,)
+    for k in range(1 if cfg.share_p else cfg.nc):
+        pk = "ch_predictor.P" if cfg.share_p else f"ch_predictor.P.{k}"
+        s[pk + ".weight"] = (cfg.nv, cfg.d)
+        s[pk + ".bias"] = (cfg.nv,)
     return s
 
 

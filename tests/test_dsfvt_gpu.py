@@ -20,16 +20,16 @@ pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-def _cfg(layers):
+def _cfg(layers, share_p=False):
     from oracle import lvt_oracle as O
     return O.VTConfig(blocks_e=tuple([(1, 16, 16)] * layers), heads_e=tuple([8] * layers),
-                      blocks_d=tuple([(1, 16, 16)] * layers), heads_d=tuple([8] * layers))
+                      blocks_d=tuple([(1, 16, 16)] * layers), heads_d=tuple([8] * layers), share_p=share_p)
 
 
-def _engine(layers):
+def _engine(layers, share_p=False):
     from lvt_b200.modeling.autoregressive import VTEngine, VTSpec
     spec = VTSpec(blocks_e=((1, 16, 16),) * layers, heads_e=(8,) * layers, blocks_d=((1, 16, 16),) * layers,
-                  heads_d=(8,) * layers)
+                  heads_d=(8,) * layers, share_p=share_p)
     return VTEngine(spec)
 
 
@@ -37,15 +37,16 @@ def _relerr(a, b):
     return ((a - b).double().norm() / (b.double().norm() + 1e-30)).item()
 
 
-@pytest.mark.parametrize("tag,layers,batch", [("dsfvt_l2", 2, 3), ("dsfvt_full", 8, 2)])
+@pytest.mark.parametrize("tag,layers,batch", [("dsfvt_l2", 2, 3), ("dsfvt_full", 8, 2), ("dsfvt_l2_sharep", 2, 3)])
 def test_dsfvt_forward_backward_vs_oracle(cuda_lib, tag, layers, batch):
     from oracle import lvt_oracle as O
     torch.set_num_threads(min(8, os.cpu_count() or 1))
-    cfg = _cfg(layers)
+    share_p = tag.endswith("sharep")  # SHARE_P True (the reference's config default): one P, four gradients summed
+    cfg = _cfg(layers, share_p)
     weights = O.synth_weights(O.dsfvt_param_shapes(cfg), seed=1234)
     context, slc, slice_idx, ignore = O.synth_vt_batch(batch, seed=77, cfg=cfg)
 
-    eng = _engine(layers)
+    eng = _engine(layers, share_p)
     eng.load_state_dict(weights)
     ws = eng.workspace(batch, cfg.slice_shape, tuple(context.shape[2:]), train=True)
     eng.set_inputs(ws, context, slc, slice_idx, ignore)

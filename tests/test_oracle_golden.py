@@ -104,11 +104,12 @@ def test_vqvae_oracle_matches_reference(init):
         assert np.allclose(wg_g[k].grad.double().norm().item(), fix[f"{init}:gG:{k}"], rtol=1e-4), k
 
 
-@pytest.mark.parametrize("tag,layers,batch", [("dsfvt_l2", 2, 3), ("dsfvt_full", 8, 2)])
+@pytest.mark.parametrize("tag,layers,batch", [("dsfvt_l2", 2, 3), ("dsfvt_full", 8, 2), ("dsfvt_l2_sharep", 2, 3)])
 def test_dsfvt_oracle_matches_reference(tag, layers, batch):
     fix = _load(tag + ".npz")
     cfg = O.VTConfig(blocks_e=tuple([(1, 16, 16)] * layers), heads_e=tuple([8] * layers),
-                     blocks_d=tuple([(1, 16, 16)] * layers), heads_d=tuple([8] * layers))
+                     blocks_d=tuple([(1, 16, 16)] * layers), heads_d=tuple([8] * layers),
+                     share_p=tag.endswith("sharep"))  # SHARE_P True: the reference's config default
     sd = {k: v.requires_grad_(True) for k, v in O.synth_weights(O.dsfvt_param_shapes(cfg), seed=1234).items()}
     context, slc, slice_idx, ignore = O.synth_vt_batch(batch, seed=77, cfg=cfg)
     assert np.array_equal(slice_idx.numpy(), fix["slice_idx"]) and context.sum().item() == fix["context_sum"]
