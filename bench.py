@@ -725,8 +725,9 @@ def main():
                               "frac": pos * 1056 / t_vq / 1e9 / hbm_peak, "positions": pos, "ms": t_vq * 1e3,
                               "positions_per_s": pos / t_vq, "frames_per_s_equiv": nfr / t_vq,
                               "note": "tf32 tcgen05 scan of all 512 codes + exact fp32 re-rank of the candidates (bit-exact "
-                                      "indices); 262144 FLOP/position: the tf32 tensor pipe (~0.27 ms per 2^20 positions) "
-                                      "and the shared-memory scan, not HBM, bound it"}
+                                      "indices); 262144 FLOP/position: the tf32 tensor pipe (~0.27 ms per 2^20 positions), "
+                                      "the alu pipe of the threshold scan and the per-tile dependency chain, not HBM, bound "
+                                      "it (DESIGN.md 5; round-1 kernel: LVT_VQ_TC1=1)"}
         del z, a, w, o
         # VQ-VAE (PR-DVQVAE2) on synthetic 16-frame 64x64 clips: 32 clips = 512 frames per step
         # (configs/vqvae/Base-VQVAE.yaml IMS_PER_BATCH 32); second half of BASELINE.json's metric.
