@@ -70,6 +70,14 @@ int lvt_vq_ema_update(float* codebook, float* running_size, float* running_sum,
                       const float* counts, const float* sums, int num, int K, int D, double decay,
                       double eps, void* stream);
 
+/* Codebook gradient when MODEL.CODEBOOK.EMA is False: the autograd of index_select under
+ * loss = mse(z_q, sg[z_e]) (vq_embedding.py:61-64, meta_arch/vqvae.py:84-85; the codebook argument of vq_st is
+ * detached, so vq_utils.py:55-63 contributes nothing there):  grad[k, :] = scale * (counts[k] * codebook[k, :]
+ * - sums[k, :]) with scale = 2 / numel(z_e) and counts / sums the per-code statistics lvt_vq_argmin accumulates.
+ * rows = num * K; all buffers fp32.                                                          */
+int lvt_vq_codebook_grad(const float* counts, const float* sums, const float* codebook, float* grad,
+                         float scale, int rows, int D, void* stream);
+
 /* Codebook gather ("emb" mode / z_q_bar): idx [n, num, hw] int64 -> out [n, num*D, hw] fp32
  * NCHW (vq_embedding.py:61-64, 92-97 followed by vqvae.py:104's permute).                   */
 int lvt_vq_gather(const int64_t* idx, const float* codebook, float* out, int n, int num, int K,

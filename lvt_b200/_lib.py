@@ -165,6 +165,7 @@ SYMBOLS = {
     "lvt_attn_row": (_i, [_vp] * 6 + [_i, _i, _i, _vp, _f, _vp, _i, _i, _i, _i, _vp]),
     "lvt_vq_argmin": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "lvt_vq_ema_update": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _d, _d, _vp]),
+    "lvt_vq_codebook_grad": (_i, [_vp, _vp, _vp, _vp, _f, _i, _i, _vp]),
     "lvt_vq_gather": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "lvt_gemm_bf16": (_i, [ctypes.POINTER(LvtGemm), _vp]),
     "lvt_attn_bwd_scratch_bytes": (_ll, []),

@@ -370,6 +370,17 @@ vq_ema_stats_kernel(const float* __restrict__ z_e, const int64_t* __restrict__ i
   }
 }
 
+// Codebook gradient of the non-EMA objective (MODEL.CODEBOOK.EMA False): loss = mse(z_q, sg[z_e]) reaches the
+// codebook through index_select (vq_embedding.py:61-64, vqvae.py:84-85); d/de_k = (2 / numel) * sum over the positions
+// assigned to k of (e_k - z_e) = scale * (counts_k * e_k - sums_k) -- the statistics the EMA path already produces.
+__global__ void __launch_bounds__(256)
+vq_codebook_grad_kernel(const float* __restrict__ counts, const float* __restrict__ sums,
+                        const float* __restrict__ codebook, float* __restrict__ grad, float scale, int rows, int D) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * D) return;
+  grad[i] = scale * (counts[i / D] * codebook[i] - sums[i]);
+}
+
 }  // namespace
 
 static int vq_argmin_impl(const float* z_e, const float* codebook, int64_t* idx_out, float* zq_out,
@@ -501,6 +512,16 @@ extern "C" int lvt_vq_ema_update(float* codebook, float* running_size, float* ru
   vq_ema_kernel<<<num, threads, smem, stream>>>(codebook, running_size, running_sum, counts, sums, K,
                                                 D, (float)decay, (float)(1.0 - decay), (float)eps,
                                                 (float)(K * eps));
+  LVT_CHECK_LAUNCH();
+  lvt_count_launch(1);
+  return LVT_OK;
+}
+
+extern "C" int lvt_vq_codebook_grad(const float* counts, const float* sums, const float* codebook, float* grad,
+                                    float scale, int rows, int D, void* stream_) {
+  LVT_CHECK_ARG(counts && sums && codebook && grad && rows > 0 && D > 0, "lvt_vq_codebook_grad: bad argument");
+  vq_codebook_grad_kernel<<<lvt_ceil_div(rows * D, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
+      counts, sums, codebook, grad, scale, rows, D);
   LVT_CHECK_LAUNCH();
   lvt_count_launch(1);
   return LVT_OK;

@@ -30,6 +30,9 @@ class _SupervisedLoss(torch.autograd.Function):
         if comm.get_world_size() > 1:
             comm.all_reduce_sum_(eng.store.grad)
             eng.store.grad.div_(comm.get_world_size())
+            if not eng.spec.ema:  # vqvae.py:46-50: the codebook is DDP-wrapped too when it is trained
+                comm.all_reduce_sum_(eng.cb_grad)
+                eng.cb_grad.div_(comm.get_world_size())
         return None, None, None
 
 
@@ -184,11 +187,14 @@ class VQVAEModel(nn.Module):
         x, seq = self.preprocess_data(data)
         if mode in ("supervised", "generator"):
             w = self._stage(x, train=True)
-            if self._graphed:
+            if self._graphed and self.use_codebook_ema:
                 losses = _GraphedSupervisedLoss.apply(self._anchor, self, w, self._graphs_for(w))
             else:
                 losses = _SupervisedLoss.apply(self._anchor, self, w)
-            return {"loss_reconstruction": losses[0], "loss_commitment": losses[1]}
+            out = {"loss_reconstruction": losses[0], "loss_commitment": losses[1]}
+            if not self.use_codebook_ema:  # vqvae.py:84-85 (the key really is 'loss_dict')
+                out["loss_dict"] = losses[2]
+            return out
         if mode == "inference":
             w = self._stage(x, train=False)
             recon, idx = self.engine.inference(w, precise=self.precise_latents)

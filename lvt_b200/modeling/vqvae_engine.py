@@ -45,9 +45,12 @@ class VQVAESpec:
     def __init__(self, in_channels=3, nf=256, res_channels=128, n_layers=2, codebook_num=4, codebook_size=512,
                  codebook_dim=256, beta=1.0, ema=True, ema_decay=0.99, ema_eps=1e-5, pixel_lambda=1.0,
                  pixel_mean=0.5, pixel_std=0.5, out_activation="tanh"):
-        if (in_channels, nf, res_channels, codebook_dim, out_activation, ema) != (3, 256, 128, 256, "tanh", True):
+        if (in_channels, nf, res_channels, codebook_dim, out_activation) != (3, 256, 128, 256, "tanh"):
             raise _lib.LvtError("lvt_b200 implements the shipped DVQ-VAE configs: 3->128->256 channels, "
-                                "RES_CHANNELS 128, CODEBOOK.DIM 256, tanh output, EMA codebook")
+                                "RES_CHANNELS 128, CODEBOOK.DIM 256, tanh output")
+        # MODEL.CODEBOOK.EMA (every shipped config: True).  False: the codebook is a trained parameter -- extra loss
+        # mse(z_q, sg[z_e]) (vqvae.py:84-85), its gradient through index_select, Adam with the generator's settings
+        self.ema = bool(ema)
         self.in_channels, self.nf, self.rc, self.n_layers = in_channels, nf, res_channels, n_layers
         self.num, self.K, self.D = codebook_num, codebook_size, codebook_dim // codebook_num
         self.beta, self.ema_decay, self.ema_eps, self.pixel_lambda = beta, ema_decay, ema_eps, pixel_lambda
@@ -85,6 +88,7 @@ class VQVAEEngine:
         self.codebook = z((s.num, s.K, s.D))
         self.running_size = z((s.num, s.K))
         self.running_sum = z((s.num, s.K, s.D))
+        self.cb_grad = z((s.num, s.K, s.D))  # codebook gradient (CODEBOOK.EMA False only)
         L, nf, rc = s.n_layers, s.nf, s.rc
         self.kG = 1 + L
         # packed weights: name -> (fwd [co][tap*ci] bf16, dgrad [ci][tap*co] bf16, fwd-layout fp32 grad)
@@ -255,7 +259,8 @@ class VQVAEEngine:
         w.Y = torch.empty((4 * M, 64), dtype=f32, device=self.device)  # output ConvT partial sums per input pixel
         w.x_tilde = e((n, 3, 64, 64), f32)
         w.recon = e((n, 3, 64, 64), f32)
-        w.loss = torch.zeros((2,), dtype=f32, device=self.device)  # [reconstruction, commitment]
+        # [reconstruction, commitment] (+ [2] = mse(z_q, sg[z_e]), the `loss_dict` entry of vqvae.py:84-85, without EMA)
+        w.loss = torch.zeros((2 if s.ema else 3,), dtype=f32, device=self.device)
         w.loss_scratch = torch.zeros((1,), dtype=f32, device=self.device)
         if train:
             w.dpre = e((n, 3, 64, 64), f32)
@@ -505,7 +510,7 @@ class VQVAEEngine:
     def forward_train(self, w, allreduce=None):
         """compute_supervised_loss (vqvae.py:66-91): losses in w.loss = [reconstruction, commitment(after bwd)]."""
         self._forward_train_a(w)
-        if allreduce is not None:
+        if allreduce is not None and self.spec.ema:  # without EMA the statistics only feed this rank's codebook gradient
             allreduce(w.counts)
             allreduce(w.sums)
         self._forward_train_b(w)
@@ -518,7 +523,11 @@ class VQVAEEngine:
     def _forward_train_b(self, w):
         """EMA codebook update (after the cross-rank sum), decoder, losses"""
         s = self.spec
-        self.ema_update(w)
+        if s.ema:
+            self.ema_update(w)
+        else:  # z_q_bar = index_select from the (trained, unchanged here) codebook (vq_embedding.py:61-64)
+            check(self.lib.lvt_vq_gather_nhwc(ptr(w.idx), ptr(self.codebook), ptr(w.zq_bar), None, w.n, s.num, s.K,
+                                              s.D, 256, stream_ptr()), "lvt_vq_gather_nhwc")
         self.decode(w)
         w.loss.zero_()
         k = self.kG
@@ -527,6 +536,9 @@ class VQVAEEngine:
                                             s.pixel_lambda, stream_ptr()), "lvt_vqvae_recon_loss")
         check(self.lib.lvt_vqvae_commit_loss(ptr(w.z_e), ptr(w.zq_bar), None, None, _vp(w.loss.data_ptr() + 4),
                                              w.M * s.nf, s.beta, stream_ptr()), "lvt_vqvae_commit_loss")
+        if not s.ema:  # the vector-quantisation objective mse(z_q, sg[z_e]): the same mean square, without beta
+            check(self.lib.lvt_vqvae_commit_loss(ptr(w.z_e), ptr(w.zq_bar), None, None, _vp(w.loss.data_ptr() + 8),
+                                                 w.M * s.nf, 1.0, stream_ptr()), "lvt_vqvae_commit_loss")
 
     def backward(self, w):
         s, st = self.spec, self.store
@@ -591,6 +603,9 @@ class VQVAEEngine:
         self._colsum(w.dact1, st.gf("E.layers.0.bias"), 4 * M, nf // 2)
         self._wgrad_plain(w.dact1, nf // 2, w.A1, 64, 4 * M, self.dw1p)
         self._fold_packed_grads()
+        if not s.ema:  # d mse(z_q, sg[z_e]) / d codebook from this rank's per-code counts / sums
+            check(self.lib.lvt_vq_codebook_grad(ptr(w.counts), ptr(w.sums), ptr(self.codebook), ptr(self.cb_grad),
+                                                2.0 / (M * nf), s.num * s.K, s.D, stream_ptr()), "lvt_vq_codebook_grad")
 
     def init_optimizer(self, lr=3e-4, betas=(0.9, 0.9), eps=1e-8):
         """torch.optim.Adam(lr=LR_G, betas=(BETA1_G, BETA2_G)) (config/defaults.py:105-114; solver/build.py:62-66);
@@ -598,6 +613,9 @@ class VQVAEEngine:
         self.opt = dict(lr=lr, betas=betas, eps=eps, step=0)
         self.opt_m = torch.zeros_like(self.store.master)
         self.opt_v = torch.zeros_like(self.store.master)
+        if not self.spec.ema:  # optimizer_c of vqvae.py:108-116: same builder, same hyper-parameters, stepped together
+            self.cb_m = torch.zeros_like(self.codebook)
+            self.cb_v = torch.zeros_like(self.codebook)
 
     def optimizer_step(self, grad_scale=1.0):
         o, st = self.opt, self.store
@@ -605,6 +623,10 @@ class VQVAEEngine:
         check(self.lib.lvt_adam_step(ptr(st.master), ptr(st.grad), ptr(self.opt_m), ptr(self.opt_v), ptr(st.shadow),
                                      st.numel, o["lr"], o["betas"][0], o["betas"][1], o["eps"], o["step"], grad_scale,
                                      stream_ptr()), "lvt_adam_step")
+        if not self.spec.ema:
+            check(self.lib.lvt_adam_step(ptr(self.codebook), ptr(self.cb_grad), ptr(self.cb_m), ptr(self.cb_v), None,
+                                         self.codebook.numel(), o["lr"], o["betas"][0], o["betas"][1], o["eps"],
+                                         o["step"], grad_scale, stream_ptr()), "lvt_adam_step")
         self.refresh_shadows(cast=False)
 
     def train_step(self, w, allreduce=None, world_size=1):
@@ -613,6 +635,8 @@ class VQVAEEngine:
         self.backward(w)
         if allreduce is not None:
             allreduce(self.store.grad)
+            if not self.spec.ema:
+                allreduce(self.cb_grad)
         self.optimizer_step(1.0 / world_size)
         return w.loss
 
@@ -624,6 +648,9 @@ class GraphedVQVAEStep:
     Adam (eager: its bias correction depends on the step count) [weight re-layout]."""
 
     def __init__(self, engine: "VQVAEEngine", w, world_size=1, allreduce=None):
+        if not engine.spec.ema:
+            raise _lib.LvtError("GraphedVQVAEStep covers the EMA codebook (every shipped config); "
+                                "CODEBOOK.EMA False runs through VQVAEEngine.train_step")
         self.engine, self.w, self.world_size, self.allreduce = engine, w, world_size, allreduce
         self.graphs = None
 

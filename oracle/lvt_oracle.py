@@ -62,6 +62,7 @@ class VQVAEConfig:
     ema_decay: float = 0.99
     ema_eps: float = 1e-5
     pixel_lambda: float = 1.0
+    ema: bool = True  # MODEL.CODEBOOK.EMA (every shipped config: True); False trains the codebook by gradient
 
 
 # ============================================================================================
@@ -176,6 +177,22 @@ def vqvae_supervised_loss(x01: Tensor, sdE, sdG, codebooks, running_size, runnin
     (vq_utils.py:50-53).  Returns (loss dict, aux dict)."""
     x = (x01 - 0.5) / 0.5
     z_e = res_encoder(x, sdE, cfg.n_layers)
+    if not cfg.ema:
+        # MODEL.CODEBOOK.EMA False (vq_embedding.py:36-38,61-66; vqvae.py:84-88): vq_st sees the DETACHED weight, so the
+        # codebook (pass it with requires_grad) gets its gradient only through index_select under the extra loss
+        # mse(z_q, sg[z_e]), which the reference stores under the key 'loss_dict'
+        with torch.no_grad():
+            idx = dvq_indices(z_e.detach(), codebooks)
+        zq_bar = dvq_embed(idx, codebooks)
+        z_st = z_e + (zq_bar.detach() - z_e).detach()
+        x_tilde = res_decoder(z_st, sdG, cfg.n_layers)
+        losses = {
+            "loss_reconstruction": cfg.pixel_lambda * F.mse_loss(x_tilde, x),
+            "loss_dict": F.mse_loss(zq_bar, z_e.detach()),
+            "loss_commitment": cfg.beta * F.mse_loss(z_e, zq_bar.detach()),
+        }
+        return losses, dict(z_e=z_e, idx=idx, x_tilde=x_tilde, codebooks=codebooks, running_size=running_size,
+                            running_sum=running_sum)
     with torch.no_grad():
         zq_st, zq_bar, idx, new_cb, new_rs, new_rsum = dvq_straight_through(
             z_e.detach(), codebooks, running_size, running_sum, cfg)

@@ -246,6 +246,43 @@ def golden_subscale():
         print(name, "loss", float(loss))
 
 
+def golden_vqvae_noema():
+    """PR-DVQVAE2 with MODEL.CODEBOOK.EMA False (no shipped config; vq_embedding.py:36-38,61-66, vqvae.py:84-88):
+    the three losses and the gradients of one supervised step, codebook included."""
+    ref_shim.install()
+    from vidgen.modeling.meta_arch import build_model
+    cfg = ref_shim.reference_cfg("configs/vqvae/PR-DVQVAE2.yaml", ["MODEL.CODEBOOK.EMA", False])
+    torch.manual_seed(0)
+    model = build_model(cfg)
+    ocfg = O.VQVAEConfig(ema=False)
+    eshape, gshape = O.vqvae_param_shapes(ocfg)
+    we, wg = O.synth_weights(eshape, seed=11), O.synth_weights(gshape, seed=12)
+    load_into(model.encoder, we)
+    load_into(model.generator, wg)
+    x = torch.rand((8, 3, 64, 64), generator=torch.Generator().manual_seed(1234))
+    with torch.no_grad():
+        z_std = model.encoder((x - 0.5) / 0.5).std()
+    cb = torch.randn((4, 512, 64), generator=torch.Generator().manual_seed(5)) * z_std
+    for g in range(4):
+        model.codebook.ve[g].embedding.weight.data.copy_(cb[g])
+    model.train()
+    model.zero_grad()
+    losses = model([{"image": x[i]} for i in range(x.shape[0])], mode="supervised")
+    sum(losses.values()).backward()
+    fix = {"spread_std": z_std.numpy()}
+    for k, v in losses.items():
+        fix["loss:" + k] = v.detach().numpy()
+    gcb = torch.stack([model.codebook.ve[g].embedding.weight.grad for g in range(4)])
+    fix["gcb_norm"] = gcb.double().norm().numpy()
+    fix["gcb_sub"] = gcb[:, ::16, ::8].numpy()
+    for k in ("layers.0.weight", "layers.4.weight", "layers.6.block.3.weight"):
+        fix[f"gE:{k}"] = dict(model.encoder.named_parameters())[k].grad.double().norm().numpy()
+    for k in ("layers.0.weight", "layers.4.weight", "layers.6.weight"):
+        fix[f"gG:{k}"] = dict(model.generator.named_parameters())[k].grad.double().norm().numpy()
+    np.savez_compressed(os.path.join(OUT, "vqvae_noema.npz"), **fix)
+    print("vqvae_noema ok", {k: float(v) for k, v in losses.items()})
+
+
 def golden_kdvqvae():
     """K-DVQVAE (configs/vqvae/K-DVQVAE.yaml, N_LAYERS 4): inference latents / reconstruction and one
     supervised step's losses (spread codebook)."""
@@ -290,7 +327,7 @@ def golden_kdvqvae():
 
 if __name__ == "__main__":
     assert ref_shim.available(), "run in the authoring container (needs /root/reference)"
-    which = sys.argv[1:] or ["vq", "vqvae", "kdvqvae", "mapper", "dsfvt", "subscale"]
+    which = sys.argv[1:] or ["vq", "vqvae", "vqvae_noema", "kdvqvae", "mapper", "dsfvt", "subscale"]
     for w in which:
-        {"vq": golden_vq_only, "vqvae": golden_vqvae, "kdvqvae": golden_kdvqvae, "mapper": golden_mapper,
+        {"vq": golden_vq_only, "vqvae": golden_vqvae, "vqvae_noema": golden_vqvae_noema, "kdvqvae": golden_kdvqvae, "mapper": golden_mapper,
          "dsfvt": golden_dsfvt, "subscale": golden_subscale}[w]()

@@ -167,6 +167,36 @@ def test_base_vqvae_single_codebook(cuda_lib, tmp_path):
     assert model.engine.store.grad.abs().sum().item() > 0
 
 
+def test_vqvae_model_without_codebook_ema(cuda_lib, tmp_path):
+    """MODEL.CODEBOOK.EMA False through the reference surface (vqvae.py:84-88,108-116): a third loss under the key
+    'loss_dict' (its value equals loss_commitment / beta), the EMA buffers stay put, and the optimizers the model
+    configures move the codebook by at most lr on the first Adam step."""
+    from lvt_b200.config.presets import preset
+    from lvt_b200.modeling import build_model
+    from lvt_b200.utils.events import EventStorage
+    cfg = preset("PR-DVQVAE2", ["OUTPUT_DIR", str(tmp_path), "MODEL.CODEBOOK.EMA", False])
+    cfg.freeze()
+    torch.manual_seed(3)
+    model = build_model(cfg)
+    with torch.no_grad():
+        model.engine.codebook.normal_(0.0, 0.05)
+    optimizers, _ = model.configure_optimizers_and_checkpointers()
+    model.train(True)
+    x = torch.rand((4, 3, 64, 64), generator=torch.Generator().manual_seed(1))
+    cb0, rs0 = model.engine.codebook.clone(), model.engine.running_size.clone()
+    with EventStorage(0):
+        losses = model([{"image": x[i]} for i in range(4)], mode="supervised")
+        sum(losses.values()).backward()
+    assert set(losses) == {"loss_reconstruction", "loss_commitment", "loss_dict"}
+    assert abs(losses["loss_dict"].item() - losses["loss_commitment"].item() / cfg.MODEL.CODEBOOK.BETA) <= 1e-6
+    assert torch.equal(model.engine.codebook, cb0) and model.engine.cb_grad.abs().sum().item() > 0
+    for o in optimizers:
+        o["optimizer"].step()
+    moved = (model.engine.codebook - cb0).abs()
+    assert 0 < moved.max().item() <= cfg.SOLVER.LR_G * 1.001
+    assert torch.equal(model.engine.running_size, rs0)
+
+
 def test_graph_sampler_matches_per_pixel_loop(cuda_lib, tmp_path):
     """VideoTransformer.sample_slice (one CUDA-graph replay per position) against the same fused per-position step
     launched eagerly and against the reference-shaped per-pixel loop (vt.py:107-134).  At temperature 1e-10 the

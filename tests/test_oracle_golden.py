@@ -104,6 +104,28 @@ def test_vqvae_oracle_matches_reference(init):
         assert np.allclose(wg_g[k].grad.double().norm().item(), fix[f"{init}:gG:{k}"], rtol=1e-4), k
 
 
+def test_vqvae_noema_oracle_matches_reference():
+    """MODEL.CODEBOOK.EMA False (no shipped config uses it): the codebook is trained by gradient
+    (vq_embedding.py:36-38,61-66, vqvae.py:84-88).  Losses and gradients of one supervised step."""
+    fix = _load("vqvae_noema.npz")
+    cfg = O.VQVAEConfig(ema=False)
+    eshape, gshape = O.vqvae_param_shapes(cfg)
+    we = {k: v.requires_grad_(True) for k, v in O.synth_weights(eshape, seed=11).items()}
+    wg = {k: v.requires_grad_(True) for k, v in O.synth_weights(gshape, seed=12).items()}
+    x = torch.rand((8, 3, 64, 64), generator=torch.Generator().manual_seed(1234))
+    cb = (torch.randn((4, 512, 64), generator=torch.Generator().manual_seed(5)) * torch.tensor(fix["spread_std"])).requires_grad_(True)
+    losses, _ = O.vqvae_supervised_loss(x, we, wg, cb, None, None, cfg)
+    sum(losses.values()).backward()
+    for k in ("loss_reconstruction", "loss_dict", "loss_commitment"):
+        assert np.allclose(losses[k].item(), fix["loss:" + k], rtol=1e-5), k
+    assert np.allclose(cb.grad.double().norm().item(), fix["gcb_norm"], rtol=1e-4)
+    assert np.allclose(cb.grad[:, ::16, ::8].numpy(), fix["gcb_sub"], rtol=1e-3, atol=1e-9)
+    for k in ("layers.0.weight", "layers.4.weight", "layers.6.block.3.weight"):
+        assert np.allclose(we[k].grad.double().norm().item(), fix[f"gE:{k}"], rtol=1e-4), k
+    for k in ("layers.0.weight", "layers.4.weight", "layers.6.weight"):
+        assert np.allclose(wg[k].grad.double().norm().item(), fix[f"gG:{k}"], rtol=1e-4), k
+
+
 @pytest.mark.parametrize("tag,layers,batch", [("dsfvt_l2", 2, 3), ("dsfvt_full", 8, 2), ("dsfvt_l2_sharep", 2, 3)])
 def test_dsfvt_oracle_matches_reference(tag, layers, batch):
     fix = _load(tag + ".npz")

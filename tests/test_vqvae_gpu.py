@@ -140,6 +140,56 @@ def test_vqvae_train_step_vs_oracle(cuda_lib):
     assert 0 < delta <= 3e-4 * 1.001
 
 
+def test_vqvae_noema_codebook_gradient_vs_oracle(cuda_lib):
+    """MODEL.CODEBOOK.EMA False (vq_embedding.py:36-38,61-66, vqvae.py:84-88): the codebook is trained by gradient.
+    Losses (1e-3), the codebook gradient of lvt_vq_codebook_grad against autograd's index_select backward (1e-4: it is
+    built from the same fp32 counts / sums) and the Adam update of the codebook against torch.optim.Adam."""
+    from oracle import lvt_oracle as O
+    from lvt_b200.modeling.vqvae_engine import VQVAEEngine, VQVAESpec
+    n, L = 8, 2
+    cfg, we, wg, x, cb, z_ref = _setup(n, L)
+    cfg = O.VQVAEConfig(n_layers=L, ema=False)
+    eng = VQVAEEngine(VQVAESpec(n_layers=L, ema=False))
+    eng.load_state_dict(we, wg, cb)
+    eng.init_optimizer()
+    w = eng.workspace(n, train=True)
+    w.x.copy_(x)
+    eng.store.grad.zero_()
+    eng.encode(w)
+    w.z_e.copy_(z_ref.permute(0, 2, 3, 1).reshape(-1, 256))   # teacher-force z_e -> identical indices
+    eng.quantize(w, train=True)
+    eng._forward_train_b(w)
+    eng.backward(w)
+    torch.cuda.synchronize()
+
+    we_g = {k_: v.clone().requires_grad_(True) for k_, v in we.items()}
+    wg_g = {k_: v.clone().requires_grad_(True) for k_, v in wg.items()}
+    cb_g = cb.clone().requires_grad_(True)
+    losses, aux = O.vqvae_supervised_loss(x, we_g, wg_g, cb_g, None, None, cfg)
+    sum(losses.values()).backward()
+    assert torch.equal(w.idx.cpu(), aux["idx"])
+    assert torch.equal(eng.codebook.cpu(), cb)                  # no EMA update happened
+    got = w.loss.tolist()
+    for i, k_ in enumerate(("loss_reconstruction", "loss_commitment", "loss_dict")):
+        assert abs(got[i] - losses[k_].item()) <= 1e-3 * losses[k_].item(), (k_, got[i], losses[k_].item())
+    g_got, g_want = eng.cb_grad.cpu(), cb_g.grad
+    assert ((g_got - g_want).double().norm() / g_want.double().norm()).item() <= 1e-4
+    # encoder gradient still carries straight-through + commitment (same tolerance as the EMA test)
+    gw, gg = we_g["layers.4.weight"].grad, eng.store.g["E.layers.4.weight"].cpu()
+    cos = (gg.double().flatten() @ gw.double().flatten() / (gg.double().norm() * gw.double().norm())).item()
+    assert cos >= 0.99 and abs((gg.double().norm() / gw.double().norm()).item() - 1) <= 0.03
+    # the codebook's Adam step (optimizer_c of vqvae.py:108-116) against torch.optim.Adam on the oracle's gradient
+    ref = cb.clone().requires_grad_(True)
+    opt = torch.optim.Adam([ref], lr=3e-4, betas=(0.9, 0.9))
+    ref.grad = g_want.clone()
+    opt.step()
+    eng.optimizer_step()
+    torch.cuda.synchronize()
+    touched = g_want.abs() > 1e-12
+    assert touched.any() and torch.allclose(eng.codebook.cpu()[touched], ref.detach()[touched], rtol=0, atol=3e-6)
+    assert torch.equal(eng.codebook.cpu()[~touched], cb[~touched])
+
+
 def test_vqvae_graphed_step_matches_eager(cuda_lib):
     """GraphedVQVAEStep (CUDA-graph replay of forward + EMA + backward, Adam outside) against the eager train_step
     from identical state.  Step 1 is compared tightly (same code indices, losses, EMA codebook; Adam's first update
