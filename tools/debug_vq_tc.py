@@ -1,3 +1,5 @@
+"""Scratch diagnostic: dumps the tf32 scores of tile 0 / group 0 (lvt_dbg_vq_scores).  Only the round-1 kernel writes them:
+run with LVT_VQ_TC1=1."""
 import os, sys, ctypes
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
