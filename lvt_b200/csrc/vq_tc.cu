@@ -937,26 +937,30 @@ vq_argmin_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __re
       VQ2_CLK(9);
       const int besti = (int)(rb[m] & 511ull);
       if (pw == 0) idx_out[((size_t)frame * num + g) * hw + s] = (int64_t)besti;
-      if (pw == 1 && (zq_out || zq_bf16)) {
-        const float* cr = cbg + (size_t)besti * TD;
-        if (NHWC) {
-          const size_t o = (size_t)pos * C + (size_t)g * TD;
-#pragma unroll
-          for (int jj = 0; jj < 16; ++jj) {
-            const float4 v = __ldg(reinterpret_cast<const float4*>(cr) + jj);
-            if (zq_out) *reinterpret_cast<float4*>(zq_out + o + 4 * jj) = v;
-            if (zq_bf16) {
-              uint2 u;
-              u.x = pack_bf16x2(v.x, v.y);
-              u.y = pack_bf16x2(v.z, v.w);
-              *reinterpret_cast<uint2*>(zq_bf16 + o + 4 * jj) = u;
-            }
+      if (NHWC && (zq_out || zq_bf16)) {
+        // z_q rows: each warp of the pair writes half of the quarter's rows; two rows per instruction, 16 lanes per
+        // row, so whole 128 / 256-byte lines are read and written (one row per lane would touch 32 lines each time)
+        const int hrow = lane >> 4, l16 = lane & 15;
+#pragma unroll 4
+        for (int rr = pw * 16; rr < pw * 16 + 16; rr += 2) {
+          const int r = rr + hrow;
+          const int kb = __shfl_sync(0xffffffffu, besti, r);
+          const float4 v = __ldg(reinterpret_cast<const float4*>(cbg + (size_t)kb * TD) + l16);
+          const size_t o = ((size_t)tile * TM + q * 32 + r) * C + (size_t)g * TD + 4 * l16;
+          if (zq_out) *reinterpret_cast<float4*>(zq_out + o) = v;
+          if (zq_bf16) {
+            uint2 u;
+            u.x = pack_bf16x2(v.x, v.y);
+            u.y = pack_bf16x2(v.z, v.w);
+            *reinterpret_cast<uint2*>(zq_bf16 + o) = u;
           }
-        } else {
-          float* zp = zq_out + ((size_t)frame * C + (size_t)g * TD) * hw + s;
-#pragma unroll 8
-          for (int j = 0; j < TD; ++j) zp[(size_t)j * hw] = __ldg(cr + j);
         }
+      }
+      if (!NHWC && zq_out) {  // NCHW: lanes are consecutive positions, each warp of the pair writes 32 of the 64 dims
+        const float* cr = cbg + (size_t)besti * TD + pw * 32;
+        float* zp = zq_out + ((size_t)frame * C + (size_t)g * TD + pw * 32) * hw + s;
+#pragma unroll 8
+        for (int j = 0; j < TD / 2; ++j) zp[(size_t)j * hw] = __ldg(cr + j);
       }
       if (pw == 0 && counts) atomicAdd(counts + (size_t)g * TK + besti, 1.f);
       if (sums) {  // each warp of the pair adds half of the row
