@@ -650,8 +650,14 @@ class VTEngine:
             ws._stage_in = [torch.empty_like(t) for t in (ws.context, ws.slice, ws.slice_idx, ws.ignore)]
             ws._copy_stream = torch.cuda.Stream()
             ws._copy_done = torch.cuda.Event()
+            ws._commit_done = None
         st = ws._stage_in
-        ws._copy_stream.wait_stream(torch.cuda.current_stream())  # the previous commit has read the staging buffers
+        # the previous commit has read the staging buffers: wait for IT, not for whatever else has been queued on the
+        # compute stream since (the caller may already have launched the step that overlaps this copy)
+        if ws._commit_done is not None:
+            ws._copy_stream.wait_event(ws._commit_done)
+        else:
+            ws._copy_stream.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(ws._copy_stream):
             st[0].copy_(context.reshape(st[0].shape), non_blocking=True)
             st[1].copy_(slc.reshape(st[1].shape), non_blocking=True)
@@ -667,6 +673,9 @@ class VTEngine:
         torch.cuda.current_stream().wait_event(ws._copy_done)
         for dst, src in zip((ws.context, ws.slice, ws.slice_idx, ws.ignore), ws._stage_in):
             dst.copy_(src, non_blocking=True)
+        if ws._commit_done is None:
+            ws._commit_done = torch.cuda.Event()
+        ws._commit_done.record()
 
     def set_inputs_from_videos(self, ws: VTWorkspace, videos, abc, n_prime=1):
         """Device-side input construction: latent videos (B, T, nc, H, W) already in HBM + slice offsets (B, 3) ->
