@@ -373,6 +373,11 @@ typedef struct LvtPermuteJob {
 } LvtPermuteJob;
 int lvt_permute4_batch(const LvtPermuteJob* jobs, int n_jobs, int total_blocks, void* stream);
 
+/* Row gather dst[r, :] = src[idx[r], :] (rows of row_bytes bytes, a multiple of 16; idx int32 [M]; src != dst): the
+ * token re-ordering of the general tiled BlockLocalAttention.forward (vt_attention.py:189-200: split the slice grid
+ * into blocks, attend inside each block, put the tokens back), applied once around a whole stack of layers.        */
+int lvt_rows_gather(const void* src, void* dst, const int* idx, int M, int row_bytes, void* stream);
+
 /* Channels-last variants used inside the VQ-VAE engine (z_e [n*hw, num*D] fp32 as written by the
  * last encoder GEMM): same arithmetic and index layout ([n, num, hw] int64) as lvt_vq_argmin;
  * zq may additionally be produced as bf16 (decoder GEMM operand).                             */

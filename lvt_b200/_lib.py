@@ -189,6 +189,7 @@ SYMBOLS = {
     "lvt_cast_bf16": (_i, [_vp, _vp, _ll, _vp]),
     "lvt_permute4": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),
     "lvt_permute4_batch": (_i, [_vp, _i, _i, _vp]),
+    "lvt_rows_gather": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
     "lvt_vq_argmin_nhwc": (_i, [_vp] * 7 + [_i] * 5 + [_vp]),
     "lvt_vq_gather_nhwc": (_i, [_vp] * 4 + [_i] * 5 + [_vp]),
     "lvt_vqvae_in_im2col": (_i, [_vp, _vp, _i, _f, _f, _vp]),

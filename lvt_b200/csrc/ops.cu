@@ -651,6 +651,18 @@ permute4_kernel(const float* __restrict__ in, void* __restrict__ out, Permute4 P
 
 // Many small re-layout jobs in ONE launch (the per-step weight packs / gradient folds of the engines are 20-70
 // launches of a few microseconds each): block b works on 1024 elements of the job whose block range contains b.
+// dst[r, :] = src[idx[r], :] for rows of row_bytes (a multiple of 16) bytes: the token re-ordering between raster
+// order of the slice grid and block-major order of the general tiled BlockLocalAttention (vt_attention.py:189-200).
+__global__ void __launch_bounds__(256)
+rows_gather_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, const int* __restrict__ idx, int M, int vec) {
+  pdl_prologue();
+  const long long total = (long long)M * vec;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / vec), c = (int)(i - (long long)r * vec);
+    dst[i] = src[(long long)idx[r] * vec + c];
+  }
+}
+
 __global__ void __launch_bounds__(256)
 permute4_batch_kernel(const LvtPermuteJob* __restrict__ jobs, int n_jobs) {
   pdl_prologue();
@@ -1029,6 +1041,16 @@ extern "C" int lvt_vt_sample_pixel(const float* logits, const float* q_exp, cons
                 "lvt_vt_sample_pixel: bad argument");
   LVT_CHECK_CUDA(lvt_launch(sample_pixel_kernel, dim3(B), dim3(256), 0, STREAM(stream), logits, q_exp, pos, slice, thw, nv, nc, k,
                             1.f / temp, logit_rows));
+  lvt_count_launch(1);
+  return LVT_OK;
+}
+
+extern "C" int lvt_rows_gather(const void* src, void* dst, const int* idx, int M, int row_bytes, void* stream) {
+  LVT_CHECK_ARG(src && dst && idx && M > 0 && row_bytes > 0 && row_bytes % 16 == 0 && src != dst, "lvt_rows_gather: bad argument");
+  const int vec = row_bytes / 16;
+  LVT_CHECK_CUDA(lvt_launch(rows_gather_kernel, dim3(flat_grid((long long)M * vec)), dim3(256), 0, STREAM(stream),
+                            reinterpret_cast<const uint4*>(src), reinterpret_cast<uint4*>(dst), idx, M, vec));
+  LVT_CHECK_LAUNCH();
   lvt_count_launch(1);
   return LVT_OK;
 }

@@ -12,6 +12,7 @@ import os
 
 import torch
 
+from ... import _lib
 from ..._lib import LvtDecodeStep, LvtRowsLinear, check, ptr, stream_ptr
 from ...ops import Operand, gemm
 from .vt_engine import LN_EPS, _vp
@@ -25,6 +26,8 @@ class IncrementalDecoder:
     def __init__(self, engine, ws):
         s = engine.spec
         assert ws.B <= MAX_ROWS
+        if ws.tiled:
+            raise _lib.LvtError("IncrementalDecoder: the slice must be one attention block (use the full decoder pass)")
         self.eng, self.ws = engine, ws
         dev = ws.slice.device
         B, d, H, da, L, nv = ws.B, s.d, s.H, s.da, ws.thw, s.nv

@@ -214,6 +214,24 @@ class VTWorkspace:
         if not train:  # ping-pong residual buffers for inference
             self.y_alt = e((M, d), f32)
         self.zl_bf16 = e((M, d), bf16)
+        # general tiled BlockLocalAttention (vt_attention.py:189-200): the slice grid is a multiple of the attention
+        # block.  The layers then run on the tokens in block-major order (every 256 consecutive rows = one block);
+        # LayerNorm, projections and the FFN are per token, so ONE re-ordering after each front and one back after
+        # each stack replaces the reference's split / stack / permute around every layer.
+        blk = spec.block
+        self.tiled = self.slice_shape != tuple(blk)
+        if self.tiled:
+            T_, H_, W_ = self.slice_shape
+            t_, h_, w_ = blk
+            r = torch.arange(B * thw, dtype=torch.int64).view(B, T_ // t_, t_, H_ // h_, h_, W_ // w_, w_)
+            perm = r.permute(0, 1, 3, 5, 2, 4, 6).reshape(-1)          # block-major position -> raster row
+            inv = torch.empty_like(perm)
+            inv[perm] = torch.arange(perm.numel())
+            self.perm, self.inv = perm.to(torch.int32).to(device), inv.to(torch.int32).to(device)
+            self.x0p, self.y0p, self.yf_r = e((M, d), f32), e((M, d), f32), e((M, d), f32)
+            self.zl_r = e((M, d), bf16)
+            if train:
+                self.tmp_f, self.tmp_b, self.tmp_b2 = e((M, d), f32), e((M, d), bf16), e((M, d), bf16)
         # predictor
         self.mean_p, self.rstd_p = e((M,), f32), e((M,), f32)
         self.ln_y = e((M, d), bf16)
@@ -419,9 +437,9 @@ class VTEngine:
     def workspace(self, B, slice_shape, ctx_shape, train=True) -> VTWorkspace:
         key = (B, tuple(slice_shape), tuple(ctx_shape), train)
         if key not in self._ws:
-            if tuple(slice_shape) != self.spec.block:
-                raise _lib.LvtError(f"slice {tuple(slice_shape)} must equal the attention block "
-                                    f"{self.spec.block} (true for every shipped config)")
+            if any(v % b for v, b in zip(slice_shape, self.spec.block)):
+                raise _lib.LvtError(f"slice {tuple(slice_shape)} must be a multiple of the attention block "
+                                    f"{self.spec.block} (vt_attention.py:178-180)")
             taps = self._live_taps(slice_shape)[0]
             self._ws[key] = VTWorkspace(self.spec, B, slice_shape, ctx_shape, len(taps), self.device, train)
         return self._ws[key]
@@ -456,6 +474,11 @@ class VTEngine:
         check(self.lib.lvt_layernorm_bwd_ex(_vp(dy), is_bf16, _vp(x), _vp(mean), _vp(rstd), _vp(g), _vp(dres), _vp(dx),
                                             _vp(dxb), _vp(dg), _vp(db), _vp(dx_colsum) if dx_colsum is not None else None,
                                             M, self.spec.d, stream_ptr()), "lvt_layernorm_bwd_ex")
+
+    def _reorder(self, src, dst, idx):
+        """dst[r] = src[idx[r]] over the M token rows (ws.perm: raster -> block-major, ws.inv: back)."""
+        check(self.lib.lvt_rows_gather(ptr(src), ptr(dst), ptr(idx), src.shape[0], src.shape[1] * src.element_size(),
+                                       stream_ptr()), "lvt_rows_gather")
 
     def _colsum(self, x, out, M, N, ld=None):
         check(self.lib.lvt_colsum_bf16(_vp(x), _vp(out), M, N, ld or N, stream_ptr()), "lvt_colsum_bf16")
@@ -704,12 +727,17 @@ class VTEngine:
         gemm(M, d, de, Operand(ws.e0.data_ptr(), de), Operand(st.pb("encoder.linear_projector.weight"), de),
              Operand(ws.x0.data_ptr(), d), out_f32=ws.x0)
         x = ws.x0
+        if ws.tiled:
+            self._reorder(ws.x0, ws.x0p, ws.perm)
+            x = ws.x0p
         for i in range(nE):
             ly = self._layer_ws(ws, i, train)
             y = ly.y if train else (ws.y_alt if x is ly.y else ly.y)
             self._layer_fwd(f"encoder.block_local_attention.{i}.", ws, ly, x, y, causal=False,
                             y_bf16=ws.zl_bf16 if i == nE - 1 else None, keep_p=train)
             x = y
+        if ws.tiled:  # the decoder front adds W_lp zl per token of the raster grid
+            self._reorder(ws.zl_bf16, ws.zl_r, ws.inv)
 
     def decoder_forward(self, ws: VTWorkspace, train=True):
         """VTDecoder.forward (videotransformer.py:91-101): ws.slice, ws.zl_bf16 -> ws.y_final, ws.ln_y."""
@@ -726,14 +754,21 @@ class VTEngine:
               "lvt_vt_dec_front_fwd")
         gemm(M, d, ntaps * de, Operand(ws.A0.data_ptr(), ntaps * de), Operand(wp.data_ptr(), ntaps * de),
              Operand(ws.y0.data_ptr(), d), out_f32=ws.y0, bias=self.posenc_table(ws.slice_shape), bias_mod=ws.thw)
-        gemm(M, d, d, Operand(ws.zl_bf16.data_ptr(), d), Operand(st.pb("decoder.linear_projector.weight"), d),
+        zl = ws.zl_r if ws.tiled else ws.zl_bf16
+        gemm(M, d, d, Operand(zl.data_ptr(), d), Operand(st.pb("decoder.linear_projector.weight"), d),
              Operand(ws.y0.data_ptr(), d), out_f32=ws.y0, res=ws.y0, bias=st.pf("decoder.conv.conv.bias"))
         x = ws.y0
+        if ws.tiled:
+            self._reorder(ws.y0, ws.y0p, ws.perm)
+            x = ws.y0p
         for i in range(nD):
             ly = self._layer_ws(ws, nE + i, train)
             y = ly.y if train else (ws.y_alt if x is ly.y else ly.y)
             self._layer_fwd(f"decoder.block_local_attention.{i}.", ws, ly, x, y, causal=True, keep_p=train)
             x = y
+        if ws.tiled:  # the predictor and the loss index tokens in raster order (ws.slice, ws.ignore)
+            self._reorder(x, ws.yf_r, ws.inv)
+            x = ws.yf_r
         ws.y_final = x
         self._ln_fwd(x, st.pf("ch_predictor.layer_norm.weight"), st.pf("ch_predictor.layer_norm.bias"), ws.ln_y,
                      ws.mean_p, ws.rstd_p, M)
@@ -834,10 +869,14 @@ class VTEngine:
                  Operand(st.pb(f"ch_predictor.U.{k}.weight"), ld, mn_major=True),
                  Operand(ws.dln.data_ptr(), d), out_f32=ws.dln, res=ws.dln if k else None)
         self._fold_special_grads_pred()
+        dy, dyb = (ws.tmp_f, ws.tmp_b) if ws.tiled else (ws.dy, ws.dy_bf16)
         self._ln_bwd(ws.dln, ws.y_final, ws.mean_p, ws.rstd_p, st.pf("ch_predictor.layer_norm.weight"), None,
-                     ws.dy, ws.dy_bf16, st.gf("ch_predictor.layer_norm.weight"),
+                     dy, dyb, st.gf("ch_predictor.layer_norm.weight"),
                      st.gf("ch_predictor.layer_norm.bias"), M,
                      dx_colsum=st.gf(f"decoder.block_local_attention.{nD - 1}.ffn.3.bias"))
+        if ws.tiled:  # gradient wrt the decoder stack's output, back in block-major order
+            self._reorder(dy, ws.dy, ws.perm)
+            self._reorder(dyb, ws.dy_bf16, ws.perm)
 
     def _bwd_dec_layers(self, ws: VTWorkspace, top, bot):
         """decoder layers top-1 .. bot"""
@@ -845,7 +884,7 @@ class VTEngine:
         nE = len(self.spec.blocks_e)
         for i in reversed(range(bot, top)):
             ly = ws.layers[nE + i]
-            x = ws.layers[nE + i - 1].y if i > 0 else ws.y0
+            x = ws.layers[nE + i - 1].y if i > 0 else (ws.y0p if ws.tiled else ws.y0)
             # every LayerNorm backward also emits the column sums of its dx: the bias gradient of whatever Linear
             # produced its input (ffn.3 of the layer below, or the masked conv for layer 0)
             below = st.gf(f"decoder.block_local_attention.{i - 1}.ffn.3.bias") if i > 0 else st.gf("decoder.conv.conv.bias")
@@ -860,8 +899,11 @@ class VTEngine:
         t, h, w = ws.slice_shape
         taps, offs, wp, dwp = self._live_taps(ws.slice_shape)
         ntaps = len(taps)
-        dyb = ws.dy_bf16.data_ptr()
-        self._wgrad(dyb, d, ws.zl_bf16.data_ptr(), d, Operand(st.gf("decoder.linear_projector.weight"), d), d, d, M)
+        if ws.tiled:  # dy0 arrives in block-major order; everything below is on the raster grid
+            self._reorder(ws.dy_bf16, ws.tmp_b, ws.inv)
+        dyb = (ws.tmp_b if ws.tiled else ws.dy_bf16).data_ptr()
+        zl = ws.zl_r if ws.tiled else ws.zl_bf16
+        self._wgrad(dyb, d, zl.data_ptr(), d, Operand(st.gf("decoder.linear_projector.weight"), d), d, d, M)
         self._wgrad(dyb, d, ws.A0.data_ptr(), ntaps * de, Operand(dwp.data_ptr(), ntaps * de), d, ntaps * de, M)
         gemm(M, ntaps * de, d, Operand(dyb, d), Operand(wp.data_ptr(), ntaps * de, mn_major=True),
              Operand(ws.dA0.data_ptr(), ntaps * de), out_f32=ws.dA0)
@@ -870,8 +912,12 @@ class VTEngine:
                                             ntaps, stream_ptr()), "lvt_vt_dec_front_bwd")
         # gradient entering the encoder stack: dzl = dy0 Wlp_d
         # (written to the dh buffers: the GEMM may not overwrite its own A operand)
+        dh, dhb = (ws.tmp_f, ws.tmp_b2) if ws.tiled else (ws.dh, ws.dh_bf16)
         gemm(M, d, d, Operand(dyb, d), Operand(st.pb("decoder.linear_projector.weight"), d, mn_major=True),
-             Operand(ws.dh.data_ptr(), d), out_f32=ws.dh, out_bf16=ws.dh_bf16)
+             Operand(dh.data_ptr(), d), out_f32=dh, out_bf16=dhb)
+        if ws.tiled:  # the encoder stack's output is in block-major order
+            self._reorder(dh, ws.dh, ws.perm)
+            self._reorder(dhb, ws.dh_bf16, ws.perm)
         self._fold_special_grads_conv(ws.slice_shape)
 
     def _bwd_enc_layers(self, ws: VTWorkspace, top, bot):
@@ -880,7 +926,7 @@ class VTEngine:
         nE = len(self.spec.blocks_e)
         for i in reversed(range(bot, top)):
             ly = ws.layers[i]
-            x = ws.layers[i - 1].y if i > 0 else ws.x0
+            x = ws.layers[i - 1].y if i > 0 else (ws.x0p if ws.tiled else ws.x0)
             first = i == nE - 1
             below = st.gf(f"encoder.block_local_attention.{i - 1}.ffn.3.bias") if i > 0 else None
             self._layer_bwd(f"encoder.block_local_attention.{i}.", ws, ly, x, ws.dh if first else ws.dy,
@@ -892,7 +938,9 @@ class VTEngine:
         """encoder front: x0 = e0 Wlp_e^T ; e0 = gather-sum + bias + slice_emb"""
         s, st = self.spec, self.store
         M, d, de, nv, nc = ws.M, s.d, s.de, s.nv, s.nc
-        dxb = ws.dy_bf16.data_ptr()
+        if ws.tiled:
+            self._reorder(ws.dy_bf16, ws.tmp_b, ws.inv)
+        dxb = (ws.tmp_b if ws.tiled else ws.dy_bf16).data_ptr()
         self._wgrad(dxb, d, ws.e0.data_ptr(), de, Operand(st.gf("encoder.linear_projector.weight"), de), d, de, M)
         gemm(M, de, d, Operand(dxb, d), Operand(st.pb("encoder.linear_projector.weight"), de, mn_major=True),
              Operand(ws.de0.data_ptr(), de), out_f32=ws.de0, out_bf16=ws.de0_bf16)

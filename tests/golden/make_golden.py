@@ -29,9 +29,10 @@ def load_into(module, weights):
     module.load_state_dict({**sd, **weights}, strict=True)
 
 
-def small_vt_cfg(layers, share_p=False):
+def small_vt_cfg(layers, share_p=False, video_shape=(16, 16, 16)):
     return O.VTConfig(blocks_e=tuple([(1, 16, 16)] * layers), heads_e=tuple([8] * layers),
-                      blocks_d=tuple([(1, 16, 16)] * layers), heads_d=tuple([8] * layers), share_p=share_p)
+                      blocks_d=tuple([(1, 16, 16)] * layers), heads_d=tuple([8] * layers), share_p=share_p,
+                      video_shape=video_shape)
 
 
 def golden_dsfvt():
@@ -40,12 +41,16 @@ def golden_dsfvt():
     ref_shim.install()
     from vidgen.modeling.meta_arch import build_model
     from vidgen.utils.events import EventStorage
-    which = os.environ.get("LVT_GOLDEN_DSFVT", "dsfvt_l2,dsfvt_full,dsfvt_l2_sharep").split(",")
+    which = os.environ.get("LVT_GOLDEN_DSFVT", "dsfvt_l2,dsfvt_full,dsfvt_l2_sharep,dsfvt_l2_tiled").split(",")
     # dsfvt_l2_sharep: MODEL.AUTOREGRESSIVE.VT.SHARE_P True, the reference's config default (config/defaults.py),
     # which every shipped YAML overrides with False
-    for tag, layers, batch, share_p in (("dsfvt_l2", 2, 3, False), ("dsfvt_full", 8, 2, False), ("dsfvt_l2_sharep", 2, 3, True)):
+    # dsfvt_l2_tiled: a 32-frame latent video => slices of (2, 16, 16) over (1, 16, 16) attention blocks: the general
+    # tiled path of BlockLocalAttention.forward (vt_attention.py:189-200), which no shipped config reaches
+    for tag, layers, batch, share_p in (("dsfvt_l2", 2, 3, False), ("dsfvt_full", 8, 2, False), ("dsfvt_l2_sharep", 2, 3, True),
+                                        ("dsfvt_l2_tiled", 2, 2, False)):
         if tag not in which:
             continue
+        vshape = (32, 16, 16) if tag.endswith("tiled") else (16, 16, 16)
         blocks = str(tuple([(1, 16, 16)] * layers))
         heads = str(tuple([8] * layers))
         cfg = ref_shim.reference_cfg("configs/vt/DSFVT.yaml", [
@@ -54,7 +59,7 @@ def golden_dsfvt():
             "MODEL.AUTOREGRESSIVE.VT.SHARE_P", share_p])
         torch.manual_seed(0)
         model = build_model(cfg)
-        ocfg = small_vt_cfg(layers, share_p)
+        ocfg = small_vt_cfg(layers, share_p, vshape)
         weights = O.synth_weights(O.dsfvt_param_shapes(ocfg), seed=1234)
         load_into(model.model, weights)
         model.train()

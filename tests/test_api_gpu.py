@@ -223,6 +223,30 @@ def test_graph_sampler_matches_per_pixel_loop(cuda_lib, tmp_path):
     assert torch.equal(outs[True][:, :, :15], video[:, :, :15].cpu())
 
 
+def test_tiled_attention_sampling_and_loss_surface(cuda_lib, tmp_path):
+    """A 32-frame latent video with the DSFVT network: slices of (2, 16, 16) over (1, 16, 16) attention blocks, i.e.
+    the general tiled path of BlockLocalAttention.forward (vt_attention.py:189-200; parity of the train step is in
+    test_dsfvt_gpu.py).  Through the model surface: the supervised loss is finite, and sample_video falls back to
+    the full decoder pass per position (the K/V-cached row decoder assumes one block per slice), samples valid codes
+    for the last frame and leaves the 31 priming frames untouched; graph replay == eager launches at temperature 1e-10."""
+    from lvt_b200.config.presets import preset
+    from lvt_b200.modeling import build_model
+    cfgv = preset("DSFVT", SMALL + ["TEST.EVALUATORS", "VTSampler", "OUTPUT_DIR", str(tmp_path)])
+    cfgv.freeze()
+    vt = build_model(cfgv)
+    vt.train(False)
+    video = torch.randint(0, 512, (1, 4, 32, 16, 16)).cuda()
+    video[:, :, 31:] = 0
+    outs = {}
+    for graph in (True, "eager"):
+        vt.sampler_graph = graph
+        torch.manual_seed(0)
+        outs[graph] = vt.sample_video(video.clone(), temp=1e-10, n_prime=31).cpu()
+    assert torch.equal(outs[True], outs["eager"])
+    assert torch.equal(outs[True][:, :, :31], video[:, :, :31].cpu())
+    assert int(outs[True].min()) >= 0 and int(outs[True].max()) < 512
+
+
 def test_codes_extractor_round_trip(cuda_lib, tmp_path):
     """VQ-VAE -> latent tree -> loader: batched extraction writes exactly the codes VQVAEModel.encode
     returns, in the reference's on-disk format, and the transformer's loader reads them back."""

@@ -20,10 +20,11 @@ pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-def _cfg(layers, share_p=False):
+def _cfg(layers, share_p=False, video_shape=(16, 16, 16)):
     from oracle import lvt_oracle as O
     return O.VTConfig(blocks_e=tuple([(1, 16, 16)] * layers), heads_e=tuple([8] * layers),
-                      blocks_d=tuple([(1, 16, 16)] * layers), heads_d=tuple([8] * layers), share_p=share_p)
+                      blocks_d=tuple([(1, 16, 16)] * layers), heads_d=tuple([8] * layers), share_p=share_p,
+                      video_shape=video_shape)
 
 
 def _engine(layers, share_p=False):
@@ -37,12 +38,14 @@ def _relerr(a, b):
     return ((a - b).double().norm() / (b.double().norm() + 1e-30)).item()
 
 
-@pytest.mark.parametrize("tag,layers,batch", [("dsfvt_l2", 2, 3), ("dsfvt_full", 8, 2), ("dsfvt_l2_sharep", 2, 3)])
+@pytest.mark.parametrize("tag,layers,batch", [("dsfvt_l2", 2, 3), ("dsfvt_full", 8, 2), ("dsfvt_l2_sharep", 2, 3),
+                                              ("dsfvt_l2_tiled", 2, 2)])
 def test_dsfvt_forward_backward_vs_oracle(cuda_lib, tag, layers, batch):
     from oracle import lvt_oracle as O
     torch.set_num_threads(min(8, os.cpu_count() or 1))
     share_p = tag.endswith("sharep")  # SHARE_P True (the reference's config default): one P, four gradients summed
-    cfg = _cfg(layers, share_p)
+    # tiled: slices of (2, 16, 16) over (1, 16, 16) attention blocks, the general path of BlockLocalAttention.forward
+    cfg = _cfg(layers, share_p, (32, 16, 16) if tag.endswith("tiled") else (16, 16, 16))
     weights = O.synth_weights(O.dsfvt_param_shapes(cfg), seed=1234)
     context, slc, slice_idx, ignore = O.synth_vt_batch(batch, seed=77, cfg=cfg)
 
@@ -79,7 +82,7 @@ def test_dsfvt_forward_backward_vs_oracle(cuda_lib, tag, layers, batch):
         if name == "decoder.conv.conv.weight":  # masked taps: reference reports a gradient for
             g_want = g_want.clone()             # weights it re-zeroes before every use
             g_want[:, :, -1, -1, 1:] = 0
-            g_want[:, :, :2] = 0                # taps that only ever see padding when t == 1
+            g_want[:, :, :max(0, 3 - cfg.slice_shape[0])] = 0   # temporal taps that only ever see padding (t < 3)
             g_got = g_got.clone()
         if name.endswith("_bank") and g_want.shape[1] == 1:
             # (H, 1) bank (t == 1): the true gradient is sum_j dS_ij == 0; only a noise floor remains

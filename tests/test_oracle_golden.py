@@ -126,12 +126,15 @@ def test_vqvae_noema_oracle_matches_reference():
         assert np.allclose(wg[k].grad.double().norm().item(), fix[f"gG:{k}"], rtol=1e-4), k
 
 
-@pytest.mark.parametrize("tag,layers,batch", [("dsfvt_l2", 2, 3), ("dsfvt_full", 8, 2), ("dsfvt_l2_sharep", 2, 3)])
+@pytest.mark.parametrize("tag,layers,batch", [("dsfvt_l2", 2, 3), ("dsfvt_full", 8, 2), ("dsfvt_l2_sharep", 2, 3),
+                                              ("dsfvt_l2_tiled", 2, 2)])
 def test_dsfvt_oracle_matches_reference(tag, layers, batch):
     fix = _load(tag + ".npz")
     cfg = O.VTConfig(blocks_e=tuple([(1, 16, 16)] * layers), heads_e=tuple([8] * layers),
                      blocks_d=tuple([(1, 16, 16)] * layers), heads_d=tuple([8] * layers),
-                     share_p=tag.endswith("sharep"))  # SHARE_P True: the reference's config default
+                     share_p=tag.endswith("sharep"),  # SHARE_P True: the reference's config default
+                     # 32 latent frames: slices of (2, 16, 16) over (1, 16, 16) blocks = the general tiled attention path
+                     video_shape=(32, 16, 16) if tag.endswith("tiled") else (16, 16, 16))
     sd = {k: v.requires_grad_(True) for k, v in O.synth_weights(O.dsfvt_param_shapes(cfg), seed=1234).items()}
     context, slc, slice_idx, ignore = O.synth_vt_batch(batch, seed=77, cfg=cfg)
     assert np.array_equal(slice_idx.numpy(), fix["slice_idx"]) and context.sum().item() == fix["context_sum"]
@@ -148,7 +151,13 @@ def test_dsfvt_oracle_matches_reference(tag, layers, batch):
             g = sd[k].grad
             assert np.allclose(g.double().norm().item(), fix[key], rtol=1e-4), k
             sub = g.reshape(-1)[::max(1, g.numel() // 64)][:64].numpy()
-            assert np.allclose(sub, fix["gsub:" + k], rtol=1e-3, atol=1e-7), k
+            if tag.endswith("tiled"):
+                # this configuration amplifies fp32 rounding: the oracle's own gradients move by 5e-4 (relative L2)
+                # between 1 and 8 CPU threads, the reference's likewise; loss, logits and norms above stay tight
+                want = fix["gsub:" + k]
+                assert np.linalg.norm(sub - want) <= 3e-3 * np.linalg.norm(want) + 1e-12, k
+            else:
+                assert np.allclose(sub, fix["gsub:" + k], rtol=1e-3, atol=1e-7), k
 
 
 @pytest.mark.parametrize("name,kernel,stride,vshape", [("DSSVT", (1, 3, 3), (1, 2, 2), (4, 16, 16)),
