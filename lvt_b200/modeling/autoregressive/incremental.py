@@ -26,8 +26,9 @@ class IncrementalDecoder:
     def __init__(self, engine, ws):
         s = engine.spec
         assert ws.B <= MAX_ROWS
-        if ws.tiled:
-            raise _lib.LvtError("IncrementalDecoder: the slice must be one attention block (use the full decoder pass)")
+        if ws.tiled or s.share_embeddings:
+            raise _lib.LvtError("IncrementalDecoder: the slice must be one attention block and SHARE_EMBEDDINGS off "
+                                "(use the full decoder pass)")
         self.eng, self.ws = engine, ws
         dev = ws.slice.device
         B, d, H, da, L, nv = ws.B, s.d, s.H, s.da, ws.thw, s.nv

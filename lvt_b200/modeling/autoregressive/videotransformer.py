@@ -165,7 +165,9 @@ class VideoTransformer(Autoregressive):
             return ws.slice.view(b, spec.nc, t, h, w).clone()
         if incremental is None:
             incremental = b <= 8  # measured: 0.50 vs 0.61 ms/position at b = 1, break-even near b = 8
-        if ws.tiled:  # slice larger than the attention block: the K/V-cached row decoder assumes one block per slice
+        if ws.tiled or spec.share_embeddings:
+            # slice larger than the attention block (the K/V-cached row decoder assumes one block per slice), or the
+            # two-stage output projection of SHARE_EMBEDDINGS: the full decoder pass per position
             incremental = False
         assert not incremental or b <= MAX_ROWS
         cache = self.__dict__.setdefault("_sample_graphs", {})

@@ -50,8 +50,13 @@ class VTSpec:
         self.heads_e, self.heads_d = tuple(heads_e), tuple(heads_d)
         self.pad_value, self.ignore_index = int(pad_value), int(ignore_index)
         self.share_p = bool(share_p)  # one P for all channels (videotransformer.py:121-123,150-151)
-        if share_embeddings or class_num:
-            raise _lib.LvtError("lvt_b200 implements SHARE_EMBEDDINGS=False, CLASS_NUM=0 (every shipped VT config)")
+        # SHARE_EMBEDDINGS: one P: d -> de for all channels, then the logits against channel k's embedding table
+        # (videotransformer.py:124-125,152-154): logits_k = (P relu(u_k)) E_k^T
+        self.share_embeddings = bool(share_embeddings)
+        if self.share_p and self.share_embeddings:
+            raise _lib.LvtError("SHARE_P and SHARE_EMBEDDINGS together do not make sense (videotransformer.py:122)")
+        if class_num:
+            raise _lib.LvtError("lvt_b200 implements CLASS_NUM=0 (every shipped VT config)")
         heads = set(self.heads_e) | set(self.heads_d)
         if len(heads) != 1:
             raise _lib.LvtError("all attention layers must use the same number of heads")
@@ -104,15 +109,16 @@ class VTSpec:
         for k in range(self.nc):
             s[f"ch_predictor.U.{k}.weight"] = (self.d, self.d + k * self.nv)
             s[f"ch_predictor.U.{k}.bias"] = (self.d,)
-        for k in range(1 if self.share_p else self.nc):
-            s[self.p_name(k) + ".weight"] = (self.nv, self.d)
-            s[self.p_name(k) + ".bias"] = (self.nv,)
+        n_out = self.de if self.share_embeddings else self.nv
+        for k in range(1 if (self.share_p or self.share_embeddings) else self.nc):
+            s[self.p_name(k) + ".weight"] = (n_out, self.d)
+            s[self.p_name(k) + ".bias"] = (n_out,)
         return s
 
     def p_name(self, k):
         """state_dict prefix of channel k's output Linear: `ch_predictor.P` when SHARE_P (one nn.Linear,
         videotransformer.py:121-123), else `ch_predictor.P.<k>` (a ModuleList, :127-130)."""
-        return "ch_predictor.P" if self.share_p else f"ch_predictor.P.{k}"
+        return "ch_predictor.P" if (self.share_p or self.share_embeddings) else f"ch_predictor.P.{k}"
 
 
 class ParamStore:
@@ -238,6 +244,10 @@ class VTWorkspace:
         self.u = e((M, d), f32)
         self.a = e((nc, M, d), bf16)
         self.logits = e((nc, M, nv), f32)
+        if spec.share_embeddings:  # P relu(u_k): kept per channel for the embedding tables' gradient
+            self.pe = e((nc, M, de), bf16)
+            if train:
+                self.dpe = e((M, de), bf16)
         if train:
             self.dlogits = e((nc, M, nv), bf16)
             self.du = e((M, d), bf16)
@@ -784,6 +794,13 @@ class VTEngine:
             check(self.lib.lvt_chpred_combine_fwd(ptr(ws.u), ptr(self.ut[k]) if k else None, ptr(ws.slice),
                                                   ptr(ws.a[k]), M, nc, nv, d, ws.thw, k, stream_ptr()),
                   "lvt_chpred_combine_fwd")
+            if s.share_embeddings:
+                de = s.de
+                gemm(M, de, d, Operand(ws.a[k].data_ptr(), d), Operand(st.pb("ch_predictor.P.weight"), d),
+                     Operand(ws.pe[k].data_ptr(), de), out_bf16=ws.pe[k], bias=st.pf("ch_predictor.P.bias"))
+                gemm(M, nv, de, Operand(ws.pe[k].data_ptr(), de), Operand(st.pb(f"decoder.ch_embedder.{k}.weight"), de),
+                     Operand(ws.logits[k].data_ptr(), nv), out_f32=ws.logits[k])
+                continue
             gemm(M, nv, d, Operand(ws.a[k].data_ptr(), d), Operand(st.pb(s.p_name(k) + ".weight"), d),
                  Operand(ws.logits[k].data_ptr(), nv), out_f32=ws.logits[k], bias=st.pf(s.p_name(k) + ".bias"))
 
@@ -855,11 +872,24 @@ class VTEngine:
         for k in range(nc):
             ld = d + k * nv
             dl = ws.dlogits[k].data_ptr()
-            # (with SHARE_P the four channels add into the same gradient: both kernels accumulate with red.add)
-            self._colsum(dl, st.gf(s.p_name(k) + ".bias"), M, nv)
-            self._wgrad(dl, nv, ws.a[k].data_ptr(), d, Operand(st.gf(s.p_name(k) + ".weight"), d), nv, d, M)
-            gemm(M, d, nv, Operand(dl, nv), Operand(st.pb(s.p_name(k) + ".weight"), d, mn_major=True),
-                 Operand(ws.du.data_ptr(), d), out_bf16=ws.du, aux=ws.a[k], flags=ops.GEMM_MASK)
+            if s.share_embeddings:
+                # logits_k = pe_k E_k^T, pe_k = a_k P^T + b: dE_k += dl^T pe_k (next to what the decoder front adds to the
+                # same table), dpe = dl E_k, dP += dpe^T a_k (all channels into one buffer), da = (dpe P) * [a_k > 0]
+                de = s.de
+                ek = f"decoder.ch_embedder.{k}.weight"
+                self._wgrad(dl, nv, ws.pe[k].data_ptr(), de, Operand(st.gf(ek), de), nv, de, M)
+                gemm(M, de, nv, Operand(dl, nv), Operand(st.pb(ek), de, mn_major=True),
+                     Operand(ws.dpe.data_ptr(), de), out_bf16=ws.dpe)
+                self._colsum(ws.dpe, st.gf("ch_predictor.P.bias"), M, de)
+                self._wgrad(ws.dpe.data_ptr(), de, ws.a[k].data_ptr(), d, Operand(st.gf("ch_predictor.P.weight"), d), de, d, M)
+                gemm(M, d, de, Operand(ws.dpe.data_ptr(), de), Operand(st.pb("ch_predictor.P.weight"), d, mn_major=True),
+                     Operand(ws.du.data_ptr(), d), out_bf16=ws.du, aux=ws.a[k], flags=ops.GEMM_MASK)
+            else:
+                # (with SHARE_P the four channels add into the same gradient: both kernels accumulate with red.add)
+                self._colsum(dl, st.gf(s.p_name(k) + ".bias"), M, nv)
+                self._wgrad(dl, nv, ws.a[k].data_ptr(), d, Operand(st.gf(s.p_name(k) + ".weight"), d), nv, d, M)
+                gemm(M, d, nv, Operand(dl, nv), Operand(st.pb(s.p_name(k) + ".weight"), d, mn_major=True),
+                     Operand(ws.du.data_ptr(), d), out_bf16=ws.du, aux=ws.a[k], flags=ops.GEMM_MASK)
             self._colsum(ws.du, st.gf(f"ch_predictor.U.{k}.bias"), M, d)
             self._wgrad(ws.du.data_ptr(), d, ws.ln_y.data_ptr(), d,
                         Operand(st.gf(f"ch_predictor.U.{k}.weight"), ld), d, d, M)

@@ -42,6 +42,7 @@ class VTConfig:
     ignore_index: int = -100
     video_shape: Tuple[int, int, int] = (16, 16, 16)  # (T, H, W) of the latent video
     share_p: bool = False  # SHARE_P: one output Linear for all channels (videotransformer.py:121-123; every shipped config: False)
+    share_embeddings: bool = False  # SHARE_EMBEDDINGS: P: d -> de, logits against ch_embedder[k] (videotransformer.py:124-125,152-154)
 
     @property
     def slice_shape(self):
@@ -404,8 +405,10 @@ def channel_predictor_logits(slc: Tensor, yl: Tensor, sd, cfg: VTConfig) -> List
     for k in range(cfg.nc):
         inp = y if k == 0 else torch.cat((y, oh[:, :, :k * cfg.nv]), dim=2)
         u = torch.relu(F.linear(inp, sd[f"ch_predictor.U.{k}.weight"], sd[f"ch_predictor.U.{k}.bias"]))
-        pk = "ch_predictor.P" if cfg.share_p else f"ch_predictor.P.{k}"  # videotransformer.py:150-155
+        pk = "ch_predictor.P" if (cfg.share_p or cfg.share_embeddings) else f"ch_predictor.P.{k}"  # videotransformer.py:150-155
         o = F.linear(u, sd[pk + ".weight"], sd[pk + ".bias"])
+        if cfg.share_embeddings:
+            o = F.linear(o, sd[f"decoder.ch_embedder.{k}.weight"])
         outs.append(o.transpose(1, 2).reshape(b, cfg.nv, t, h, w))
     return outs
 
@@ -493,10 +496,11 @@ def dsfvt_param_shapes(cfg: VTConfig) -> Dict[str, Tuple[int, ...]]:
     for k in range(cfg.nc):
         s[f"ch_predictor.U.{k}.weight"] = (cfg.d, cfg.d + k * cfg.nv)
         s[f"ch_predictor.U.{k}.bias"] = (cfg.d,)
-    for k in range(1 if cfg.share_p else cfg.nc):
-        pk = "ch_predictor.P" if cfg.share_p else f"ch_predictor.P.{k}"
-        s[pk + ".weight"] = (cfg.nv, cfg.d)
-        s[pk + ".bias"] = (cfg.nv,)
+    shared = cfg.share_p or cfg.share_embeddings
+    for k in range(1 if shared else cfg.nc):
+        pk = "ch_predictor.P" if shared else f"ch_predictor.P.{k}"
+        s[pk + ".weight"] = (cfg.de if cfg.share_embeddings else cfg.nv, cfg.d)
+        s[pk + ".bias"] = (cfg.de if cfg.share_embeddings else cfg.nv,)
     return s
 
 

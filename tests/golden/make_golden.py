@@ -29,10 +29,10 @@ def load_into(module, weights):
     module.load_state_dict({**sd, **weights}, strict=True)
 
 
-def small_vt_cfg(layers, share_p=False, video_shape=(16, 16, 16)):
+def small_vt_cfg(layers, share_p=False, video_shape=(16, 16, 16), share_embeddings=False):
     return O.VTConfig(blocks_e=tuple([(1, 16, 16)] * layers), heads_e=tuple([8] * layers),
                       blocks_d=tuple([(1, 16, 16)] * layers), heads_d=tuple([8] * layers), share_p=share_p,
-                      video_shape=video_shape)
+                      video_shape=video_shape, share_embeddings=share_embeddings)
 
 
 def golden_dsfvt():
@@ -41,25 +41,26 @@ def golden_dsfvt():
     ref_shim.install()
     from vidgen.modeling.meta_arch import build_model
     from vidgen.utils.events import EventStorage
-    which = os.environ.get("LVT_GOLDEN_DSFVT", "dsfvt_l2,dsfvt_full,dsfvt_l2_sharep,dsfvt_l2_tiled").split(",")
+    which = os.environ.get("LVT_GOLDEN_DSFVT", "dsfvt_l2,dsfvt_full,dsfvt_l2_sharep,dsfvt_l2_tiled,dsfvt_l2_shareemb").split(",")
     # dsfvt_l2_sharep: MODEL.AUTOREGRESSIVE.VT.SHARE_P True, the reference's config default (config/defaults.py),
     # which every shipped YAML overrides with False
     # dsfvt_l2_tiled: a 32-frame latent video => slices of (2, 16, 16) over (1, 16, 16) attention blocks: the general
     # tiled path of BlockLocalAttention.forward (vt_attention.py:189-200), which no shipped config reaches
     for tag, layers, batch, share_p in (("dsfvt_l2", 2, 3, False), ("dsfvt_full", 8, 2, False), ("dsfvt_l2_sharep", 2, 3, True),
-                                        ("dsfvt_l2_tiled", 2, 2, False)):
+                                        ("dsfvt_l2_tiled", 2, 2, False), ("dsfvt_l2_shareemb", 2, 3, False)):
         if tag not in which:
             continue
         vshape = (32, 16, 16) if tag.endswith("tiled") else (16, 16, 16)
+        share_emb = tag.endswith("shareemb")  # SHARE_EMBEDDINGS: P: d -> de, logits against the channel's embedding table
         blocks = str(tuple([(1, 16, 16)] * layers))
         heads = str(tuple([8] * layers))
         cfg = ref_shim.reference_cfg("configs/vt/DSFVT.yaml", [
             "MODEL.AUTOREGRESSIVE.VT.BLOCKS_E", blocks, "MODEL.AUTOREGRESSIVE.VT.N_HEAD_E", heads,
             "MODEL.AUTOREGRESSIVE.VT.BLOCKS_D", blocks, "MODEL.AUTOREGRESSIVE.VT.N_HEAD_D", heads,
-            "MODEL.AUTOREGRESSIVE.VT.SHARE_P", share_p])
+            "MODEL.AUTOREGRESSIVE.VT.SHARE_P", share_p, "MODEL.AUTOREGRESSIVE.VT.SHARE_EMBEDDINGS", share_emb])
         torch.manual_seed(0)
         model = build_model(cfg)
-        ocfg = small_vt_cfg(layers, share_p, vshape)
+        ocfg = small_vt_cfg(layers, share_p, vshape, share_emb)
         weights = O.synth_weights(O.dsfvt_param_shapes(ocfg), seed=1234)
         load_into(model.model, weights)
         model.train()
@@ -79,8 +80,8 @@ def golden_dsfvt():
                "slice_idx": slice_idx.numpy(), "context_sum": context.sum().numpy()}
         for k in ("encoder.conv.weight", "encoder.slice_embedding.weight", "decoder.conv.conv.weight",
                   "decoder.ch_embedder.1.weight", "ch_predictor.U.2.weight",
-                  "ch_predictor.P.bias" if share_p else "ch_predictor.P.3.bias",
-                  "ch_predictor.P.weight" if share_p else "ch_predictor.P.0.weight",
+                  "ch_predictor.P.bias" if (share_p or share_emb) else "ch_predictor.P.3.bias",
+                  "ch_predictor.P.weight" if (share_p or share_emb) else "ch_predictor.P.0.weight",
                   f"decoder.block_local_attention.{layers - 1}.dh_bank",
                   "encoder.block_local_attention.0.mha.w_k", "encoder.block_local_attention.0.ffn.1.weight",
                   "decoder.block_local_attention.0.mha.proj.weight", "decoder.linear_projector.weight"):

@@ -20,17 +20,17 @@ pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-def _cfg(layers, share_p=False, video_shape=(16, 16, 16)):
+def _cfg(layers, share_p=False, video_shape=(16, 16, 16), share_embeddings=False):
     from oracle import lvt_oracle as O
     return O.VTConfig(blocks_e=tuple([(1, 16, 16)] * layers), heads_e=tuple([8] * layers),
                       blocks_d=tuple([(1, 16, 16)] * layers), heads_d=tuple([8] * layers), share_p=share_p,
-                      video_shape=video_shape)
+                      video_shape=video_shape, share_embeddings=share_embeddings)
 
 
-def _engine(layers, share_p=False):
+def _engine(layers, share_p=False, share_embeddings=False):
     from lvt_b200.modeling.autoregressive import VTEngine, VTSpec
     spec = VTSpec(blocks_e=((1, 16, 16),) * layers, heads_e=(8,) * layers, blocks_d=((1, 16, 16),) * layers,
-                  heads_d=(8,) * layers, share_p=share_p)
+                  heads_d=(8,) * layers, share_p=share_p, share_embeddings=share_embeddings)
     return VTEngine(spec)
 
 
@@ -39,17 +39,18 @@ def _relerr(a, b):
 
 
 @pytest.mark.parametrize("tag,layers,batch", [("dsfvt_l2", 2, 3), ("dsfvt_full", 8, 2), ("dsfvt_l2_sharep", 2, 3),
-                                              ("dsfvt_l2_tiled", 2, 2)])
+                                              ("dsfvt_l2_tiled", 2, 2), ("dsfvt_l2_shareemb", 2, 3)])
 def test_dsfvt_forward_backward_vs_oracle(cuda_lib, tag, layers, batch):
     from oracle import lvt_oracle as O
     torch.set_num_threads(min(8, os.cpu_count() or 1))
     share_p = tag.endswith("sharep")  # SHARE_P True (the reference's config default): one P, four gradients summed
     # tiled: slices of (2, 16, 16) over (1, 16, 16) attention blocks, the general path of BlockLocalAttention.forward
-    cfg = _cfg(layers, share_p, (32, 16, 16) if tag.endswith("tiled") else (16, 16, 16))
+    share_emb = tag.endswith("shareemb")  # SHARE_EMBEDDINGS: logits_k = (P relu(u_k)) E_k^T
+    cfg = _cfg(layers, share_p, (32, 16, 16) if tag.endswith("tiled") else (16, 16, 16), share_emb)
     weights = O.synth_weights(O.dsfvt_param_shapes(cfg), seed=1234)
     context, slc, slice_idx, ignore = O.synth_vt_batch(batch, seed=77, cfg=cfg)
 
-    eng = _engine(layers, share_p)
+    eng = _engine(layers, share_p, share_emb)
     eng.load_state_dict(weights)
     ws = eng.workspace(batch, cfg.slice_shape, tuple(context.shape[2:]), train=True)
     eng.set_inputs(ws, context, slc, slice_idx, ignore)

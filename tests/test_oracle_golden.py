@@ -127,12 +127,13 @@ def test_vqvae_noema_oracle_matches_reference():
 
 
 @pytest.mark.parametrize("tag,layers,batch", [("dsfvt_l2", 2, 3), ("dsfvt_full", 8, 2), ("dsfvt_l2_sharep", 2, 3),
-                                              ("dsfvt_l2_tiled", 2, 2)])
+                                              ("dsfvt_l2_tiled", 2, 2), ("dsfvt_l2_shareemb", 2, 3)])
 def test_dsfvt_oracle_matches_reference(tag, layers, batch):
     fix = _load(tag + ".npz")
     cfg = O.VTConfig(blocks_e=tuple([(1, 16, 16)] * layers), heads_e=tuple([8] * layers),
                      blocks_d=tuple([(1, 16, 16)] * layers), heads_d=tuple([8] * layers),
                      share_p=tag.endswith("sharep"),  # SHARE_P True: the reference's config default
+                     share_embeddings=tag.endswith("shareemb"),
                      # 32 latent frames: slices of (2, 16, 16) over (1, 16, 16) blocks = the general tiled attention path
                      video_shape=(32, 16, 16) if tag.endswith("tiled") else (16, 16, 16))
     sd = {k: v.requires_grad_(True) for k, v in O.synth_weights(O.dsfvt_param_shapes(cfg), seed=1234).items()}
