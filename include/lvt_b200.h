@@ -373,6 +373,20 @@ typedef struct LvtPermuteJob {
 } LvtPermuteJob;
 int lvt_permute4_batch(const LvtPermuteJob* jobs, int n_jobs, int total_blocks, void* stream);
 
+/* Class conditioning of VTEncoder (CLASS_NUM > 0; videotransformer.py:29-33,54-57): the class embedding is
+ * concatenated to the de channels of every position before the 1x1x1 projector (weight (d, 2de)), which equals a
+ * per-sample bias.  w2 = &W[0][de] with row stride ldw = 2de, emb [class_num, de], cls int64 [B], all fp32.
+ *   lvt_vt_class_bias       cb[b, :] = W2 emb[cls[b]]                                  (forward)
+ *   lvt_rows_add_group_bias x[r, :] += cb[r / rows_per_group, :]                       (x fp32 [M, d], in place)
+ *   lvt_colsum_groups_bf16  out[g, :] = sum of the rows of group g of x (bf16 [groups*rows, N]) (backward: S)
+ *   lvt_vt_class_grad       dW2 += S^T emb[cls];  demb[cls[b]] += S[b] W2              (backward)            */
+int lvt_vt_class_bias(const float* w2, long long ldw, const float* emb, const int64_t* cls, float* cb, int B, int d,
+                      int de, void* stream);
+int lvt_rows_add_group_bias(float* x, const float* cb, long long M, int d, int rows_per_group, void* stream);
+int lvt_colsum_groups_bf16(const void* x_bf16, float* out, int groups, int rows, int N, void* stream);
+int lvt_vt_class_grad(const float* S, const float* emb, const int64_t* cls, const float* w2, float* dw2, long long ldw,
+                      float* demb, int B, int d, int de, void* stream);
+
 /* Row gather dst[r, :] = src[idx[r], :] (rows of row_bytes bytes, a multiple of 16; idx int32 [M]; src != dst): the
  * token re-ordering of the general tiled BlockLocalAttention.forward (vt_attention.py:189-200: split the slice grid
  * into blocks, attend inside each block, put the tokens back), applied once around a whole stack of layers.        */

@@ -190,6 +190,10 @@ SYMBOLS = {
     "lvt_permute4": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),
     "lvt_permute4_batch": (_i, [_vp, _i, _i, _vp]),
     "lvt_rows_gather": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
+    "lvt_vt_class_bias": (_i, [_vp, _ll, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "lvt_rows_add_group_bias": (_i, [_vp, _vp, _ll, _i, _i, _vp]),
+    "lvt_colsum_groups_bf16": (_i, [_vp, _vp, _i, _i, _i, _vp]),
+    "lvt_vt_class_grad": (_i, [_vp, _vp, _vp, _vp, _vp, _ll, _vp, _i, _i, _i, _vp]),
     "lvt_vq_argmin_nhwc": (_i, [_vp] * 7 + [_i] * 5 + [_vp]),
     "lvt_vq_gather_nhwc": (_i, [_vp] * 4 + [_i] * 5 + [_vp]),
     "lvt_vqvae_in_im2col": (_i, [_vp, _vp, _i, _f, _f, _vp]),

@@ -651,6 +651,79 @@ permute4_kernel(const float* __restrict__ in, void* __restrict__ out, Permute4 P
 
 // Many small re-layout jobs in ONE launch (the per-step weight packs / gradient folds of the engines are 20-70
 // launches of a few microseconds each): block b works on 1024 elements of the job whose block range contains b.
+// Class conditioning of VTEncoder (videotransformer.py:29-33,54-57): the class embedding is concatenated to every
+// position's de channels before the 1x1x1 projector, i.e. each sample gets the extra bias W[:, de:] . E_class[cls].
+// cb[b, o] = sum_i W2[o, i] * emb[cls[b], i]  (W2 = the second de columns of the (d, 2de) projector weight, fp32)
+__global__ void __launch_bounds__(256)
+class_bias_kernel(const float* __restrict__ w2, long long ldw, const float* __restrict__ emb,
+                  const int64_t* __restrict__ cls, float* __restrict__ cb, int B, int d, int de) {
+  const int o = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+  if (o >= d) return;
+  const float* e = emb + (long long)cls[b] * de;
+  const float* w = w2 + (long long)o * ldw;
+  float acc = 0.f;
+  for (int i = 0; i < de; ++i) acc = fmaf(w[i], e[i], acc);
+  cb[(long long)b * d + o] = acc;
+}
+// x[r, :] += cb[r / rows_per_group, :]
+__global__ void __launch_bounds__(256)
+rows_add_group_bias_kernel(float* __restrict__ x, const float* __restrict__ cb, long long M, int d4, int rows_per_group) {
+  const long long total = M * d4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / d4;
+    const int c = (int)(i - r * d4);
+    float4 v = ld4(x + 4 * i);
+    const float4 bvec = ld4(cb + ((r / rows_per_group) * d4 + c) * 4);
+    v.x += bvec.x; v.y += bvec.y; v.z += bvec.z; v.w += bvec.w;
+    st4(x + 4 * i, v);
+  }
+}
+// out[g, c] = sum over the rows of group g of x[g * rows + r, c]  (bf16 in, fp32 out; one block per (64 columns, group))
+__global__ void __launch_bounds__(256)
+colsum_groups_bf16_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, int rows, int N) {
+  __shared__ float s[8][64];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 64 + tx * 2, g = blockIdx.y;
+  float a = 0.f, b = 0.f;
+  if (c < N) {
+    const __nv_bfloat16* xg = x + (size_t)g * rows * N;
+    for (int r = ty; r < rows; r += 8) {
+      const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(xg + (size_t)r * N + c));
+      a += v.x;
+      b += v.y;
+    }
+  }
+  s[ty][tx * 2] = a;
+  s[ty][tx * 2 + 1] = b;
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += s[w][threadIdx.x];
+    const int cc = blockIdx.x * 64 + threadIdx.x;
+    if (cc < N) out[(size_t)g * N + cc] = t;
+  }
+}
+// gradients of the class term from S[b, o] = sum over the sample's positions of d(projector output):
+// dW2[o, i] += sum_b S[b, o] * emb[cls[b], i];  demb[cls[b], i] += sum_o S[b, o] * W2[o, i]
+__global__ void __launch_bounds__(256)
+class_grad_kernel(const float* __restrict__ S, const float* __restrict__ emb, const int64_t* __restrict__ cls,
+                  const float* __restrict__ w2, float* __restrict__ dw2, long long ldw, float* __restrict__ demb,
+                  int B, int d, int de) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < d * de) {  // one (o, i) of dW2
+    const int o = t / de, i = t - o * de;
+    float acc = 0.f;
+    for (int b = 0; b < B; ++b) acc = fmaf(S[(long long)b * d + o], emb[(long long)cls[b] * de + i], acc);
+    dw2[(long long)o * ldw + i] += acc;
+  } else if (t < d * de + B * de) {  // one (b, i) of demb
+    const int u = t - d * de, b = u / de, i = u - b * de;
+    float acc = 0.f;
+    for (int o = 0; o < d; ++o) acc = fmaf(S[(long long)b * d + o], w2[(long long)o * ldw + i], acc);
+    atomicAdd(demb + (long long)cls[b] * de + i, acc);  // several samples may share a class
+  }
+}
+
 // dst[r, :] = src[idx[r], :] for rows of row_bytes (a multiple of 16) bytes: the token re-ordering between raster
 // order of the slice grid and block-major order of the general tiled BlockLocalAttention (vt_attention.py:189-200).
 __global__ void __launch_bounds__(256)
@@ -1050,6 +1123,42 @@ extern "C" int lvt_rows_gather(const void* src, void* dst, const int* idx, int M
   const int vec = row_bytes / 16;
   LVT_CHECK_CUDA(lvt_launch(rows_gather_kernel, dim3(flat_grid((long long)M * vec)), dim3(256), 0, STREAM(stream),
                             reinterpret_cast<const uint4*>(src), reinterpret_cast<uint4*>(dst), idx, M, vec));
+  LVT_CHECK_LAUNCH();
+  lvt_count_launch(1);
+  return LVT_OK;
+}
+
+extern "C" int lvt_vt_class_bias(const float* w2, long long ldw, const float* emb, const int64_t* cls, float* cb, int B,
+                                 int d, int de, void* stream) {
+  LVT_CHECK_ARG(w2 && emb && cls && cb && B > 0 && d > 0 && de > 0, "lvt_vt_class_bias: bad argument");
+  class_bias_kernel<<<dim3(lvt_ceil_div(d, 256), B), 256, 0, STREAM(stream)>>>(w2, ldw, emb, cls, cb, B, d, de);
+  LVT_CHECK_LAUNCH();
+  lvt_count_launch(1);
+  return LVT_OK;
+}
+
+extern "C" int lvt_rows_add_group_bias(float* x, const float* cb, long long M, int d, int rows_per_group, void* stream) {
+  LVT_CHECK_ARG(x && cb && M > 0 && d % 4 == 0 && rows_per_group > 0 && M % rows_per_group == 0,
+                "lvt_rows_add_group_bias: bad argument");
+  rows_add_group_bias_kernel<<<flat_grid(M * (d / 4)), 256, 0, STREAM(stream)>>>(x, cb, M, d / 4, rows_per_group);
+  LVT_CHECK_LAUNCH();
+  lvt_count_launch(1);
+  return LVT_OK;
+}
+
+extern "C" int lvt_colsum_groups_bf16(const void* x, float* out, int groups, int rows, int N, void* stream) {
+  LVT_CHECK_ARG(x && out && groups > 0 && rows > 0 && N > 0 && N % 2 == 0, "lvt_colsum_groups_bf16: bad argument");
+  colsum_groups_bf16_kernel<<<dim3(lvt_ceil_div(N, 64), groups), 256, 0, STREAM(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), out, rows, N);
+  LVT_CHECK_LAUNCH();
+  lvt_count_launch(1);
+  return LVT_OK;
+}
+
+extern "C" int lvt_vt_class_grad(const float* S, const float* emb, const int64_t* cls, const float* w2, float* dw2,
+                                 long long ldw, float* demb, int B, int d, int de, void* stream) {
+  LVT_CHECK_ARG(S && emb && cls && w2 && dw2 && demb && B > 0 && d > 0 && de > 0, "lvt_vt_class_grad: bad argument");
+  class_grad_kernel<<<lvt_ceil_div(d * de + B * de, 256), 256, 0, STREAM(stream)>>>(S, emb, cls, w2, dw2, ldw, demb, B, d, de);
   LVT_CHECK_LAUNCH();
   lvt_count_launch(1);
   return LVT_OK;

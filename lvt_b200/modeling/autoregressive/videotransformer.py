@@ -105,11 +105,11 @@ class VideoTransformer(Autoregressive):
         self.engine.shadows_fresh = False
         return out
 
-    def _stage(self, context, slc, slice_idx, ignore_mask, train):
+    def _stage(self, context, slc, slice_idx, ignore_mask, train, class_idx=None):
         eng = self.engine
         B = context.shape[0]
         ws = eng.workspace(B, tuple(slc.shape[2:]), tuple(context.shape[2:]), train=train)
-        eng.set_inputs(ws, context, slc, slice_idx, ignore_mask)
+        eng.set_inputs(ws, context, slc, slice_idx, ignore_mask, class_idx=class_idx)
         return ws
 
     def forward(self, context, slice, slice_idx, mode="logits", pixel=None, zl=None, temp=1.0, drop_mask=None,
@@ -120,12 +120,12 @@ class VideoTransformer(Autoregressive):
         b = context.shape[0]
         t, h, w = slice.shape[2:]
         if mode == "logits":
-            ws = self._stage(context, slice, slice_idx, None, train=False)
+            ws = self._stage(context, slice, slice_idx, None, train=False, class_idx=class_idx)
             eng.forward(ws, train=False, want_loss=False)
             lg = ws.logits.view(spec.nc, b, t, h, w, spec.nv)
             return [lg[k].permute(0, 4, 1, 2, 3).contiguous() for k in range(spec.nc)]
         if mode == "sample_pixel":
-            ws = self._stage(context, slice, slice_idx, None, train=False)
+            ws = self._stage(context, slice, slice_idx, None, train=False, class_idx=class_idx)
             if zl is None:
                 eng.encoder_forward(ws, train=False)  # cached across the pixels of one slice, like `zl`
                 zl = ws
@@ -144,7 +144,8 @@ class VideoTransformer(Autoregressive):
         raise ValueError("|mode| is invalid")
 
     @torch.no_grad()
-    def sample_slice(self, context, slice, slice_idx, prime_mask=None, temp=1.0, use_graph=True, incremental=None):
+    def sample_slice(self, context, slice, slice_idx, prime_mask=None, temp=1.0, use_graph=True, incremental=None,
+                     class_idx=None):
         """Every non-primed position of one slice in raster order — the inner loops of
         VideoTransformerModel.sample_video (meta_arch/vt.py:107-134) around mode "sample_pixel"
         (videotransformer.py:161-185, 240-246): encoder once per slice, then per position the masked decoder and the
@@ -157,7 +158,7 @@ class VideoTransformer(Autoregressive):
         b = context.shape[0]
         t, h, w = slice.shape[2:]
         thw = t * h * w
-        ws = self._stage(context, slice, slice_idx, None, train=False)
+        ws = self._stage(context, slice, slice_idx, None, train=False, class_idx=class_idx)
         eng.encoder_forward(ws, train=False)
         primed = torch.zeros(thw, dtype=torch.bool) if prime_mask is None else prime_mask.reshape(-1).cpu()
         todo = [p for p in range(thw) if not bool(primed[p])]

@@ -55,8 +55,9 @@ class VTSpec:
         self.share_embeddings = bool(share_embeddings)
         if self.share_p and self.share_embeddings:
             raise _lib.LvtError("SHARE_P and SHARE_EMBEDDINGS together do not make sense (videotransformer.py:122)")
-        if class_num:
-            raise _lib.LvtError("lvt_b200 implements CLASS_NUM=0 (every shipped VT config)")
+        # CLASS_NUM > 0: a class embedding concatenated to every position before the encoder's projector
+        # (videotransformer.py:29-33,54-57) = a per-sample bias W[:, de:] . E_class[class]
+        self.class_num = int(class_num)
         heads = set(self.heads_e) | set(self.heads_d)
         if len(heads) != 1:
             raise _lib.LvtError("all attention layers must use the same number of heads")
@@ -76,7 +77,9 @@ class VTSpec:
         s["encoder.conv.weight"] = (self.de, self.nc * self.nv, kt, kh, kw)
         s["encoder.conv.bias"] = (self.de,)
         s["encoder.slice_embedding.weight"] = (self.stride[0] * self.stride[1] * self.stride[2], self.de)
-        s["encoder.linear_projector.weight"] = (self.d, self.de, 1, 1, 1)
+        if self.class_num:
+            s["encoder.class_embedding.weight"] = (self.class_num, self.de)
+        s["encoder.linear_projector.weight"] = (self.d, self.de * (2 if self.class_num else 1), 1, 1, 1)
 
         def bla(prefix):
             t, h, w = self.block
@@ -193,6 +196,10 @@ class VTWorkspace:
         self.context = torch.zeros((B, nc) + self.ctx_shape, dtype=torch.int64, device=device)
         self.slice = torch.zeros((B, nc) + self.slice_shape, dtype=torch.int64, device=device)
         self.slice_idx = torch.zeros((B,), dtype=torch.int64, device=device)
+        if spec.class_num:
+            self.class_idx = torch.zeros((B,), dtype=torch.int64, device=device)
+            self.cbias = torch.zeros((B, spec.d), dtype=f32, device=device)   # W[:, de:] . E_class[class] per sample
+            self.csum = torch.zeros((B, spec.d), dtype=f32, device=device)    # per-sample column sums of d(projector output)
         self.ignore = torch.zeros((B, thw), dtype=torch.uint8, device=device)
         self.loss = torch.zeros((1,), dtype=f32, device=device)
         self.count = torch.zeros((1,), dtype=torch.int32, device=device)
@@ -664,8 +671,12 @@ class VTEngine:
              alpha=scale)
 
     # ------------------------------------------------------------------ whole network
-    def set_inputs(self, ws: VTWorkspace, context, slc, slice_idx, ignore_mask=None):
+    def set_inputs(self, ws: VTWorkspace, context, slc, slice_idx, ignore_mask=None, class_idx=None):
         """Stage one batch into the static input buffers (H2D copies when given host tensors)."""
+        if self.spec.class_num:
+            if class_idx is None:
+                raise _lib.LvtError("CLASS_NUM > 0: class_idx (b,) is required (videotransformer.py:54-57)")
+            ws.class_idx.copy_(torch.as_tensor(class_idx).reshape(-1), non_blocking=True)
         ws.context.copy_(context.reshape(ws.context.shape), non_blocking=True)
         ws.slice.copy_(slc.reshape(ws.slice.shape), non_blocking=True)
         ws.slice_idx.copy_(slice_idx.reshape(-1), non_blocking=True)
@@ -734,8 +745,15 @@ class VTEngine:
                                             _vp(st.pf("encoder.slice_embedding.weight")), ptr(ws.e0), ws.B, nc, nv,
                                             de, _i3(ws.ctx_shape), _i3(s.kernel), _i3(s.stride), s.pad_value,
                                             stream_ptr()), "lvt_vt_enc_front_fwd")
-        gemm(M, d, de, Operand(ws.e0.data_ptr(), de), Operand(st.pb("encoder.linear_projector.weight"), de),
+        ldw = de * (2 if s.class_num else 1)   # with classes the projector weight is (d, 2de): [W1 | W2]
+        gemm(M, d, de, Operand(ws.e0.data_ptr(), de), Operand(st.pb("encoder.linear_projector.weight"), ldw),
              Operand(ws.x0.data_ptr(), d), out_f32=ws.x0)
+        if s.class_num:
+            w2 = ctypes.c_void_p(st.pf("encoder.linear_projector.weight") + 4 * de)
+            check(self.lib.lvt_vt_class_bias(w2, ldw, _vp(st.pf("encoder.class_embedding.weight")), ptr(ws.class_idx),
+                                             ptr(ws.cbias), ws.B, d, de, stream_ptr()), "lvt_vt_class_bias")
+            check(self.lib.lvt_rows_add_group_bias(ptr(ws.x0), ptr(ws.cbias), M, d, ws.thw, stream_ptr()),
+                  "lvt_rows_add_group_bias")
         x = ws.x0
         if ws.tiled:
             self._reorder(ws.x0, ws.x0p, ws.perm)
@@ -971,8 +989,18 @@ class VTEngine:
         if ws.tiled:
             self._reorder(ws.dy_bf16, ws.tmp_b, ws.inv)
         dxb = (ws.tmp_b if ws.tiled else ws.dy_bf16).data_ptr()
-        self._wgrad(dxb, d, ws.e0.data_ptr(), de, Operand(st.gf("encoder.linear_projector.weight"), de), d, de, M)
-        gemm(M, de, d, Operand(dxb, d), Operand(st.pb("encoder.linear_projector.weight"), de, mn_major=True),
+        ldw = de * (2 if s.class_num else 1)
+        self._wgrad(dxb, d, ws.e0.data_ptr(), de, Operand(st.gf("encoder.linear_projector.weight"), ldw), d, de, M)
+        if s.class_num:  # the class term: per-sample column sums of dx0, then two tiny contractions
+            w2 = ctypes.c_void_p(st.pf("encoder.linear_projector.weight") + 4 * de)
+            dw2 = ctypes.c_void_p(st.gf("encoder.linear_projector.weight") + 4 * de)
+            check(self.lib.lvt_colsum_groups_bf16(ctypes.c_void_p(dxb), ptr(ws.csum), ws.B, ws.thw, d, stream_ptr()),
+                  "lvt_colsum_groups_bf16")
+            check(self.lib.lvt_vt_class_grad(ptr(ws.csum), _vp(st.pf("encoder.class_embedding.weight")),
+                                             ptr(ws.class_idx), w2, dw2, ldw,
+                                             _vp(st.gf("encoder.class_embedding.weight")), ws.B, d, de, stream_ptr()),
+                  "lvt_vt_class_grad")
+        gemm(M, de, d, Operand(dxb, d), Operand(st.pb("encoder.linear_projector.weight"), ldw, mn_major=True),
              Operand(ws.de0.data_ptr(), de), out_f32=ws.de0, out_bf16=ws.de0_bf16)
         self._colsum(ws.de0_bf16, st.gf("encoder.conv.bias"), M, de)
         check(self.lib.lvt_vt_enc_front_bwd(ptr(ws.context), ptr(ws.slice_idx), ptr(ws.de0), ptr(self.enc_dwt),

@@ -174,7 +174,7 @@ class VideoTransformerModel(nn.Module):
         """vt.py:301-314: mean over channels of CE(pred_k, target_k), ignore_index = MODEL.IGNORE_INDEX."""
         eng = self.model.engine
         ws = eng.workspace(context.shape[0], tuple(slc.shape[2:]), tuple(context.shape[2:]), train=True)
-        eng.set_inputs(ws, context, slc, slice_idx, ignore_mask)
+        eng.set_inputs(ws, context, slc, slice_idx, ignore_mask, class_idx=class_idx)
         if self._graphed:
             return {"loss_cross_entropy": _GraphedSupervisedLoss.apply(self._anchor, eng, ws, self._graph_for(eng, ws))}
         return {"loss_cross_entropy": _SupervisedLoss.apply(self._anchor, eng, ws)}
@@ -233,7 +233,8 @@ class VideoTransformerModel(nn.Module):
                 # same loops, one CUDA-graph replay per position (VideoTransformer.sample_slice)
                 slc = self.model.sample_slice(context, slc, sidx, prime_slice, temp=temp,
                                               use_graph=self.sampler_graph != "eager",
-                                              incremental=getattr(self.model, "sample_incremental", None))
+                                              incremental=getattr(self.model, "sample_incremental", None),
+                                              class_idx=class_idx)
             else:
                 zl = None
                 for ti in range(t):

@@ -43,6 +43,7 @@ class VTConfig:
     video_shape: Tuple[int, int, int] = (16, 16, 16)  # (T, H, W) of the latent video
     share_p: bool = False  # SHARE_P: one output Linear for all channels (videotransformer.py:121-123; every shipped config: False)
     share_embeddings: bool = False  # SHARE_EMBEDDINGS: P: d -> de, logits against ch_embedder[k] (videotransformer.py:124-125,152-154)
+    class_num: int = 0  # CLASS_NUM: class embedding concatenated before the encoder's projector (videotransformer.py:29-33,54-57)
 
     @property
     def slice_shape(self):
@@ -354,7 +355,7 @@ def _sub(sd, prefix):
     return {k[n:]: v for k, v in sd.items() if k.startswith(prefix)}
 
 
-def vt_encoder(context: Tensor, slice_idx: Tensor, sd, cfg: VTConfig) -> Tensor:
+def vt_encoder(context: Tensor, slice_idx: Tensor, sd, cfg: VTConfig, class_idx: Tensor = None) -> Tensor:
     """VTEncoder.forward (videotransformer.py:35-59). context (b, nc, Tc, Hc, Wc) int64 with
     pad_value entries; the one-hot of a padded entry is all-zero (:41-48).  positional_encoder
     exists but is never applied (:18)."""
@@ -364,6 +365,8 @@ def vt_encoder(context: Tensor, slice_idx: Tensor, sd, cfg: VTConfig) -> Tensor:
     xin = oh.permute(0, 1, 5, 2, 3, 4).reshape(b, nc * nv, Tc, Hc, Wc).float()
     x = F.conv3d(xin, sd["encoder.conv.weight"], sd["encoder.conv.bias"], stride=tuple(cfg.stride))
     x = x + sd["encoder.slice_embedding.weight"][slice_idx][:, :, None, None, None]
+    if cfg.class_num > 0 and class_idx is not None:  # videotransformer.py:54-57
+        x = torch.cat([x, sd["encoder.class_embedding.weight"][class_idx][:, :, None, None, None].expand_as(x)], dim=1)
     x = F.conv3d(x, sd["encoder.linear_projector.weight"])
     for i, blk in enumerate(cfg.blocks_e):
         x = block_local_attention(x, _sub(sd, f"encoder.block_local_attention.{i}."), blk, causal=False)
@@ -413,16 +416,16 @@ def channel_predictor_logits(slc: Tensor, yl: Tensor, sd, cfg: VTConfig) -> List
     return outs
 
 
-def vt_logits(context, slc, slice_idx, sd, cfg: VTConfig) -> List[Tensor]:
+def vt_logits(context, slc, slice_idx, sd, cfg: VTConfig, class_idx=None) -> List[Tensor]:
     """VideoTransformer.forward(mode="logits") (videotransformer.py:232-239)."""
-    zl = vt_encoder(context, slice_idx, sd, cfg)
+    zl = vt_encoder(context, slice_idx, sd, cfg, class_idx)
     return channel_predictor_logits(slc, vt_decoder(slc, zl, sd, cfg), sd, cfg)
 
 
-def vt_supervised_loss(context, slc, slice_idx, ignore_mask, sd, cfg: VTConfig) -> Tensor:
+def vt_supervised_loss(context, slc, slice_idx, ignore_mask, sd, cfg: VTConfig, class_idx=None) -> Tensor:
     """VideoTransformerModel.compute_supervised_loss (meta_arch/vt.py:301-314)."""
     target = slc.masked_fill(ignore_mask, cfg.ignore_index)
-    pred = vt_logits(context, slc, slice_idx, sd, cfg)
+    pred = vt_logits(context, slc, slice_idx, sd, cfg, class_idx)
     loss = sum(F.cross_entropy(pred[k], target[:, k], ignore_index=cfg.ignore_index) for k in range(cfg.nc))
     return loss / cfg.nc
 
@@ -463,7 +466,9 @@ def dsfvt_param_shapes(cfg: VTConfig) -> Dict[str, Tuple[int, ...]]:
     s["encoder.conv.weight"] = (cfg.de, cfg.nc * cfg.nv, kt, kh, kw)
     s["encoder.conv.bias"] = (cfg.de,)
     s["encoder.slice_embedding.weight"] = (cfg.stride[0] * cfg.stride[1] * cfg.stride[2], cfg.de)
-    s["encoder.linear_projector.weight"] = (cfg.d, cfg.de, 1, 1, 1)
+    if cfg.class_num:
+        s["encoder.class_embedding.weight"] = (cfg.class_num, cfg.de)
+    s["encoder.linear_projector.weight"] = (cfg.d, cfg.de * (2 if cfg.class_num else 1), 1, 1, 1)
 
     def bla(prefix, block, heads):
         t, h, w = block

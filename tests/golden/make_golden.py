@@ -29,10 +29,10 @@ def load_into(module, weights):
     module.load_state_dict({**sd, **weights}, strict=True)
 
 
-def small_vt_cfg(layers, share_p=False, video_shape=(16, 16, 16), share_embeddings=False):
+def small_vt_cfg(layers, share_p=False, video_shape=(16, 16, 16), share_embeddings=False, class_num=0):
     return O.VTConfig(blocks_e=tuple([(1, 16, 16)] * layers), heads_e=tuple([8] * layers),
                       blocks_d=tuple([(1, 16, 16)] * layers), heads_d=tuple([8] * layers), share_p=share_p,
-                      video_shape=video_shape, share_embeddings=share_embeddings)
+                      video_shape=video_shape, share_embeddings=share_embeddings, class_num=class_num)
 
 
 def golden_dsfvt():
@@ -41,44 +41,53 @@ def golden_dsfvt():
     ref_shim.install()
     from vidgen.modeling.meta_arch import build_model
     from vidgen.utils.events import EventStorage
-    which = os.environ.get("LVT_GOLDEN_DSFVT", "dsfvt_l2,dsfvt_full,dsfvt_l2_sharep,dsfvt_l2_tiled,dsfvt_l2_shareemb").split(",")
+    which = os.environ.get("LVT_GOLDEN_DSFVT", "dsfvt_l2,dsfvt_full,dsfvt_l2_sharep,dsfvt_l2_tiled,dsfvt_l2_shareemb,dsfvt_l2_class").split(",")
     # dsfvt_l2_sharep: MODEL.AUTOREGRESSIVE.VT.SHARE_P True, the reference's config default (config/defaults.py),
     # which every shipped YAML overrides with False
     # dsfvt_l2_tiled: a 32-frame latent video => slices of (2, 16, 16) over (1, 16, 16) attention blocks: the general
     # tiled path of BlockLocalAttention.forward (vt_attention.py:189-200), which no shipped config reaches
     for tag, layers, batch, share_p in (("dsfvt_l2", 2, 3, False), ("dsfvt_full", 8, 2, False), ("dsfvt_l2_sharep", 2, 3, True),
-                                        ("dsfvt_l2_tiled", 2, 2, False), ("dsfvt_l2_shareemb", 2, 3, False)):
+                                        ("dsfvt_l2_tiled", 2, 2, False), ("dsfvt_l2_shareemb", 2, 3, False),
+                                        ("dsfvt_l2_class", 2, 4, False)):
         if tag not in which:
             continue
         vshape = (32, 16, 16) if tag.endswith("tiled") else (16, 16, 16)
         share_emb = tag.endswith("shareemb")  # SHARE_EMBEDDINGS: P: d -> de, logits against the channel's embedding table
+        class_num = 5 if tag.endswith("class") else 0  # CLASS_NUM: class-conditioned encoder (two samples share a class)
         blocks = str(tuple([(1, 16, 16)] * layers))
         heads = str(tuple([8] * layers))
         cfg = ref_shim.reference_cfg("configs/vt/DSFVT.yaml", [
             "MODEL.AUTOREGRESSIVE.VT.BLOCKS_E", blocks, "MODEL.AUTOREGRESSIVE.VT.N_HEAD_E", heads,
             "MODEL.AUTOREGRESSIVE.VT.BLOCKS_D", blocks, "MODEL.AUTOREGRESSIVE.VT.N_HEAD_D", heads,
-            "MODEL.AUTOREGRESSIVE.VT.SHARE_P", share_p, "MODEL.AUTOREGRESSIVE.VT.SHARE_EMBEDDINGS", share_emb])
+            "MODEL.AUTOREGRESSIVE.VT.SHARE_P", share_p, "MODEL.AUTOREGRESSIVE.VT.SHARE_EMBEDDINGS", share_emb,
+            "MODEL.AUTOREGRESSIVE.VT.CLASS_NUM", class_num])
         torch.manual_seed(0)
         model = build_model(cfg)
-        ocfg = small_vt_cfg(layers, share_p, vshape, share_emb)
+        ocfg = small_vt_cfg(layers, share_p, vshape, share_emb, class_num)
         weights = O.synth_weights(O.dsfvt_param_shapes(ocfg), seed=1234)
         load_into(model.model, weights)
         model.train()
         context, slc, slice_idx, ignore = O.synth_vt_batch(batch, seed=77, cfg=ocfg)
         data = [{"context": context[i], "slice": slc[i], "slice_idx": slice_idx[i], "ignore_mask": ignore[i]}
                 for i in range(batch)]
+        class_idx = None
+        if class_num:
+            class_idx = torch.tensor([3, 0, 3, 4][:batch])
+            for i in range(batch):
+                data[i]["class"] = class_idx[i]
         with EventStorage(0):
             loss = model(data, mode="supervised")["loss_cross_entropy"]
         loss.backward()
         with torch.no_grad():
-            logits = model.model(context, slc, slice_idx)  # list nc x (b, nv, t, h, w)
+            logits = model.model(context, slc, slice_idx, class_idx=class_idx)  # list nc x (b, nv, t, h, w)
         grads = {k: p.grad for k, p in model.model.named_parameters()}
         # the reference's own data path must agree with the oracle's restatement of the mapper
         fix = {"loss": loss.detach().numpy(),
                "logits_sub": torch.stack(logits)[:, :, ::7, 0, ::3, ::5].numpy(),
                "logits_sum": torch.stack(logits).double().sum().numpy(),
                "slice_idx": slice_idx.numpy(), "context_sum": context.sum().numpy()}
-        for k in ("encoder.conv.weight", "encoder.slice_embedding.weight", "decoder.conv.conv.weight",
+        for k in (("encoder.class_embedding.weight", "encoder.linear_projector.weight") if class_num else ()) + \
+                 ("encoder.conv.weight", "encoder.slice_embedding.weight", "decoder.conv.conv.weight",
                   "decoder.ch_embedder.1.weight", "ch_predictor.U.2.weight",
                   "ch_predictor.P.bias" if (share_p or share_emb) else "ch_predictor.P.3.bias",
                   "ch_predictor.P.weight" if (share_p or share_emb) else "ch_predictor.P.0.weight",

@@ -247,6 +247,40 @@ def test_tiled_attention_sampling_and_loss_surface(cuda_lib, tmp_path):
     assert int(outs[True].min()) >= 0 and int(outs[True].max()) < 512
 
 
+def test_class_conditioned_model_surface(cuda_lib, tmp_path):
+    """MODEL.AUTOREGRESSIVE.VT.CLASS_NUM > 0 through the model surface (videotransformer.py:29-33,54-57, meta_arch/vt.py:
+    284-299): the "class" entry of the data dicts reaches the encoder, its embedding gets a gradient, the logits
+    depend on the class, and a batch without classes is refused like the reference's shape error."""
+    from lvt_b200 import _lib
+    from lvt_b200.config.presets import preset
+    from lvt_b200.modeling import build_model
+    from lvt_b200.utils.events import EventStorage
+    from oracle import lvt_oracle as O
+    cfgv = preset("DSFVT", SMALL + ["MODEL.AUTOREGRESSIVE.VT.CLASS_NUM", 3, "OUTPUT_DIR", str(tmp_path)])
+    cfgv.freeze()
+    vt = build_model(cfgv)
+    sd = vt.model.state_dict()
+    assert tuple(sd["encoder.class_embedding.weight"].shape) == (3, 128)
+    assert tuple(sd["encoder.linear_projector.weight"].shape) == (512, 256, 1, 1, 1)
+    ocfg = O.VTConfig(blocks_e=((1, 16, 16),) * 2, heads_e=(8, 8), blocks_d=((1, 16, 16),) * 2, heads_d=(8, 8))
+    context, slc, slice_idx, ignore = O.synth_vt_batch(2, seed=5, cfg=ocfg)
+    data = [{"context": context[i], "slice": slc[i], "slice_idx": slice_idx[i], "ignore_mask": ignore[i],
+             "class": torch.tensor(i + 1)} for i in range(2)]
+    vt.train(True)
+    with EventStorage(0):
+        loss = vt(data, mode="supervised")["loss_cross_entropy"]
+        loss.backward()
+    g = vt.model.engine.store.g["encoder.class_embedding.weight"]
+    assert torch.isfinite(loss) and g[0].abs().sum().item() == 0 and g[1].abs().sum().item() > 0 and g[2].abs().sum().item() > 0
+    vt.train(False)
+    with torch.no_grad():
+        a = torch.stack(vt.model(context.cuda(), slc.cuda(), slice_idx.cuda(), class_idx=torch.tensor([0, 0]).cuda()))
+        b = torch.stack(vt.model(context.cuda(), slc.cuda(), slice_idx.cuda(), class_idx=torch.tensor([0, 2]).cuda()))
+    assert torch.equal(a[:, 0], b[:, 0]) and not torch.equal(a[:, 1], b[:, 1])
+    with pytest.raises(_lib.LvtError):
+        vt.model(context.cuda(), slc.cuda(), slice_idx.cuda())
+
+
 def test_codes_extractor_round_trip(cuda_lib, tmp_path):
     """VQ-VAE -> latent tree -> loader: batched extraction writes exactly the codes VQVAEModel.encode
     returns, in the reference's on-disk format, and the transformer's loader reads them back."""

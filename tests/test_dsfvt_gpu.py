@@ -20,17 +20,17 @@ pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-def _cfg(layers, share_p=False, video_shape=(16, 16, 16), share_embeddings=False):
+def _cfg(layers, share_p=False, video_shape=(16, 16, 16), share_embeddings=False, class_num=0):
     from oracle import lvt_oracle as O
     return O.VTConfig(blocks_e=tuple([(1, 16, 16)] * layers), heads_e=tuple([8] * layers),
                       blocks_d=tuple([(1, 16, 16)] * layers), heads_d=tuple([8] * layers), share_p=share_p,
-                      video_shape=video_shape, share_embeddings=share_embeddings)
+                      video_shape=video_shape, share_embeddings=share_embeddings, class_num=class_num)
 
 
-def _engine(layers, share_p=False, share_embeddings=False):
+def _engine(layers, share_p=False, share_embeddings=False, class_num=0):
     from lvt_b200.modeling.autoregressive import VTEngine, VTSpec
     spec = VTSpec(blocks_e=((1, 16, 16),) * layers, heads_e=(8,) * layers, blocks_d=((1, 16, 16),) * layers,
-                  heads_d=(8,) * layers, share_p=share_p, share_embeddings=share_embeddings)
+                  heads_d=(8,) * layers, share_p=share_p, share_embeddings=share_embeddings, class_num=class_num)
     return VTEngine(spec)
 
 
@@ -39,21 +39,24 @@ def _relerr(a, b):
 
 
 @pytest.mark.parametrize("tag,layers,batch", [("dsfvt_l2", 2, 3), ("dsfvt_full", 8, 2), ("dsfvt_l2_sharep", 2, 3),
-                                              ("dsfvt_l2_tiled", 2, 2), ("dsfvt_l2_shareemb", 2, 3)])
+                                              ("dsfvt_l2_tiled", 2, 2), ("dsfvt_l2_shareemb", 2, 3),
+                                              ("dsfvt_l2_class", 2, 4)])
 def test_dsfvt_forward_backward_vs_oracle(cuda_lib, tag, layers, batch):
     from oracle import lvt_oracle as O
     torch.set_num_threads(min(8, os.cpu_count() or 1))
     share_p = tag.endswith("sharep")  # SHARE_P True (the reference's config default): one P, four gradients summed
     # tiled: slices of (2, 16, 16) over (1, 16, 16) attention blocks, the general path of BlockLocalAttention.forward
     share_emb = tag.endswith("shareemb")  # SHARE_EMBEDDINGS: logits_k = (P relu(u_k)) E_k^T
-    cfg = _cfg(layers, share_p, (32, 16, 16) if tag.endswith("tiled") else (16, 16, 16), share_emb)
+    class_num = 5 if tag.endswith("class") else 0   # CLASS_NUM: class embedding concatenated before the encoder projector
+    class_idx = torch.tensor([3, 0, 3, 4][:batch]) if class_num else None   # two samples share class 3
+    cfg = _cfg(layers, share_p, (32, 16, 16) if tag.endswith("tiled") else (16, 16, 16), share_emb, class_num)
     weights = O.synth_weights(O.dsfvt_param_shapes(cfg), seed=1234)
     context, slc, slice_idx, ignore = O.synth_vt_batch(batch, seed=77, cfg=cfg)
 
-    eng = _engine(layers, share_p, share_emb)
+    eng = _engine(layers, share_p, share_emb, class_num)
     eng.load_state_dict(weights)
     ws = eng.workspace(batch, cfg.slice_shape, tuple(context.shape[2:]), train=True)
-    eng.set_inputs(ws, context, slc, slice_idx, ignore)
+    eng.set_inputs(ws, context, slc, slice_idx, ignore, class_idx=class_idx)
     eng.zero_grad()
     loss = eng.forward(ws, train=True)
     eng.backward(ws)
@@ -63,10 +66,10 @@ def test_dsfvt_forward_backward_vs_oracle(cuda_lib, tag, layers, batch):
 
     # oracle (CPU fp32)
     sd = {k: v.clone().requires_grad_(True) for k, v in weights.items()}
-    want_loss = O.vt_supervised_loss(context, slc, slice_idx, ignore, sd, cfg)
+    want_loss = O.vt_supervised_loss(context, slc, slice_idx, ignore, sd, cfg, class_idx)
     want_loss.backward()
     with torch.no_grad():
-        want_logits = torch.stack(O.vt_logits(context, slc, slice_idx, sd, cfg))  # nc, b, nv, t,h,w
+        want_logits = torch.stack(O.vt_logits(context, slc, slice_idx, sd, cfg, class_idx))  # nc, b, nv, t,h,w
     want_logits = want_logits.reshape(cfg.nc, batch, cfg.nv, -1).permute(0, 1, 3, 2)
 
     fix = np.load(os.path.join(GOLD, tag + ".npz"))

@@ -127,23 +127,26 @@ def test_vqvae_noema_oracle_matches_reference():
 
 
 @pytest.mark.parametrize("tag,layers,batch", [("dsfvt_l2", 2, 3), ("dsfvt_full", 8, 2), ("dsfvt_l2_sharep", 2, 3),
-                                              ("dsfvt_l2_tiled", 2, 2), ("dsfvt_l2_shareemb", 2, 3)])
+                                              ("dsfvt_l2_tiled", 2, 2), ("dsfvt_l2_shareemb", 2, 3),
+                                              ("dsfvt_l2_class", 2, 4)])
 def test_dsfvt_oracle_matches_reference(tag, layers, batch):
     fix = _load(tag + ".npz")
     cfg = O.VTConfig(blocks_e=tuple([(1, 16, 16)] * layers), heads_e=tuple([8] * layers),
                      blocks_d=tuple([(1, 16, 16)] * layers), heads_d=tuple([8] * layers),
                      share_p=tag.endswith("sharep"),  # SHARE_P True: the reference's config default
                      share_embeddings=tag.endswith("shareemb"),
+                     class_num=5 if tag.endswith("class") else 0,   # CLASS_NUM: class-conditioned encoder
                      # 32 latent frames: slices of (2, 16, 16) over (1, 16, 16) blocks = the general tiled attention path
                      video_shape=(32, 16, 16) if tag.endswith("tiled") else (16, 16, 16))
     sd = {k: v.requires_grad_(True) for k, v in O.synth_weights(O.dsfvt_param_shapes(cfg), seed=1234).items()}
     context, slc, slice_idx, ignore = O.synth_vt_batch(batch, seed=77, cfg=cfg)
     assert np.array_equal(slice_idx.numpy(), fix["slice_idx"]) and context.sum().item() == fix["context_sum"]
-    loss = O.vt_supervised_loss(context, slc, slice_idx, ignore, sd, cfg)
+    class_idx = torch.tensor([3, 0, 3, 4][:batch]) if cfg.class_num else None
+    loss = O.vt_supervised_loss(context, slc, slice_idx, ignore, sd, cfg, class_idx)
     loss.backward()
     assert np.allclose(loss.item(), fix["loss"], rtol=1e-6)
     with torch.no_grad():
-        logits = torch.stack(O.vt_logits(context, slc, slice_idx, sd, cfg))
+        logits = torch.stack(O.vt_logits(context, slc, slice_idx, sd, cfg, class_idx))
     assert np.allclose(logits[:, :, ::7, 0, ::3, ::5].numpy(), fix["logits_sub"], rtol=1e-4, atol=1e-5)
     assert np.allclose(logits.double().sum().item(), fix["logits_sum"], rtol=1e-5)
     for key in fix.files:
