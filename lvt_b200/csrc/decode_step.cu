@@ -29,30 +29,37 @@ constexpr int GRID = 32;     // CTAs (co-resident: the kernel runs alone on its 
 
 LVT_DEVICE_INLINE float round_bf16(float v) { return __bfloat162float(__float2bfloat16(v)); }
 
-// generation barrier over the whole grid (state: [0] arrivals, [1] generation; both return to a consistent state, so
-// the same two words serve every launch)
-LVT_DEVICE_INLINE void grid_sync(unsigned* state) {
+// Barrier over the whole grid: state[0] counts arrivals and only grows inside a launch -- barrier number k completes
+// when it reaches k * gridDim.x -- so a CTA needs ONE fire-and-forget red plus the polling loop per barrier (the
+// previous generation barrier also read the generation word first and had the last arriver reset / publish: two
+// more dependent L2 round trips; 2.5 us per barrier, 52 barriers per position).  state[1] counts the CTAs that have
+// left the kernel; the last one puts both words back to zero, so the same two words serve every launch.
+LVT_DEVICE_INLINE void grid_sync(unsigned* state, unsigned& k) {
+  ++k;
   __syncthreads();
   if (threadIdx.x == 0) {
-    volatile unsigned* gen = state + 1;
-    const unsigned g = *gen;
-    __threadfence();
-    if (atomicAdd(state, 1u) == gridDim.x - 1) {
-      state[0] = 0u;
-      __threadfence();
-      atomicAdd(state + 1, 1u);
-    } else {
-      unsigned spins = 0;
-      while (*gen == g) {
-        if (++spins > (1u << 26)) {
-          printf("lvt_b200: decode step grid barrier timeout (block %d)\n", blockIdx.x);
-          __trap();
-        }
+    const unsigned target = k * gridDim.x;
+    __threadfence();  // this CTA's writes of the stage before the barrier
+    asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(state) : "memory");
+    unsigned spins = 0, v;
+    for (;;) {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(state) : "memory");
+      if (v >= target) break;
+      if (++spins > (1u << 26)) {
+        printf("lvt_b200: decode step grid barrier timeout (block %d)\n", blockIdx.x);
+        __trap();
       }
     }
     __threadfence();
   }
   __syncthreads();
+}
+LVT_DEVICE_INLINE void grid_exit(unsigned* state) {
+  if (threadIdx.x == 0 && atomicAdd(state + 1, 1u) == gridDim.x - 1) {  // every other CTA is past its last barrier
+    state[0] = 0u;
+    state[1] = 0u;
+    __threadfence();
+  }
 }
 
 struct RowsArgs {
@@ -500,6 +507,7 @@ decode_step_kernel(const __grid_constant__ LvtDecodeStep p) {
     ++nstamp;
   };
   stamp();
+  unsigned nbar = 0;    // grid barriers passed so far in this launch
   uint32_t wreg[WPRE];  // weights of the next rows stage, requested before the barrier in front of it
   uint32_t wq[32];      // ... of the next q | k | v stage
   // ---- stage 0: row `pos` of embed-sum + causal im2col (dec_front_fwd_kernel, ops.cu: bf16-rounded), then the conv row
@@ -534,7 +542,7 @@ decode_step_kernel(const __grid_constant__ LvtDecodeStep p) {
     }
     stage_rows<R>(p, a, sh, pos, wreg);
   }
-  stamp(); grid_sync(p.barrier); stamp();
+  stamp(); grid_sync(p.barrier, nbar); stamp();
   float* x = p.xa;
   float* y = p.xb;
   for (int i = 0; i < p.n_layers; ++i) {
@@ -543,21 +551,21 @@ decode_step_kernel(const __grid_constant__ LvtDecodeStep p) {
     {
       const RowsArgs a = args_proj(ly, x);
       rows_prefetch(a, wreg);  // (stays in registers across the attention stage)
-      stamp(); grid_sync(p.barrier); stamp();
+      stamp(); grid_sync(p.barrier, nbar); stamp();
       stage_attn(p, ly, pos);
-      stamp(); grid_sync(p.barrier); stamp();
+      stamp(); grid_sync(p.barrier, nbar); stamp();
       stage_rows<R>(p, a, sh, pos, wreg);
     }
     {
       const RowsArgs a = args_ffn1(ly);
       rows_prefetch(a, wreg);
-      stamp(); grid_sync(p.barrier); stamp();
+      stamp(); grid_sync(p.barrier, nbar); stamp();
       stage_rows<R>(p, a, sh, pos, wreg);
     }
     {
       const RowsArgs a = args_ffn3(ly, y);
       rows_prefetch(a, wreg);
-      stamp(); grid_sync(p.barrier); stamp();
+      stamp(); grid_sync(p.barrier, nbar); stamp();
       stage_rows<R>(p, a, sh, pos, wreg);
     }
     float* t = x; x = y; y = t;
@@ -567,9 +575,12 @@ decode_step_kernel(const __grid_constant__ LvtDecodeStep p) {
       const RowsArgs a = args_U(0, x);
       rows_prefetch(a, wreg);
     }
-    if (i + 1 < p.n_layers || p.do_sample) stamp(); grid_sync(p.barrier); stamp();
+    if (i + 1 < p.n_layers || p.do_sample) stamp(); grid_sync(p.barrier, nbar); stamp();
   }
-  if (!p.do_sample) return;
+  if (!p.do_sample) {
+    grid_exit(p.barrier);
+    return;
+  }
   if (p.n_layers == 0) {
     const RowsArgs a = args_U(0, x);
     rows_prefetch(a, wreg);
@@ -582,17 +593,18 @@ decode_step_kernel(const __grid_constant__ LvtDecodeStep p) {
     {
       const RowsArgs a = args_P(k);
       rows_prefetch(a, wreg);
-      stamp(); grid_sync(p.barrier); stamp();
+      stamp(); grid_sync(p.barrier, nbar); stamp();
       stage_rows<R>(p, a, sh, pos, wreg);
     }
-    stamp(); grid_sync(p.barrier); stamp();
+    stamp(); grid_sync(p.barrier, nbar); stamp();
     stage_sample(p, k, pos);
     if (k + 1 < p.nc) {
       const RowsArgs a = args_U(k + 1, x);
       rows_prefetch(a, wreg);
-      stamp(); grid_sync(p.barrier); stamp();
+      stamp(); grid_sync(p.barrier, nbar); stamp();
     }
   }
+  grid_exit(p.barrier);
 }
 
 }  // namespace
