@@ -752,11 +752,20 @@ permute4_batch_kernel(const LvtPermuteJob* __restrict__ jobs, int n_jobs) {
   for (int u = 0; u < 4; ++u) {
     const long long i = base + u * 256 + threadIdx.x;
     if (i >= total) break;
-    long long r = i;
-    const int i3 = (int)(r % J.dims[3]); r /= J.dims[3];
-    const int i2 = (int)(r % J.dims[2]); r /= J.dims[2];
-    const int i1 = (int)(r % J.dims[1]); r /= J.dims[1];
-    const int i0 = (int)r;
+    int i0, i1, i2, i3;
+    if (total < (1ll << 31)) {  // 32-bit index arithmetic (three 64-bit divisions per element bound this kernel)
+      unsigned r = (unsigned)i;
+      i3 = (int)(r % (unsigned)J.dims[3]); r /= (unsigned)J.dims[3];
+      i2 = (int)(r % (unsigned)J.dims[2]); r /= (unsigned)J.dims[2];
+      i1 = (int)(r % (unsigned)J.dims[1]); r /= (unsigned)J.dims[1];
+      i0 = (int)r;
+    } else {
+      long long r = i;
+      i3 = (int)(r % J.dims[3]); r /= J.dims[3];
+      i2 = (int)(r % J.dims[2]); r /= J.dims[2];
+      i1 = (int)(r % J.dims[1]); r /= J.dims[1];
+      i0 = (int)r;
+    }
     const long long so = i0 * J.in_strides[0] + i1 * J.in_strides[1] + i2 * J.in_strides[2] + i3 * J.in_strides[3];
     const long long oo = i0 * J.out_strides[0] + i1 * J.out_strides[1] + i2 * J.out_strides[2] + i3 * J.out_strides[3];
     const float v = J.in[so];

@@ -422,9 +422,11 @@ class VTEngine:
     def _fold_enc_jobs(self):
         s, st = self.spec, self.store
         ktaps = s.kernel[0] * s.kernel[1] * s.kernel[2]
+        # (dims ordered so that the WRITE side -- a read-modify-write here -- is contiguous over the fastest two dims:
+        # the strided side should be the read, whose 32-byte sectors are reused out of L2)
         self._permute4(self.enc_dwt, st.gf("encoder.conv.weight"), False, True,
-                       (s.nc, ktaps, s.nv, s.de), (ktaps * s.nv * s.de, s.nv * s.de, s.de, 1),
-                       (s.nv * ktaps, 1, ktaps, s.nc * s.nv * ktaps))
+                       (s.de, s.nc, s.nv, ktaps), (1, ktaps * s.nv * s.de, s.de, s.nv * s.de),
+                       (s.nc * s.nv * ktaps, s.nv * ktaps, ktaps, 1))
 
     def _fold_special_grads_pred(self):
         """... one-hot half of the predictor's U[k] (complete after the predictor backward)"""
@@ -435,7 +437,7 @@ class VTEngine:
         for k in range(1, s.nc):
             ld = s.d + k * s.nv
             self._permute4(self.dut[k], st.gf(f"ch_predictor.U.{k}.weight") + 4 * s.d, False, True,
-                           (1, 1, k * s.nv, s.d), (0, 0, s.d, 1), (0, 0, 1, ld))
+                           (1, 1, s.d, k * s.nv), (0, 0, 1, s.d), (0, 0, ld, 1))   # contiguous writes (see _fold_enc_jobs)
 
     def _fold_special_grads_conv(self, slice_shape):
         """... live taps of the masked conv (complete after the decoder front)"""

@@ -210,7 +210,8 @@ class VQVAEEngine:
                        (48, 1, 16, 0))
         for name, e in self.pk.items():
             co, ci, T = e["co"], e["ci"], e["T"]
-            self._permute4(e["grad"], st.gf(name), False, True, (co, T, ci, 1), (T * ci, ci, 1, 0), (ci * T, 1, T, 0))
+            # (fastest dim = the taps, over which the destination of this read-modify-write is contiguous)
+            self._permute4(e["grad"], st.gf(name), False, True, (1, co, ci, T), (0, T * ci, 1, ci), (0, ci * T, T, 1))
         wct = f"G.layers.{self.kG + 1}.weight"
         ci, co = nf, nf // 2
         for ph in range(2):
