@@ -306,6 +306,21 @@ struct EncFrontDims {
   int B, nc, nv, de, Tc, Hc, Wc, kt, kh, kw, st, sh, sw, to, ho, wo, pad_value;
 };
 
+// code of tap `tap` (= ((c*kt + i)*kh + j)*kw + l, the row-block order of the re-laid-out weight) at output (b, to, ho, wo)
+LVT_DEVICE_INLINE long long enc_tap_code(const int64_t* __restrict__ ctx, const EncFrontDims& D, int b, int to, int ho,
+                                         int wo, int tap) {
+  const int l = tap % D.kw;
+  int r = tap / D.kw;
+  const int j = r % D.kh;
+  r /= D.kh;
+  const int i = r % D.kt, c = r / D.kt;
+  const int tt = to * D.st + i, hh = ho * D.sh + j, ww = wo * D.sw + l;
+  return ctx[((((size_t)b * D.nc + c) * D.Tc + tt) * D.Hc + hh) * D.Wc + ww];
+}
+
+// One warp per output position.  The taps' codes are read by the lanes (one tap each, 32 independent loads) and handed
+// round by shuffle, and the weight rows are fetched four at a time: two dependent L2 round trips per 32 taps instead of
+// two per tap.  The rows are still added in tap order, so the result is bit for bit what the sequential loop gave.
 __global__ void __launch_bounds__(256)
 enc_front_fwd_kernel(const int64_t* __restrict__ ctx, const int64_t* __restrict__ slice_idx,
                      const float* __restrict__ wt, const float* __restrict__ bias,
@@ -322,26 +337,37 @@ enc_front_fwd_kernel(const int64_t* __restrict__ ctx, const int64_t* __restrict_
   r -= to * D.ho * D.wo;
   const int ho = r / D.wo, wo = r - ho * D.wo;
   const float* se = slice_emb + (size_t)slice_idx[b] * D.de;
-  for (int c0 = lane * 4; c0 < D.de; c0 += 128) {
-    float4 acc = ld4(bias + c0);
-    const float4 s4 = ld4(se + c0);
-    acc.x += s4.x; acc.y += s4.y; acc.z += s4.z; acc.w += s4.w;
-    for (int c = 0; c < D.nc; ++c)
-      for (int i = 0; i < D.kt; ++i)
-        for (int j = 0; j < D.kh; ++j)
-          for (int l = 0; l < D.kw; ++l) {
-            const int tt = to * D.st + i, hh = ho * D.sh + j, ww = wo * D.sw + l;
-            const long long code = ctx[((((size_t)b * D.nc + c) * D.Tc + tt) * D.Hc + hh) * D.Wc + ww];
-            if (code == D.pad_value) continue;
-            const size_t rowi = ((((size_t)c * D.kt + i) * D.kh + j) * D.kw + l) * D.nv + (size_t)code;
-            const float4 w4 = ld4(wt + rowi * D.de + c0);
-            acc.x += w4.x; acc.y += w4.y; acc.z += w4.z; acc.w += w4.w;
-          }
-    st_bf16x4(out + (size_t)pos * D.de + c0, acc.x, acc.y, acc.z, acc.w);
+  const int ntap = D.nc * D.kt * D.kh * D.kw;
+  for (int c0 = lane * 4; c0 - lane * 4 < D.de; c0 += 128) {  // every lane runs every pass (shuffles inside)
+    const bool act = c0 < D.de;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (act) {
+      acc = ld4(bias + c0);
+      const float4 s4 = ld4(se + c0);
+      acc.x += s4.x; acc.y += s4.y; acc.z += s4.z; acc.w += s4.w;
+    }
+    for (int t0 = 0; t0 < ntap; t0 += 32) {
+      const long long mycode = (t0 + lane < ntap) ? enc_tap_code(ctx, D, b, to, ho, wo, t0 + lane) : (long long)D.pad_value;
+      const int nn = min(32, ntap - t0);
+      for (int u = 0; u < nn; u += 4) {
+        float4 w4[4];
+        bool ok[4];
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          const long long code = __shfl_sync(0xffffffffu, mycode, min(u + v, 31));
+          ok[v] = act && u + v < nn && code != D.pad_value;
+          if (ok[v]) w4[v] = ld4(wt + ((size_t)(t0 + u + v) * D.nv + (size_t)code) * D.de + c0);
+        }
+#pragma unroll
+        for (int v = 0; v < 4; ++v)
+          if (ok[v]) { acc.x += w4[v].x; acc.y += w4[v].y; acc.z += w4[v].z; acc.w += w4[v].w; }
+      }
+    }
+    if (act) st_bf16x4(out + (size_t)pos * D.de + c0, acc.x, acc.y, acc.z, acc.w);
   }
 }
 
-// backward: scatter d_out rows into the re-laid-out weight gradient and the slice embedding.
+// backward: scatter d_out rows into the re-laid-out weight gradient and the slice embedding (codes as in the forward).
 __global__ void __launch_bounds__(256)
 enc_front_bwd_kernel(const int64_t* __restrict__ ctx, const int64_t* __restrict__ slice_idx,
                      const float* __restrict__ dout, float* __restrict__ dwt,
@@ -357,19 +383,23 @@ enc_front_bwd_kernel(const int64_t* __restrict__ ctx, const int64_t* __restrict_
   r -= to * D.ho * D.wo;
   const int ho = r / D.wo, wo = r - ho * D.wo;
   float* se = dslice_emb + (size_t)slice_idx[b] * D.de;
-  for (int c0 = lane * 4; c0 < D.de; c0 += 128) {
-    const float4 g = ld4(dout + (size_t)pos * D.de + c0);
-    red_add_f32x4(se + c0, g.x, g.y, g.z, g.w);
-    for (int c = 0; c < D.nc; ++c)
-      for (int i = 0; i < D.kt; ++i)
-        for (int j = 0; j < D.kh; ++j)
-          for (int l = 0; l < D.kw; ++l) {
-            const int tt = to * D.st + i, hh = ho * D.sh + j, ww = wo * D.sw + l;
-            const long long code = ctx[((((size_t)b * D.nc + c) * D.Tc + tt) * D.Hc + hh) * D.Wc + ww];
-            if (code == D.pad_value) continue;
-            const size_t rowi = ((((size_t)c * D.kt + i) * D.kh + j) * D.kw + l) * D.nv + (size_t)code;
-            red_add_f32x4(dwt + rowi * D.de + c0, g.x, g.y, g.z, g.w);
-          }
+  const int ntap = D.nc * D.kt * D.kh * D.kw;
+  for (int c0 = lane * 4; c0 - lane * 4 < D.de; c0 += 128) {
+    const bool act = c0 < D.de;
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (act) {
+      g = ld4(dout + (size_t)pos * D.de + c0);
+      red_add_f32x4(se + c0, g.x, g.y, g.z, g.w);
+    }
+    for (int t0 = 0; t0 < ntap; t0 += 32) {
+      const long long mycode = (t0 + lane < ntap) ? enc_tap_code(ctx, D, b, to, ho, wo, t0 + lane) : (long long)D.pad_value;
+      const int nn = min(32, ntap - t0);
+      for (int u = 0; u < nn; ++u) {
+        const long long code = __shfl_sync(0xffffffffu, mycode, u);
+        if (act && code != D.pad_value)
+          red_add_f32x4(dwt + ((size_t)(t0 + u) * D.nv + (size_t)code) * D.de + c0, g.x, g.y, g.z, g.w);
+      }
+    }
   }
 }
 
