@@ -436,6 +436,9 @@ int lvt_vqvae_out_convt_g(const float* dpre, void* g_bf16, int n, void* stream);
 int lvt_vqvae_commit_loss(const float* z_e, const float* zq_bar, const float* dz_st, void* dz_bf16,
                           float* loss, long long numel, float beta, void* stream);
 /* out = (a [+ b]) * (mask_src > 0), all bf16 (ReLU backward merged with a skip gradient).     */
+/* x (fp32, n elements, n % 4 == 0) += a (bf16): the skip connection added to the fp32 output z_e of the last encoder
+ * ResBlock (resencoder.py:19-21) after its 1x1 convolution has gone through the TMA-store GEMM epilogue. */
+int lvt_add_bf16_to_f32(float* x, const void* a_bf16, long long n, void* stream);
 int lvt_relu_bwd_add(const void* a_bf16, const void* b_bf16, const void* mask_src_bf16, void* out_bf16,
                      long long n, void* stream);
 int lvt_cast_relu_bf16(const float* in, void* out_bf16, long long n, int relu, void* stream);

@@ -204,6 +204,7 @@ SYMBOLS = {
     "lvt_vqvae_out_convt_g": (_i, [_vp, _vp, _i, _vp]),
     "lvt_vqvae_commit_loss": (_i, [_vp] * 5 + [_ll, _f, _vp]),
     "lvt_relu_bwd_add": (_i, [_vp] * 4 + [_ll, _vp]),
+    "lvt_add_bf16_to_f32": (_i, [_vp, _vp, _ll, _vp]),
     "lvt_cast_relu_bf16": (_i, [_vp, _vp, _ll, _i, _vp]),
     "lvt_denorm_clamp": (_i, [_vp, _vp, _ll, _f, _f, _f, _f, _vp]),
 }

@@ -245,6 +245,20 @@ relu_bwd_add_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __
   }
 }
 
+// x (fp32) += a (bf16), four elements per thread: the skip connection of the last encoder ResBlock, whose fp32 output
+// (z_e) cannot take a bf16 addend inside the TMA-store GEMM epilogue (resencoder.py:19-21)
+__global__ void __launch_bounds__(256)
+add_bf16_to_f32_kernel(float* __restrict__ x, const __nv_bfloat16* __restrict__ a, long long n4) {
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
+    float4 v = reinterpret_cast<float4*>(x)[i];
+    const uint2 u = reinterpret_cast<const uint2*>(a)[i];
+    const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+    const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+    v.x += lo.x; v.y += lo.y; v.z += hi.x; v.w += hi.y;
+    reinterpret_cast<float4*>(x)[i] = v;
+  }
+}
+
 // fp32 -> bf16 with optional ReLU (z_q / activations entering a conv)
 __global__ void __launch_bounds__(256)
 cast_relu_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n, int relu) {
@@ -343,6 +357,14 @@ extern "C" int lvt_relu_bwd_add(const void* a_bf16, const void* b_bf16, const vo
   relu_bwd_add_kernel<<<grid_for(n / 2), 256, 0, STREAM(stream)>>>(
       reinterpret_cast<const __nv_bfloat16*>(a_bf16), reinterpret_cast<const __nv_bfloat16*>(b_bf16),
       reinterpret_cast<const __nv_bfloat16*>(mask_src_bf16), reinterpret_cast<__nv_bfloat16*>(out_bf16), n / 2);
+  LVT_CHECK_LAUNCH();
+  lvt_count_launch(1);
+  return LVT_OK;
+}
+
+extern "C" int lvt_add_bf16_to_f32(float* x, const void* a_bf16, long long n, void* stream) {
+  LVT_CHECK_ARG(x && a_bf16 && n > 0 && n % 4 == 0, "lvt_add_bf16_to_f32: bad argument");
+  add_bf16_to_f32_kernel<<<grid_for(n / 4), 256, 0, STREAM(stream)>>>(x, reinterpret_cast<const __nv_bfloat16*>(a_bf16), n / 4);
   LVT_CHECK_LAUNCH();
   lvt_count_launch(1);
   return LVT_OK;

@@ -311,6 +311,13 @@ class VQVAEEngine:
         wA, wB = f"{pre}.block.1.weight", f"{pre}.block.3.weight"
         self._conv(r, s.nf, n, self.pk[wA]["fwd"], 9 * s.nf, s.rc, h, st.pf(f"{pre}.block.1.bias"), TAPS3)
         M = n * 256
+        if last_f32 and not relu_out:
+            # fp32 output (z_e) with a bf16 skip: the TMA-store epilogue has no such pair (the staged generic epilogue took
+            # 145 us for it at 512 frames), so the 1x1 convolution stores fp32 through TMA and one pass adds the skip
+            gemm(M, s.nf, s.rc, Operand(h.data_ptr(), s.rc), Operand(st.pb(wB), s.rc), Operand(out.data_ptr(), s.nf),
+                 out_f32=out, bias=st.pf(f"{pre}.block.3.bias"))
+            check(self.lib.lvt_add_bf16_to_f32(ptr(out), ptr(r), M * s.nf, stream_ptr()), "lvt_add_bf16_to_f32")
+            return
         gemm(M, s.nf, s.rc, Operand(h.data_ptr(), s.rc), Operand(st.pb(wB), s.rc), Operand(out.data_ptr(), s.nf),
              out_f32=out if last_f32 else None, out_bf16=None if last_f32 else out, bias=st.pf(f"{pre}.block.3.bias"),
              aux=r, flags=ops.GEMM_AUX_ADD | (ops.GEMM_RELU if relu_out else 0))
