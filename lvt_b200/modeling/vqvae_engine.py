@@ -115,6 +115,20 @@ class VQVAEEngine:
         # output ConvTranspose2d(nf/2 -> 3) weight [c][co][kh][kw] as GEMM operands (rows beyond 48 stay zero)
         self.w_out_fwd = z((64, nf // 2), bf16)           # [(kh*4+kw)*3 + co][c]
         self.w_out_dg = z((nf // 2, 64), bf16)            # [c][co*16 + kh*4 + kw]
+        # the packed fp32 weight gradients live in ONE flat buffer, so that zeroing them is one launch per step, not ten
+        pg = [("dw1p", None), ("ct1_grad", None), ("dw_out", None)] + [("pk", k) for k in self.pk]
+        get = lambda a, k: getattr(self, a) if k is None else self.pk[k]["grad"]  # noqa: E731
+        sizes = [(get(a, k).numel() + 3) // 4 * 4 for a, k in pg]
+        self._pg_flat = z((sum(sizes),))
+        off = 0
+        for (a, k), n in zip(pg, sizes):
+            t = get(a, k)
+            view = self._pg_flat[off:off + t.numel()].view(t.shape)
+            if k is None:
+                setattr(self, a, view)
+            else:
+                self.pk[k]["grad"] = view
+            off += n
         self._ws = {}
         self.shadows_fresh = False
         self.opt = None
@@ -225,11 +239,7 @@ class VQVAEEngine:
                        (64, 1, 0, 0), (48, 1, 0, 0))
 
     def _zero_packed_grads(self):
-        self.dw1p.zero_()
-        for e in self.pk.values():
-            e["grad"].zero_()
-        self.ct1_grad.zero_()
-        self.dw_out.zero_()
+        self._pg_flat.zero_()
 
     # ------------------------------------------------------------------ workspace
     def workspace(self, n, train=True):
