@@ -98,3 +98,23 @@ def test_gradient_buckets_tile_the_flat_buffer_in_backward_order():
             for i in range(cd[j + 1], cd[j]):
                 assert bucket_of(f"decoder.block_local_attention.{i}.ffn.1.weight") == j
                 assert bucket_of(f"encoder.block_local_attention.{i}.ffn.1.weight") == parts + j
+
+
+def test_reference_arm_line_contract():
+    """`bench.py --impl reference` (CPU only: the reference's own implementation of the path, or the oracle port when
+    baseline/_ref is absent) prints ONE JSON line with the keys the driver reads."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "latent tokens/sec DSFVT train step"
+    assert line["unit"] == "latent tokens/s" and line["higher_is_better"] is True and line["value"] > 0
+    assert line["steps"] == 1 and line["warmup"] == 1 and line["config"]["per_gpu_batch"] == 8
+    assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["value"] == line["value"]
+    assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert line["gpu_launches"] == 0
